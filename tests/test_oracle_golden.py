@@ -1,0 +1,78 @@
+"""The oracle against the reference's goldens (CPU; pins the oracle).
+
+Fixtures in tests/golden/ were produced by the unmodified reference
+(tests/golden/make_golden.py).  Tolerances: the reference's own noise floor across
+thread counts is ~1e-14 relative on the ELBO; we require
+1e-9 relative on the ELBO trajectory, identical trial counts / L schedule, and
+rtol 1e-6 (+ atol 1e-9) on parameters.
+"""
+import numpy as np
+import pytest
+
+from oracle.ld_np import BlockDiagonalLD, LowRankBlock
+from oracle.vi_np import OracleVI
+from _fixtures import VI_CASES, build_ld, load_case, vi_kwargs
+
+
+def make_oracle(fx):
+    return OracleVI(ld_mats=build_ld(fx, LowRankBlock, BlockDiagonalLD), **vi_kwargs(fx))
+
+
+@pytest.mark.parametrize('name', VI_CASES)
+def test_precompute_and_init(name):
+    fx = load_case(name)
+    vi = make_oracle(fx)
+    assert np.allclose(vi.ld_diags, fx['pre_ld_diags'], rtol=1e-10, atol=1e-12)
+    assert np.allclose(vi.adj_marginal_effects, fx['pre_adj_marginal_effects'],
+                       rtol=1e-8, atol=1e-10 * np.abs(fx['pre_adj_marginal_effects']).max())
+    assert np.allclose(vi.chi_stat, fx['pre_chi_stat'], rtol=1e-9)
+    assert np.array_equal(vi.ld_ranks, fx['pre_ld_ranks'])
+    assert np.allclose(vi.inverse_betas, fx['pre_inverse_betas'], rtol=1e-7,
+                       atol=1e-10 * np.abs(fx['pre_inverse_betas']).max())
+    np.random.seed(int(fx['seed']))
+    mu, delta, hyper = vi._initialize()
+    assert np.allclose(mu, fx['init_vi_mu'], rtol=1e-7, atol=1e-12)
+    assert np.allclose(delta, fx['init_vi_delta'], rtol=1e-7, atol=1e-300)
+    assert np.allclose(hyper, fx['init_hyper_delta'], rtol=1e-9)
+    assert np.allclose(vi.nat_grad_vi_delta, fx['init_nat_grad_vi_delta'], rtol=1e-9, atol=1e-12)
+    params = (fx['init_vi_mu'], fx['init_vi_delta'], fx['init_hyper_delta'])
+    assert np.isclose(vi._log_likelihood(params), float(fx['init_loglik']), rtol=1e-11)
+    assert np.isclose(vi._beta_KL(*params), float(fx['init_beta_kl']), rtol=1e-11)
+    assert np.isclose(vi.elbo(params), float(fx['init_elbo']), rtol=1e-11)
+    assert np.allclose(vi.real_posterior_mean(*params), fx['init_post_mean'], rtol=1e-10, atol=1e-14)
+    assert np.allclose(vi.real_posterior_variance(*params), fx['init_post_var'], rtol=1e-10, atol=1e-16)
+
+
+@pytest.mark.parametrize('name', VI_CASES)
+def test_trajectory(name):
+    fx = load_case(name)
+    vi = make_oracle(fx)
+    np.random.seed(int(fx['seed']))
+    traj = {}
+    params = vi.optimize(None, trajectory=traj)
+    assert len(traj['elbo_out']) == len(fx['traj_elbo_out'])
+    assert traj['trials'] == fx['traj_trials'].tolist()
+    assert np.array_equal(np.array(traj['L0']), fx['traj_L0'])
+    assert np.allclose(traj['elbo_out'], fx['traj_elbo_out'], rtol=1e-9, atol=0)
+    assert np.allclose(np.array(traj['tau']), fx['traj_tau'], rtol=1e-8)
+    assert np.allclose(params[0], fx['final_vi_mu'], rtol=1e-6, atol=1e-9)
+    assert np.allclose(params[1], fx['final_vi_delta'], rtol=1e-6, atol=1e-12)
+    assert np.allclose(params[2], fx['final_hyper_delta'], rtol=1e-6, atol=1e-12)
+    assert np.allclose(vi.real_posterior_mean(*params), fx['final_post_mean'], rtol=1e-6, atol=1e-9)
+    assert np.allclose(vi.real_posterior_variance(*params), fx['final_post_var'], rtol=1e-6, atol=1e-12)
+    assert np.allclose(vi.vi_sigma, fx['final_vi_sigma'], rtol=1e-8)
+
+
+@pytest.mark.parametrize('name', [n for n in VI_CASES if 'resume_ckpt_vi_mu' in load_case(n)])
+def test_resume(name):
+    fx = load_case(name)
+    vi = make_oracle(fx)
+    ckpt = {k[len('resume_ckpt_'):]: v for k, v in fx.items() if k.startswith('resume_ckpt_')}
+    traj = {}
+    params = vi.optimize(ckpt, trajectory=traj)
+    assert traj['trials'] == fx['resume_traj_trials'].tolist()
+    assert np.array_equal(np.array(traj['L0']), fx['resume_traj_L0'])
+    assert np.allclose(traj['elbo_out'], fx['resume_traj_elbo_out'], rtol=1e-9)
+    assert np.allclose(params[0], fx['resume_final_vi_mu'], rtol=1e-6, atol=1e-9)
+    assert np.allclose(params[2], fx['resume_final_hyper_delta'], rtol=1e-6, atol=1e-12)
+    assert np.allclose(vi.error_scaling, fx['resume_final_error_scaling'], rtol=1e-8)
