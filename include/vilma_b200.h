@@ -1,0 +1,128 @@
+/* vilma_b200 -- C ABI of the B200-native `vilma fit` hot path (libvilma_b200.so).
+ *
+ * The reference (jeffspence/vilma v0.0.16) is pure Python and has no FFI: the de-facto
+ * contract of its hot path is the VIScheme/MultiPopVI API (variational_inference.py:27-889)
+ * over BlockDiagonalMatrix.dot (matrix_structures.py:389-408).  This header is what a
+ * maintainer of the reference would bind (ctypes) to replace, one for
+ * one, the array operations of that path.  Each entry point cites the reference code it
+ * replaces (paths relative to /root/reference/src/vilma/).
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error; vb_last_error() gives the text;
+ *    no C++ exception crosses the boundary; nothing falls back to the CPU.
+ *  - plain pointers and sizes only.  `*_host` pointers are host memory, `*_dev` device
+ *    memory (fp64 unless noted).  The library never frees caller memory.
+ *  - one CUDA stream per context (given at creation; 0 = legacy default stream).  Calls are
+ *    asynchronous on that stream unless they return data through a `*_host` pointer.
+ *  - device layouts: vi_mu [K][P][M], vi_delta [K][M] (the TRANSPOSE of the reference's
+ *    [M][K]), per-SNP vectors [P][M]; M is the number of SNPs owned by this rank.
+ */
+#ifndef VILMA_B200_H
+#define VILMA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vb_ctx vb_ctx;
+typedef struct vb_ld vb_ld; /* one cohort's block-diagonal LD operator, resident in HBM */
+
+#define VB_ABI_VERSION 1
+#define VB_MAX_POPS 6 /* cohorts compiled into the per-SNP kernels */
+
+/* ---- context ------------------------------------------------------------------------ */
+int vb_abi_version(void);
+const char* vb_last_error(void);
+/* device: CUDA ordinal; stream: cudaStream_t (may be NULL). */
+int vb_ctx_create(int device, void* stream, vb_ctx** out);
+int vb_ctx_destroy(vb_ctx* ctx);
+int vb_ctx_sync(vb_ctx* ctx);
+/* number of kernels launched by this context since creation (bench.py "gpu_launches") */
+int64_t vb_ctx_launch_count(const vb_ctx* ctx);
+
+/* ---- LD operator ---------------------------------------------------------------------
+ * Replaces BlockDiagonalMatrix(matrices, perm, missing) and its .dot
+ * (matrix_structures.py:277-331, :389-408) over LowRankMatrix.dot (:148-152).
+ *
+ * vb_ld_create     declare the blocks: n[b] rows, rank[b] columns of the factor (rank[b] < 0:
+ *                  block b is given dense).  M = SNPs on this rank.
+ * vb_ld_set_dense  block b as a dense symmetric n x n matrix, row stride `ld` doubles.
+ * vb_ld_set_factor block b as U (n x r, row-major, row stride r) and s (r):  R_b = U diag(s) U^T
+ *                  (the reference's u, s; its v is u^T and D must be zero on this path).
+ * vb_ld_finalize   perm[j] = SNP index (0..M-1, this rank's numbering) of block-order
+ *                  position j, for j < sum_b n[b]; SNPs not listed are "missing" (zero rows).
+ * vb_ld_dot        y = R x in SNP order (x, y device vectors of length M).
+ * vb_ld_bytes      algorithmic bytes one mat-vec reads from the LD store.
+ */
+int vb_ld_create(vb_ctx* ctx, int64_t M, int64_t nblocks, const int64_t* n, const int64_t* rank,
+                 vb_ld** out);
+int vb_ld_destroy(vb_ld* ld);
+int vb_ld_set_dense(vb_ld* ld, int64_t b, const double* R, int64_t ldr, int on_device);
+int vb_ld_set_factor(vb_ld* ld, int64_t b, const double* U, const double* s, int on_device);
+int vb_ld_finalize(vb_ld* ld, const int64_t* perm_host, int64_t nperm);
+int vb_ld_dot(vb_ld* ld, const double* x_dev, double* y_dev);
+int64_t vb_ld_bytes(const vb_ld* ld);
+
+/* ---- fit state ----------------------------------------------------------------------
+ * vb_fit_create       allocate the device state for K components, P cohorts, M SNPs, A annotations
+ *                     over the P finalized LD operators `lds` (same context, same M).
+ * vb_fit_set_snp_data adj_marginal_effects, std_errs, scaled_ld_diags, scalings [P][M] and the
+ *                     annotation label per SNP (variational_inference.py:205-259).
+ * vb_fit_set_mixture  mixture_prec [K][P][P] and log_det [K]            (:622-626)
+ * vb_fit_set_hyper    hyper_delta [A][K] used by the KL term (fast_delta_kl, numerics.py:132-141)
+ * vb_fit_set_delta_grad  nat_grad_vi_delta as an [A][K-1] table: fast_vi_delta_grad's value
+ *                     for annotation a (numerics.py:149-164; variational_inference.py:694, :706, :844)
+ * vb_fit_set_tau      error_scaling [P]; implies _set_vi_sigma()        (:712-738)
+ * vb_fit_set_params / vb_fit_get_params   accepted state, host arrays in DEVICE layout.
+ */
+int vb_fit_create(vb_ctx* ctx, int K, int P, int64_t M, int A, vb_ld* const* lds);
+int vb_fit_destroy(vb_ctx* ctx);
+int vb_fit_set_snp_data(vb_ctx* ctx, const double* adj_host, const double* se_host,
+                        const double* sld_host, const double* scalings_host,
+                        const int32_t* ann_host);
+int vb_fit_set_mixture(vb_ctx* ctx, const double* prec_host, const double* logdet_host);
+int vb_fit_set_hyper(vb_ctx* ctx, const double* hyper_host);
+int vb_fit_set_delta_grad(vb_ctx* ctx, const double* table_host);
+int vb_fit_set_tau(vb_ctx* ctx, const double* tau_host);
+int vb_fit_set_params(vb_ctx* ctx, const double* vi_mu_host, const double* vi_delta_km_host);
+int vb_fit_get_params(vb_ctx* ctx, double* vi_mu_host, double* vi_delta_km_host);
+
+/* ---- evaluations: each fills stats_dev[0 .. 3P+3) for ONE parameter state -------------
+ *   [0,P)   A_p = sum_i pm adj      [P,2P)  C_p = sum_i sld pv      [2P,3P) B_p = sum_i z (R z)
+ *   3P KL_delta  3P+1 KL_quad  3P+2 KL_sigma
+ * from which  loglik = sum_p [(-(C_p+B_p)/2 + A_p - chi_p/2)/tau_p - rank_p log(tau_p)/2]
+ * (numerics.py:31-46) and beta_KL = KL_delta + KL_quad + KL_sigma (variational_inference.py:873-885).
+ *
+ * vb_fit_eval           the accepted state as it stands           (_log_likelihood :452-470, _beta_KL)
+ * vb_fit_beta_trial     accepted -> trial at step size `step`     (_update_beta loop body :778-787,
+ *                                                                  _nat_grad_beta :804-823)
+ * vb_fit_refresh_delta  trial := (accepted mu, delta recomputed from the current hyper/tau)
+ *                                                                 (_nat_to_not_vi_delta :632-641)
+ * vb_fit_accept         trial becomes the accepted state.
+ */
+int vb_fit_eval(vb_ctx* ctx, double* stats_dev);
+int vb_fit_beta_trial(vb_ctx* ctx, double step, double* stats_dev);
+int vb_fit_refresh_delta(vb_ctx* ctx, double* stats_dev);
+int vb_fit_accept(vb_ctx* ctx);
+
+/* sum_annotations of the accepted delta -> out_dev [A][K]   (numerics.py:118-129) */
+int vb_fit_sum_annotations(vb_ctx* ctx, double* out_dev);
+/* accepted state's posterior mean / marginal variance, in model units (NOT multiplied by
+ * scalings) -> host [P][M]  (_posterior_mean, _posterior_marginal_variance :753-760) */
+int vb_fit_posterior(vb_ctx* ctx, double* pm_host, double* pv_host);
+/* convergence bookkeeping on the real posterior mean (:376-377 allclose, :292-331 _dump_info):
+ * out_dev[0..10) = {#violations, sum|d|, sum d^2, sum|d_ckpt|, sum d_ckpt^2,
+ *                   max|new|, max rel, max abs, max rel ckpt, max abs ckpt};
+ * the first five are sums over SNPs (all-reduce SUM), the last five maxima (MAX).
+ * Then prev := new.  vb_fit_pm_mark(which): 0 -> prev := current, 1 -> ckpt := current. */
+int vb_fit_pm_diff(vb_ctx* ctx, double atol, double rtol, double* out_dev);
+int vb_fit_pm_mark(vb_ctx* ctx, int which);
+/* vi_sigma[k0:k1][P][P][M] in the reference layout -> host  (:712-724) */
+int vb_fit_vi_sigma(vb_ctx* ctx, int k0, int k1, double* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VILMA_B200_H */

@@ -1,0 +1,437 @@
+// Fused per-SNP kernels of the vilma fit loop for sm_100a (fp64, thread per SNP).
+//
+// One launch replaces, per evaluated parameter state, the reference's chain of numba
+// kernels and einsums (/root/reference/src/vilma/):
+//   numerics.py:68-80   fast_nat_inner_product_m2   eta_old = Lambda mu
+//   variational_inference.py:804-823 _nat_grad_beta (fast_divide, fast_linked_ests and the
+//                                                   K-fold broadcast einsum 'p,pi,k->kpi')
+//   numerics.py:11-15   sum_betas                   eta = t g + (1-t) eta_old
+//   numerics.py:83-95   fast_nat_inner_product      mu' = S eta
+//   numerics.py:198-213 fast_invert_nat_vi_delta -> :179-195 invert_nat_cat_2D (softmax, floor)
+//   numerics.py:49-65   fast_posterior_mean, fast_pmv
+//   numerics.py:132-146, :98-115  fast_delta_kl, fast_beta_kl, fast_inner_product_comp
+//   variational_inference.py:712-733 _set_vi_sigma: S_ki = (Prec_k + diag(sld_i/tau))^-1,
+//       its log-det, tr(Prec_k S_ki) and sigma_summary are RECOMPUTED per (k,i) in
+//       registers instead of streaming three [K,P,P,M] arrays from HBM.
+//
+// Device layouts: mu[K][P][M], delta[K][M], per-SNP vectors [P][M]  (M innermost, so a warp
+// reads 32 consecutive SNPs = coalesced 256-byte segments).
+#pragma once
+#include "vb_common.cuh"
+
+enum { VB_MODE_TRIAL = 0, VB_MODE_REFRESH = 1, VB_MODE_EVAL = 2 };
+
+// Number of doubles each CTA of the SNP kernel contributes: A_p[P], C_p[P], KL_delta, KL_quad, KL_sigma
+#define VB_NSNPSTAT(P) (2 * (P) + 3)
+
+struct VbSnpArgs {
+    int K, A;
+    int64_t M;
+    // static per-SNP data [P][M]
+    const double* adj;
+    const double* se;
+    const double* sld;
+    const int32_t* ann;          // [M]
+    // mixture constants
+    const double* prec;          // [K][P][P]
+    const double* logdet;        // [K]
+    const double* logh;          // [A][K]  log hyper_delta (KL term)
+    const double* gfull;         // [A][K]  nat_grad_vi_delta table, last column 0 (logits)
+    double inv_tau[VB_MAXP];
+    // input state
+    const double* mu_in;         // [K][P][M]
+    const double* delta_in;      // [K][M]     (EVAL only)
+    const double* pm_in;         // [P][M]     (TRIAL: accepted posterior mean)
+    const double* linked_in;     // [P][M]     (TRIAL: accepted R z)
+    double step;                 // TRIAL: 1/L
+    // output state
+    double* mu_out;              // [K][P][M]  (TRIAL)
+    double* delta_out;           // [K][M]     (TRIAL, REFRESH)
+    double* pm_out;              // [P][M]
+    double* z_out;               // [P][M]     pm / se
+    double* pv_out;              // [P][M] or null
+    double* partial;             // [gridDim.x][VB_NSNPSTAT(P)]
+};
+
+// ---- symmetric P x P helpers, lower-triangular packed: idx(i,j) = i(i+1)/2 + j, j <= i
+#define VB_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
+
+// Given Lambda (SPD, packed), produce S = Lambda^-1 (packed) and c = log det S.
+template <int P>
+__device__ __forceinline__ void vb_spd_inverse(const double (&lam)[P * (P + 1) / 2],
+                                               double (&S)[P * (P + 1) / 2], double& logdetS) {
+    if constexpr (P == 1) {
+        S[0] = 1.0 / lam[0];
+        logdetS = -log(lam[0]);
+    } else if constexpr (P == 2) {
+        // closed form, as numerics.py:223-232 / :264-268
+        const double det = lam[0] * lam[2] - lam[1] * lam[1];
+        const double idet = 1.0 / det;
+        S[0] = lam[2] * idet;
+        S[2] = lam[0] * idet;
+        S[1] = -lam[1] * idet;
+        logdetS = -log(det);
+    } else {
+        // Cholesky Lambda = L L^T, Linv, S = Linv^T Linv   (reference: LAPACK inv / slogdet)
+        double L[P * (P + 1) / 2];
+        double ld = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            double d = lam[VB_TRI(j, j)];
+#pragma unroll
+            for (int k = 0; k < j; ++k) d -= L[VB_TRI(j, k)] * L[VB_TRI(j, k)];
+            ld += log(d);
+            const double ljj = sqrt(d);
+            const double inv = 1.0 / ljj;
+            L[VB_TRI(j, j)] = inv;   // store the reciprocal of the diagonal
+#pragma unroll
+            for (int i = j + 1; i < P; ++i) {
+                double v = lam[VB_TRI(i, j)];
+#pragma unroll
+                for (int k = 0; k < j; ++k) v -= L[VB_TRI(i, k)] * L[VB_TRI(j, k)];
+                L[VB_TRI(i, j)] = v * inv;
+            }
+        }
+        logdetS = -ld;
+        // Linv (lower): Linv[j][j] = 1/L[j][j];  Linv[i][j] = -(sum_{k=j}^{i-1} L[i][k] Linv[k][j]) / L[i][i]
+        double W[P * (P + 1) / 2];
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            W[VB_TRI(j, j)] = L[VB_TRI(j, j)];
+#pragma unroll
+            for (int i = j + 1; i < P; ++i) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = j; k < i; ++k) v += L[VB_TRI(i, k)] * W[VB_TRI(k, j)];
+                W[VB_TRI(i, j)] = -v * L[VB_TRI(i, i)];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                double v = 0.0;
+#pragma unroll
+                for (int k = i; k < P; ++k) v += W[VB_TRI(k, i)] * W[VB_TRI(k, j)];
+                S[VB_TRI(i, j)] = v;
+            }
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void vb_sym_matvec(const double (&A)[P * (P + 1) / 2],
+                                              const double (&x)[P], double (&y)[P]) {
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) v += A[i >= j ? VB_TRI(i, j) : VB_TRI(j, i)] * x[j];
+        y[i] = v;
+    }
+}
+
+template <int P, int MODE>
+__global__ void __launch_bounds__(128) vb_snp_kernel(const VbSnpArgs a) {
+    constexpr int NT = P * (P + 1) / 2;
+    constexpr int NS = VB_NSNPSTAT(P);
+    __shared__ double scratch[32];
+    const int K = a.K;
+    const int64_t M = a.M;
+    const size_t PM = (size_t)P * M;
+
+    double tA[P], tC[P], tKd = 0.0, tKq = 0.0, tKs = 0.0;
+#pragma unroll
+    for (int p = 0; p < P; ++p) { tA[p] = 0.0; tC[p] = 0.0; }
+
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double dt[P], sld[P], g[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            sld[p] = a.sld[(size_t)p * M + i];
+            dt[p] = sld[p] * a.inv_tau[p] ;
+        }
+        // NOTE reference: sld / tau (division).  inv_tau is exact 1/tau computed on the host;
+        // x * (1/tau) vs x / tau differ by <= 1 ulp.
+        if constexpr (MODE == VB_MODE_TRIAL) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const double se = a.se[(size_t)p * M + i];
+                const double lk = a.linked_in[(size_t)p * M + i] / se -
+                                  a.pm_in[(size_t)p * M + i] * sld[p];
+                g[p] = (a.adj[(size_t)p * M + i] - lk) * a.inv_tau[p];
+            }
+        }
+        const int an = a.ann[i];
+        const double* logh = a.logh + (size_t)an * K;
+        const double* gfull = a.gfull + (size_t)an * K;
+
+        // online-softmax accumulators (weights e_k = exp(l_k - mx))
+        double mx = -1.0e300, s0 = 0.0, sKd = 0.0, sKq = 0.0, sKs = 0.0;
+        double spm[P], sm2[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) { spm[p] = 0.0; sm2[p] = 0.0; }
+
+        for (int k = 0; k < K; ++k) {
+            const double* prec = a.prec + (size_t)k * P * P;
+            double lam[NT], S[NT], mu[P], eta[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+#pragma unroll
+                for (int q = 0; q <= p; ++q) lam[VB_TRI(p, q)] = prec[p * P + q];
+                lam[VB_TRI(p, p)] += dt[p];
+                mu[p] = a.mu_in[(size_t)k * PM + (size_t)p * M + i];
+            }
+            double c;
+            vb_spd_inverse<P>(lam, S, c);
+            // tr(Prec_k S)
+            double tr = 0.0;
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+#pragma unroll
+                for (int q = 0; q < P; ++q)
+                    tr += prec[p * P + q] * S[p >= q ? VB_TRI(p, q) : VB_TRI(q, p)];
+            const double ldk = a.logdet[k];
+            const double sigsum = ldk - c + tr;
+
+            double w;   // weight of this component
+            double lk = 0.0;
+            if constexpr (MODE == VB_MODE_EVAL) {
+                w = a.delta_in[(size_t)k * M + i];
+            } else {
+                vb_sym_matvec<P>(lam, mu, eta);            // eta_old = Lambda mu
+                if constexpr (MODE == VB_MODE_TRIAL) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p)
+                        eta[p] = a.step * g[p] + (1.0 - a.step) * eta[p];
+                    vb_sym_matvec<P>(S, eta, mu);          // mu' = S eta
+#pragma unroll
+                    for (int p = 0; p < P; ++p)
+                        a.mu_out[(size_t)k * PM + (size_t)p * M + i] = mu[p];
+                }
+                double dot = 0.0;
+#pragma unroll
+                for (int p = 0; p < P; ++p) dot += mu[p] * eta[p];
+                lk = 0.5 * (c + dot) + gfull[k];
+                a.delta_out[(size_t)k * M + i] = lk;       // logits parked; normalised below
+                if (lk > mx) {
+                    const double r = exp(mx - lk);
+                    s0 *= r; sKd *= r; sKq *= r; sKs *= r;
+#pragma unroll
+                    for (int p = 0; p < P; ++p) { spm[p] *= r; sm2[p] *= r; }
+                    mx = lk;
+                }
+                w = exp(lk - mx);
+            }
+            // quadratic form mu'^T Prec_k mu'
+            double quad = 0.0;
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+#pragma unroll
+                for (int q = 0; q < P; ++q) quad += mu[p] * mu[q] * prec[q * P + p];
+            s0 += w;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                spm[p] = fma(w, mu[p], spm[p]);
+                sm2[p] = fma(w, S[VB_TRI(p, p)] + mu[p] * mu[p], sm2[p]);
+            }
+            if constexpr (MODE == VB_MODE_EVAL) {
+                sKd = fma(w, log(w) - logh[k], sKd);
+            } else {
+                sKd = fma(w, lk - logh[k], sKd);           // log delta_k = l_k - mx - log(denom)
+            }
+            sKq = fma(w, quad, sKq);
+            sKs = fma(w, sigsum, sKs);
+        }
+
+        double inv_den = 1.0, log_norm = 0.0;
+        if constexpr (MODE != VB_MODE_EVAL) {
+            inv_den = 1.0 / s0;
+            log_norm = mx + log(s0);
+            // second pass: delta_k = max(exp(l_k - mx) / denom, EPSILON)   (numerics.py:188-194)
+            for (int k = 0; k < K; ++k) {
+                const double lk = a.delta_out[(size_t)k * M + i];
+                a.delta_out[(size_t)k * M + i] = fmax(exp(lk - mx) * inv_den, VB_EPSILON);
+            }
+        }
+        // moments and per-SNP objective pieces
+        if constexpr (MODE == VB_MODE_EVAL) {
+            tKd += sKd;
+        } else {
+            tKd += sKd * inv_den - log_norm;
+        }
+        tKq += 0.5 * sKq * inv_den;
+        tKs += 0.5 * sKs * inv_den;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const double pm = spm[p] * inv_den;
+            const double pv = sm2[p] * inv_den - pm * pm;
+            a.pm_out[(size_t)p * M + i] = pm;
+            a.z_out[(size_t)p * M + i] = pm / a.se[(size_t)p * M + i];
+            if (a.pv_out) a.pv_out[(size_t)p * M + i] = pv;
+            tA[p] = fma(pm, a.adj[(size_t)p * M + i], tA[p]);
+            tC[p] = fma(sld[p], pv, tC[p]);
+        }
+    }
+
+    // deterministic block reduction -> partial[blockIdx][NS]
+    double* out = a.partial + (size_t)blockIdx.x * NS;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        double v = vb_block_sum(tA[p], scratch);
+        if (threadIdx.x == 0) out[p] = v;
+        v = vb_block_sum(tC[p], scratch);
+        if (threadIdx.x == 0) out[P + p] = v;
+    }
+    double v = vb_block_sum(tKd, scratch);
+    if (threadIdx.x == 0) out[2 * P] = v;
+    v = vb_block_sum(tKq, scratch);
+    if (threadIdx.x == 0) out[2 * P + 1] = v;
+    v = vb_block_sum(tKs, scratch);
+    if (threadIdx.x == 0) out[2 * P + 2] = v;
+}
+
+// Final fixed-order reduction of all partials of one evaluation into the stats vector:
+//   stats[0..P)   A_p = sum_i pm adj          stats[P..2P)  C_p = sum_i sld pv
+//   stats[2P..3P) B_p = sum_i z (R z)         stats[3P..3P+3) KL_delta, KL_quad, KL_sigma
+__global__ void vb_stats_finalize_kernel(const double* __restrict__ part_snp, int n_part_snp, int P,
+                                         const double* __restrict__ part_fin, int n_part_fin,
+                                         double* __restrict__ stats) {
+    __shared__ double scratch[32];
+    const int NS = VB_NSNPSTAT(P);
+    for (int s = 0; s < NS; ++s) {
+        double acc = 0.0;
+        for (int b = threadIdx.x; b < n_part_snp; b += blockDim.x) acc += part_snp[(size_t)b * NS + s];
+        acc = vb_block_sum(acc, scratch);
+        if (threadIdx.x == 0) stats[s < 2 * P ? s : s + P] = acc;
+    }
+    for (int p = 0; p < P; ++p) {
+        double acc = 0.0;
+        for (int b = threadIdx.x; b < n_part_fin; b += blockDim.x) acc += part_fin[(size_t)p * n_part_fin + b];
+        acc = vb_block_sum(acc, scratch);
+        if (threadIdx.x == 0) stats[2 * P + p] = acc;
+    }
+}
+
+// Per-annotation column sums of delta (numerics.py:118-129 sum_annotations), deterministic.
+// grid = (chunks, K).  partial[(chunk*K + k)*A + a]
+#define VB_ANN_TILE 8
+__global__ void vb_sum_annotations_kernel(const double* __restrict__ delta, const int32_t* __restrict__ ann,
+                                          int64_t M, int K, int A, double* __restrict__ partial) {
+    __shared__ double scratch[32];
+    const int k = blockIdx.y;
+    for (int a0 = 0; a0 < A; a0 += VB_ANN_TILE) {
+        double acc[VB_ANN_TILE];
+#pragma unroll
+        for (int t = 0; t < VB_ANN_TILE; ++t) acc[t] = 0.0;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+             i += (int64_t)gridDim.x * blockDim.x) {
+            const int an = ann[i] - a0;
+            const double d = delta[(size_t)k * M + i];
+#pragma unroll
+            for (int t = 0; t < VB_ANN_TILE; ++t) acc[t] += (an == t) ? d : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < VB_ANN_TILE; ++t) {
+            if (a0 + t < A) {
+                const double v = vb_block_sum(acc[t], scratch);
+                if (threadIdx.x == 0) partial[((size_t)blockIdx.x * K + k) * A + a0 + t] = v;
+            }
+        }
+    }
+}
+__global__ void vb_sum_annotations_final_kernel(const double* __restrict__ partial, int nchunk, int K, int A,
+                                                double* __restrict__ out /*[A][K]*/) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= K * A) return;
+    const int k = idx / A, a = idx % A;
+    double acc = 0.0;
+    for (int c = 0; c < nchunk; ++c) acc += partial[((size_t)c * K + k) * A + a];
+    out[(size_t)a * K + k] = acc;
+}
+
+// Convergence bookkeeping on the real posterior mean (variational_inference.py:376-377 allclose,
+// :292-331 _dump_info).  Compares pm*scal against prev / ckpt, then overwrites prev.
+//   sums[0] = #violations of |new-old| <= atol + rtol*|old|;  sums[1] = sum|new-old|; sums[2] = sum (new-old)^2
+//   sums[3] = sum|new-ckpt|; sums[4] = sum (new-ckpt)^2
+//   maxs[0] = max|new|; maxs[1] = max rel(prev); maxs[2] = max abs(prev); maxs[3] = max rel(ckpt); maxs[4] = max abs(ckpt)
+__global__ void vb_pm_diff_kernel(const double* __restrict__ pm, const double* __restrict__ scal,
+                                  double* __restrict__ prev, const double* __restrict__ ckpt, int64_t n,
+                                  double atol, double rtol, double* __restrict__ part /*[grid][10]*/) {
+    __shared__ double scratch[32];
+    double viol = 0, sab = 0, ssq = 0, cab = 0, csq = 0, mnew = 0, mrel = 0, mabs = 0, crel = 0, cabs = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = pm[i] * scal[i];
+        const double o = prev[i], c = ckpt[i];
+        const double d = fabs(v - o), dc = fabs(v - c);
+        if (!(d <= atol + rtol * fabs(o))) viol += 1.0;
+        sab += d; ssq += d * d; cab += dc; csq += dc * dc;
+        mnew = fmax(mnew, fabs(v));
+        mabs = fmax(mabs, d); cabs = fmax(cabs, dc);
+        mrel = fmax(mrel, fabs((v - o) / (o + VB_EPSILON)));
+        crel = fmax(crel, fabs((v - c) / (c + VB_EPSILON)));
+        prev[i] = v;
+    }
+    double* out = part + (size_t)blockIdx.x * 10;
+    double r;
+    r = vb_block_sum(viol, scratch); if (threadIdx.x == 0) out[0] = r;
+    r = vb_block_sum(sab, scratch);  if (threadIdx.x == 0) out[1] = r;
+    r = vb_block_sum(ssq, scratch);  if (threadIdx.x == 0) out[2] = r;
+    r = vb_block_sum(cab, scratch);  if (threadIdx.x == 0) out[3] = r;
+    r = vb_block_sum(csq, scratch);  if (threadIdx.x == 0) out[4] = r;
+    r = vb_block_max(mnew, scratch); if (threadIdx.x == 0) out[5] = r;
+    r = vb_block_max(mrel, scratch); if (threadIdx.x == 0) out[6] = r;
+    r = vb_block_max(mabs, scratch); if (threadIdx.x == 0) out[7] = r;
+    r = vb_block_max(crel, scratch); if (threadIdx.x == 0) out[8] = r;
+    r = vb_block_max(cabs, scratch); if (threadIdx.x == 0) out[9] = r;
+}
+__global__ void vb_pm_diff_final_kernel(const double* __restrict__ part, int nblk, double* __restrict__ out) {
+    __shared__ double scratch[32];
+    for (int s = 0; s < 10; ++s) {
+        double acc = 0.0;
+        if (s < 5) {
+            for (int b = threadIdx.x; b < nblk; b += blockDim.x) acc += part[(size_t)b * 10 + s];
+            acc = vb_block_sum(acc, scratch);
+        } else {
+            for (int b = threadIdx.x; b < nblk; b += blockDim.x) acc = fmax(acc, part[(size_t)b * 10 + s]);
+            acc = vb_block_max(acc, scratch);
+        }
+        if (threadIdx.x == 0) out[s] = acc;
+    }
+}
+// dst[i] = src[i] * scal[i]
+__global__ void vb_scale_copy_kernel(const double* __restrict__ src, const double* __restrict__ scal,
+                                     double* __restrict__ dst, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[i] * scal[i];
+}
+
+// Materialise vi_sigma[k0:k1][P][P][M] (reference layout) for the final .npz
+// (variational_inference.py:712-724).
+template <int P>
+__global__ void vb_vi_sigma_kernel(const double* __restrict__ prec, const double* __restrict__ sld,
+                                   const double* inv_tau_dev, int64_t M, int k0, int k1,
+                                   double* __restrict__ out) {
+    constexpr int NT = P * (P + 1) / 2;
+    const int k = k0 + blockIdx.y;
+    if (k >= k1) return;
+    const double* pr = prec + (size_t)k * P * P;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double lam[NT], S[NT], c;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+#pragma unroll
+            for (int q = 0; q <= p; ++q) lam[VB_TRI(p, q)] = pr[p * P + q];
+            lam[VB_TRI(p, p)] += sld[(size_t)p * M + i] * inv_tau_dev[p];
+        }
+        vb_spd_inverse<P>(lam, S, c);
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+#pragma unroll
+            for (int q = 0; q < P; ++q)
+                out[(((size_t)(k - k0) * P + p) * P + q) * M + i] = S[p >= q ? VB_TRI(p, q) : VB_TRI(q, p)];
+    }
+}

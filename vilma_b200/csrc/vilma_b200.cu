@@ -1,0 +1,804 @@
+// libvilma_b200.so -- host side of the C ABI declared in include/vilma_b200.h.
+// Builds the HBM layout of the LD store, owns the fit state and sequences the kernels
+// in ld_kernels.cuh / snp_kernels.cuh on one CUDA stream.  sm_100a only; no CPU path.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/vilma_b200.h"
+#include "ld_kernels.cuh"
+#include "snp_kernels.cuh"
+
+static_assert(VB_MAX_POPS <= VB_MAXP, "header / kernel cohort limits disagree");
+
+// ------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int vb_fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return vb_fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                           __LINE__);                                                     \
+    } while (0)
+#define CK_LAUNCH(ctx)                                                                    \
+    do {                                                                                  \
+        (ctx)->launches++;                                                                \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess)                                                           \
+            return vb_fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__),   \
+                           __FILE__, __LINE__);                                           \
+    } while (0)
+
+static inline int64_t even_up(int64_t v) { return (v + 1) & ~int64_t(1); }
+
+// ------------------------------------------------------------------------------------
+// state
+// ------------------------------------------------------------------------------------
+struct LdSlab {          // a row-major matrix rows x ld (ld even), the unit the items cut up
+    size_t off;          // offset in doubles into LdPop::mat
+    int64_t rows, cols, ld;
+    int64_t x_off;       // offset (doubles, even) into xall of the x segment
+    int64_t y_off;       // output offset (doubles) of row 0
+};
+struct LdBlock {
+    int64_t n, r;                  // r < 0: dense
+    int64_t xpos, tpos;            // padded block-order / rank-space offsets
+    std::vector<int> slabs1;       // indices into LdPop::slabs (phase 1: V' = diag(s) U^T)
+    std::vector<int> slabs2;       // phase 2: dense R or U
+    bool filled = false;
+};
+struct LdPop {
+    bool begun = false, finalized = false;
+    int64_t M = 0, xb_len = 0, tb_len = 0;
+    int nslab1 = 1, nslab2 = 1;    // max column slabs per phase
+    std::vector<LdBlock> blocks;
+    std::vector<LdSlab> slabs;
+    double* mat = nullptr;
+    size_t mat_len = 0;
+    double* xall = nullptr;        // [xb | tb]
+    double* yb = nullptr;          // [nslab2][xb_len]
+    double* tbs = nullptr;         // [nslab1][tb_len] when nslab1 > 1
+    VbLdItem *items1 = nullptr, *items2 = nullptr;
+    uint32_t *cta1 = nullptr, *cta2 = nullptr;
+    int64_t n_items1 = 0, n_items2 = 0;
+    int32_t *pos = nullptr, *snp = nullptr;
+    int64_t nreal = 0;
+    int64_t bytes = 0;             // algorithmic bytes per mat-vec
+};
+
+struct Fit {
+    bool created = false;
+    int K = 0, P = 0, A = 0;
+    int64_t M = 0;
+    double *adj = nullptr, *se = nullptr, *sld = nullptr, *scal = nullptr;
+    int32_t* ann = nullptr;
+    double *prec = nullptr, *logdet = nullptr, *logh = nullptr, *gfull = nullptr, *inv_tau_dev = nullptr;
+    double inv_tau[VB_MAXP];
+    double* mu[2] = {nullptr, nullptr};
+    double* delta[2] = {nullptr, nullptr};
+    double *pm[2] = {nullptr, nullptr}, *z[2] = {nullptr, nullptr}, *linked[2] = {nullptr, nullptr};
+    int cur_mu = 0, cur_delta = 0, cur_vec = 0;
+    int trial_kind = -1;           // -1 none, 0 beta trial (new mu+delta), 1 refresh (new delta)
+    double* scratch3 = nullptr;    // [3][P][M]
+    double *pm_prev = nullptr, *pm_ckpt = nullptr;
+    double* part_snp = nullptr;
+    int grid_snp = 0;
+    double* part_fin = nullptr;
+    int grid_fin = 0;
+    double* part_ann = nullptr;
+    int grid_ann = 0;
+    double* part_diff = nullptr;
+    int grid_diff = 0;
+};
+
+struct vb_ld;
+struct vb_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    std::vector<vb_ld*> fit_ld;   // the P operators the fit state uses (not owned)
+    Fit fit;
+};
+struct vb_ld {
+    vb_ctx* ctx = nullptr;
+    LdPop L;
+};
+
+// ------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------
+extern "C" int vb_abi_version(void) { return VB_ABI_VERSION; }
+extern "C" const char* vb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int vb_ctx_create(int device, void* stream, vb_ctx** out) {
+    if (!out) return vb_fail("vb_ctx_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return vb_fail("vb_ctx_create: no CUDA device available (%s); vilma_b200 has no CPU path",
+                       cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return vb_fail("vb_ctx_create: bad device %d", device);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return vb_fail("vb_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                       device, prop.major, prop.minor);
+    vb_ctx* c = new vb_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    c->stream = reinterpret_cast<cudaStream_t>(stream);
+    CK(cudaFuncSetAttribute(vb_ld_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            VB_LD_SMEM));
+    *out = c;
+    return 0;
+}
+
+static void free_ld(LdPop& L) {
+    cudaFree(L.mat); cudaFree(L.xall); cudaFree(L.yb); cudaFree(L.tbs);
+    cudaFree(L.items1); cudaFree(L.items2); cudaFree(L.cta1); cudaFree(L.cta2);
+    cudaFree(L.pos); cudaFree(L.snp);
+    L = LdPop();
+}
+static void free_fit(Fit& f) {
+    cudaFree(f.adj); cudaFree(f.se); cudaFree(f.sld); cudaFree(f.scal); cudaFree(f.ann);
+    cudaFree(f.prec); cudaFree(f.logdet); cudaFree(f.logh); cudaFree(f.gfull); cudaFree(f.inv_tau_dev);
+    for (int s = 0; s < 2; ++s) {
+        cudaFree(f.mu[s]); cudaFree(f.delta[s]); cudaFree(f.pm[s]); cudaFree(f.z[s]);
+        cudaFree(f.linked[s]);
+    }
+    cudaFree(f.scratch3); cudaFree(f.pm_prev); cudaFree(f.pm_ckpt);
+    cudaFree(f.part_snp); cudaFree(f.part_fin); cudaFree(f.part_ann); cudaFree(f.part_diff);
+    f = Fit();
+}
+
+extern "C" int vb_ctx_destroy(vb_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_fit(ctx->fit);
+    delete ctx;
+    return 0;
+}
+extern "C" int vb_ctx_sync(vb_ctx* ctx) {
+    if (!ctx) return vb_fail("null ctx");
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int64_t vb_ctx_launch_count(const vb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------------------------
+// LD store
+// ------------------------------------------------------------------------------------
+static void add_slabs(LdPop& L, std::vector<int>& into, int64_t rows, int64_t cols, int64_t x_base,
+                      int64_t y_base, int64_t y_slab_stride, size_t& cursor, int& nslab_max) {
+    const int nsl = (int)((cols + VB_LD_CMAX - 1) / VB_LD_CMAX);
+    int64_t width = even_up((cols + nsl - 1) / nsl);
+    for (int s = 0; s < nsl; ++s) {
+        const int64_t c0 = s * width;
+        const int64_t c1 = std::min(cols, c0 + width);
+        LdSlab sl;
+        sl.off = cursor;
+        sl.rows = rows;
+        sl.cols = c1 - c0;
+        sl.ld = even_up(c1 - c0);
+        sl.x_off = x_base + c0;
+        sl.y_off = y_base + (int64_t)s * y_slab_stride;
+        cursor += (size_t)rows * sl.ld;
+        into.push_back((int)L.slabs.size());
+        L.slabs.push_back(sl);
+    }
+    nslab_max = std::max(nslab_max, nsl);
+}
+
+static int build_items(vb_ctx* ctx, LdPop& L, int phase, VbLdItem** d_items, uint32_t** d_cta,
+                       int64_t* n_items) {
+    std::vector<VbLdItem> items;
+    std::vector<uint64_t> cum;   // cumulative bytes after each item
+    uint64_t total = 0;
+    for (auto& b : L.blocks) {
+        const std::vector<int>& sl = phase == 1 ? b.slabs1 : b.slabs2;
+        for (int si : sl) {
+            const LdSlab& s = L.slabs[si];
+            int64_t rows_per = std::max<int64_t>(1, VB_LD_STAGE_A / (s.ld * 8));
+            rows_per = std::min<int64_t>(rows_per, 65535);
+            for (int64_t r0 = 0; r0 < s.rows; r0 += rows_per) {
+                const int64_t nr = std::min(rows_per, s.rows - r0);
+                VbLdItem it;
+                const size_t a_off = s.off + (size_t)r0 * s.ld;          // doubles, even
+                if ((a_off >> 1) > 0xffffffffull)
+                    return vb_fail("LD store of one cohort exceeds 64 GiB on this rank");
+                it.a_off16 = (uint32_t)(a_off >> 1);
+                it.x_off2 = (uint32_t)(s.x_off >> 1);
+                it.y_off = (uint32_t)(s.y_off + r0);
+                it.nrows = (uint16_t)nr;
+                it.ld2 = (uint16_t)(s.ld >> 1);
+                items.push_back(it);
+                total += (uint64_t)nr * s.ld * 8 + s.ld * 8;
+                cum.push_back(total);
+            }
+        }
+    }
+    *n_items = (int64_t)items.size();
+    const int G = ctx->num_sms;
+    std::vector<uint32_t> start(G + 1, 0);
+    // contiguous ranges of ~equal bytes per CTA
+    size_t it = 0;
+    for (int c = 0; c < G; ++c) {
+        start[c] = (uint32_t)it;
+        const double target = (double)total * (c + 1) / G;
+        while (it < items.size() && (double)cum[it] <= target + 0.5) ++it;
+    }
+    start[G] = (uint32_t)items.size();
+    for (int c = 1; c <= G; ++c) start[c] = std::max(start[c], start[c - 1]);
+    start[G] = (uint32_t)items.size();
+    if (!items.empty()) {
+        CK(cudaMalloc(d_items, items.size() * sizeof(VbLdItem)));
+        CK(cudaMemcpy(*d_items, items.data(), items.size() * sizeof(VbLdItem), cudaMemcpyHostToDevice));
+    }
+    CK(cudaMalloc(d_cta, (G + 1) * sizeof(uint32_t)));
+    CK(cudaMemcpy(*d_cta, start.data(), (G + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int64_t* n,
+                    const int64_t* rank);
+
+extern "C" int vb_ld_create(vb_ctx* ctx, int64_t M, int64_t nblocks, const int64_t* n,
+                            const int64_t* rank, vb_ld** out) {
+    if (!ctx || !out) return vb_fail("vb_ld_create: null argument");
+    if (M < 1 || nblocks < 0) return vb_fail("vb_ld_create: bad sizes");
+    CK(cudaSetDevice(ctx->device));
+    vb_ld* h = new vb_ld();
+    h->ctx = ctx;
+    if (ld_begin(ctx, h->L, M, nblocks, n, rank)) {
+        free_ld(h->L);
+        delete h;
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+extern "C" int vb_ld_destroy(vb_ld* ld) {
+    if (!ld) return 0;
+    cudaSetDevice(ld->ctx->device);
+    cudaStreamSynchronize(ld->ctx->stream);
+    free_ld(ld->L);
+    delete ld;
+    return 0;
+}
+
+static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int64_t* n,
+                    const int64_t* rank) {
+    L.begun = true;
+    L.M = M;
+    L.blocks.resize(nblocks);
+    int64_t xpos = 0, tpos = 0;
+    for (int64_t b = 0; b < nblocks; ++b) {
+        if (n[b] <= 0) return vb_fail("vb_ld_create: block %lld has n=%lld", (long long)b, (long long)n[b]);
+        L.blocks[b].n = n[b];
+        L.blocks[b].r = rank[b];
+        L.blocks[b].xpos = xpos;
+        xpos += even_up(n[b]);
+        if (rank[b] >= 0) {
+            if (rank[b] == 0) return vb_fail("vb_ld_create: factor block %lld has rank 0", (long long)b);
+            L.blocks[b].tpos = tpos;
+            tpos += even_up(rank[b]);
+        }
+    }
+    L.xb_len = std::max<int64_t>(xpos, 2);
+    L.tb_len = tpos;
+    if (L.xb_len + L.tb_len > 0x7fffffffll) return vb_fail("vb_ld_create: too many SNPs for 32-bit positions");
+    // first pass to learn the slab counts (y strides depend on them)
+    size_t cursor = 0;
+    int ns1 = 1, ns2 = 1;
+    for (auto& b : L.blocks) {
+        if (b.r < 0) ns2 = std::max(ns2, (int)((b.n + VB_LD_CMAX - 1) / VB_LD_CMAX));
+        else {
+            ns1 = std::max(ns1, (int)((b.n + VB_LD_CMAX - 1) / VB_LD_CMAX));
+            ns2 = std::max(ns2, (int)((b.r + VB_LD_CMAX - 1) / VB_LD_CMAX));
+        }
+    }
+    L.nslab1 = ns1;
+    L.nslab2 = ns2;
+    int dummy1 = 1, dummy2 = 1;
+    L.bytes = 0;
+    for (auto& b : L.blocks) {
+        if (b.r < 0) {
+            add_slabs(L, b.slabs2, b.n, b.n, b.xpos, b.xpos, L.xb_len, cursor, dummy2);
+            L.bytes += 8 * b.n * b.n;
+        } else {
+            // phase 1: t = V' x, V' = diag(s) U^T  (r x n), x from xb, out to tb
+            add_slabs(L, b.slabs1, b.r, b.n, b.xpos, b.tpos, L.tb_len, cursor, dummy1);
+            // phase 2: y = U t  (n x r), x from tb (stored behind xb in xall), out to yb
+            add_slabs(L, b.slabs2, b.n, b.r, L.xb_len + b.tpos, b.xpos, L.xb_len, cursor, dummy2);
+            L.bytes += 16 * b.n * b.r;
+        }
+    }
+    L.mat_len = std::max<size_t>(cursor, 2);
+    CK(cudaMalloc(&L.mat, L.mat_len * sizeof(double)));
+    CK(cudaMemsetAsync(L.mat, 0, L.mat_len * sizeof(double), ctx->stream));
+    CK(cudaMalloc(&L.xall, (size_t)(L.xb_len + L.tb_len) * sizeof(double)));
+    CK(cudaMemsetAsync(L.xall, 0, (size_t)(L.xb_len + L.tb_len) * sizeof(double), ctx->stream));
+    CK(cudaMalloc(&L.yb, (size_t)L.nslab2 * L.xb_len * sizeof(double)));
+    CK(cudaMemsetAsync(L.yb, 0, (size_t)L.nslab2 * L.xb_len * sizeof(double), ctx->stream));
+    if (L.nslab1 > 1) {
+        CK(cudaMalloc(&L.tbs, (size_t)L.nslab1 * L.tb_len * sizeof(double)));
+        CK(cudaMemsetAsync(L.tbs, 0, (size_t)L.nslab1 * L.tb_len * sizeof(double), ctx->stream));
+    }
+    if (build_items(ctx, L, 1, &L.items1, &L.cta1, &L.n_items1)) return 1;
+    if (build_items(ctx, L, 2, &L.items2, &L.cta2, &L.n_items2)) return 1;
+    return 0;
+}
+
+extern "C" int vb_ld_set_dense(vb_ld* h, int64_t b, const double* R, int64_t ld, int on_device) {
+    if (!h) return vb_fail("vb_ld_set_dense: null handle");
+    vb_ctx* ctx = h->ctx;
+    LdPop& L = h->L;
+    if (b < 0 || b >= (int64_t)L.blocks.size()) return vb_fail("vb_ld_set_dense: bad block");
+    LdBlock& B = L.blocks[b];
+    if (B.r >= 0) return vb_fail("vb_ld_set_dense: block %lld was declared as a factor", (long long)b);
+    CK(cudaSetDevice(ctx->device));
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    int64_t c0 = 0;
+    for (int si : B.slabs2) {
+        const LdSlab& s = L.slabs[si];
+        CK(cudaMemcpy2DAsync(L.mat + s.off, s.ld * sizeof(double), R + c0, ld * sizeof(double),
+                             s.cols * sizeof(double), s.rows, kind, ctx->stream));
+        c0 += s.cols;
+    }
+    if (!on_device) CK(cudaStreamSynchronize(ctx->stream));   // caller may reuse its buffer
+    B.filled = true;
+    return 0;
+}
+
+// out[c][j] = s[c] * U[j][c]   (V' = diag(s) U^T), written into a slab with leading dim ld
+__global__ void vb_pack_vprime_kernel(const double* __restrict__ U, const double* __restrict__ s,
+                                      int64_t n, int64_t r, int64_t c0, int64_t cols, int64_t ld,
+                                      double* __restrict__ out) {
+    // out is r x ld; column j of out = SNP (c0 + j)
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < r * cols;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t k = idx / cols, j = idx % cols;
+        out[k * ld + j] = s[k] * U[(c0 + j) * r + k];
+    }
+}
+
+extern "C" int vb_ld_set_factor(vb_ld* h, int64_t b, const double* U, const double* s,
+                                int on_device) {
+    if (!h) return vb_fail("vb_ld_set_factor: null handle");
+    vb_ctx* ctx = h->ctx;
+    LdPop& L = h->L;
+    if (b < 0 || b >= (int64_t)L.blocks.size()) return vb_fail("vb_ld_set_factor: bad block");
+    LdBlock& B = L.blocks[b];
+    if (B.r < 0) return vb_fail("vb_ld_set_factor: block %lld was declared dense", (long long)b);
+    CK(cudaSetDevice(ctx->device));
+    const int64_t n = B.n, r = B.r;
+    const double *dU = U, *ds = s;
+    double *tmpU = nullptr, *tmps = nullptr;
+    if (!on_device) {
+        CK(cudaMalloc(&tmpU, (size_t)n * r * sizeof(double)));
+        CK(cudaMalloc(&tmps, (size_t)r * sizeof(double)));
+        CK(cudaMemcpyAsync(tmpU, U, (size_t)n * r * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(tmps, s, (size_t)r * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        dU = tmpU;
+        ds = tmps;
+    }
+    int64_t c0 = 0;
+    for (int si : B.slabs1) {
+        const LdSlab& sl = L.slabs[si];
+        const int64_t tot = r * sl.cols;
+        const int grid = (int)std::min<int64_t>((tot + 255) / 256, 4096);
+        vb_pack_vprime_kernel<<<grid, 256, 0, ctx->stream>>>(dU, ds, n, r, c0, sl.cols, sl.ld,
+                                                              L.mat + sl.off);
+        CK_LAUNCH(ctx);
+        c0 += sl.cols;
+    }
+    c0 = 0;
+    for (int si : B.slabs2) {
+        const LdSlab& sl = L.slabs[si];
+        CK(cudaMemcpy2DAsync(L.mat + sl.off, sl.ld * sizeof(double), dU + c0, r * sizeof(double),
+                             sl.cols * sizeof(double), sl.rows, cudaMemcpyDeviceToDevice, ctx->stream));
+        c0 += sl.cols;
+    }
+    if (!on_device) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(tmpU);
+        cudaFree(tmps);
+    }
+    B.filled = true;
+    return 0;
+}
+
+extern "C" int vb_ld_finalize(vb_ld* h, const int64_t* perm_host, int64_t nperm) {
+    if (!h) return vb_fail("vb_ld_finalize: null handle");
+    vb_ctx* ctx = h->ctx;
+    LdPop& L = h->L;
+    CK(cudaSetDevice(ctx->device));
+    int64_t tot = 0;
+    for (auto& b : L.blocks) {
+        if (!b.filled) return vb_fail("vb_ld_finalize: a block was never set");
+        tot += b.n;
+    }
+    if (tot != nperm) return vb_fail("vb_ld_finalize: perm has %lld entries, blocks hold %lld SNPs",
+                                     (long long)nperm, (long long)tot);
+    std::vector<int32_t> pos(std::max<int64_t>(nperm, 1)), snp(std::max<int64_t>(nperm, 1));
+    std::vector<char> seen(L.M, 0);
+    int64_t j = 0;
+    for (auto& b : L.blocks)
+        for (int64_t t = 0; t < b.n; ++t, ++j) {
+            const int64_t i = perm_host[j];
+            if (i < 0 || i >= L.M) return vb_fail("vb_ld_finalize: perm[%lld]=%lld out of range", (long long)j, (long long)i);
+            if (seen[i]) return vb_fail("vb_ld_finalize: SNP %lld appears twice in perm", (long long)i);
+            seen[i] = 1;
+            pos[j] = (int32_t)(b.xpos + t);
+            snp[j] = (int32_t)i;
+        }
+    L.nreal = nperm;
+    CK(cudaMalloc(&L.pos, pos.size() * sizeof(int32_t)));
+    CK(cudaMalloc(&L.snp, snp.size() * sizeof(int32_t)));
+    CK(cudaMemcpy(L.pos, pos.data(), pos.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(L.snp, snp.data(), snp.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    L.finalized = true;
+    return 0;
+}
+
+extern "C" int64_t vb_ld_bytes(const vb_ld* h) { return h ? h->L.bytes : -1; }
+
+// x (SNP order, device) -> linked (SNP order, device), optional partial sums of x.y
+static int ld_apply(vb_ctx* ctx, LdPop& L, const double* x_snp, double* y_snp, double* partial,
+                    int grid_fin) {
+    if (!L.finalized) return vb_fail("LD operator used before vb_ld_finalize");
+    cudaStream_t st = ctx->stream;
+    if (L.nreal > 0) {
+        const int g = (int)std::min<int64_t>((L.nreal + 255) / 256, 1184);
+        vb_ld_gather_kernel<<<g, 256, 0, st>>>(x_snp, L.pos, L.snp, L.nreal, L.xall);
+        CK_LAUNCH(ctx);
+    }
+    if (L.n_items1 > 0) {
+        double* out1 = L.nslab1 > 1 ? L.tbs : L.xall + L.xb_len;
+        vb_ld_matvec_kernel<<<ctx->num_sms, VB_LD_THREADS, VB_LD_SMEM, st>>>(L.mat, L.items1, L.cta1,
+                                                                             L.xall, out1);
+        CK_LAUNCH(ctx);
+        if (L.nslab1 > 1) {
+            const int g = (int)std::min<int64_t>((L.tb_len + 255) / 256, 1184);
+            vb_ld_slab_sum_kernel<<<g, 256, 0, st>>>(L.tbs, L.tb_len, L.nslab1, L.xall + L.xb_len);
+            CK_LAUNCH(ctx);
+        }
+    }
+    if (L.n_items2 > 0) {
+        vb_ld_matvec_kernel<<<ctx->num_sms, VB_LD_THREADS, VB_LD_SMEM, st>>>(L.mat, L.items2, L.cta2,
+                                                                             L.xall, L.yb);
+        CK_LAUNCH(ctx);
+    }
+    vb_ld_finish_kernel<<<grid_fin, 256, 0, st>>>(L.yb, L.xb_len, L.nslab2, L.xall, L.pos, L.snp,
+                                                  L.nreal, y_snp, partial);
+    CK_LAUNCH(ctx);
+    return 0;
+}
+
+extern "C" int vb_ld_dot(vb_ld* h, const double* x_dev, double* y_dev) {
+    if (!h) return vb_fail("vb_ld_dot: null handle");
+    vb_ctx* ctx = h->ctx;
+    CK(cudaSetDevice(ctx->device));
+    LdPop& L = h->L;
+    CK(cudaMemsetAsync(y_dev, 0, (size_t)L.M * sizeof(double), ctx->stream));
+    return ld_apply(ctx, L, x_dev, y_dev, nullptr, 296);
+}
+
+// ------------------------------------------------------------------------------------
+// fit state
+// ------------------------------------------------------------------------------------
+extern "C" int vb_fit_create(vb_ctx* ctx, int K, int P, int64_t M, int A, vb_ld* const* lds) {
+    if (!ctx || !lds) return vb_fail("vb_fit_create: null argument");
+    if (P < 1 || P > VB_MAX_POPS)
+        return vb_fail("vb_fit_create: %d cohorts requested; kernels are compiled for 1..%d", P, VB_MAX_POPS);
+    if (K < 1 || A < 1 || M < 1) return vb_fail("vb_fit_create: bad sizes K=%d A=%d M=%lld", K, A, (long long)M);
+    CK(cudaSetDevice(ctx->device));
+    Fit& f = ctx->fit;
+    if (f.created) free_fit(f);
+    f.created = true;
+    f.K = K; f.P = P; f.A = A; f.M = M;
+    const size_t PM = (size_t)P * M, KM = (size_t)K * M;
+    CK(cudaMalloc(&f.adj, PM * 8)); CK(cudaMalloc(&f.se, PM * 8)); CK(cudaMalloc(&f.sld, PM * 8));
+    CK(cudaMalloc(&f.scal, PM * 8)); CK(cudaMalloc(&f.ann, (size_t)M * 4));
+    CK(cudaMalloc(&f.prec, (size_t)K * P * P * 8)); CK(cudaMalloc(&f.logdet, (size_t)K * 8));
+    CK(cudaMalloc(&f.logh, (size_t)A * K * 8)); CK(cudaMalloc(&f.inv_tau_dev, VB_MAXP * 8));
+    CK(cudaMalloc(&f.gfull, (size_t)A * K * 8));
+    CK(cudaMemsetAsync(f.gfull, 0, (size_t)A * K * 8, ctx->stream));
+    CK(cudaMemsetAsync(f.logh, 0, (size_t)A * K * 8, ctx->stream));
+    for (int s = 0; s < 2; ++s) {
+        CK(cudaMalloc(&f.mu[s], KM * P * 8));
+        CK(cudaMalloc(&f.delta[s], KM * 8));
+        CK(cudaMalloc(&f.pm[s], PM * 8)); CK(cudaMalloc(&f.z[s], PM * 8));
+        CK(cudaMalloc(&f.linked[s], PM * 8));
+        CK(cudaMemsetAsync(f.linked[s], 0, PM * 8, ctx->stream));
+        CK(cudaMemsetAsync(f.pm[s], 0, PM * 8, ctx->stream));
+        CK(cudaMemsetAsync(f.z[s], 0, PM * 8, ctx->stream));
+    }
+    CK(cudaMalloc(&f.scratch3, 3 * PM * 8));
+    CK(cudaMalloc(&f.pm_prev, PM * 8)); CK(cudaMalloc(&f.pm_ckpt, PM * 8));
+    CK(cudaMemsetAsync(f.pm_prev, 0, PM * 8, ctx->stream));
+    CK(cudaMemsetAsync(f.pm_ckpt, 0, PM * 8, ctx->stream));
+    f.grid_snp = (int)std::min<int64_t>((M + 127) / 128, (int64_t)ctx->num_sms * 16);
+    f.grid_fin = 2 * ctx->num_sms;
+    f.grid_ann = (int)std::min<int64_t>((M + 255) / 256, (int64_t)ctx->num_sms);
+    f.grid_diff = (int)std::min<int64_t>((int64_t)(PM + 255) / 256, (int64_t)ctx->num_sms * 4);
+    CK(cudaMalloc(&f.part_snp, (size_t)f.grid_snp * VB_NSNPSTAT(P) * 8));
+    CK(cudaMalloc(&f.part_fin, (size_t)P * f.grid_fin * 8));
+    CK(cudaMemsetAsync(f.part_fin, 0, (size_t)P * f.grid_fin * 8, ctx->stream));
+    CK(cudaMalloc(&f.part_ann, (size_t)f.grid_ann * K * A * 8));
+    CK(cudaMalloc(&f.part_diff, (size_t)f.grid_diff * 10 * 8));
+    for (int p = 0; p < VB_MAXP; ++p) f.inv_tau[p] = 1.0;
+    CK(cudaMemcpyAsync(f.inv_tau_dev, f.inv_tau, VB_MAXP * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    f.cur_mu = f.cur_delta = f.cur_vec = 0;
+    f.trial_kind = -1;
+    ctx->fit_ld.assign(lds, lds + P);
+    for (int p = 0; p < P; ++p) {
+        if (!lds[p] || lds[p]->ctx != ctx) return vb_fail("vb_fit_create: LD operator %d belongs to another context", p);
+        if (!lds[p]->L.finalized) return vb_fail("vb_fit_create: LD operator %d is not finalized", p);
+        if (lds[p]->L.M != M) return vb_fail("vb_fit_create: LD operator %d has M=%lld, fit has M=%lld", p, (long long)lds[p]->L.M, (long long)M);
+    }
+    return 0;
+}
+extern "C" int vb_fit_destroy(vb_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_fit(ctx->fit);
+    ctx->fit_ld.clear();
+    return 0;
+}
+
+#define NEED_FIT(ctx)                                                      \
+    if (!(ctx) || !(ctx)->fit.created) return vb_fail("fit state not created"); \
+    CK(cudaSetDevice((ctx)->device));                                      \
+    Fit& f = (ctx)->fit;
+
+extern "C" int vb_fit_set_snp_data(vb_ctx* ctx, const double* adj, const double* se, const double* sld,
+                                   const double* scal, const int32_t* ann) {
+    NEED_FIT(ctx);
+    const size_t PM = (size_t)f.P * f.M;
+    CK(cudaMemcpyAsync(f.adj, adj, PM * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f.se, se, PM * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f.sld, sld, PM * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f.scal, scal, PM * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f.ann, ann, (size_t)f.M * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int vb_fit_set_mixture(vb_ctx* ctx, const double* prec, const double* logdet) {
+    NEED_FIT(ctx);
+    CK(cudaMemcpyAsync(f.prec, prec, (size_t)f.K * f.P * f.P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f.logdet, logdet, (size_t)f.K * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int vb_fit_set_hyper(vb_ctx* ctx, const double* hyper) {
+    NEED_FIT(ctx);
+    std::vector<double> lh((size_t)f.A * f.K);
+    for (size_t t = 0; t < lh.size(); ++t) lh[t] = std::log(hyper[t]);
+    CK(cudaMemcpyAsync(f.logh, lh.data(), lh.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int vb_fit_set_delta_grad(vb_ctx* ctx, const double* g) {
+    NEED_FIT(ctx);
+    std::vector<double> full((size_t)f.A * f.K, 0.0);
+    for (int a = 0; a < f.A; ++a)
+        for (int k = 0; k + 1 < f.K; ++k) full[(size_t)a * f.K + k] = g[(size_t)a * (f.K - 1) + k];
+    CK(cudaMemcpyAsync(f.gfull, full.data(), full.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int vb_fit_set_tau(vb_ctx* ctx, const double* tau) {
+    NEED_FIT(ctx);
+    for (int p = 0; p < f.P; ++p) f.inv_tau[p] = 1.0 / tau[p];
+    CK(cudaMemcpyAsync(f.inv_tau_dev, f.inv_tau, VB_MAXP * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int vb_fit_set_params(vb_ctx* ctx, const double* mu, const double* delta_km) {
+    NEED_FIT(ctx);
+    const size_t KM = (size_t)f.K * f.M;
+    CK(cudaMemcpyAsync(f.mu[f.cur_mu], mu, KM * f.P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f.delta[f.cur_delta], delta_km, KM * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    f.trial_kind = -1;
+    return 0;
+}
+extern "C" int vb_fit_get_params(vb_ctx* ctx, double* mu, double* delta_km) {
+    NEED_FIT(ctx);
+    const size_t KM = (size_t)f.K * f.M;
+    if (mu) CK(cudaMemcpyAsync(mu, f.mu[f.cur_mu], KM * f.P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (delta_km)
+        CK(cudaMemcpyAsync(delta_km, f.delta[f.cur_delta], KM * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+template <int MODE>
+static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
+    cudaStream_t st = ctx->stream;
+    switch (P) {
+        case 1: vb_snp_kernel<1, MODE><<<grid, 128, 0, st>>>(a); break;
+        case 2: vb_snp_kernel<2, MODE><<<grid, 128, 0, st>>>(a); break;
+        case 3: vb_snp_kernel<3, MODE><<<grid, 128, 0, st>>>(a); break;
+        case 4: vb_snp_kernel<4, MODE><<<grid, 128, 0, st>>>(a); break;
+        case 5: vb_snp_kernel<5, MODE><<<grid, 128, 0, st>>>(a); break;
+        case 6: vb_snp_kernel<6, MODE><<<grid, 128, 0, st>>>(a); break;
+        default: return vb_fail("unsupported cohort count %d", P);
+    }
+    CK_LAUNCH(ctx);
+    return 0;
+}
+
+static void base_args(const Fit& f, VbSnpArgs& a) {
+    std::memset(&a, 0, sizeof(a));
+    a.K = f.K; a.A = f.A; a.M = f.M;
+    a.adj = f.adj; a.se = f.se; a.sld = f.sld; a.ann = f.ann;
+    a.prec = f.prec; a.logdet = f.logdet; a.logh = f.logh; a.gfull = f.gfull;
+    for (int p = 0; p < VB_MAXP; ++p) a.inv_tau[p] = f.inv_tau[p];
+    a.partial = f.part_snp;
+}
+
+// mat-vecs of every cohort for the vectors in slot v, then the fixed-order final reduction
+static int finish_eval(vb_ctx* ctx, int v, double* stats_dev) {
+    Fit& f = ctx->fit;
+    for (int p = 0; p < f.P; ++p) {
+        LdPop& L = ctx->fit_ld[p]->L;
+        if (ld_apply(ctx, L, f.z[v] + (size_t)p * f.M, f.linked[v] + (size_t)p * f.M,
+                     f.part_fin + (size_t)p * f.grid_fin, f.grid_fin))
+            return 1;
+    }
+    vb_stats_finalize_kernel<<<1, 256, 0, ctx->stream>>>(f.part_snp, f.grid_snp, f.P, f.part_fin,
+                                                         f.grid_fin, stats_dev);
+    CK_LAUNCH(ctx);
+    return 0;
+}
+
+extern "C" int vb_fit_eval(vb_ctx* ctx, double* stats_dev) {
+    NEED_FIT(ctx);
+    VbSnpArgs a;
+    base_args(f, a);
+    a.mu_in = f.mu[f.cur_mu];
+    a.delta_in = f.delta[f.cur_delta];
+    a.pm_out = f.pm[f.cur_vec];
+    a.z_out = f.z[f.cur_vec];
+    if (launch_snp<VB_MODE_EVAL>(ctx, a, f.P, f.grid_snp)) return 1;
+    f.trial_kind = -1;
+    return finish_eval(ctx, f.cur_vec, stats_dev);
+}
+
+extern "C" int vb_fit_beta_trial(vb_ctx* ctx, double step, double* stats_dev) {
+    NEED_FIT(ctx);
+    VbSnpArgs a;
+    base_args(f, a);
+    const int tv = 1 - f.cur_vec;
+    a.mu_in = f.mu[f.cur_mu];
+    a.pm_in = f.pm[f.cur_vec];
+    a.linked_in = f.linked[f.cur_vec];
+    a.step = step;
+    a.mu_out = f.mu[1 - f.cur_mu];
+    a.delta_out = f.delta[1 - f.cur_delta];
+    a.pm_out = f.pm[tv];
+    a.z_out = f.z[tv];
+    if (launch_snp<VB_MODE_TRIAL>(ctx, a, f.P, f.grid_snp)) return 1;
+    f.trial_kind = 0;
+    return finish_eval(ctx, tv, stats_dev);
+}
+
+extern "C" int vb_fit_refresh_delta(vb_ctx* ctx, double* stats_dev) {
+    NEED_FIT(ctx);
+    VbSnpArgs a;
+    base_args(f, a);
+    const int tv = 1 - f.cur_vec;
+    a.mu_in = f.mu[f.cur_mu];
+    a.delta_out = f.delta[1 - f.cur_delta];
+    a.pm_out = f.pm[tv];
+    a.z_out = f.z[tv];
+    if (launch_snp<VB_MODE_REFRESH>(ctx, a, f.P, f.grid_snp)) return 1;
+    f.trial_kind = 1;
+    return finish_eval(ctx, tv, stats_dev);
+}
+
+extern "C" int vb_fit_accept(vb_ctx* ctx) {
+    NEED_FIT(ctx);
+    if (f.trial_kind < 0) return vb_fail("vb_fit_accept: no trial state pending");
+    if (f.trial_kind == 0) f.cur_mu = 1 - f.cur_mu;
+    f.cur_delta = 1 - f.cur_delta;
+    f.cur_vec = 1 - f.cur_vec;
+    f.trial_kind = -1;
+    return 0;
+}
+
+extern "C" int vb_fit_sum_annotations(vb_ctx* ctx, double* out_dev) {
+    NEED_FIT(ctx);
+    dim3 grid(f.grid_ann, f.K);
+    vb_sum_annotations_kernel<<<grid, 256, 0, ctx->stream>>>(f.delta[f.cur_delta], f.ann, f.M, f.K,
+                                                             f.A, f.part_ann);
+    CK_LAUNCH(ctx);
+    const int tot = f.K * f.A;
+    vb_sum_annotations_final_kernel<<<(tot + 127) / 128, 128, 0, ctx->stream>>>(f.part_ann, f.grid_ann,
+                                                                                f.K, f.A, out_dev);
+    CK_LAUNCH(ctx);
+    return 0;
+}
+
+extern "C" int vb_fit_posterior(vb_ctx* ctx, double* pm_host, double* pv_host) {
+    NEED_FIT(ctx);
+    const size_t PM = (size_t)f.P * f.M;
+    VbSnpArgs a;
+    base_args(f, a);
+    a.mu_in = f.mu[f.cur_mu];
+    a.delta_in = f.delta[f.cur_delta];
+    a.pm_out = f.scratch3;
+    a.z_out = f.scratch3 + PM;
+    a.pv_out = f.scratch3 + 2 * PM;
+    if (launch_snp<VB_MODE_EVAL>(ctx, a, f.P, f.grid_snp)) return 1;
+    if (pm_host) CK(cudaMemcpyAsync(pm_host, f.scratch3, PM * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pv_host) CK(cudaMemcpyAsync(pv_host, f.scratch3 + 2 * PM, PM * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int vb_fit_pm_diff(vb_ctx* ctx, double atol, double rtol, double* out_dev) {
+    NEED_FIT(ctx);
+    const int64_t n = (int64_t)f.P * f.M;
+    vb_pm_diff_kernel<<<f.grid_diff, 256, 0, ctx->stream>>>(f.pm[f.cur_vec], f.scal, f.pm_prev,
+                                                            f.pm_ckpt, n, atol, rtol, f.part_diff);
+    CK_LAUNCH(ctx);
+    vb_pm_diff_final_kernel<<<1, 256, 0, ctx->stream>>>(f.part_diff, f.grid_diff, out_dev);
+    CK_LAUNCH(ctx);
+    return 0;
+}
+extern "C" int vb_fit_pm_mark(vb_ctx* ctx, int which) {
+    NEED_FIT(ctx);
+    const int64_t n = (int64_t)f.P * f.M;
+    vb_scale_copy_kernel<<<f.grid_diff, 256, 0, ctx->stream>>>(f.pm[f.cur_vec], f.scal,
+                                                               which == 0 ? f.pm_prev : f.pm_ckpt, n);
+    CK_LAUNCH(ctx);
+    return 0;
+}
+
+extern "C" int vb_fit_vi_sigma(vb_ctx* ctx, int k0, int k1, double* out_host) {
+    NEED_FIT(ctx);
+    if (k0 < 0 || k1 > f.K || k0 >= k1) return vb_fail("vb_fit_vi_sigma: bad slice [%d,%d)", k0, k1);
+    const size_t len = (size_t)(k1 - k0) * f.P * f.P * f.M;
+    double* buf = nullptr;
+    CK(cudaMalloc(&buf, len * 8));
+    dim3 grid((unsigned)std::min<int64_t>((f.M + 127) / 128, 2048), k1 - k0);
+    switch (f.P) {
+        case 1: vb_vi_sigma_kernel<1><<<grid, 128, 0, ctx->stream>>>(f.prec, f.sld, f.inv_tau_dev, f.M, k0, k1, buf); break;
+        case 2: vb_vi_sigma_kernel<2><<<grid, 128, 0, ctx->stream>>>(f.prec, f.sld, f.inv_tau_dev, f.M, k0, k1, buf); break;
+        case 3: vb_vi_sigma_kernel<3><<<grid, 128, 0, ctx->stream>>>(f.prec, f.sld, f.inv_tau_dev, f.M, k0, k1, buf); break;
+        case 4: vb_vi_sigma_kernel<4><<<grid, 128, 0, ctx->stream>>>(f.prec, f.sld, f.inv_tau_dev, f.M, k0, k1, buf); break;
+        case 5: vb_vi_sigma_kernel<5><<<grid, 128, 0, ctx->stream>>>(f.prec, f.sld, f.inv_tau_dev, f.M, k0, k1, buf); break;
+        case 6: vb_vi_sigma_kernel<6><<<grid, 128, 0, ctx->stream>>>(f.prec, f.sld, f.inv_tau_dev, f.M, k0, k1, buf); break;
+        default: cudaFree(buf); return vb_fail("unsupported cohort count %d", f.P);
+    }
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, buf, len * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(buf);
+    if (e != cudaSuccess) return vb_fail("vb_fit_vi_sigma: %s", cudaGetErrorString(e));
+    return 0;
+}

@@ -1,0 +1,235 @@
+"""Device engine: thin Python wrapper over the C ABI (include/vilma_b200.h).
+
+PyTorch appears here only as the owner of small device/pinned buffers (the statistics
+vectors that may be all-reduced over NCCL); all compute is in libvilma_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class DeviceContext:
+    """One CUDA context handle (vb_ctx) per (process, device); shared by LD operators and fits."""
+
+    _instances = {}
+
+    def __init__(self, device):
+        torch = _torch()
+        if not torch.cuda.is_available():
+            raise _lib.VilmaB200Error(
+                'vilma_b200 needs a CUDA device (B200, sm_100a); none is visible and there is '
+                'no CPU fallback.')
+        self.lib = _lib.load()
+        self.device = int(device)
+        torch.cuda.set_device(self.device)
+        torch.cuda.init()
+        self.handle = C.c_void_p()
+        # stream 0 = the legacy default stream, which is also torch's default stream
+        _lib.check(self.lib.vb_ctx_create(self.device, None, C.byref(self.handle)))
+
+    @classmethod
+    def get(cls, device=None):
+        if device is None:
+            torch = _torch()
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        if device not in cls._instances:
+            cls._instances[device] = cls(device)
+        return cls._instances[device]
+
+    def sync(self):
+        _lib.check(self.lib.vb_ctx_sync(self.handle))
+
+    def launch_count(self):
+        return int(self.lib.vb_ctx_launch_count(self.handle))
+
+
+def choose_storage(n, r):
+    """'dense' when the reconstructed n x n block is no larger than the two factor passes."""
+    return 'dense' if n * n <= 2 * n * r else 'factor'
+
+
+class DeviceLD:
+    """One cohort's block-diagonal LD operator resident in HBM (vb_ld).
+
+    blocks: list of dicts {'n', 'kind': 'dense'|'factor', 'R' | ('U','s')}; arrays may be
+    host numpy (float64, C order) or torch CUDA tensors.  perm_local[j] = local SNP index of
+    block-order position j.  M = number of SNPs on this rank.
+    """
+
+    def __init__(self, ctx, M, blocks, perm_local):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.M = int(M)
+        nb = len(blocks)
+        n = np.array([b['n'] for b in blocks], dtype=np.int64)
+        rank = np.array([-1 if b['kind'] == 'dense' else b['U'].shape[1] for b in blocks],
+                        dtype=np.int64)
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.vb_ld_create(
+            ctx.handle, self.M, nb, n.ctypes.data_as(_lib.c_i64p),
+            rank.ctypes.data_as(_lib.c_i64p), C.byref(self.handle)))
+        for b, blk in enumerate(blocks):
+            if blk['kind'] == 'dense':
+                ptr, on_dev, keep = self._ptr(blk['R'])
+                _lib.check(self.lib.vb_ld_set_dense(self.handle, b, ptr, int(blk['n']), on_dev))
+            else:
+                pu, on_dev, keep = self._ptr(blk['U'])
+                ps, on_dev2, keep2 = self._ptr(blk['s'])
+                assert on_dev == on_dev2
+                _lib.check(self.lib.vb_ld_set_factor(self.handle, b, pu, ps, on_dev))
+        perm = np.ascontiguousarray(perm_local, dtype=np.int64)
+        _lib.check(self.lib.vb_ld_finalize(self.handle, perm.ctypes.data_as(_lib.c_i64p),
+                                           perm.shape[0]))
+        self.bytes = int(self.lib.vb_ld_bytes(self.handle))
+
+    @staticmethod
+    def _ptr(a):
+        if isinstance(a, np.ndarray):
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            return C.c_void_p(a.ctypes.data), 0, a
+        torch = _torch()
+        assert a.is_cuda and a.dtype == torch.float64
+        a = a.contiguous()
+        return C.c_void_p(a.data_ptr()), 1, a
+
+    def dot(self, x):
+        """y = R x for a host vector in this rank's SNP order."""
+        torch = _torch()
+        xd = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).cuda(self.ctx.device)
+        yd = torch.empty_like(xd)
+        _lib.check(self.lib.vb_ld_dot(self.handle, C.c_void_p(xd.data_ptr()),
+                                      C.c_void_p(yd.data_ptr())))
+        return yd.cpu().numpy()
+
+    def dot_device(self, xd, yd):
+        _lib.check(self.lib.vb_ld_dot(self.handle, C.c_void_p(xd.data_ptr()),
+                                      C.c_void_p(yd.data_ptr())))
+
+    def close(self):
+        if self.handle:
+            self.lib.vb_ld_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CudaEngine:
+    """Device-resident fit state + the fused kernels, for the SNPs owned by this rank.
+
+    All arrays passed in are in this rank's SNP order.  Statistics come back as small torch
+    CUDA tensors so the caller can all-reduce them before reading.
+    """
+
+    N_DIFF = 10
+
+    def __init__(self, ctx, lds, K, P, M, A, adj, se, sld, scalings, annotations,
+                 mixture_prec, log_det):
+        torch = _torch()
+        self.ctx, self.lib = ctx, ctx.lib
+        self.lds = list(lds)
+        self.K, self.P, self.M, self.A = int(K), int(P), int(M), int(A)
+        arr = (C.c_void_p * P)(*[ld.handle for ld in self.lds])
+        _lib.check(self.lib.vb_fit_create(ctx.handle, self.K, self.P, self.M, self.A,
+                                          C.cast(arr, C.POINTER(C.c_void_p))))
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        adj, se, sld, scalings = f64(adj), f64(se), f64(sld), f64(scalings)
+        ann = np.ascontiguousarray(annotations, dtype=np.int32)
+        assert adj.shape == (P, M) and ann.shape == (M,)
+        _lib.check(self.lib.vb_fit_set_snp_data(ctx.handle, _lib.np_ptr(adj), _lib.np_ptr(se),
+                                                _lib.np_ptr(sld), _lib.np_ptr(scalings),
+                                                _lib.np_ptr(ann)))
+        prec, ld = f64(mixture_prec).reshape(K, P, P), f64(log_det)
+        _lib.check(self.lib.vb_fit_set_mixture(ctx.handle, _lib.np_ptr(prec), _lib.np_ptr(ld)))
+        dev = torch.device('cuda', ctx.device)
+        self.n_stats = 3 * P + 3
+        self._stats = torch.zeros(self.n_stats, dtype=torch.float64, device=dev)
+        self._ann = torch.zeros(A * K, dtype=torch.float64, device=dev)
+        self._diff = torch.zeros(self.N_DIFF, dtype=torch.float64, device=dev)
+        self.ld_bytes = sum(ld_.bytes for ld_ in self.lds)
+
+    # ---- small inputs
+    def set_hyper(self, hyper):
+        h = np.ascontiguousarray(hyper, dtype=np.float64)
+        assert h.shape == (self.A, self.K)
+        _lib.check(self.lib.vb_fit_set_hyper(self.ctx.handle, _lib.np_ptr(h)))
+
+    def set_delta_grad(self, table):
+        g = np.ascontiguousarray(table, dtype=np.float64)
+        assert g.shape == (self.A, self.K - 1)
+        if self.K > 1:
+            _lib.check(self.lib.vb_fit_set_delta_grad(self.ctx.handle, _lib.np_ptr(g)))
+
+    def set_tau(self, tau):
+        t = np.ascontiguousarray(tau, dtype=np.float64)
+        assert t.shape == (self.P,)
+        _lib.check(self.lib.vb_fit_set_tau(self.ctx.handle, _lib.np_ptr(t)))
+
+    # ---- state transfer (reference host layouts in, device layouts inside)
+    def set_params(self, vi_mu, vi_delta):
+        mu = np.ascontiguousarray(vi_mu, dtype=np.float64)
+        dkm = np.ascontiguousarray(np.asarray(vi_delta, dtype=np.float64).T)
+        assert mu.shape == (self.K, self.P, self.M) and dkm.shape == (self.K, self.M)
+        _lib.check(self.lib.vb_fit_set_params(self.ctx.handle, _lib.np_ptr(mu), _lib.np_ptr(dkm)))
+
+    def get_params(self):
+        mu = np.empty((self.K, self.P, self.M))
+        dkm = np.empty((self.K, self.M))
+        _lib.check(self.lib.vb_fit_get_params(self.ctx.handle, _lib.np_ptr(mu), _lib.np_ptr(dkm)))
+        return mu, np.ascontiguousarray(dkm.T)
+
+    # ---- evaluations (return the device stats tensor, valid until the next evaluation)
+    def eval(self):
+        _lib.check(self.lib.vb_fit_eval(self.ctx.handle, C.c_void_p(self._stats.data_ptr())))
+        return self._stats
+
+    def beta_trial(self, step):
+        _lib.check(self.lib.vb_fit_beta_trial(self.ctx.handle, float(step),
+                                              C.c_void_p(self._stats.data_ptr())))
+        return self._stats
+
+    def refresh_delta(self):
+        _lib.check(self.lib.vb_fit_refresh_delta(self.ctx.handle,
+                                                 C.c_void_p(self._stats.data_ptr())))
+        return self._stats
+
+    def accept(self):
+        _lib.check(self.lib.vb_fit_accept(self.ctx.handle))
+
+    def sum_annotations(self):
+        _lib.check(self.lib.vb_fit_sum_annotations(self.ctx.handle,
+                                                   C.c_void_p(self._ann.data_ptr())))
+        return self._ann
+
+    def posterior(self):
+        pm = np.empty((self.P, self.M))
+        pv = np.empty((self.P, self.M))
+        _lib.check(self.lib.vb_fit_posterior(self.ctx.handle, _lib.np_ptr(pm), _lib.np_ptr(pv)))
+        return pm, pv
+
+    def pm_diff(self, atol, rtol):
+        _lib.check(self.lib.vb_fit_pm_diff(self.ctx.handle, float(atol), float(rtol),
+                                           C.c_void_p(self._diff.data_ptr())))
+        return self._diff
+
+    def pm_mark(self, which):
+        _lib.check(self.lib.vb_fit_pm_mark(self.ctx.handle, int(which)))
+
+    def vi_sigma(self, k0=0, k1=None):
+        k1 = self.K if k1 is None else k1
+        out = np.empty((k1 - k0, self.P, self.P, self.M))
+        _lib.check(self.lib.vb_fit_vi_sigma(self.ctx.handle, k0, k1, _lib.np_ptr(out)))
+        return out
+
+    def close(self):
+        self.lib.vb_fit_destroy(self.ctx.handle)

@@ -1,0 +1,699 @@
+"""Variational-inference engine of `vilma fit`, B200-native.
+
+Host mirror of ``vilma.variational_inference`` (/root/reference/src/vilma/
+variational_inference.py): the same classes (``VIScheme`` :27-564, ``MultiPopVI``
+:567-889), constructor arguments, method names, return layouts, exceptions and
+control-flow constants -- but the parameters live in HBM for the whole of
+``optimize()`` and every array operation of the loop is a CUDA kernel
+(``csrc/snp_kernels.cuh``, ``csrc/ld_kernels.cuh``) reached through the C ABI.
+
+What changes relative to the reference (none of it changes a result beyond rounding):
+
+* each parameter state is evaluated ONCE (one fused per-SNP pass + one LD mat-vec per
+  cohort); the objective, the mat-vec output and the sufficient statistics are cached with
+  the state, which removes the reference's 3-4x re-evaluation of unchanged states
+  (:766, :829, :442) and the K-fold broadcast of the gradient (:817-821);
+* ``vi_sigma`` / ``nat_sigma`` / log-dets / traces (:712-733) are recomputed in registers per
+  (k, SNP) instead of being stored as three [K,P,P,M] arrays;
+* LD blocks are sharded over ranks; one small all-reduce per evaluated state.
+
+The methods that take / return host ``params`` tuples (``elbo``, ``_update_beta``,
+``_nat_grad_step``, ``_optimize_step``, ...) keep the reference semantics (inputs are never
+mutated, new arrays are returned) by uploading, running the device path and downloading.
+"""
+import logging
+
+import numpy as np
+
+from . import numerics
+from . import matrix_structures
+from .dist import default_comm
+from .partition import host_block_lists, local_blocks, partition_snps
+
+L_MAX = 1e12        # sets minimum natural gradient stepsize is 1/L_MAX   (:18)
+REL_TOL = 1e-6      # (:19)
+ABS_TOL = 1e-6      # (:20)
+ELBO_TOL = 0.1      # (:21)
+EM_TOL = 10         # (:22)
+ELBO_MOMENTUM = 0.5  # (:23)
+MAX_NUM_ITERS = 20  # (:24)
+
+
+class DeviceBlockDiagonalMatrix():
+    """An LD operator that already lives in HBM (this rank's shard), for callers that build
+    LD on the device.  Carries no host factors, so the constructor's host-side set-up
+    (pseudo-inverse, ridge) cannot run on it: pass ``precomputed=`` to the VI class."""
+
+    def __init__(self, device_ld, shape):
+        self.device_ld = device_ld
+        self.shape = tuple(shape)
+
+
+class VIScheme():
+    """Parent class for VI models of GWAS summary statistics (reference :27-564)."""
+
+    def __init__(self,
+                 marginal_effects=None,
+                 std_errs=None,
+                 ld_mats=None,
+                 annotations=None,
+                 mixture_covs=None,
+                 checkpoint=True,
+                 checkpoint_freq=5,
+                 scaled=False,
+                 scale_se=False,
+                 output='vilma_output',
+                 gwas_N=None,
+                 init_hg=None,
+                 num_its=None,
+                 comm=None,
+                 device=None,
+                 precomputed=None,
+                 local_snps=None,
+                 engine_factory=None):
+        for val, name in [(init_hg, 'init_hg'), (gwas_N, 'gwas_N'),
+                          (marginal_effects, 'marginal_effects'), (std_errs, 'std_errs'),
+                          (ld_mats, 'ld_mats'), (annotations, 'annotations'),
+                          (mixture_covs, 'mixture_covs'), (num_its, 'num_its')]:
+            if val is None:
+                raise ValueError('%s must be specified when calling VIScheme()' % name)
+        marginal_effects = np.asarray(marginal_effects, dtype=np.float64)
+        std_errs = np.asarray(std_errs, dtype=np.float64)
+        if not np.all(np.isfinite(marginal_effects)):
+            raise ValueError('Encountered an infinite or NaN value in the GWAS effect '
+                             'size estimates')
+        if not np.all(np.isfinite(std_errs)):
+            raise ValueError('Encountered an infinity or NaN value in the GWAS standard '
+                             'errors')
+        self.scaled = scaled
+        self.scale_se = scale_se
+        self.error_scaling = np.ones(marginal_effects.shape[0])
+        self.checkpoint = checkpoint
+        self.checkpoint_path = '%s-checkpoint' % output
+        self.num_pops, self.num_loci = marginal_effects.shape
+        if len(ld_mats) != self.num_pops:
+            raise ValueError('Fewer LD matrices than populations.')
+        for ld in ld_mats:
+            if not isinstance(ld, (matrix_structures.BlockDiagonalMatrix,
+                                   DeviceBlockDiagonalMatrix)):
+                raise ValueError('LD Matrices must be of type BlockDiagonalMatrix.')
+        host_ld = all(isinstance(ld, matrix_structures.BlockDiagonalMatrix) for ld in ld_mats)
+        if not host_ld and precomputed is None:
+            raise ValueError('device-resident LD operators need precomputed= set-up values')
+        for ld in ld_mats:
+            if host_ld and ld.shape != (self.num_loci, self.num_loci):
+                raise ValueError('LD matrix shape does not match GWAS marginal effect '
+                                 'size shape.')
+        annotations = np.asarray(annotations)
+        if not np.allclose(annotations.sum(axis=1), 1):
+            raise ValueError('Some SNPs are either missing annotations or have more than '
+                             'one annotation.')
+        self.num_annotations = annotations.shape[1]
+        if annotations.shape[0] != self.num_loci:
+            raise ValueError('annotations dimension does not match GWAS marginal effect '
+                             'size shape.')
+
+        self._comm = comm if comm is not None else default_comm()
+        self._device = device
+        self._engine_factory = engine_factory
+        self._ctx = None
+
+        self.marginal_effects = np.copy(marginal_effects)
+        if self.scaled:
+            self.marginal_effects = self.marginal_effects / (std_errs + numerics.EPSILON)
+            self.std_errs = np.ones_like(std_errs)
+            self.scalings = (std_errs + numerics.EPSILON)
+        else:
+            self.std_errs = np.copy(std_errs)
+            self.scalings = np.ones_like(std_errs)
+        self.ld_mats = ld_mats
+        self.annotations = np.copy(np.where(annotations)[1])
+        self.annotation_counts = annotations.sum(axis=0)
+        self.checkpoint_freq = checkpoint_freq
+        self.init_hg = init_hg
+        self.gwas_N = gwas_N
+        self.num_its = num_its
+        self.param_names = None
+
+        if precomputed is not None:
+            # set-up values supplied by the caller (device-built LD): same meaning as below
+            self.ld_diags = np.array(precomputed['ld_diags'], dtype=np.float64)
+            self.adj_marginal_effects = np.array(precomputed['adj_marginal_effects'],
+                                                 dtype=np.float64)
+            self.chi_stat = np.array(precomputed['chi_stat'], dtype=np.float64)
+            self.ld_ranks = np.array(precomputed['ld_ranks'], dtype=np.float64)
+            self.inverse_betas = np.array(precomputed['inverse_betas'], dtype=np.float64)
+        else:
+            self.ld_diags = np.concatenate(
+                [ld.diag().reshape((1, -1)) for ld in ld_mats], axis=0)
+        self.scaled_ld_diags = self.std_errs**-2 * self.ld_diags
+
+        if precomputed is None:
+            # adjusted marginal effects S^-1 X X^+ S^-1 beta_hat, chi statistic, LD rank and the
+            # LDpred-inf style ridge start (reference :226-252).  Pseudo-inverse and ridge solve
+            # are one-off host LAPACK; the R @ mle product is the GPU operator.
+            self.adj_marginal_effects = np.zeros_like(self.marginal_effects)
+            self.chi_stat = np.zeros(self.num_pops)
+            self.ld_ranks = np.zeros(self.num_pops)
+            self.inverse_betas = np.zeros_like(self.marginal_effects)
+            for p in range(self.num_pops):
+                z_scores = self.marginal_effects[p] / self.std_errs[p]
+                mle = ld_mats[p].inverse.dot(z_scores)
+                self.chi_stat[p] = z_scores.dot(mle)
+                this_adj_marg = ld_mats[p].dot(np.copy(mle), ctx=self._context())
+                this_adj_marg = this_adj_marg / self.std_errs[p]
+                self.adj_marginal_effects[p, :] = this_adj_marg
+                self.ld_ranks[p] = ld_mats[p].get_rank()
+                prior = (2 * gwas_N[p] * init_hg[p] / (self.std_errs[p, :]**-2).sum())
+                inv_z_scores = ld_mats[p].ridge_inverse_dot(
+                    this_adj_marg * self.std_errs[p], self.std_errs[p, :]**2 / prior)
+                self.inverse_betas[p, :] = inv_z_scores * self.std_errs[p]
+
+        if not np.allclose(self.adj_marginal_effects[np.isclose(self.ld_diags, 0)], 0):
+            raise ValueError('Some SNPs that are missing in the LD matrix are not being '
+                             'treated as missing.')
+
+        # which SNPs this rank owns
+        if local_snps is not None:
+            self._snps = np.asarray(local_snps, dtype=np.int64)
+        elif self._comm.world == 1:
+            self._snps = np.arange(self.num_loci, dtype=np.int64)
+        else:
+            parts = partition_snps(host_block_lists(ld_mats), self.num_loci, self._comm.world)
+            self._snps = parts[self._comm.rank]
+
+    # ------------------------------------------------------------------ device plumbing
+    def _context(self):
+        if self._engine_factory is not None:
+            return None
+        if self._ctx is None:
+            from .engine import DeviceContext
+            self._ctx = DeviceContext(self._device if self._device is not None
+                                      else _current_device())
+        return self._ctx
+
+    def _dump_info(self, num_its, diff):
+        """Log information about convergence (reference :292-331), from device reductions."""
+        n = self.num_pops * self.num_loci
+        logging.info('Completed iteration %d', num_its + 1)
+        logging.info('Maximum posterior mean beta: %e', diff[5])
+        logging.info('SE scaling is: %r', self.error_scaling)
+        logging.info('Max relative difference is: %e', diff[6])
+        logging.info('Max absolute difference is: %e', diff[7])
+        logging.info('Mean absolute difference is: %e', diff[1] / n)
+        logging.info('RMSE difference is: %e', np.sqrt(diff[2] / n))
+        logging.info('Max relative difference (checkpoint iterations) is: %e', diff[8])
+        logging.info('Max absolute difference (checkpoint iterations) is: %e', diff[9])
+        logging.info('Mean absolute difference (checkpoint iterations) is: %e', diff[3] / n)
+        logging.info('RMSE difference (checkpoint iterations) is: %e', np.sqrt(diff[4] / n))
+
+    def create_dump_dict(self, params):
+        dump_dict = dict(zip(self.param_names, params))
+        dump_dict['error_scaling'] = self.error_scaling
+        dump_dict['scalings'] = self.scalings
+        return dump_dict
+
+    # ------------------------------------------------------------------ the loop
+    def optimize(self, loaded_checkpoint=None):
+        """Initialize params and optimize objective function (reference :340-394)."""
+        if loaded_checkpoint is None:
+            params = self._initialize()
+        else:
+            params = [np.asarray(loaded_checkpoint[p_name]) for p_name in self.param_names]
+            try:
+                self.error_scaling = np.array(loaded_checkpoint['error_scaling'],
+                                              dtype=np.float64)
+            except KeyError:
+                logging.warning('Did not find "error_scaling" in the loaded '
+                                'checkpoint. That is okay, but we will have '
+                                'to assume that the error scalings are 1.')
+            self._set_state(params)
+        converged = False
+        elbo = self.elbo(params)        # uploads; the state is resident from here on
+        running_elbo_delta = None
+        num_its = 0
+        L = np.ones(5)
+        eng = self._eng
+        eng.pm_mark(0)                  # post_mean
+        eng.pm_mark(1)                  # ckp_post_mean
+        self.trajectory = {'elbo': [], 'L0': [], 'trials': [], 'running': []}
+        want_info = logging.getLogger().isEnabledFor(logging.INFO)
+        while num_its < self.num_its and not converged:
+            if num_its % self.checkpoint_freq == 0 and self.checkpoint:
+                eng.pm_mark(1)
+                fname = '{}.{}'.format(self.checkpoint_path, num_its)
+                dump_dict = self.create_dump_dict(self._download())
+                if self._comm.rank == 0:
+                    np.savez(fname, **dump_dict)
+            trials0 = self.n_trials
+            L, elbo, running_elbo_delta = self._optimize_step_dev(
+                L, elbo, 2., running_elbo_delta)
+
+            diff_dev = eng.pm_diff(ABS_TOL, REL_TOL)
+            diff = self._comm.sum(diff_dev)
+            converged = diff[0] == 0
+            converged = converged or bool(np.isclose(running_elbo_delta, 0,
+                                                     atol=ELBO_TOL, rtol=0))
+            if num_its < 10 and loaded_checkpoint is None:
+                converged = False
+            if want_info:
+                if self._comm.world > 1:
+                    diff[5:] = self._comm.max(diff_dev)[5:]
+                self._dump_info(num_its, diff)
+            self.trajectory['elbo'].append(float(elbo))
+            self.trajectory['L0'].append(float(L[0]))
+            self.trajectory['trials'].append(self.n_trials - trials0)
+            self.trajectory['running'].append(float(running_elbo_delta))
+            num_its += 1
+
+        if num_its == self.num_its:
+            logging.warning('Failed to converge')
+        logging.info('Optimization ran for %d iterations', num_its)
+        self.num_its_run = num_its
+        return self._download()
+
+    def _optimize_step_dev(self, L, curr_elbo, line_search_rate, running_elbo_delta):
+        logging.info('Current ELBO = %f and L = %f,%f,%f,%f,%f',
+                     curr_elbo, L[0], L[1], L[2], L[3], L[4])
+        L_new, elbo_change = self._nat_grad_step_dev(L, line_search_rate, running_elbo_delta)
+        elbo = curr_elbo + elbo_change
+        if running_elbo_delta is None:
+            running_elbo_delta = elbo_change
+        running_elbo_delta *= ELBO_MOMENTUM
+        running_elbo_delta += (1 - ELBO_MOMENTUM) * np.maximum(elbo_change, 0)
+        return L_new, elbo, running_elbo_delta
+
+    def _optimize_step(self, params, L, curr_elbo, line_search_rate=1.25,
+                       running_elbo_delta=None):
+        """Update each set of params and tally up improvement in ELBo (reference :396-410)."""
+        self._make_resident(params)
+        L_new, elbo, running = self._optimize_step_dev(L, curr_elbo, line_search_rate,
+                                                       running_elbo_delta)
+        return self._download(), L_new, elbo, running
+
+    def elbo(self, params):
+        """ELBo of the state `params` (reference :412-417; annotation KL is zero)."""
+        self._make_resident(params)
+        return self._res_obj
+
+    def _nat_grad_step(self, params, L, line_search_rate, running_elbo_delta=None):
+        """One iteration of updating each set of (hyper)parameters (reference :419-450)."""
+        self._make_resident(params)
+        L, delta = self._nat_grad_step_dev(L, line_search_rate, running_elbo_delta)
+        return self._download(), L, delta
+
+    def _nat_grad_step_dev(self, L, line_search_rate, running_elbo_delta=None):
+        updates = [self._update_beta_dev, self._update_hyper_delta_dev,
+                   self._update_annotation_dev]
+        conv_tol = (float('inf') if running_elbo_delta is None
+                    else 0.1 * running_elbo_delta)
+        new_elbo_delta = 0
+        for idx, update in enumerate(updates):
+            orig_obj = None
+            for update_iter in range(MAX_NUM_ITERS):
+                L[idx] = max([1., L[idx] / 1.25])
+                logging.info('...Updating paramset %d, L=%f', idx, L[idx])
+                L, orig_obj, new_obj = update(orig_obj, L, idx, line_search_rate)
+                new_elbo_delta += new_obj - orig_obj
+                with np.errstate(invalid='ignore'):
+                    small = np.isclose(new_obj - orig_obj, 0, atol=conv_tol, rtol=0)
+                if small or L[idx] == 1 or L[idx] > L_MAX:
+                    break
+                orig_obj = new_obj
+
+        if self.scale_se and new_elbo_delta < EM_TOL:
+            orig_obj = self._res_obj
+            self._update_error_scaling_dev()
+            new_obj = self._refresh_delta_dev()
+            new_elbo_delta += new_obj - orig_obj
+            logging.info('...Updating error_scaling, old ELBo=%f, new ELBo=%f',
+                         orig_obj, new_obj)
+        return L, new_elbo_delta
+
+    # -- objective pieces from the reduced statistics of the resident state
+    def _objective(self, stats):
+        P = self.num_pops
+        A_, C_, B_ = stats[0:P], stats[P:2 * P], stats[2 * P:3 * P]
+        per_pop = (-0.5 * (C_ + B_) + A_) - 0.5 * self.chi_stat       # numerics.py:39-44
+        loglik = (per_pop / self.error_scaling
+                  - 0.5 * self.ld_ranks * np.log(self.error_scaling)).sum()
+        kl = stats[3 * P] + stats[3 * P + 1] + stats[3 * P + 2]
+        return float(loglik), float(kl)
+
+    def _log_likelihood(self, params):
+        self._make_resident(params)
+        return self._objective(self._res_stats)[0]
+
+    def _beta_objective(self, params):
+        return self.elbo(params)
+
+    def _update_error_scaling_dev(self):
+        """tau_p = [chi_p - 2 pm.adj + z^T R z + sum sld pv] / rank_p   (reference :472-486)."""
+        P = self.num_pops
+        s = self._res_stats
+        self.error_scaling = (self.chi_stat - 2 * s[0:P] + s[2 * P:3 * P] + s[P:2 * P]) \
+            / self.ld_ranks
+        self._eng.set_tau(self.error_scaling)
+        self._res_valid = False
+
+    def _update_error_scaling(self, params):
+        self._make_resident(params)
+        self._update_error_scaling_dev()
+
+
+def _current_device():
+    import torch
+    return torch.cuda.current_device() if torch.cuda.is_available() else 0
+
+
+class MultiPopVI(VIScheme):
+    """Standard VI scheme for GWAS across one or more populations (reference :567-889)."""
+
+    def __init__(self, mixture_covs=None, **kwargs):
+        num_pops = np.asarray(kwargs['marginal_effects']).shape[0]
+        for mc in mixture_covs:
+            if np.asarray(mc).shape != (num_pops, num_pops):
+                raise ValueError('Mixture component has a covariance matrix of the wrong '
+                                 'shape.')
+        signs, _ = np.linalg.slogdet(np.array(mixture_covs))
+        if not np.all(signs == 1):
+            raise ValueError('Mixture component has a non-positive definite covariance '
+                             'matrix.')
+        self.num_mix = len(mixture_covs)
+        VIScheme.__init__(self, mixture_covs=mixture_covs, **kwargs)
+        self.param_names = ['vi_mu', 'vi_delta', 'hyper_delta']
+
+        covs = np.array(mixture_covs, dtype=np.float64)
+        self.mixture_prec = numerics.small_inverse(covs)[:, :, :, None]     # [K,P,P,1]
+        self.log_det = np.copy(numerics.small_log_det(covs))
+
+        self._gtable = None             # nat_grad_vi_delta as an [A,K-1] table
+        self._resident = None           # host arrays the device state corresponds to
+        self._res_valid = False
+        self._res_obj = None
+        self._res_stats = None
+        self._hyper = None
+        self.n_trials = 0
+        self.n_evals = 0
+        self._build_engine()
+
+    # ------------------------------------------------------------------ engine
+    def _build_engine(self):
+        snps = self._snps
+        M = self.num_loci
+        if len(snps) == 0:
+            raise ValueError('rank %d owns no SNPs; use fewer ranks' % self._comm.rank)
+        pieces = dict(K=self.num_mix, P=self.num_pops, M=len(snps), A=self.num_annotations,
+                      adj=self.adj_marginal_effects[:, snps], se=self.std_errs[:, snps],
+                      sld=self.scaled_ld_diags[:, snps], scalings=self.scalings[:, snps],
+                      annotations=self.annotations[snps],
+                      mixture_prec=self.mixture_prec[..., 0], log_det=self.log_det)
+        if self._engine_factory is not None:
+            self._eng = self._engine_factory(self, snps, pieces)
+        else:
+            from .engine import CudaEngine, DeviceLD
+            ctx = self._context()
+            lds = []
+            for ld in self.ld_mats:
+                if isinstance(ld, DeviceBlockDiagonalMatrix):
+                    lds.append(ld.device_ld)
+                elif self._comm.world == 1 and len(snps) == M:
+                    lds.append(ld.to_device(ctx))
+                else:
+                    ld.release_device()
+                    ids, perm_local = local_blocks(ld, snps, M)
+                    lds.append(DeviceLD(ctx, len(snps), ld.device_blocks(ids), perm_local))
+            self._eng = CudaEngine(ctx, lds, **pieces)
+        self._eng.set_tau(self.error_scaling)
+
+    # ------------------------------------------------------------------ hidden state
+    @property
+    def nat_grad_vi_delta(self):
+        if self._gtable is None:
+            return None
+        return self._gtable[self.annotations]
+
+    @nat_grad_vi_delta.setter
+    def nat_grad_vi_delta(self, value):
+        if value is None:
+            self._gtable = None
+            return
+        value = np.asarray(value, dtype=np.float64)
+        table = np.zeros((self.num_annotations, self.num_mix - 1))
+        for a in range(self.num_annotations):
+            rows = np.where(self.annotations == a)[0]
+            if len(rows):
+                table[a] = value[rows[0]]
+        if not np.array_equal(table[self.annotations], value):
+            raise ValueError('nat_grad_vi_delta must be constant within an annotation')
+        self._set_gtable(table)
+
+    def _set_gtable(self, table):
+        self._gtable = np.array(table, dtype=np.float64)
+        self._eng.set_delta_grad(self._gtable)
+        self._res_valid = False
+
+    def _covariances(self):
+        """(vi_sigma [K,P,P,M], Lambda) on the host from the device kernel -- outputs/tests only."""
+        return self._comm.gather_snp_axis(self._eng.vi_sigma(), self._snps, self.num_loci, 3)
+
+    @property
+    def vi_sigma(self):
+        """S_ki = (Prec_k + diag(sld_i/tau))^-1, [K,P,P,M]   (reference :712-724)."""
+        self._eng.set_tau(self.error_scaling)
+        return self._covariances()
+
+    @property
+    def nat_sigma(self):
+        K, P, M = self.num_mix, self.num_pops, self.num_loci
+        lam = np.zeros((K, P, P, M))
+        idx = np.arange(P)
+        lam[:, idx, idx, :] = self.scaled_ld_diags / self.error_scaling.reshape((-1, 1))
+        lam += self.mixture_prec
+        return -0.5 * lam
+
+    @property
+    def vi_sigma_log_det(self):
+        S = np.transpose(self.vi_sigma, (0, 3, 1, 2))        # [K,M,P,P]
+        return np.linalg.slogdet(S)[1]
+
+    @property
+    def vi_sigma_matches(self):
+        return np.einsum('kpq,kqpi->ik', self.mixture_prec[..., 0], self.vi_sigma)
+
+    @property
+    def sigma_summary(self):
+        return self.log_det - self.vi_sigma_log_det.T + self.vi_sigma_matches
+
+    def _set_vi_sigma(self):
+        """vi_sigma is a function of tau only and is recomputed on the device on the fly."""
+        self._eng.set_tau(self.error_scaling)
+        self._res_valid = False
+
+    # ------------------------------------------------------------------ host <-> device
+    def _same(self, params):
+        if self._resident is None or not self._res_valid:
+            return False
+        return all(a is b for a, b in zip(params, self._resident))
+
+    def _make_resident(self, params):
+        """Upload a host state (unless it is the resident one) and evaluate it."""
+        if self._same(params):
+            return
+        vi_mu, vi_delta, hyper_delta = (np.asarray(x, dtype=np.float64) for x in params)
+        self._upload(vi_mu, vi_delta, hyper_delta)
+        stats = self._comm.sum(self._eng.eval())
+        self.n_evals += 1
+        self._set_result(stats, tuple(params))
+
+    def _upload(self, vi_mu, vi_delta, hyper_delta):
+        snps = self._snps
+        self._hyper = np.array(hyper_delta, dtype=np.float64)
+        self._eng.set_hyper(self._hyper)
+        self._eng.set_tau(self.error_scaling)
+        if self._gtable is not None:
+            self._eng.set_delta_grad(self._gtable)
+        self._eng.set_params(vi_mu[:, :, snps], vi_delta[snps])
+
+    def _set_result(self, stats, resident):
+        """Cache the reduced statistics / objective of the (new) accepted device state.
+        `resident` is the host tuple it corresponds to, or None if it only lives in HBM."""
+        self._res_stats = stats
+        ll, kl = self._objective(stats)
+        self._res_obj = ll - kl
+        self._resident = resident
+        self._res_valid = True
+
+    def _download(self):
+        """Resident state -> host tuple (new arrays, reference layouts)."""
+        if self._resident is not None:
+            return self._resident
+        mu, delta = self._eng.get_params()
+        mu = self._comm.gather_snp_axis(mu, self._snps, self.num_loci, 2)
+        delta = self._comm.gather_snp_axis(delta, self._snps, self.num_loci, 0)
+        self._resident = (mu, delta, np.array(self._hyper))
+        return self._resident
+
+    # ------------------------------------------------------------------ moments
+    def real_posterior_mean(self, vi_mu, vi_delta, hyper_delta):
+        return self._posterior_mean(vi_mu, vi_delta, hyper_delta) * self.scalings
+
+    def real_posterior_variance(self, vi_mu, vi_delta, hyper_delta):
+        self._make_resident((vi_mu, vi_delta, hyper_delta))
+        pv = self._gather_pp(self._eng.posterior()[1])
+        return pv * (self.scalings**2)
+
+    def _posterior_mean(self, vi_mu, vi_delta, hyper_delta):
+        self._make_resident((vi_mu, vi_delta, hyper_delta))
+        return self._gather_pp(self._eng.posterior()[0])
+
+    def _posterior_marginal_variance(self, mean, vi_mu, vi_delta, hyper_delta):
+        self._make_resident((vi_mu, vi_delta, hyper_delta))
+        return self._gather_pp(self._eng.posterior()[1])
+
+    def _gather_pp(self, local):
+        return self._comm.gather_snp_axis(local, self._snps, self.num_loci, 1)
+
+    # ------------------------------------------------------------------ initialisation
+    def _initialize(self):
+        """Starting values of the variational parameters (reference :643-700).
+
+        One-off and seed dependent: consumes np.random.normal exactly as the reference does,
+        on the host; the covariances it needs come from the device kernel."""
+        real_mu = self.inverse_betas
+        logging.info('Largest inverse_beta is %f', np.max(np.abs(real_mu)))
+        missing = np.isclose(self.ld_diags, 0)
+        fake_mu = np.copy(real_mu)
+        fake_mu = np.random.normal(loc=fake_mu, scale=1e-3 * self.std_errs,
+                                   size=fake_mu.shape)
+        fake_mu[missing] = np.nan
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore', category=RuntimeWarning)
+            mu_fill = np.tile(np.nanmean(fake_mu, axis=0), [fake_mu.shape[0], 1])
+        fake_mu[missing] = mu_fill[missing]
+        fake_mu[np.isnan(fake_mu)] = 0.
+        vi_sigma = self.vi_sigma
+        matches = np.einsum('kpq,kqpi->ik', self.mixture_prec[..., 0], vi_sigma)
+        probs = np.einsum('pi,oi,kpo->ik', 1.6 * fake_mu, 1.6 * fake_mu,
+                          self.mixture_prec[..., 0])
+        probs += matches
+        probs -= self.log_det
+        probs = np.exp(-0.5 * (probs - np.min(probs, axis=1, keepdims=True)))
+        vi_delta = np.maximum(probs / probs.sum(axis=1, keepdims=True), numerics.EPSILON)
+        real_hyper_delta = numerics.sum_annotations_host(vi_delta, self.annotations,
+                                                         self.num_annotations)
+        real_hyper_delta += 1.
+        real_hyper_delta /= np.sum(real_hyper_delta, axis=1, keepdims=True)
+        real_hyper_delta = np.maximum(real_hyper_delta, numerics.EPSILON)
+        self._set_gtable(numerics.vi_delta_grad_table(real_hyper_delta, self.log_det))
+        avg_mats = np.einsum('kpqi,ik->ipq', vi_sigma, vi_delta)
+        inv_avg_mats = np.linalg.inv(avg_mats)
+        temp_nat_mu = np.einsum('pi,iqp->qi', fake_mu, inv_avg_mats)
+        vi_mu = np.einsum('kqpi,pi->kqi', vi_sigma, temp_nat_mu)
+        _, vi_delta, _ = self._nat_to_not_vi_delta((vi_mu, vi_delta, real_hyper_delta))
+        return vi_mu, vi_delta, real_hyper_delta
+
+    def _set_state(self, params):
+        """Set internal values given parameter values (reference :702-710)."""
+        vi_mu, vi_delta, hyper_delta = params
+        self._set_vi_sigma()
+        self._set_gtable(numerics.vi_delta_grad_table(
+            np.asarray(hyper_delta, dtype=np.float64), self.log_det))
+
+    # ------------------------------------------------------------------ updates (device)
+    def _refresh_delta_dev(self):
+        """delta := softmax from the resident mu under the current gtable / tau; accept."""
+        stats = self._comm.sum(self._eng.refresh_delta())
+        self.n_evals += 1
+        self._eng.accept()
+        self._set_result(stats, None)
+        return self._res_obj
+
+    def _nat_to_not_vi_delta(self, params):
+        """Convert natural parameterization of delta to delta (reference :632-641)."""
+        vi_mu, vi_delta, hyper_delta = params
+        vi_mu = np.asarray(vi_mu, dtype=np.float64)
+        self._upload(vi_mu, np.asarray(vi_delta, dtype=np.float64),
+                     np.asarray(hyper_delta, dtype=np.float64))
+        self._refresh_delta_dev()
+        _, delta = self._eng.get_params()
+        delta = self._comm.gather_snp_axis(delta, self._snps, self.num_loci, 0)
+        out = (vi_mu, delta, hyper_delta)
+        self._resident = out
+        return out
+
+    def _update_beta_dev(self, orig_obj, L, idx, lsr):
+        """Natural-gradient step on (vi_mu, vi_delta) with backtracking (reference :762-802)."""
+        if orig_obj is None:
+            orig_obj = self._res_obj
+        if self._gtable is None:
+            raise RuntimeError('nat_grad_vi_delta must always be set prior to running '
+                               '_update_beta')
+        while True:
+            step_size = 1. / L[idx]
+            stats = self._comm.sum(self._eng.beta_trial(step_size))
+            self.n_trials += 1
+            self.n_evals += 1
+            ll, kl = self._objective(stats)
+            new_obj = ll - kl
+            logging.info('...Old objective = %f, new objective = %f', orig_obj, new_obj)
+            if new_obj >= orig_obj - REL_TOL * np.abs(orig_obj) - ABS_TOL:
+                if L[idx] > L_MAX:
+                    if not np.isclose(orig_obj, new_obj):
+                        raise RuntimeError('Encountered a numerical error.')
+                break
+            if L[idx] > L_MAX:
+                if not np.isclose(orig_obj, new_obj):
+                    raise RuntimeError('Encountered a numerical error.')
+                return L, orig_obj, orig_obj
+            L[idx] *= lsr
+        self._eng.accept()
+        self._set_result(stats, None)
+        return L, orig_obj, new_obj
+
+    def _update_beta(self, vi_mu, vi_delta, hyper_delta, orig_obj, L, idx, lsr):
+        self._make_resident((vi_mu, vi_delta, hyper_delta))
+        L, orig_obj, new_obj = self._update_beta_dev(orig_obj, L, idx, lsr)
+        return self._download(), L, orig_obj, new_obj
+
+    def _update_hyper_delta_dev(self, orig_obj, L, idx, lsr):
+        """Mixture-weight update (reference :825-860): per-annotation mean of delta."""
+        if orig_obj is None:
+            orig_obj = self._res_obj
+        sums = self._comm.sum(self._eng.sum_annotations()).reshape(
+            self.num_annotations, self.num_mix)
+        new_hyper_delta = np.maximum(
+            sums / (self.annotation_counts.reshape((-1, 1)) + numerics.EPSILON),
+            numerics.EPSILON)
+        new_hyper_delta /= new_hyper_delta.sum(axis=1, keepdims=True)
+        self._hyper = new_hyper_delta
+        self._eng.set_hyper(new_hyper_delta)
+        self._set_gtable(numerics.vi_delta_grad_table(new_hyper_delta, self.log_det))
+        new_obj = self._refresh_delta_dev()
+        logging.info('...Old objective = %f, new objective = %f', orig_obj, new_obj)
+        return L, orig_obj, new_obj
+
+    def _update_hyper_delta(self, vi_mu, vi_delta, hyper_delta, orig_obj, L, idx, lsr):
+        self._make_resident((vi_mu, vi_delta, hyper_delta))
+        L, orig_obj, new_obj = self._update_hyper_delta_dev(orig_obj, L, idx, lsr)
+        return self._download(), L, orig_obj, new_obj
+
+    def _update_annotation_dev(self, orig_obj, L, idx, lsr):
+        """In this VI scheme, this does nothing (reference :862-866)."""
+        return L, 0., 0.
+
+    def _update_annotation(self, vi_mu, vi_delta, hyper_delta, orig_obj, L, idx, lsr):
+        return (vi_mu, vi_delta, hyper_delta), L, 0., 0.
+
+    # ------------------------------------------------------------------ KL pieces
+    def _delta_KL(self, vi_mu, vi_delta, hyper_delta):
+        self._make_resident((vi_mu, vi_delta, hyper_delta))
+        return float(self._res_stats[3 * self.num_pops])
+
+    def _beta_KL(self, vi_mu, vi_delta, hyper_delta):
+        self._make_resident((vi_mu, vi_delta, hyper_delta))
+        return self._objective(self._res_stats)[1]
+
+    def _annotation_KL(self, *params):
+        return 0.
