@@ -51,7 +51,12 @@ def test_precompute_and_state_eval(name):
     assert np.isclose(vi._log_likelihood(params), float(fx['init_loglik']), rtol=1e-11)
     assert np.isclose(vi._beta_KL(*params), float(fx['init_beta_kl']), rtol=1e-11)
     assert np.allclose(vi.real_posterior_mean(*params), fx['init_post_mean'], rtol=1e-10, atol=1e-14)
-    assert np.allclose(vi.real_posterior_variance(*params), fx['init_post_var'], rtol=1e-10, atol=1e-16)
+    # pv = E[b^2] - E[b]^2 cancels catastrophically when |mean| >> sd (here up to E[b]^2/pv ~ 3e9):
+    # the reference's own value is only accurate to eps * E[b^2] (it is 1.5e-7 relative away from a
+    # long-double evaluation on this fixture), so that is the meaningful bound.
+    pm_ref, pv_ref = fx['init_post_mean'], fx['init_post_var']
+    pv = vi.real_posterior_variance(*params)
+    assert np.all(np.abs(pv - pv_ref) <= 1e-10 * pv_ref + 64 * np.finfo(float).eps * (pv_ref + pm_ref**2))
     # seeded initialisation consumes the legacy RNG stream like the reference
     np.random.seed(int(fx['seed']))
     mu, delta, hyper = vi._initialize()
