@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""Benchmark of the `vilma fit` hot path: SNP-updates/s on BASELINE.json configs[1].
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (configs[1]): synthetic single cohort, 1.2M SNPs (1 % without LD) in 1,700 dense
+LD blocks (log-normal sizes, CV 0.6), default mixture grid (-K 12 -> 14 components).
+A "step" is one outer iteration of MultiPopVI.optimize() (reference
+variational_inference.py:361-389); metric = M x (line-search trials executed) / time,
+as defined in SURVEY.md section 8(d).  The problem size is fixed as N grows (strong scaling).
+
+`value`  : state resident in HBM, timed with CUDA events on the launching stream.
+`e2e`    : the public call -- MultiPopVI.optimize(checkpoint) with HOST parameter arrays:
+           upload, K iterations, download of the fitted parameters, all inside the region.
+`roofline`: the LD mat-vec kernel, timed per launch with CUDA events inside the region.
+`cpu_baseline` / `--impl reference`: the NumPy oracle port of the reference loop on a
+           bounded sample of the same workload, on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_TOTAL = 1_200_000
+N_BLOCKS = 1_700
+MISSING_FRAC = 0.01
+K_GRID = 12
+N_GWAS = 3e5
+INIT_HG = 0.3
+SAMPLE_BLOCKS = 85          # CPU sample: 5 % of the blocks (~60k SNPs)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# problem construction
+# --------------------------------------------------------------------------------------
+def layout(M_total=M_TOTAL, n_blocks=N_BLOCKS):
+    from vilma_b200 import synth
+    M_ld = int(round(M_total * (1 - MISSING_FRAC)))
+    n = synth.block_sizes(M_ld, n_blocks)
+    starts = np.concatenate([[0], np.cumsum(n)])
+    return M_ld, n, starts
+
+
+def build_gpu_problem(comm, device, M_total=M_TOTAL, n_blocks=N_BLOCKS, num_its=1000):
+    """Generate this rank's LD shard in HBM and build the MultiPopVI over it."""
+    import torch
+    from vilma_b200 import synth
+    from vilma_b200.engine import DeviceContext, DeviceLD
+    from vilma_b200.variational_inference import DeviceBlockDiagonalMatrix, MultiPopVI
+
+    dev = torch.device('cuda', device)
+    M_ld, n_all, starts = layout(M_total, n_blocks)
+    mine = synth.assign_blocks(n_all, comm.world)[comm.rank]
+    # SNPs without LD are dealt round-robin
+    miss_all = np.arange(M_ld, M_total, dtype=np.int64)
+    miss_mine = miss_all[comm.rank::comm.world]
+    snps_ld = np.concatenate([np.arange(starts[b], starts[b + 1]) for b in mine])
+    snps = np.sort(np.concatenate([snps_ld, miss_mine]))
+    g2l = np.full(M_total, -1, dtype=np.int64)
+    g2l[snps] = np.arange(len(snps))
+
+    t0 = time.time()
+    # pass 1: standard errors (global sum of se^-2 sets the ridge prior, reference :246-247)
+    se_blocks = {}
+    inv_se2 = 0.0
+    for b in mine:
+        se_blocks[b] = synth.block_se(int(n_all[b]), 42, b, N_GWAS, dev)
+        inv_se2 += float((se_blocks[b] ** -2).sum())
+    inv_se2 = float(comm.sum(np.array([inv_se2]))[0]) + (M_total - M_ld) * 1.0
+    prior = 2 * N_GWAS * INIT_HG / inv_se2
+
+    # pass 2: LD blocks straight into the library's HBM store + per-SNP set-up values
+    ctx = DeviceContext(device)
+    ld = DeviceLD(ctx, len(snps), n=n_all[mine], rank=-np.ones(len(mine), dtype=np.int64))
+    beta_hat = np.zeros(M_total)
+    se = np.ones(M_total)
+    adj = np.zeros(M_total)
+    inv_betas = np.zeros(M_total)
+    chi = 0.0
+    for j, b in enumerate(mine):
+        nb = int(n_all[b])
+        r, bh = synth.make_block_sumstats(nb, 42, b, se_blocks[b], M_total, dev)
+        ld.set_dense(j, r)
+        c, a, ib = synth.precompute_block_full_rank(r, bh, se_blocks[b], prior)
+        chi += c
+        sl = slice(starts[b], starts[b + 1])
+        beta_hat[sl] = bh.cpu().numpy()
+        se[sl] = se_blocks[b].cpu().numpy()
+        adj[sl] = a.cpu().numpy()
+        inv_betas[sl] = ib.cpu().numpy()
+        del r, bh
+    ld.finalize(g2l[snps_ld])
+    torch.cuda.synchronize()
+    del se_blocks
+    torch.cuda.empty_cache()
+    # global per-SNP vectors (each rank filled only its own entries; the rest are zero)
+    if comm.world > 1:
+        beta_hat, adj, inv_betas = (comm.sum(x) for x in (beta_hat, adj, inv_betas))
+        se = comm.sum(se - 1.0) + 1.0
+    chi = float(comm.sum(np.array([chi]))[0])
+    ld_diags = np.zeros(M_total)
+    ld_diags[:M_ld] = 1.0
+    covs = synth.mixture_grid_single(beta_hat, se, K_GRID)
+    pre = dict(ld_diags=ld_diags[None], adj_marginal_effects=adj[None], chi_stat=np.array([chi]),
+               ld_ranks=np.array([float(M_ld)]), inverse_betas=inv_betas[None])
+    vi = MultiPopVI(marginal_effects=beta_hat[None], std_errs=se[None],
+                    ld_mats=[DeviceBlockDiagonalMatrix(ld, (M_total, M_total))],
+                    mixture_covs=covs, annotations=np.ones((M_total, 1)), checkpoint=False,
+                    checkpoint_freq=-1, output='bench', scaled=False, scale_se=False,
+                    gwas_N=np.array([N_GWAS]), init_hg=np.array([INIT_HG]), num_its=num_its,
+                    comm=comm, device=device, precomputed=pre, local_snps=snps, context=ctx)
+    info = dict(M=M_total, M_ld=M_ld, blocks=int(n_blocks), K=len(covs), P=1,
+                ld_bytes_total=int(8 * (n_all.astype(np.float64) ** 2).sum()),
+                ld_bytes_rank=int(ld.bytes), setup_s=time.time() - t0,
+                n_max=int(n_all.max()))
+    return vi, ctx, info
+
+
+def build_cpu_sample(n_blocks=SAMPLE_BLOCKS):
+    """The bounded CPU sample: the first `n_blocks` blocks of the same generator, as oracle
+    objects (LowRankBlock does the reference's eigendecomposition, matrix_structures.py:15-28)."""
+    import torch
+    from oracle.ld_np import BlockDiagonalLD, LowRankBlock
+    from oracle.vi_np import OracleVI
+    from vilma_b200 import synth
+
+    M_ld_full, n_all, _ = layout()
+    n = n_all[:n_blocks]
+    M_ld = int(n.sum())
+    n_miss = int(round(M_ld * MISSING_FRAC / (1 - MISSING_FRAC)))
+    M = M_ld + n_miss
+    dev = torch.device('cpu')
+    blocks, bh, se = [], [], []
+    for b in range(n_blocks):
+        s = synth.block_se(int(n[b]), 42, b, N_GWAS, dev)
+        r, beta_hat = synth.make_block_sumstats(int(n[b]), 42, b, s, M_TOTAL, dev)
+        blocks.append(LowRankBlock(X=r.numpy(), t=1.0))
+        bh.append(beta_hat.numpy())
+        se.append(s.numpy())
+    missing = np.arange(M_ld, M, dtype=np.int64)
+    ld = BlockDiagonalLD(blocks, perm=np.arange(M), missing=missing)
+    beta_hat = np.concatenate(bh + [np.zeros(n_miss)])
+    std = np.concatenate(se + [np.ones(n_miss)])
+    covs = synth.mixture_grid_single(beta_hat, std, K_GRID)
+    vi = OracleVI(marginal_effects=beta_hat[None], std_errs=std[None], ld_mats=[ld],
+                  mixture_covs=covs, annotations=np.ones((M, 1)), scaled=False, scale_se=False,
+                  gwas_N=np.array([N_GWAS]), init_hg=np.array([INIT_HG]), num_its=1000)
+    return vi, M, n_blocks
+
+
+def time_cpu(steps, warmup):
+    """Oracle port of the reference loop on the sample: returns (value, seconds, trials, M, info)."""
+    t_setup = time.time()
+    vi, M, nb = build_cpu_sample()
+    np.random.seed(42)
+    params = vi._initialize()
+    elbo = vi.elbo(params)
+    L = np.ones(5)
+    running = None
+    t_setup = time.time() - t_setup
+    for _ in range(warmup):
+        params, L, elbo, running = vi._optimize_step(params, L=L, curr_elbo=elbo,
+                                                     line_search_rate=2.,
+                                                     running_elbo_delta=running)
+        params = tuple(params)
+    t0 = time.perf_counter()
+    tr0, mv0 = vi.counters['trials'], vi.counters['matvec']
+    for _ in range(steps):
+        params, L, elbo, running = vi._optimize_step(params, L=L, curr_elbo=elbo,
+                                                     line_search_rate=2.,
+                                                     running_elbo_delta=running)
+        params = tuple(params)
+    dt = time.perf_counter() - t0
+    trials = vi.counters['trials'] - tr0
+    cores = os.cpu_count() or 1
+    sample = ('first %d of the %d LD blocks of the same generator (M=%d SNPs), %d warm-up + %d '
+              'timed outer iterations, %d trials, %d LD mat-vecs; NumPy/OpenBLAS oracle port of '
+              'the reference loop' % (nb, N_BLOCKS, M, warmup, steps, trials,
+                                      vi.counters['matvec'] - mv0))
+    return M * trials / dt, dt, trials, M, dict(cores=cores, sample=sample, setup_s=t_setup)
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.FIELDS,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(',')]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, parts[3:7]):
+                    if val.lower().startswith('active'):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# --------------------------------------------------------------------------------------
+# arms
+# --------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from vilma_b200.dist import SingleComm, TorchComm
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        comm = TorchComm()
+    else:
+        comm = SingleComm()
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device; vilma_b200 has no CPU path')
+    device = local_rank
+    torch.cuda.set_device(device)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
+
+    vi, ctx, info = build_gpu_problem(comm, device, M_total=args.snps, n_blocks=args.blocks)
+    log('[rank %d] problem built in %.1fs: %s' % (comm.rank, info['setup_s'], info))
+    M = info['M']
+
+    # initial parameters: host arrays in pinned memory (e2e uploads them)
+    np.random.seed(42)
+    t0 = time.time()
+    init = vi._initialize()
+    log('[rank %d] _initialize %.1fs' % (comm.rank, time.time() - t0))
+    pin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in init]
+    init = tuple(t.numpy() for t in pin)
+    ckpt = {'vi_mu': init[0], 'vi_delta': init[1], 'hyper_delta': init[2],
+            'error_scaling': np.ones(1)}
+
+    # ---------------- device-resident run: warm-up then timed ----------------
+    vi._set_state(init)
+    state = vi.begin_loop(init)
+    state = vi.run_loop(state, args.warmup, fresh=True)
+    comm.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(device)
+    if comm.rank == 0:
+        sampler.start()
+    ctx.profile(True)
+    launches0 = ctx.launch_count()
+    trials0 = vi.n_trials
+    evals0 = vi.n_evals
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    state = vi.run_loop(state, args.warmup + args.steps, fresh=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    comm.barrier()
+    ms = ev0.elapsed_time(ev1)
+    ms = float(comm.max(np.array([ms]))[0])
+    clocks = sampler.stop() if comm.rank == 0 else {}
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    trials = vi.n_trials - trials0
+    evals = vi.n_evals - evals0
+    launches = ctx.launch_count() - launches0
+    steps_done = state['num_its'] - args.warmup
+    value = M * trials / (ms * 1e-3)
+
+    # roofline of the dominant kernel (LD mat-vec), this rank's launches
+    mv_ms, mv_n = prof['ld_matvec']
+    snp_ms, snp_n = prof['snp']
+    mv_avg = mv_ms / max(mv_n, 1)
+    achieved = info['ld_bytes_rank'] / (mv_avg * 1e-3) / 1e9 if mv_n else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ld_matvec_traffic.json')))['bytes_per_launch']
+    except Exception:
+        pass
+    bytes_trial = info['ld_bytes_total'] + 16 * info['K'] * 2 * M + 64 * M
+
+    # ---------------- end-to-end: the public call with host buffers ----------------
+    vi.num_its = args.steps
+    comm.barrier()
+    torch.cuda.synchronize()
+    tr0 = vi.n_trials
+    t0 = time.perf_counter()
+    out = vi.optimize(ckpt)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_s = float(comm.max(np.array([e2e_s]))[0])
+    e2e_trials = vi.n_trials - tr0
+    e2e_steps = vi.num_its_run
+    n_local = len(vi._snps)
+    h2d = (info['K'] * n_local * 2 + info['K']) * 8 / max(e2e_steps, 1)
+    d2h = (info['K'] * n_local * 2) * 8 / max(e2e_steps, 1) + (3 + 3 + 10) * 8 * 2
+    e2e_value = M * e2e_trials / e2e_s
+
+    result = {
+        'metric': 'CAVI SNP-updates/sec (1.2M SNPs, 1/2/4/8 B200)',
+        'value': value, 'unit': 'SNP-updates/s', 'n_gpus': comm.world, 'steps': int(steps_done),
+        'warmup': args.warmup, 'ms_per_step': ms / max(steps_done, 1),
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {
+            'workload': 'BASELINE configs[1]: synthetic single cohort, %d SNPs (1%% without LD) in '
+                        '%d dense LD blocks (lognormal sizes, CV 0.6, max n=%d), -K 12 -> %d '
+                        'mixture components, P=1' % (M, info['blocks'], info['n_max'], info['K']),
+            'M': M, 'blocks': info['blocks'], 'K': info['K'], 'P': 1,
+            'ld_store': 'dense fp64, every element read once per mat-vec',
+            'ld_bytes': info['ld_bytes_total'], 'algorithmic_bytes_per_trial': bytes_trial,
+            'trials': int(trials), 'state_evaluations': int(evals),
+            'trials_per_step': trials / max(steps_done, 1),
+            'l2': 'inputs larger than L2: the %.1f GB LD store is re-read from HBM by every '
+                  'evaluation' % (info['ld_bytes_rank'] / 1e9),
+            'parallelism': 'LD blocks sharded over %d rank(s), LPT by n^2; one all-reduce of '
+                           '%d doubles per evaluated state' % (comm.world, 6),
+            'setup_s': info['setup_s'],
+        },
+        'clocks': {k: clocks.get(k) for k in ('sm_mhz', 'sm_max_mhz', 'reasons')},
+        'e2e': {'value': e2e_value, 'unit': 'SNP-updates/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h, 'steps': int(e2e_steps), 'seconds': e2e_s,
+                'call': 'MultiPopVI.optimize(checkpoint) with pinned host parameter arrays'},
+        'gpu_launches': int(launches),
+        'roofline': {'bound': 'hbm', 'kernel': 'vb_ld_matvec_kernel', 'achieved': achieved,
+                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
+                     'traffic': traffic, 'peak_source': peak_src,
+                     'bytes_per_launch': info['ld_bytes_rank'], 'avg_launch_ms': mv_avg,
+                     'launches_timed': int(mv_n),
+                     'share_of_step': mv_ms / ms if ms else None,
+                     'snp_kernel_avg_ms': snp_ms / max(snp_n, 1),
+                     'whole_trial_frac': (bytes_trial / comm.world) * evals / (ms * 1e-3) / 1e9 / hbm_peak},
+    }
+    if comm.rank == 0 and comm.world == 1 and not args.no_cpu:
+        v, dt, tr, Ms, extra = time_cpu(steps=3, warmup=1)
+        result['cpu_baseline'] = {'value': v, 'unit': 'SNP-updates/s', 'cores': extra['cores'],
+                                  'kind': 'port', 'sample': extra['sample'], 'seconds': dt}
+    if comm.rank == 0:
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    v, dt, trials, M, extra = time_cpu(steps=args.steps, warmup=args.warmup)
+    result = {
+        'impl': 'reference',
+        'metric': 'CAVI SNP-updates/sec (1.2M SNPs, 1/2/4/8 B200)',
+        'value': v, 'unit': 'SNP-updates/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': dt * 1e3 / max(args.steps, 1),
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': 'BASELINE configs[1] (bounded sample): ' + extra['sample']},
+        'cpu_baseline': {'value': v, 'unit': 'SNP-updates/s', 'cores': extra['cores'],
+                         'kind': 'port', 'sample': extra['sample']},
+        'e2e': {'value': v, 'unit': 'SNP-updates/s', 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(result), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--snps', type=int, default=M_TOTAL)
+    ap.add_argument('--blocks', type=int, default=N_BLOCKS)
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -41,6 +41,11 @@ int vb_ctx_destroy(vb_ctx* ctx);
 int vb_ctx_sync(vb_ctx* ctx);
 /* number of kernels launched by this context since creation (bench.py "gpu_launches") */
 int64_t vb_ctx_launch_count(const vb_ctx* ctx);
+/* per-kernel timing with CUDA events on the context's stream (bench.py roofline leg):
+ * enable / reset, then read {total ms, launches} for category 0 = LD mat-vec kernel,
+ * 1 = fused per-SNP kernel.  At most 4096 launches per category are timed between reads. */
+int vb_ctx_profile(vb_ctx* ctx, int enable);
+int vb_ctx_profile_read(vb_ctx* ctx, double* total_ms2, int64_t* count2);
 
 /* ---- LD operator ---------------------------------------------------------------------
  * Replaces BlockDiagonalMatrix(matrices, perm, missing) and its .dot
@@ -75,7 +80,8 @@ int64_t vb_ld_bytes(const vb_ld* ld);
  * vb_fit_set_delta_grad  nat_grad_vi_delta as an [A][K-1] table: fast_vi_delta_grad's value
  *                     for annotation a (numerics.py:149-164; variational_inference.py:694, :706, :844)
  * vb_fit_set_tau      error_scaling [P]; implies _set_vi_sigma()        (:712-738)
- * vb_fit_set_params / vb_fit_get_params   accepted state, host arrays in DEVICE layout.
+ * vb_fit_set_params / vb_fit_get_params   accepted state, host arrays in the REFERENCE layouts
+ *                     vi_mu [K][P][M], vi_delta [M][K] (transposed to [K][M] on the device).
  */
 int vb_fit_create(vb_ctx* ctx, int K, int P, int64_t M, int A, vb_ld* const* lds);
 int vb_fit_destroy(vb_ctx* ctx);
@@ -86,8 +92,8 @@ int vb_fit_set_mixture(vb_ctx* ctx, const double* prec_host, const double* logde
 int vb_fit_set_hyper(vb_ctx* ctx, const double* hyper_host);
 int vb_fit_set_delta_grad(vb_ctx* ctx, const double* table_host);
 int vb_fit_set_tau(vb_ctx* ctx, const double* tau_host);
-int vb_fit_set_params(vb_ctx* ctx, const double* vi_mu_host, const double* vi_delta_km_host);
-int vb_fit_get_params(vb_ctx* ctx, double* vi_mu_host, double* vi_delta_km_host);
+int vb_fit_set_params(vb_ctx* ctx, const double* vi_mu_host, const double* vi_delta_mk_host);
+int vb_fit_get_params(vb_ctx* ctx, double* vi_mu_host, double* vi_delta_mk_host);
 
 /* ---- evaluations: each fills stats_dev[0 .. 3P+3) for ONE parameter state -------------
  *   [0,P)   A_p = sum_i pm adj      [P,2P)  C_p = sum_i sld pv      [2P,3P) B_p = sum_i z (R z)

@@ -18,6 +18,8 @@ SIGNATURES = {
     'vb_ctx_destroy': (C.c_int, [C.c_void_p]),
     'vb_ctx_sync': (C.c_int, [C.c_void_p]),
     'vb_ctx_launch_count': (C.c_int64, [C.c_void_p]),
+    'vb_ctx_profile': (C.c_int, [C.c_void_p, C.c_int]),
+    'vb_ctx_profile_read': (C.c_int, [C.c_void_p, c_dp, c_i64p]),
     'vb_ld_create': (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_i64p, c_i64p, C.POINTER(C.c_void_p)]),
     'vb_ld_destroy': (C.c_int, [C.c_void_p]),
     'vb_ld_set_dense': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int]),

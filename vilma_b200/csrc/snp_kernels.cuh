@@ -435,3 +435,17 @@ __global__ void vb_vi_sigma_kernel(const double* __restrict__ prec, const double
                 out[(((size_t)(k - k0) * P + p) * P + q) * M + i] = S[p >= q ? VB_TRI(p, q) : VB_TRI(q, p)];
     }
 }
+
+// [M][K] (reference layout of vi_delta) <-> [K][M] (device layout)
+__global__ void vb_mk_to_km_kernel(const double* __restrict__ mk, int64_t M, int K,
+                                   double* __restrict__ km) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x)
+        for (int k = 0; k < K; ++k) km[(size_t)k * M + i] = mk[(size_t)i * K + k];
+}
+__global__ void vb_km_to_mk_kernel(const double* __restrict__ km, int64_t M, int K,
+                                   double* __restrict__ mk) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x)
+        for (int k = 0; k < K; ++k) mk[(size_t)i * K + k] = km[(size_t)k * M + i];
+}

@@ -114,7 +114,22 @@ struct vb_ctx {
     int64_t launches = 0;
     std::vector<vb_ld*> fit_ld;   // the P operators the fit state uses (not owned)
     Fit fit;
+    // optional per-kernel timing with CUDA events on `stream` (bench.py roofline leg)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev[2];     // category 0: LD mat-vec, 1: per-SNP kernel; start/stop pairs
+    size_t ev_used[2] = {0, 0};
 };
+#define VB_PROF_PAIRS 4096
+static inline void prof_begin(vb_ctx* c, int cat) {
+    if (c->profiling && c->ev_used[cat] + 2 <= c->ev[cat].size())
+        cudaEventRecord(c->ev[cat][c->ev_used[cat]], c->stream);
+}
+static inline void prof_end(vb_ctx* c, int cat) {
+    if (c->profiling && c->ev_used[cat] + 2 <= c->ev[cat].size()) {
+        cudaEventRecord(c->ev[cat][c->ev_used[cat] + 1], c->stream);
+        c->ev_used[cat] += 2;
+    }
+}
 struct vb_ld {
     vb_ctx* ctx = nullptr;
     LdPop L;
@@ -173,7 +188,40 @@ extern "C" int vb_ctx_destroy(vb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     free_fit(ctx->fit);
+    for (int cat = 0; cat < 2; ++cat)
+        for (auto& e : ctx->ev[cat]) cudaEventDestroy(e);
     delete ctx;
+    return 0;
+}
+extern "C" int vb_ctx_profile(vb_ctx* ctx, int enable) {
+    if (!ctx) return vb_fail("null ctx");
+    CK(cudaSetDevice(ctx->device));
+    if (enable && ctx->ev[0].empty()) {
+        for (int cat = 0; cat < 2; ++cat) {
+            ctx->ev[cat].resize(2 * VB_PROF_PAIRS);
+            for (auto& e : ctx->ev[cat]) CK(cudaEventCreate(&e));
+        }
+    }
+    ctx->profiling = enable != 0;
+    ctx->ev_used[0] = ctx->ev_used[1] = 0;
+    return 0;
+}
+// total_ms[cat], count[cat] of the launches timed since profiling was (re-)enabled; resets.
+extern "C" int vb_ctx_profile_read(vb_ctx* ctx, double* total_ms, int64_t* count) {
+    if (!ctx) return vb_fail("null ctx");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int cat = 0; cat < 2; ++cat) {
+        double tot = 0.0;
+        for (size_t i = 0; i + 1 < ctx->ev_used[cat]; i += 2) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, ctx->ev[cat][i], ctx->ev[cat][i + 1]));
+            tot += ms;
+        }
+        total_ms[cat] = tot;
+        count[cat] = (int64_t)(ctx->ev_used[cat] / 2);
+        ctx->ev_used[cat] = 0;
+    }
     return 0;
 }
 extern "C" int vb_ctx_sync(vb_ctx* ctx) {
@@ -473,8 +521,10 @@ static int ld_apply(vb_ctx* ctx, LdPop& L, const double* x_snp, double* y_snp, d
     }
     if (L.n_items1 > 0) {
         double* out1 = L.nslab1 > 1 ? L.tbs : L.xall + L.xb_len;
+        prof_begin(ctx, 0);
         vb_ld_matvec_kernel<<<ctx->num_sms, VB_LD_THREADS, VB_LD_SMEM, st>>>(L.mat, L.items1, L.cta1,
                                                                              L.xall, out1);
+        prof_end(ctx, 0);
         CK_LAUNCH(ctx);
         if (L.nslab1 > 1) {
             const int g = (int)std::min<int64_t>((L.tb_len + 255) / 256, 1184);
@@ -483,8 +533,10 @@ static int ld_apply(vb_ctx* ctx, LdPop& L, const double* x_snp, double* y_snp, d
         }
     }
     if (L.n_items2 > 0) {
+        prof_begin(ctx, 0);
         vb_ld_matvec_kernel<<<ctx->num_sms, VB_LD_THREADS, VB_LD_SMEM, st>>>(L.mat, L.items2, L.cta2,
                                                                              L.xall, L.yb);
+        prof_end(ctx, 0);
         CK_LAUNCH(ctx);
     }
     vb_ld_finish_kernel<<<grid_fin, 256, 0, st>>>(L.yb, L.xb_len, L.nslab2, L.xall, L.pos, L.snp,
@@ -615,21 +667,32 @@ extern "C" int vb_fit_set_tau(vb_ctx* ctx, const double* tau) {
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
-extern "C" int vb_fit_set_params(vb_ctx* ctx, const double* mu, const double* delta_km) {
+extern "C" int vb_fit_set_params(vb_ctx* ctx, const double* mu, const double* delta_mk) {
     NEED_FIT(ctx);
     const size_t KM = (size_t)f.K * f.M;
     CK(cudaMemcpyAsync(f.mu[f.cur_mu], mu, KM * f.P * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(f.delta[f.cur_delta], delta_km, KM * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // vi_delta arrives in the reference layout [M][K]; stage it in the trial slot, transpose on device
+    double* stage = f.delta[1 - f.cur_delta];
+    CK(cudaMemcpyAsync(stage, delta_mk, KM * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const int grid = (int)std::min<int64_t>((f.M + 255) / 256, 4096);
+    vb_mk_to_km_kernel<<<grid, 256, 0, ctx->stream>>>(stage, f.M, f.K, f.delta[f.cur_delta]);
+    CK_LAUNCH(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
     f.trial_kind = -1;
     return 0;
 }
-extern "C" int vb_fit_get_params(vb_ctx* ctx, double* mu, double* delta_km) {
+extern "C" int vb_fit_get_params(vb_ctx* ctx, double* mu, double* delta_mk) {
     NEED_FIT(ctx);
     const size_t KM = (size_t)f.K * f.M;
     if (mu) CK(cudaMemcpyAsync(mu, f.mu[f.cur_mu], KM * f.P * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if (delta_km)
-        CK(cudaMemcpyAsync(delta_km, f.delta[f.cur_delta], KM * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (delta_mk) {
+        double* stage = f.delta[1 - f.cur_delta];      // any pending trial is discarded
+        const int grid = (int)std::min<int64_t>((f.M + 255) / 256, 4096);
+        vb_km_to_mk_kernel<<<grid, 256, 0, ctx->stream>>>(f.delta[f.cur_delta], f.M, f.K, stage);
+        CK_LAUNCH(ctx);
+        CK(cudaMemcpyAsync(delta_mk, stage, KM * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        f.trial_kind = -1;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -637,6 +700,7 @@ extern "C" int vb_fit_get_params(vb_ctx* ctx, double* mu, double* delta_km) {
 template <int MODE>
 static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
     cudaStream_t st = ctx->stream;
+    prof_begin(ctx, 1);
     switch (P) {
         case 1: vb_snp_kernel<1, MODE><<<grid, 128, 0, st>>>(a); break;
         case 2: vb_snp_kernel<2, MODE><<<grid, 128, 0, st>>>(a); break;
@@ -646,6 +710,7 @@ static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
         case 6: vb_snp_kernel<6, MODE><<<grid, 128, 0, st>>>(a); break;
         default: return vb_fail("unsupported cohort count %d", P);
     }
+    prof_end(ctx, 1);
     CK_LAUNCH(ctx);
     return 0;
 }

@@ -49,6 +49,16 @@ class DeviceContext:
     def launch_count(self):
         return int(self.lib.vb_ctx_launch_count(self.handle))
 
+    def profile(self, enable=True):
+        _lib.check(self.lib.vb_ctx_profile(self.handle, 1 if enable else 0))
+
+    def profile_read(self):
+        """{'ld_matvec': (total_ms, launches), 'snp': (total_ms, launches)} since last reset."""
+        ms = (C.c_double * 2)()
+        cnt = (C.c_int64 * 2)()
+        _lib.check(self.lib.vb_ctx_profile_read(self.handle, ms, cnt))
+        return {'ld_matvec': (ms[0], cnt[0]), 'snp': (ms[1], cnt[1])}
+
 
 def choose_storage(n, r):
     """'dense' when the reconstructed n x n block is no larger than the two factor passes."""
@@ -63,27 +73,42 @@ class DeviceLD:
     block-order position j.  M = number of SNPs on this rank.
     """
 
-    def __init__(self, ctx, M, blocks, perm_local):
+    def __init__(self, ctx, M, blocks=None, perm_local=None, n=None, rank=None):
+        """Either pass `blocks` + `perm_local` (everything at once) or `n` / `rank` arrays and
+        then call set_dense / set_factor per block and finalize(perm_local) (streaming build)."""
         self.ctx = ctx
         self.lib = ctx.lib
         self.M = int(M)
-        nb = len(blocks)
-        n = np.array([b['n'] for b in blocks], dtype=np.int64)
-        rank = np.array([-1 if b['kind'] == 'dense' else b['U'].shape[1] for b in blocks],
-                        dtype=np.int64)
+        if blocks is not None:
+            n = np.array([b['n'] for b in blocks], dtype=np.int64)
+            rank = np.array([-1 if b['kind'] == 'dense' else b['U'].shape[1] for b in blocks],
+                            dtype=np.int64)
+        n = np.ascontiguousarray(n, dtype=np.int64)
+        rank = np.ascontiguousarray(rank, dtype=np.int64)
         self.handle = C.c_void_p()
+        self.bytes = 0
         _lib.check(self.lib.vb_ld_create(
-            ctx.handle, self.M, nb, n.ctypes.data_as(_lib.c_i64p),
+            ctx.handle, self.M, len(n), n.ctypes.data_as(_lib.c_i64p),
             rank.ctypes.data_as(_lib.c_i64p), C.byref(self.handle)))
-        for b, blk in enumerate(blocks):
-            if blk['kind'] == 'dense':
-                ptr, on_dev, keep = self._ptr(blk['R'])
-                _lib.check(self.lib.vb_ld_set_dense(self.handle, b, ptr, int(blk['n']), on_dev))
-            else:
-                pu, on_dev, keep = self._ptr(blk['U'])
-                ps, on_dev2, keep2 = self._ptr(blk['s'])
-                assert on_dev == on_dev2
-                _lib.check(self.lib.vb_ld_set_factor(self.handle, b, pu, ps, on_dev))
+        if blocks is not None:
+            for b, blk in enumerate(blocks):
+                if blk['kind'] == 'dense':
+                    self.set_dense(b, blk['R'])
+                else:
+                    self.set_factor(b, blk['U'], blk['s'])
+            self.finalize(perm_local)
+
+    def set_dense(self, b, R):
+        ptr, on_dev, keep = self._ptr(R)
+        _lib.check(self.lib.vb_ld_set_dense(self.handle, b, ptr, int(R.shape[1]), on_dev))
+
+    def set_factor(self, b, U, s):
+        pu, on_dev, keep = self._ptr(U)
+        ps, on_dev2, keep2 = self._ptr(s)
+        assert on_dev == on_dev2
+        _lib.check(self.lib.vb_ld_set_factor(self.handle, b, pu, ps, on_dev))
+
+    def finalize(self, perm_local):
         perm = np.ascontiguousarray(perm_local, dtype=np.int64)
         _lib.check(self.lib.vb_ld_finalize(self.handle, perm.ctypes.data_as(_lib.c_i64p),
                                            perm.shape[0]))
@@ -178,15 +203,15 @@ class CudaEngine:
     # ---- state transfer (reference host layouts in, device layouts inside)
     def set_params(self, vi_mu, vi_delta):
         mu = np.ascontiguousarray(vi_mu, dtype=np.float64)
-        dkm = np.ascontiguousarray(np.asarray(vi_delta, dtype=np.float64).T)
-        assert mu.shape == (self.K, self.P, self.M) and dkm.shape == (self.K, self.M)
-        _lib.check(self.lib.vb_fit_set_params(self.ctx.handle, _lib.np_ptr(mu), _lib.np_ptr(dkm)))
+        dmk = np.ascontiguousarray(vi_delta, dtype=np.float64)
+        assert mu.shape == (self.K, self.P, self.M) and dmk.shape == (self.M, self.K)
+        _lib.check(self.lib.vb_fit_set_params(self.ctx.handle, _lib.np_ptr(mu), _lib.np_ptr(dmk)))
 
-    def get_params(self):
-        mu = np.empty((self.K, self.P, self.M))
-        dkm = np.empty((self.K, self.M))
-        _lib.check(self.lib.vb_fit_get_params(self.ctx.handle, _lib.np_ptr(mu), _lib.np_ptr(dkm)))
-        return mu, np.ascontiguousarray(dkm.T)
+    def get_params(self, out_mu=None, out_delta=None):
+        mu = np.empty((self.K, self.P, self.M)) if out_mu is None else out_mu
+        dmk = np.empty((self.M, self.K)) if out_delta is None else out_delta
+        _lib.check(self.lib.vb_fit_get_params(self.ctx.handle, _lib.np_ptr(mu), _lib.np_ptr(dmk)))
+        return mu, dmk
 
     # ---- evaluations (return the device stats tensor, valid until the next evaluation)
     def eval(self):

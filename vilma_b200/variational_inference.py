@@ -70,7 +70,8 @@ class VIScheme():
                  device=None,
                  precomputed=None,
                  local_snps=None,
-                 engine_factory=None):
+                 engine_factory=None,
+                 context=None):
         for val, name in [(init_hg, 'init_hg'), (gwas_N, 'gwas_N'),
                           (marginal_effects, 'marginal_effects'), (std_errs, 'std_errs'),
                           (ld_mats, 'ld_mats'), (annotations, 'annotations'),
@@ -116,7 +117,7 @@ class VIScheme():
         self._comm = comm if comm is not None else default_comm()
         self._device = device
         self._engine_factory = engine_factory
-        self._ctx = None
+        self._ctx = context
 
         self.marginal_effects = np.copy(marginal_effects)
         if self.scaled:
@@ -228,17 +229,32 @@ class VIScheme():
                                 'checkpoint. That is okay, but we will have '
                                 'to assume that the error scalings are 1.')
             self._set_state(params)
-        converged = False
+        state = self.begin_loop(params)
+        state = self.run_loop(state, self.num_its, fresh=loaded_checkpoint is None)
+        num_its = state['num_its']
+        if num_its == self.num_its:
+            logging.warning('Failed to converge')
+        logging.info('Optimization ran for %d iterations', num_its)
+        self.num_its_run = num_its
+        return self._download()
+
+    def begin_loop(self, params):
+        """Make `params` resident and set up the loop state of optimize() (reference :353-360)."""
         elbo = self.elbo(params)        # uploads; the state is resident from here on
-        running_elbo_delta = None
-        num_its = 0
-        L = np.ones(5)
-        eng = self._eng
-        eng.pm_mark(0)                  # post_mean
-        eng.pm_mark(1)                  # ckp_post_mean
+        self._eng.pm_mark(0)            # post_mean
+        self._eng.pm_mark(1)            # ckp_post_mean
         self.trajectory = {'elbo': [], 'L0': [], 'trials': [], 'running': []}
+        return {'elbo': elbo, 'running': None, 'num_its': 0, 'L': np.ones(5),
+                'converged': False}
+
+    def run_loop(self, state, max_its, fresh=True):
+        """The while-loop of optimize() (reference :361-389) on the device-resident state, until
+        convergence or `max_its` total iterations.  Returns the updated loop state."""
+        eng = self._eng
+        L, elbo, running_elbo_delta = state['L'], state['elbo'], state['running']
+        num_its, converged = state['num_its'], state['converged']
         want_info = logging.getLogger().isEnabledFor(logging.INFO)
-        while num_its < self.num_its and not converged:
+        while num_its < max_its and not converged:
             if num_its % self.checkpoint_freq == 0 and self.checkpoint:
                 eng.pm_mark(1)
                 fname = '{}.{}'.format(self.checkpoint_path, num_its)
@@ -254,7 +270,7 @@ class VIScheme():
             converged = diff[0] == 0
             converged = converged or bool(np.isclose(running_elbo_delta, 0,
                                                      atol=ELBO_TOL, rtol=0))
-            if num_its < 10 and loaded_checkpoint is None:
+            if num_its < 10 and fresh:
                 converged = False
             if want_info:
                 if self._comm.world > 1:
@@ -265,12 +281,8 @@ class VIScheme():
             self.trajectory['trials'].append(self.n_trials - trials0)
             self.trajectory['running'].append(float(running_elbo_delta))
             num_its += 1
-
-        if num_its == self.num_its:
-            logging.warning('Failed to converge')
-        logging.info('Optimization ran for %d iterations', num_its)
-        self.num_its_run = num_its
-        return self._download()
+        return {'elbo': elbo, 'running': running_elbo_delta, 'num_its': num_its, 'L': L,
+                'converged': converged}
 
     def _optimize_step_dev(self, L, curr_elbo, line_search_rate, running_elbo_delta):
         logging.info('Current ELBO = %f and L = %f,%f,%f,%f,%f',
@@ -513,7 +525,10 @@ class MultiPopVI(VIScheme):
         self._eng.set_tau(self.error_scaling)
         if self._gtable is not None:
             self._eng.set_delta_grad(self._gtable)
-        self._eng.set_params(vi_mu[:, :, snps], vi_delta[snps])
+        if len(snps) == self.num_loci:
+            self._eng.set_params(vi_mu, vi_delta)
+        else:
+            self._eng.set_params(vi_mu[:, :, snps], vi_delta[snps])
 
     def _set_result(self, stats, resident):
         """Cache the reduced statistics / objective of the (new) accepted device state.
