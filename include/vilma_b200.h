@@ -35,6 +35,9 @@ typedef struct vb_ld vb_ld; /* one cohort's block-diagonal LD operator, resident
 /* ---- context ------------------------------------------------------------------------ */
 int vb_abi_version(void);
 const char* vb_last_error(void);
+/* process-wide options read when an LD operator is created:
+ *   "ld_symmetric" (default 1): store dense blocks of n <= 4096 symmetric-packed (half the bytes) */
+int vb_set_option(const char* name, int64_t value);
 /* device: CUDA ordinal; stream: cudaStream_t (may be NULL). */
 int vb_ctx_create(int device, void* stream, vb_ctx** out);
 int vb_ctx_destroy(vb_ctx* ctx);
@@ -59,7 +62,8 @@ int vb_ctx_profile_read(vb_ctx* ctx, double* total_ms2, int64_t* count2);
  * vb_ld_finalize   perm[j] = SNP index (0..M-1, this rank's numbering) of block-order
  *                  position j, for j < sum_b n[b]; SNPs not listed are "missing" (zero rows).
  * vb_ld_dot        y = R x in SNP order (x, y device vectors of length M).
- * vb_ld_bytes      algorithmic bytes one mat-vec reads from the LD store.
+ * vb_ld_bytes      algorithmic bytes one mat-vec reads from the LD store: 4 n (n+1) per
+ *                  symmetric-packed dense block, 8 n^2 per full dense block, 16 n r per factor block.
  */
 int vb_ld_create(vb_ctx* ctx, int64_t M, int64_t nblocks, const int64_t* n, const int64_t* rank,
                  vb_ld** out);

@@ -139,28 +139,46 @@ def test_line_search_from_huge_L():
     assert np.allclose(params[0], new_params[0])
 
 
-def test_big_block_slabs_and_factor():
-    """Blocks wider than one column slab (n > 2048) and tall factor blocks."""
-    from vilma_b200.engine import DeviceContext, DeviceLD
+@pytest.mark.parametrize('symmetric', [1, 0])
+def test_big_block_slabs_and_factor(symmetric):
+    """Symmetric-packed blocks (ragged sizes, many panels/groups), full-storage blocks wider than
+    one column slab (n > 2048 with packing off, n > 4096 always) and tall factor blocks."""
+    from vilma_b200.engine import DeviceContext, DeviceLD, set_option
     rng = np.random.default_rng(0)
     ctx = DeviceContext.get()
-    n1, n2, n3, r3 = 2500, 37, 700, 150
-    a = rng.standard_normal((n1, n1)); R1 = a + a.T
-    b = rng.standard_normal((n2, n2)); R2 = b + b.T
+    sizes = [2500, 37, 1, 8, 515, 4100]
+    mats = []
+    for n in sizes:
+        a = rng.standard_normal((n, n))
+        mats.append(a + a.T)
+    n3, r3 = 700, 150
     U = np.linalg.qr(rng.standard_normal((n3, r3)))[0]
     s = rng.uniform(0.5, 2.0, r3)
-    M = n1 + n2 + n3 + 5
-    perm = rng.permutation(M)[:n1 + n2 + n3]
-    ld = DeviceLD(ctx, M, [{'n': n1, 'kind': 'dense', 'R': R1}, {'n': n2, 'kind': 'dense', 'R': R2},
-                           {'n': n3, 'kind': 'factor', 'U': U, 's': s}], perm)
+    tot = sum(sizes) + n3
+    M = tot + 5
+    perm = rng.permutation(M)[:tot]
+    blocks = [{'n': n, 'kind': 'dense', 'R': R} for n, R in zip(sizes, mats)]
+    blocks.append({'n': n3, 'kind': 'factor', 'U': U, 's': s})
+    set_option('ld_symmetric', symmetric)
+    try:
+        ld = DeviceLD(ctx, M, blocks, perm)
+    finally:
+        set_option('ld_symmetric', 1)
     x = rng.standard_normal(M)
     y = ld.dot(x)
     ref = np.zeros(M)
-    ref[perm[:n1]] = R1 @ x[perm[:n1]]
-    ref[perm[n1:n1 + n2]] = R2 @ x[perm[n1:n1 + n2]]
-    ref[perm[n1 + n2:]] = U @ (s * (U.T @ x[perm[n1 + n2:]]))
+    off = 0
+    for n, R in zip(sizes, mats):
+        idx = perm[off:off + n]
+        ref[idx] = R @ x[idx]
+        off += n
+    idx = perm[off:]
+    ref[idx] = U @ (s * (U.T @ x[idx]))
     assert np.allclose(y, ref, rtol=1e-12, atol=1e-11 * np.abs(ref).max())
-    assert ld.bytes == 8 * (n1 * n1 + n2 * n2) + 16 * n3 * r3
+    dense = sum((4 * n * (n + 1) if (symmetric and n <= 4096) else 8 * n * n) for n in sizes)
+    assert ld.bytes == dense + 16 * n3 * r3
+    # bit-reproducible across launches (dynamic scheduling must not change the summation order)
+    assert np.array_equal(y, ld.dot(x))
     ld.close()
 
 

@@ -9,7 +9,8 @@
 // run of whole rows is ONE contiguous, 16-byte aligned byte range.  The unit of work
 // ("item") is such a run of rows sized to fill one shared-memory stage.
 //
-// Kernel: persistent, one CTA per SM.  Warp 8 is the TMA producer: for each item it
+// Kernel: persistent, one CTA per SM, items claimed dynamically from a global counter.
+// Warp 8 is the TMA producer: for each item it
 // issues two 1-D bulk copies (cp.async.bulk -> UBLKCP): the row panel and the slab's
 // x segment, into a 4-deep ring of shared-memory stages guarded by full/empty
 // mbarriers.  Warps 0-7 consume: one row per warp at a time, lanes stride the row with
@@ -24,7 +25,7 @@
 #define VB_LD_STAGES 4
 #define VB_LD_CONSUMER_WARPS 8
 #define VB_LD_THREADS ((VB_LD_CONSUMER_WARPS + 1) * 32)
-#define VB_LD_SMEM (VB_LD_STAGES * (VB_LD_STAGE_A + VB_LD_STAGE_X) + 2 * VB_LD_STAGES * 8)
+#define VB_LD_SMEM (VB_LD_STAGES * (VB_LD_STAGE_A + VB_LD_STAGE_X) + 2 * VB_LD_STAGES * 8 + VB_LD_STAGES * 16)
 
 struct __align__(16) VbLdItem {
     uint32_t a_off16;   // matrix offset of the first row, in 16-byte units
@@ -34,15 +35,22 @@ struct __align__(16) VbLdItem {
     uint16_t ld2;       // leading dimension / 2
 };
 
+#define VB_LD_CHUNK 4      // items claimed per atomic (dynamic scheduling granularity, ~160 KB)
+
+// sched[0] = next unclaimed item, sched[1] = CTAs that ran out of work; both are zero on entry
+// and are reset to zero by the last CTA to finish, so back-to-back launches need no memset.
+// Items are claimed dynamically because per-SM HBM throughput differs by ~25 % across the two
+// dies (ncu: sm__cycles_active min/avg/max = 2.33M/2.62M/3.02M with a static equal-bytes split);
+// the result does not depend on which CTA computes a row (one warp, fixed order per row).
 __global__ void __launch_bounds__(VB_LD_THREADS, 1)
 vb_ld_matvec_kernel(const double* __restrict__ mat, const VbLdItem* __restrict__ items,
-                    const uint32_t* __restrict__ cta_start, const double* __restrict__ x,
+                    uint32_t n_items, uint32_t* __restrict__ sched, const double* __restrict__ x,
                     double* __restrict__ y) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + VB_LD_STAGES * (VB_LD_STAGE_A + VB_LD_STAGE_X));
     uint64_t* empty = full + VB_LD_STAGES;
+    VbLdItem* slot = reinterpret_cast<VbLdItem*>(empty + VB_LD_STAGES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t it0 = cta_start[blockIdx.x], it1 = cta_start[blockIdx.x + 1];
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < VB_LD_STAGES; ++s) {
@@ -59,26 +67,43 @@ vb_ld_matvec_kernel(const double* __restrict__ mat, const VbLdItem* __restrict__
             const uint64_t pol_stream = vb_policy_evict_first();
             const uint64_t pol_keep = vb_policy_evict_last();
             uint32_t stage = 0, phase = 0;
-            for (uint32_t it = it0; it < it1; ++it) {
-                const VbLdItem item = items[it];
-                vb_mbar_wait(&empty[stage], phase ^ 1);
-                unsigned char* sa = smem + stage * (VB_LD_STAGE_A + VB_LD_STAGE_X);
-                const uint32_t bytes_a = (uint32_t)item.nrows * item.ld2 * 16u;
-                const uint32_t bytes_x = (uint32_t)item.ld2 * 16u;
-                vb_mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_x);
-                vb_bulk_g2s(sa, reinterpret_cast<const unsigned char*>(mat) + (size_t)item.a_off16 * 16,
-                            bytes_a, &full[stage], pol_stream);
-                vb_bulk_g2s(sa + VB_LD_STAGE_A, x + (size_t)item.x_off2 * 2, bytes_x, &full[stage],
-                            pol_keep);
-                if (++stage == VB_LD_STAGES) { stage = 0; phase ^= 1; }
+            uint32_t next = atomicAdd(&sched[0], VB_LD_CHUNK);
+            while (next < n_items) {
+                const uint32_t end = min(next + VB_LD_CHUNK, n_items);
+                const uint32_t following = atomicAdd(&sched[0], VB_LD_CHUNK);   // claimed early
+                for (uint32_t it = next; it < end; ++it) {
+                    const VbLdItem item = items[it];
+                    vb_mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* sa = smem + stage * (VB_LD_STAGE_A + VB_LD_STAGE_X);
+                    const uint32_t bytes_a = (uint32_t)item.nrows * item.ld2 * 16u;
+                    const uint32_t bytes_x = (uint32_t)item.ld2 * 16u;
+                    slot[stage] = item;
+                    vb_mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_x);
+                    vb_bulk_g2s(sa, reinterpret_cast<const unsigned char*>(mat) + (size_t)item.a_off16 * 16,
+                                bytes_a, &full[stage], pol_stream);
+                    vb_bulk_g2s(sa + VB_LD_STAGE_A, x + (size_t)item.x_off2 * 2, bytes_x,
+                                &full[stage], pol_keep);
+                    if (++stage == VB_LD_STAGES) { stage = 0; phase ^= 1; }
+                }
+                next = following;
+            }
+            // sentinel: an empty item tells the consumers to stop
+            vb_mbar_wait(&empty[stage], phase ^ 1);
+            slot[stage].nrows = 0;
+            vb_mbar_arrive(&full[stage]);
+            const uint32_t done = atomicAdd(&sched[1], 1u);
+            if (done == gridDim.x - 1) {
+                sched[0] = 0;
+                sched[1] = 0;
             }
         }
     } else {
         // ---------------- consumers ----------------
         uint32_t stage = 0, phase = 0;
-        for (uint32_t it = it0; it < it1; ++it) {
-            const VbLdItem item = items[it];
+        while (true) {
             vb_mbar_wait(&full[stage], phase);
+            const VbLdItem item = slot[stage];
+            if (item.nrows == 0) break;
             const double2* sa = reinterpret_cast<const double2*>(smem + stage * (VB_LD_STAGE_A + VB_LD_STAGE_X));
             const double2* sx = reinterpret_cast<const double2*>(
                 smem + stage * (VB_LD_STAGE_A + VB_LD_STAGE_X) + VB_LD_STAGE_A);
@@ -151,6 +176,273 @@ __global__ void vb_ld_finish_kernel(const double* __restrict__ yb, int64_t len, 
         const int32_t q = pos[j];
         double v = yb[q];
         for (int s = 1; s < nslab; ++s) v += yb[(size_t)s * len + q];
+        y_snp[snp[j]] = v;
+        acc = fma(xb[q], v, acc);
+    }
+    acc = vb_block_sum(acc, scratch);
+    if (threadIdx.x == 0 && partial) partial[blockIdx.x] = acc;
+}
+
+// =====================================================================================
+// Symmetric-packed dense blocks: only the lower triangle is stored and streamed.
+//
+// A block (n <= VB_SYM_NMAX) is cut into panels of 8 rows; panel p holds rows [8p, 8p+8) and
+// columns [0, 8p+8) (the diagonal 8x8 tile is stored in full), i.e. n^2/2 + 4n elements per
+// block instead of n^2.  A panel is stored as column chunks of <= 512 columns, each chunk
+// 8 x wc row-major and contiguous, so one chunk = one 1-D TMA bulk copy = one pipeline stage.
+// Every staged element A[i][c] is used twice from shared memory:
+//     row part     y[8p+i] += A[i][c] x[c]         (all columns of the panel)
+//     column part  y[c]    += A[i][c] x[8p+i]      (columns left of the diagonal tile only)
+// Thread (warp w, lane l) owns column pair 32w+l of every chunk, so a given column of the
+// block is always accumulated by the same thread (race-free, fixed order); the row sums are
+// reduced across lanes by a 9-step transposing butterfly and across the 8 warps through a
+// small shared array once per panel.  Both parts accumulate in shared memory over a *group*
+// of consecutive panels (~0.5 MB, the unit of dynamic scheduling); a group writes one partial
+// vector which vb_ld_finish_kernel sums in fixed order.  Algorithmic bytes: 4 n (n + 1).
+// =====================================================================================
+#define VB_SYM_R 8
+#define VB_SYM_CC 512
+#define VB_SYM_NMAX 4096
+#define VB_SYM_STAGE_A (VB_SYM_R * VB_SYM_CC * 8)
+#define VB_SYM_STAGE_X (VB_SYM_CC * 8)
+#define VB_SYM_STAGE_XR 64
+#define VB_SYM_STAGE (VB_SYM_STAGE_A + VB_SYM_STAGE_X + VB_SYM_STAGE_XR)
+#define VB_SYM_STAGES 4
+#define VB_SYM_ACC (VB_SYM_NMAX + 16)
+#define VB_SYM_SMEM (VB_SYM_STAGES * VB_SYM_STAGE + 2 * VB_SYM_ACC * 8 + 2 * 8 * 8 * 8 + \
+                     2 * VB_SYM_STAGES * 8 + VB_SYM_STAGES * 32)
+#define VB_SYM_GROUP_BYTES (512 * 1024)
+
+enum { VB_SYM_FIRST = 1, VB_SYM_LASTPANEL = 2, VB_SYM_LASTGROUP = 4, VB_SYM_VALID = 0x8000 };
+
+struct __align__(16) VbSymItem {
+    uint32_t a_off16;    // chunk offset in the LD store, 16-byte units
+    uint32_t x_off2;     // x offset of the chunk's first column, units of 2 doubles
+    uint32_t xr_off2;    // x offset of the panel's first row
+    uint16_t wc2;        // chunk width / 2
+    uint16_t c0_2;       // chunk's first column within the block / 2
+    uint16_t elig2;      // column pairs of this chunk left of the diagonal tile
+    uint16_t flags;
+    uint32_t r0;         // panel's first row within the block
+    uint32_t out_off;    // LASTGROUP: offset of the group's partial vector
+    uint32_t out_len;    // LASTGROUP: its length
+};
+struct VbSymGroup {
+    uint32_t first_item, n_items;
+};
+
+__global__ void __launch_bounds__(VB_LD_THREADS, 1)
+vb_ld_sym_kernel(const double* __restrict__ mat, const VbSymItem* __restrict__ items,
+                 const VbSymGroup* __restrict__ groups, uint32_t n_groups,
+                 uint32_t* __restrict__ sched, const double* __restrict__ x,
+                 double* __restrict__ ypart) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    double* acccol = reinterpret_cast<double*>(smem + VB_SYM_STAGES * VB_SYM_STAGE);
+    double* accrow = acccol + VB_SYM_ACC;
+    double* rowpart = accrow + VB_SYM_ACC;                         // [2][8 warps][8 rows]
+    uint64_t* full = reinterpret_cast<uint64_t*>(rowpart + 2 * 8 * 8);
+    uint64_t* empty = full + VB_SYM_STAGES;
+    VbSymItem* slot = reinterpret_cast<VbSymItem*>(empty + VB_SYM_STAGES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < VB_SYM_STAGES; ++s) {
+            vb_mbar_init(&full[s], 1);
+            vb_mbar_init(&empty[s], VB_LD_CONSUMER_WARPS);
+        }
+        vb_fence_mbar_init();
+    }
+    for (int j = threadIdx.x; j < 2 * VB_SYM_ACC; j += blockDim.x) acccol[j] = 0.0;
+    __syncthreads();
+
+    if (warp == VB_LD_CONSUMER_WARPS) {
+        if (lane == 0) {
+            const uint64_t pol_stream = vb_policy_evict_first();
+            const uint64_t pol_keep = vb_policy_evict_last();
+            uint32_t stage = 0, phase = 0;
+            uint32_t g = atomicAdd(&sched[0], 1u);
+            while (g < n_groups) {
+                const uint32_t g_next = atomicAdd(&sched[0], 1u);
+                const VbSymGroup grp = groups[g];
+                for (uint32_t it = grp.first_item; it < grp.first_item + grp.n_items; ++it) {
+                    const VbSymItem item = items[it];
+                    vb_mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* sa = smem + stage * VB_SYM_STAGE;
+                    const uint32_t bytes_x = (uint32_t)item.wc2 * 16u;
+                    const uint32_t bytes_a = bytes_x * VB_SYM_R;
+                    slot[stage] = item;
+                    vb_mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_x + VB_SYM_STAGE_XR);
+                    vb_bulk_g2s(sa, reinterpret_cast<const unsigned char*>(mat) + (size_t)item.a_off16 * 16,
+                                bytes_a, &full[stage], pol_stream);
+                    vb_bulk_g2s(sa + VB_SYM_STAGE_A, x + (size_t)item.x_off2 * 2, bytes_x,
+                                &full[stage], pol_keep);
+                    vb_bulk_g2s(sa + VB_SYM_STAGE_A + VB_SYM_STAGE_X, x + (size_t)item.xr_off2 * 2,
+                                VB_SYM_STAGE_XR, &full[stage], pol_keep);
+                    if (++stage == VB_SYM_STAGES) { stage = 0; phase ^= 1; }
+                }
+                g = g_next;
+            }
+            vb_mbar_wait(&empty[stage], phase ^ 1);
+            slot[stage].flags = 0;
+            vb_mbar_arrive(&full[stage]);
+            const uint32_t done = atomicAdd(&sched[1], 1u);
+            if (done == gridDim.x - 1) {
+                sched[0] = 0;
+                sched[1] = 0;
+            }
+        }
+    } else {
+        uint32_t stage = 0, phase = 0;
+        int par = 0;
+        double rowacc[VB_SYM_R], xr[VB_SYM_R];
+#pragma unroll
+        for (int i = 0; i < VB_SYM_R; ++i) { rowacc[i] = 0.0; xr[i] = 0.0; }
+        const int cp = warp * 32 + lane;                  // column pair owned in every chunk
+        double2* acccol2 = reinterpret_cast<double2*>(acccol);
+        while (true) {
+            vb_mbar_wait(&full[stage], phase);
+            const VbSymItem item = slot[stage];
+            if (!(item.flags & VB_SYM_VALID)) break;
+            const unsigned char* base = smem + stage * VB_SYM_STAGE;
+            const double2* sa = reinterpret_cast<const double2*>(base);
+            const double2* sx = reinterpret_cast<const double2*>(base + VB_SYM_STAGE_A);
+            const double2* sxr = reinterpret_cast<const double2*>(base + VB_SYM_STAGE_A + VB_SYM_STAGE_X);
+            if (item.flags & VB_SYM_FIRST) {
+#pragma unroll
+                for (int i = 0; i < VB_SYM_R / 2; ++i) {
+                    const double2 v = sxr[i];
+                    xr[2 * i] = v.x;
+                    xr[2 * i + 1] = v.y;
+                    rowacc[2 * i] = 0.0;
+                    rowacc[2 * i + 1] = 0.0;
+                }
+            }
+            const int wc2 = item.wc2;
+            double2 cacc = make_double2(0.0, 0.0);
+            if (cp < wc2) {
+                const double2 xc = sx[cp];
+#pragma unroll
+                for (int i = 0; i < VB_SYM_R; ++i) {
+                    const double2 a = sa[i * wc2 + cp];
+                    rowacc[i] = fma(a.x, xc.x, rowacc[i]);
+                    rowacc[i] = fma(a.y, xc.y, rowacc[i]);
+                    cacc.x = fma(a.x, xr[i], cacc.x);
+                    cacc.y = fma(a.y, xr[i], cacc.y);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) vb_mbar_arrive(&empty[stage]);
+            if (cp < item.elig2) {
+                double2 v = acccol2[item.c0_2 + cp];
+                v.x += cacc.x;
+                v.y += cacc.y;
+                acccol2[item.c0_2 + cp] = v;
+            }
+            if (item.flags & VB_SYM_LASTPANEL) {
+                // transposing butterfly: 8 per-lane partial row sums -> one full row sum per lane
+                double t4[4], t2[2], t1;
+                const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double send = hi16 ? rowacc[j] : rowacc[j + 4];
+                    const double keep = hi16 ? rowacc[j + 4] : rowacc[j];
+                    t4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const double send = hi8 ? t4[j] : t4[j + 2];
+                    const double keep = hi8 ? t4[j + 2] : t4[j];
+                    t2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+                {
+                    const double send = hi4 ? t2[0] : t2[1];
+                    const double keep = hi4 ? t2[1] : t2[0];
+                    t1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+                t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+                const int row = (hi16 ? 4 : 0) + (hi8 ? 2 : 0) + (hi4 ? 1 : 0);
+                if ((lane & 3) == 0) rowpart[(par * 8 + warp) * 8 + row] = t1;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (warp == 0 && lane < VB_SYM_R) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int w = 0; w < VB_LD_CONSUMER_WARPS; ++w) s += rowpart[(par * 8 + w) * 8 + lane];
+                    accrow[item.r0 + lane] = s;
+                }
+                par ^= 1;
+            }
+            if (item.flags & VB_SYM_LASTGROUP) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                for (uint32_t j = threadIdx.x; j < item.out_len; j += VB_LD_CONSUMER_WARPS * 32) {
+                    ypart[(size_t)item.out_off + j] = acccol[j] + accrow[j];
+                }
+                for (uint32_t j = threadIdx.x; j < item.out_len + VB_SYM_R; j += VB_LD_CONSUMER_WARPS * 32) {
+                    acccol[j] = 0.0;
+                    accrow[j] = 0.0;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            if (++stage == VB_SYM_STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+}
+
+// Pack a dense symmetric n x n block (row stride ld) into the panel/chunk layout above.
+// grid.x = number of panels.  Panel p starts at 32 p (p + 1) doubles (closed form, see host).
+__global__ void vb_pack_sym_kernel(const double* __restrict__ R, int64_t ld, int n,
+                                   double* __restrict__ out) {
+    const int p = blockIdx.x;
+    const int r0 = p * VB_SYM_R;
+    int W = min(r0 + VB_SYM_R, n);
+    W = (W + 1) & ~1;
+    double* pout = out + (size_t)32 * p * (p + 1);
+    for (int c0 = 0; c0 < W; c0 += VB_SYM_CC) {
+        const int wc = min(VB_SYM_CC, W - c0);
+        double* cout = pout + (size_t)c0 * VB_SYM_R;
+        for (int idx = threadIdx.x; idx < VB_SYM_R * wc; idx += blockDim.x) {
+            const int i = idx / wc, c = idx % wc;
+            const int r = r0 + i, col = c0 + c;
+            cout[idx] = (r < n && col < n) ? R[(size_t)r * ld + col] : 0.0;
+        }
+    }
+}
+
+// Finish for operators with symmetric blocks: positions of symmetric blocks sum their block's
+// group partial vectors (fixed order); other positions take the slab outputs as before.
+struct VbSymBlockRef {
+    uint32_t g0, ng;     // groups of this block: [g0, g0+ng)
+};
+struct VbSymGroupOut {
+    uint32_t off, len;
+};
+__global__ void vb_ld_finish_sym_kernel(const double* __restrict__ yb, int64_t len, int nslab,
+                                        const double* __restrict__ ypart,
+                                        const int32_t* __restrict__ blk, const int32_t* __restrict__ loc,
+                                        const VbSymBlockRef* __restrict__ bref,
+                                        const VbSymGroupOut* __restrict__ gout,
+                                        const double* __restrict__ xb, const int32_t* __restrict__ pos,
+                                        const int32_t* __restrict__ snp, int64_t nreal,
+                                        double* __restrict__ y_snp, double* __restrict__ partial) {
+    __shared__ double scratch[32];
+    double acc = 0.0;
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < nreal;
+         j += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t q = pos[j];
+        const int32_t b = blk[j];
+        double v;
+        if (b >= 0) {
+            const VbSymBlockRef br = bref[b];
+            const uint32_t l = (uint32_t)loc[j];
+            v = 0.0;
+            for (uint32_t g = br.g0; g < br.g0 + br.ng; ++g) {
+                const VbSymGroupOut go = gout[g];
+                if (l < go.len) v += ypart[(size_t)go.off + l];
+            }
+        } else {
+            v = yb[q];
+            for (int s = 1; s < nslab; ++s) v += yb[(size_t)s * len + q];
+        }
         y_snp[snp[j]] = v;
         acc = fma(xb[q], v, acc);
     }

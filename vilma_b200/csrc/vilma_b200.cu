@@ -45,6 +45,7 @@ static int vb_fail(const char* fmt, ...) {
     } while (0)
 
 static inline int64_t even_up(int64_t v) { return (v + 1) & ~int64_t(1); }
+static bool g_disable_sym = false;   // vb_set_option("ld_symmetric", 0): store dense blocks in full
 
 // ------------------------------------------------------------------------------------
 // state
@@ -61,6 +62,9 @@ struct LdBlock {
     std::vector<int> slabs1;       // indices into LdPop::slabs (phase 1: V' = diag(s) U^T)
     std::vector<int> slabs2;       // phase 2: dense R or U
     bool filled = false;
+    bool sym = false;              // dense block stored symmetric-packed
+    size_t sym_off = 0;            // offset (doubles) of its packed panels in LdPop::mat
+    uint32_t g0 = 0, ng = 0;       // its groups
 };
 struct LdPop {
     bool begun = false, finalized = false;
@@ -74,10 +78,18 @@ struct LdPop {
     double* yb = nullptr;          // [nslab2][xb_len]
     double* tbs = nullptr;         // [nslab1][tb_len] when nslab1 > 1
     VbLdItem *items1 = nullptr, *items2 = nullptr;
-    uint32_t *cta1 = nullptr, *cta2 = nullptr;
+    uint32_t* sched = nullptr;     // [2][2] dynamic-scheduling counters per phase
     int64_t n_items1 = 0, n_items2 = 0;
     int32_t *pos = nullptr, *snp = nullptr;
     int64_t nreal = 0;
+    // symmetric-packed blocks
+    VbSymItem* sitems = nullptr;
+    VbSymGroup* sgroups = nullptr;
+    VbSymGroupOut* gout = nullptr;
+    VbSymBlockRef* bref = nullptr;
+    int64_t n_sgroups = 0;
+    double* ypart = nullptr;
+    int32_t *blk = nullptr, *loc = nullptr;
     int64_t bytes = 0;             // algorithmic bytes per mat-vec
 };
 
@@ -139,6 +151,15 @@ struct vb_ld {
 // context
 // ------------------------------------------------------------------------------------
 extern "C" int vb_abi_version(void) { return VB_ABI_VERSION; }
+// Process-wide options read when an LD operator is created.
+//   "ld_symmetric" (default 1): store dense blocks with n <= 4096 symmetric-packed.
+extern "C" int vb_set_option(const char* name, int64_t value) {
+    if (name && std::strcmp(name, "ld_symmetric") == 0) {
+        g_disable_sym = (value == 0);
+        return 0;
+    }
+    return vb_fail("vb_set_option: unknown option '%s'", name ? name : "(null)");
+}
 extern "C" const char* vb_last_error(void) { return g_err.c_str(); }
 
 extern "C" int vb_ctx_create(int device, void* stream, vb_ctx** out) {
@@ -161,14 +182,18 @@ extern "C" int vb_ctx_create(int device, void* stream, vb_ctx** out) {
     c->stream = reinterpret_cast<cudaStream_t>(stream);
     CK(cudaFuncSetAttribute(vb_ld_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             VB_LD_SMEM));
+    CK(cudaFuncSetAttribute(vb_ld_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            VB_SYM_SMEM));
     *out = c;
     return 0;
 }
 
 static void free_ld(LdPop& L) {
     cudaFree(L.mat); cudaFree(L.xall); cudaFree(L.yb); cudaFree(L.tbs);
-    cudaFree(L.items1); cudaFree(L.items2); cudaFree(L.cta1); cudaFree(L.cta2);
+    cudaFree(L.items1); cudaFree(L.items2); cudaFree(L.sched);
     cudaFree(L.pos); cudaFree(L.snp);
+    cudaFree(L.sitems); cudaFree(L.sgroups); cudaFree(L.gout); cudaFree(L.bref); cudaFree(L.ypart);
+    cudaFree(L.blk); cudaFree(L.loc);
     L = LdPop();
 }
 static void free_fit(Fit& f) {
@@ -255,11 +280,8 @@ static void add_slabs(LdPop& L, std::vector<int>& into, int64_t rows, int64_t co
     nslab_max = std::max(nslab_max, nsl);
 }
 
-static int build_items(vb_ctx* ctx, LdPop& L, int phase, VbLdItem** d_items, uint32_t** d_cta,
-                       int64_t* n_items) {
+static int build_items(vb_ctx* ctx, LdPop& L, int phase, VbLdItem** d_items, int64_t* n_items) {
     std::vector<VbLdItem> items;
-    std::vector<uint64_t> cum;   // cumulative bytes after each item
-    uint64_t total = 0;
     for (auto& b : L.blocks) {
         const std::vector<int>& sl = phase == 1 ? b.slabs1 : b.slabs2;
         for (int si : sl) {
@@ -278,30 +300,15 @@ static int build_items(vb_ctx* ctx, LdPop& L, int phase, VbLdItem** d_items, uin
                 it.nrows = (uint16_t)nr;
                 it.ld2 = (uint16_t)(s.ld >> 1);
                 items.push_back(it);
-                total += (uint64_t)nr * s.ld * 8 + s.ld * 8;
-                cum.push_back(total);
             }
         }
     }
     *n_items = (int64_t)items.size();
-    const int G = ctx->num_sms;
-    std::vector<uint32_t> start(G + 1, 0);
-    // contiguous ranges of ~equal bytes per CTA
-    size_t it = 0;
-    for (int c = 0; c < G; ++c) {
-        start[c] = (uint32_t)it;
-        const double target = (double)total * (c + 1) / G;
-        while (it < items.size() && (double)cum[it] <= target + 0.5) ++it;
-    }
-    start[G] = (uint32_t)items.size();
-    for (int c = 1; c <= G; ++c) start[c] = std::max(start[c], start[c - 1]);
-    start[G] = (uint32_t)items.size();
+    if (items.size() > 0xfffffff0ull) return vb_fail("too many LD work items");
     if (!items.empty()) {
         CK(cudaMalloc(d_items, items.size() * sizeof(VbLdItem)));
         CK(cudaMemcpy(*d_items, items.data(), items.size() * sizeof(VbLdItem), cudaMemcpyHostToDevice));
     }
-    CK(cudaMalloc(d_cta, (G + 1) * sizeof(uint32_t)));
-    CK(cudaMemcpy(*d_cta, start.data(), (G + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -367,8 +374,75 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
     L.nslab2 = ns2;
     int dummy1 = 1, dummy2 = 1;
     L.bytes = 0;
-    for (auto& b : L.blocks) {
-        if (b.r < 0) {
+    std::vector<VbSymItem> sitems;
+    std::vector<VbSymGroup> sgroups;
+    std::vector<VbSymGroupOut> gout;
+    std::vector<VbSymBlockRef> bref(L.blocks.size());
+    size_t ypart_len = 0;
+    for (size_t bi = 0; bi < L.blocks.size(); ++bi) {
+        LdBlock& b = L.blocks[bi];
+        bref[bi].g0 = bref[bi].ng = 0;
+        if (b.r < 0 && b.n <= VB_SYM_NMAX && !g_disable_sym) {
+            // symmetric-packed: panels of 8 rows, chunks of <= 512 columns, groups of ~0.5 MB
+            b.sym = true;
+            b.sym_off = cursor;
+            b.g0 = (uint32_t)sgroups.size();
+            const int64_t n = b.n, npan = (n + VB_SYM_R - 1) / VB_SYM_R;
+            size_t group_bytes = 0;
+            VbSymGroup cur;
+            cur.first_item = (uint32_t)sitems.size();
+            cur.n_items = 0;
+            for (int64_t p = 0; p < npan; ++p) {
+                const int64_t r0 = p * VB_SYM_R;
+                const int64_t W = even_up(std::min<int64_t>(r0 + VB_SYM_R, n));
+                const size_t poff = cursor + (size_t)32 * p * (p + 1);
+                for (int64_t c0 = 0; c0 < W; c0 += VB_SYM_CC) {
+                    const int64_t wc = std::min<int64_t>(VB_SYM_CC, W - c0);
+                    VbSymItem it;
+                    const size_t a_off = poff + (size_t)c0 * VB_SYM_R;
+                    if ((a_off >> 1) > 0xffffffffull)
+                        return vb_fail("LD store of one cohort exceeds 64 GiB on this rank");
+                    it.a_off16 = (uint32_t)(a_off >> 1);
+                    it.x_off2 = (uint32_t)((b.xpos + c0) >> 1);
+                    it.xr_off2 = (uint32_t)((b.xpos + r0) >> 1);
+                    it.wc2 = (uint16_t)(wc >> 1);
+                    it.c0_2 = (uint16_t)(c0 >> 1);
+                    const int64_t elig = std::max<int64_t>(0, std::min<int64_t>(wc, r0 - c0));
+                    it.elig2 = (uint16_t)(elig >> 1);
+                    it.flags = VB_SYM_VALID;
+                    if (c0 == 0) it.flags |= VB_SYM_FIRST;
+                    if (c0 + VB_SYM_CC >= W) it.flags |= VB_SYM_LASTPANEL;
+                    it.r0 = (uint32_t)r0;
+                    it.out_off = 0;
+                    it.out_len = 0;
+                    sitems.push_back(it);
+                    cur.n_items++;
+                    group_bytes += (size_t)wc * VB_SYM_R * 8;
+                }
+                if (group_bytes >= VB_SYM_GROUP_BYTES || p == npan - 1) {
+                    VbSymItem& last = sitems.back();
+                    last.flags |= VB_SYM_LASTGROUP;
+                    last.out_off = (uint32_t)ypart_len;
+                    last.out_len = (uint32_t)std::min<int64_t>(r0 + VB_SYM_R, n);
+                    VbSymGroupOut go;
+                    go.off = last.out_off;
+                    go.len = last.out_len;
+                    if (ypart_len + go.len > 0xffffffffull) return vb_fail("LD partial buffer too large");
+                    ypart_len += go.len;
+                    gout.push_back(go);
+                    sgroups.push_back(cur);
+                    cur.first_item = (uint32_t)sitems.size();
+                    cur.n_items = 0;
+                    group_bytes = 0;
+                }
+            }
+            b.ng = (uint32_t)sgroups.size() - b.g0;
+            bref[bi].g0 = b.g0;
+            bref[bi].ng = b.ng;
+            const int64_t pf = n / VB_SYM_R;
+            cursor += (size_t)32 * pf * (pf + 1) + ((n % VB_SYM_R) ? (size_t)VB_SYM_R * even_up(n) : 0);
+            L.bytes += 4 * n * (n + 1);
+        } else if (b.r < 0) {
             add_slabs(L, b.slabs2, b.n, b.n, b.xpos, b.xpos, L.xb_len, cursor, dummy2);
             L.bytes += 8 * b.n * b.n;
         } else {
@@ -382,16 +456,32 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
     L.mat_len = std::max<size_t>(cursor, 2);
     CK(cudaMalloc(&L.mat, L.mat_len * sizeof(double)));
     CK(cudaMemsetAsync(L.mat, 0, L.mat_len * sizeof(double), ctx->stream));
-    CK(cudaMalloc(&L.xall, (size_t)(L.xb_len + L.tb_len) * sizeof(double)));
-    CK(cudaMemsetAsync(L.xall, 0, (size_t)(L.xb_len + L.tb_len) * sizeof(double), ctx->stream));
+    // + slack: the symmetric kernel reads 8 x values per panel even for a ragged last panel
+    CK(cudaMalloc(&L.xall, (size_t)(L.xb_len + L.tb_len + 16) * sizeof(double)));
+    CK(cudaMemsetAsync(L.xall, 0, (size_t)(L.xb_len + L.tb_len + 16) * sizeof(double), ctx->stream));
+    L.n_sgroups = (int64_t)sgroups.size();
+    if (L.n_sgroups > 0) {
+        CK(cudaMalloc(&L.sitems, sitems.size() * sizeof(VbSymItem)));
+        CK(cudaMemcpy(L.sitems, sitems.data(), sitems.size() * sizeof(VbSymItem), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&L.sgroups, sgroups.size() * sizeof(VbSymGroup)));
+        CK(cudaMemcpy(L.sgroups, sgroups.data(), sgroups.size() * sizeof(VbSymGroup), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&L.gout, gout.size() * sizeof(VbSymGroupOut)));
+        CK(cudaMemcpy(L.gout, gout.data(), gout.size() * sizeof(VbSymGroupOut), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&L.bref, bref.size() * sizeof(VbSymBlockRef)));
+        CK(cudaMemcpy(L.bref, bref.data(), bref.size() * sizeof(VbSymBlockRef), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&L.ypart, std::max<size_t>(ypart_len, 1) * sizeof(double)));
+        CK(cudaMemsetAsync(L.ypart, 0, std::max<size_t>(ypart_len, 1) * sizeof(double), ctx->stream));
+    }
     CK(cudaMalloc(&L.yb, (size_t)L.nslab2 * L.xb_len * sizeof(double)));
     CK(cudaMemsetAsync(L.yb, 0, (size_t)L.nslab2 * L.xb_len * sizeof(double), ctx->stream));
     if (L.nslab1 > 1) {
         CK(cudaMalloc(&L.tbs, (size_t)L.nslab1 * L.tb_len * sizeof(double)));
         CK(cudaMemsetAsync(L.tbs, 0, (size_t)L.nslab1 * L.tb_len * sizeof(double), ctx->stream));
     }
-    if (build_items(ctx, L, 1, &L.items1, &L.cta1, &L.n_items1)) return 1;
-    if (build_items(ctx, L, 2, &L.items2, &L.cta2, &L.n_items2)) return 1;
+    if (build_items(ctx, L, 1, &L.items1, &L.n_items1)) return 1;
+    if (build_items(ctx, L, 2, &L.items2, &L.n_items2)) return 1;
+    CK(cudaMalloc(&L.sched, 6 * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(L.sched, 0, 6 * sizeof(uint32_t), ctx->stream));
     return 0;
 }
 
@@ -403,6 +493,27 @@ extern "C" int vb_ld_set_dense(vb_ld* h, int64_t b, const double* R, int64_t ld,
     LdBlock& B = L.blocks[b];
     if (B.r >= 0) return vb_fail("vb_ld_set_dense: block %lld was declared as a factor", (long long)b);
     CK(cudaSetDevice(ctx->device));
+    if (B.sym) {
+        const double* dR = R;
+        double* tmp = nullptr;
+        int64_t dld = ld;
+        if (!on_device) {
+            CK(cudaMalloc(&tmp, (size_t)B.n * B.n * sizeof(double)));
+            CK(cudaMemcpy2DAsync(tmp, B.n * sizeof(double), R, ld * sizeof(double), B.n * sizeof(double),
+                                 B.n, cudaMemcpyHostToDevice, ctx->stream));
+            dR = tmp;
+            dld = B.n;
+        }
+        const int npan = (int)((B.n + VB_SYM_R - 1) / VB_SYM_R);
+        vb_pack_sym_kernel<<<npan, 256, 0, ctx->stream>>>(dR, dld, (int)B.n, L.mat + B.sym_off);
+        CK_LAUNCH(ctx);
+        if (!on_device) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            cudaFree(tmp);
+        }
+        B.filled = true;
+        return 0;
+    }
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     int64_t c0 = 0;
     for (int si : B.slabs2) {
@@ -488,9 +599,13 @@ extern "C" int vb_ld_finalize(vb_ld* h, const int64_t* perm_host, int64_t nperm)
                                      (long long)nperm, (long long)tot);
     std::vector<int32_t> pos(std::max<int64_t>(nperm, 1)), snp(std::max<int64_t>(nperm, 1));
     std::vector<char> seen(L.M, 0);
+    std::vector<int32_t> blk(std::max<int64_t>(nperm, 1)), loc(std::max<int64_t>(nperm, 1));
     int64_t j = 0;
-    for (auto& b : L.blocks)
+    for (size_t bi = 0; bi < L.blocks.size(); ++bi) {
+        LdBlock& b = L.blocks[bi];
         for (int64_t t = 0; t < b.n; ++t, ++j) {
+            blk[j] = b.sym ? (int32_t)bi : -1;
+            loc[j] = (int32_t)t;
             const int64_t i = perm_host[j];
             if (i < 0 || i >= L.M) return vb_fail("vb_ld_finalize: perm[%lld]=%lld out of range", (long long)j, (long long)i);
             if (seen[i]) return vb_fail("vb_ld_finalize: SNP %lld appears twice in perm", (long long)i);
@@ -498,7 +613,14 @@ extern "C" int vb_ld_finalize(vb_ld* h, const int64_t* perm_host, int64_t nperm)
             pos[j] = (int32_t)(b.xpos + t);
             snp[j] = (int32_t)i;
         }
+    }
     L.nreal = nperm;
+    if (L.n_sgroups > 0) {
+        CK(cudaMalloc(&L.blk, blk.size() * sizeof(int32_t)));
+        CK(cudaMalloc(&L.loc, loc.size() * sizeof(int32_t)));
+        CK(cudaMemcpy(L.blk, blk.data(), blk.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(L.loc, loc.data(), loc.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
     CK(cudaMalloc(&L.pos, pos.size() * sizeof(int32_t)));
     CK(cudaMalloc(&L.snp, snp.size() * sizeof(int32_t)));
     CK(cudaMemcpy(L.pos, pos.data(), pos.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
@@ -522,8 +644,8 @@ static int ld_apply(vb_ctx* ctx, LdPop& L, const double* x_snp, double* y_snp, d
     if (L.n_items1 > 0) {
         double* out1 = L.nslab1 > 1 ? L.tbs : L.xall + L.xb_len;
         prof_begin(ctx, 0);
-        vb_ld_matvec_kernel<<<ctx->num_sms, VB_LD_THREADS, VB_LD_SMEM, st>>>(L.mat, L.items1, L.cta1,
-                                                                             L.xall, out1);
+        vb_ld_matvec_kernel<<<ctx->num_sms, VB_LD_THREADS, VB_LD_SMEM, st>>>(
+            L.mat, L.items1, (uint32_t)L.n_items1, L.sched, L.xall, out1);
         prof_end(ctx, 0);
         CK_LAUNCH(ctx);
         if (L.nslab1 > 1) {
@@ -534,14 +656,26 @@ static int ld_apply(vb_ctx* ctx, LdPop& L, const double* x_snp, double* y_snp, d
     }
     if (L.n_items2 > 0) {
         prof_begin(ctx, 0);
-        vb_ld_matvec_kernel<<<ctx->num_sms, VB_LD_THREADS, VB_LD_SMEM, st>>>(L.mat, L.items2, L.cta2,
-                                                                             L.xall, L.yb);
+        vb_ld_matvec_kernel<<<ctx->num_sms, VB_LD_THREADS, VB_LD_SMEM, st>>>(
+            L.mat, L.items2, (uint32_t)L.n_items2, L.sched + 2, L.xall, L.yb);
         prof_end(ctx, 0);
         CK_LAUNCH(ctx);
     }
-    vb_ld_finish_kernel<<<grid_fin, 256, 0, st>>>(L.yb, L.xb_len, L.nslab2, L.xall, L.pos, L.snp,
-                                                  L.nreal, y_snp, partial);
-    CK_LAUNCH(ctx);
+    if (L.n_sgroups > 0) {
+        prof_begin(ctx, 0);
+        vb_ld_sym_kernel<<<ctx->num_sms, VB_LD_THREADS, VB_SYM_SMEM, st>>>(
+            L.mat, L.sitems, L.sgroups, (uint32_t)L.n_sgroups, L.sched + 4, L.xall, L.ypart);
+        prof_end(ctx, 0);
+        CK_LAUNCH(ctx);
+        vb_ld_finish_sym_kernel<<<grid_fin, 256, 0, st>>>(L.yb, L.xb_len, L.nslab2, L.ypart, L.blk,
+                                                          L.loc, L.bref, L.gout, L.xall, L.pos, L.snp,
+                                                          L.nreal, y_snp, partial);
+        CK_LAUNCH(ctx);
+    } else {
+        vb_ld_finish_kernel<<<grid_fin, 256, 0, st>>>(L.yb, L.xb_len, L.nslab2, L.xall, L.pos, L.snp,
+                                                      L.nreal, y_snp, partial);
+        CK_LAUNCH(ctx);
+    }
     return 0;
 }
 

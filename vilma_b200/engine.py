@@ -60,9 +60,21 @@ class DeviceContext:
         return {'ld_matvec': (ms[0], cnt[0]), 'snp': (ms[1], cnt[1])}
 
 
+SYM_NMAX = 4096     # csrc/ld_kernels.cuh VB_SYM_NMAX
+
+
+def dense_bytes(n):
+    """Bytes one mat-vec streams for a dense block: symmetric-packed up to SYM_NMAX, else full."""
+    return 4 * n * (n + 1) if n <= SYM_NMAX else 8 * n * n
+
+
 def choose_storage(n, r):
-    """'dense' when the reconstructed n x n block is no larger than the two factor passes."""
-    return 'dense' if n * n <= 2 * n * r else 'factor'
+    """'dense' when streaming the (packed) n x n block costs no more than the two factor passes."""
+    return 'dense' if dense_bytes(n) <= 16 * n * r else 'factor'
+
+
+def set_option(name, value):
+    _lib.check(_lib.load().vb_set_option(name.encode(), int(value)))
 
 
 class DeviceLD:

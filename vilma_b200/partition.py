@@ -9,8 +9,9 @@ import numpy as np
 
 
 def block_cost(n, r):
-    """Bytes one mat-vec reads for a block (dense n^2 vs two factor passes 2 n r)."""
-    return float(min(n * n, 2 * n * r))
+    """Bytes one mat-vec reads for a block (packed dense vs two factor passes)."""
+    dense = 4 * n * (n + 1) if n <= 4096 else 8 * n * n
+    return float(min(dense, 16 * n * r))
 
 
 def _find(parent, i):
