@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libvilma_b200.so')
+LIB_PATH = os.environ.get('VILMA_B200_LIB', os.path.join(_HERE, 'libvilma_b200.so'))
 _lib = None
 
 c_dp = C.POINTER(C.c_double)

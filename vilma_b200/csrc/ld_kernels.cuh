@@ -36,6 +36,9 @@ struct __align__(16) VbLdItem {
 };
 
 #define VB_LD_CHUNK 4      // items claimed per atomic (dynamic scheduling granularity, ~160 KB)
+#ifndef VB_LD_PREFETCH
+#define VB_LD_PREFETCH 0   // warp-parallel descriptor prefetch measured slower than the simple producer
+#endif
 
 // sched[0] = next unclaimed item, sched[1] = CTAs that ran out of work; both are zero on entry
 // and are reset to zero by the last CTA to finish, so back-to-back launches need no memset.
@@ -62,6 +65,70 @@ vb_ld_matvec_kernel(const double* __restrict__ mat, const VbLdItem* __restrict__
     __syncthreads();
 
     if (warp == VB_LD_CONSUMER_WARPS) {
+#if VB_LD_PREFETCH
+        // ---------------- producer warp ----------------
+        // Lanes fetch the descriptors of a whole claimed chunk with one coalesced load, one chunk
+        // ahead of use (a dependent global load per item would bound the issue rate); lane 0
+        // issues the TMA copies.
+        const uint64_t pol_stream = vb_policy_evict_first();
+        const uint64_t pol_keep = vb_policy_evict_last();
+        uint32_t stage = 0, phase = 0;
+        uint32_t next = 0, following = 0;
+        if (lane == 0) {
+            next = atomicAdd(&sched[0], VB_LD_CHUNK);
+            following = atomicAdd(&sched[0], VB_LD_CHUNK);
+        }
+        next = __shfl_sync(0xffffffffu, next, 0);
+        following = __shfl_sync(0xffffffffu, following, 0);
+        uint4 cur = make_uint4(0, 0, 0, 0);
+        if (next + lane < n_items && lane < VB_LD_CHUNK)
+            cur = reinterpret_cast<const uint4*>(items)[next + lane];
+        while (next < n_items) {
+            uint4 nxt = make_uint4(0, 0, 0, 0);
+            if (following + lane < n_items && lane < VB_LD_CHUNK)
+                nxt = reinterpret_cast<const uint4*>(items)[following + lane];
+            uint32_t after = 0;
+            if (lane == 0) after = atomicAdd(&sched[0], VB_LD_CHUNK);
+            const uint32_t cnt = min((uint32_t)VB_LD_CHUNK, n_items - next);
+            for (uint32_t j = 0; j < cnt; ++j) {
+                uint4 raw;
+                raw.x = __shfl_sync(0xffffffffu, cur.x, j);
+                raw.y = __shfl_sync(0xffffffffu, cur.y, j);
+                raw.z = __shfl_sync(0xffffffffu, cur.z, j);
+                raw.w = __shfl_sync(0xffffffffu, cur.w, j);
+                if (lane == 0) {
+                    VbLdItem item;
+                    item.a_off16 = raw.x; item.x_off2 = raw.y; item.y_off = raw.z;
+                    item.nrows = (uint16_t)(raw.w & 0xffffu); item.ld2 = (uint16_t)(raw.w >> 16);
+                    vb_mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* sa = smem + stage * (VB_LD_STAGE_A + VB_LD_STAGE_X);
+                    const uint32_t bytes_a = (uint32_t)item.nrows * item.ld2 * 16u;
+                    const uint32_t bytes_x = (uint32_t)item.ld2 * 16u;
+                    slot[stage] = item;
+                    vb_mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_x);
+                    vb_bulk_g2s(sa, reinterpret_cast<const unsigned char*>(mat) + (size_t)item.a_off16 * 16,
+                                bytes_a, &full[stage], pol_stream);
+                    vb_bulk_g2s(sa + VB_LD_STAGE_A, x + (size_t)item.x_off2 * 2, bytes_x,
+                                &full[stage], pol_keep);
+                }
+                if (++stage == VB_LD_STAGES) { stage = 0; phase ^= 1; }
+            }
+            next = following;
+            following = __shfl_sync(0xffffffffu, after, 0);
+            cur = nxt;
+        }
+        if (lane == 0) {
+            // sentinel: an empty item tells the consumers to stop
+            vb_mbar_wait(&empty[stage], phase ^ 1);
+            slot[stage].nrows = 0;
+            vb_mbar_arrive(&full[stage]);
+            const uint32_t done = atomicAdd(&sched[1], 1u);
+            if (done == gridDim.x - 1) {
+                sched[0] = 0;
+                sched[1] = 0;
+            }
+        }
+#else
         // ---------------- producer (one elected lane) ----------------
         if (lane == 0) {
             const uint64_t pol_stream = vb_policy_evict_first();
@@ -97,6 +164,7 @@ vb_ld_matvec_kernel(const double* __restrict__ mat, const VbLdItem* __restrict__
                 sched[1] = 0;
             }
         }
+#endif
     } else {
         // ---------------- consumers ----------------
         uint32_t stage = 0, phase = 0;
@@ -200,6 +268,9 @@ __global__ void vb_ld_finish_kernel(const double* __restrict__ yb, int64_t len, 
 // of consecutive panels (~0.5 MB, the unit of dynamic scheduling); a group writes one partial
 // vector which vb_ld_finish_kernel sums in fixed order.  Algorithmic bytes: 4 n (n + 1).
 // =====================================================================================
+#ifndef VB_SYM_PREFETCH
+#define VB_SYM_PREFETCH 0   // see VB_LD_PREFETCH
+#endif
 #define VB_SYM_R 8
 #define VB_SYM_CC 512
 #define VB_SYM_NMAX 4096
@@ -209,9 +280,12 @@ __global__ void vb_ld_finish_kernel(const double* __restrict__ yb, int64_t len, 
 #define VB_SYM_STAGE (VB_SYM_STAGE_A + VB_SYM_STAGE_X + VB_SYM_STAGE_XR)
 #define VB_SYM_STAGES 4
 #define VB_SYM_ACC (VB_SYM_NMAX + 16)
-#define VB_SYM_SMEM (VB_SYM_STAGES * VB_SYM_STAGE + 2 * VB_SYM_ACC * 8 + 2 * 8 * 8 * 8 + \
+#define VB_SYM_GROUP_ROWS 512                 // max rows of a group (per-warp row partials in smem)
+#define VB_SYM_SMEM (VB_SYM_STAGES * VB_SYM_STAGE + VB_SYM_ACC * 8 + 8 * VB_SYM_GROUP_ROWS * 8 + \
                      2 * VB_SYM_STAGES * 8 + VB_SYM_STAGES * 32)
+#ifndef VB_SYM_GROUP_BYTES
 #define VB_SYM_GROUP_BYTES (512 * 1024)
+#endif
 
 enum { VB_SYM_FIRST = 1, VB_SYM_LASTPANEL = 2, VB_SYM_LASTGROUP = 4, VB_SYM_VALID = 0x8000 };
 
@@ -223,7 +297,8 @@ struct __align__(16) VbSymItem {
     uint16_t c0_2;       // chunk's first column within the block / 2
     uint16_t elig2;      // column pairs of this chunk left of the diagonal tile
     uint16_t flags;
-    uint32_t r0;         // panel's first row within the block
+    uint16_t r0;         // panel's first row within the block
+    uint16_t grow0;      // first row of the panel's group
     uint32_t out_off;    // LASTGROUP: offset of the group's partial vector
     uint32_t out_len;    // LASTGROUP: its length
 };
@@ -238,9 +313,8 @@ vb_ld_sym_kernel(const double* __restrict__ mat, const VbSymItem* __restrict__ i
                  double* __restrict__ ypart) {
     extern __shared__ __align__(128) unsigned char smem[];
     double* acccol = reinterpret_cast<double*>(smem + VB_SYM_STAGES * VB_SYM_STAGE);
-    double* accrow = acccol + VB_SYM_ACC;
-    double* rowpart = accrow + VB_SYM_ACC;                         // [2][8 warps][8 rows]
-    uint64_t* full = reinterpret_cast<uint64_t*>(rowpart + 2 * 8 * 8);
+    double* rowpart = acccol + VB_SYM_ACC;            // [8 warps][VB_SYM_GROUP_ROWS] row partials
+    uint64_t* full = reinterpret_cast<uint64_t*>(rowpart + 8 * VB_SYM_GROUP_ROWS);
     uint64_t* empty = full + VB_SYM_STAGES;
     VbSymItem* slot = reinterpret_cast<VbSymItem*>(empty + VB_SYM_STAGES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -252,9 +326,90 @@ vb_ld_sym_kernel(const double* __restrict__ mat, const VbSymItem* __restrict__ i
         }
         vb_fence_mbar_init();
     }
-    for (int j = threadIdx.x; j < 2 * VB_SYM_ACC; j += blockDim.x) acccol[j] = 0.0;
+    for (int j = threadIdx.x; j < VB_SYM_ACC + 8 * VB_SYM_GROUP_ROWS; j += blockDim.x) acccol[j] = 0.0;
     __syncthreads();
 
+#if VB_SYM_PREFETCH
+    if (warp == VB_LD_CONSUMER_WARPS) {
+        // producer warp: descriptors are fetched 32 at a time (coalesced), one batch ahead of use;
+        // lane 0 issues the three TMA copies of each item.
+        const uint64_t pol_stream = vb_policy_evict_first();
+        const uint64_t pol_keep = vb_policy_evict_last();
+        uint32_t stage = 0, phase = 0;
+        uint32_t g = 0, g_next = 0;
+        if (lane == 0) {
+            g = atomicAdd(&sched[0], 1u);
+            g_next = atomicAdd(&sched[0], 1u);
+        }
+        g = __shfl_sync(0xffffffffu, g, 0);
+        g_next = __shfl_sync(0xffffffffu, g_next, 0);
+        VbSymGroup grp;
+        grp.first_item = 0; grp.n_items = 0;
+        if (g < n_groups) grp = groups[g];
+        uint32_t boff = 0;
+        const uint4* items4 = reinterpret_cast<const uint4*>(items);
+        uint4 cur_lo = make_uint4(0, 0, 0, 0), cur_hi = make_uint4(0, 0, 0, 0);
+        if (g < n_groups && lane < grp.n_items) {
+            cur_lo = items4[2 * (size_t)(grp.first_item + lane)];
+            cur_hi = items4[2 * (size_t)(grp.first_item + lane) + 1];
+        }
+        while (g < n_groups) {
+            // which batch comes next: the rest of this group, or the first batch of the next one
+            uint32_t ng = g, nboff = boff + 32;
+            VbSymGroup ngrp = grp;
+            uint32_t after = 0;
+            if (nboff >= grp.n_items) {
+                ng = g_next;
+                nboff = 0;
+                if (lane == 0) after = atomicAdd(&sched[0], 1u);
+                after = __shfl_sync(0xffffffffu, after, 0);
+                g_next = after;
+                ngrp.first_item = 0; ngrp.n_items = 0;
+                if (ng < n_groups) ngrp = groups[ng];
+            }
+            uint4 nxt_lo = make_uint4(0, 0, 0, 0), nxt_hi = make_uint4(0, 0, 0, 0);
+            if (ng < n_groups && nboff + lane < ngrp.n_items) {
+                nxt_lo = items4[2 * (size_t)(ngrp.first_item + nboff + lane)];
+                nxt_hi = items4[2 * (size_t)(ngrp.first_item + nboff + lane) + 1];
+            }
+            const uint32_t cnt = min(32u, grp.n_items - boff);
+            for (uint32_t j = 0; j < cnt; ++j) {
+                uint4 lo, hi;
+                lo.x = __shfl_sync(0xffffffffu, cur_lo.x, j); lo.y = __shfl_sync(0xffffffffu, cur_lo.y, j);
+                lo.z = __shfl_sync(0xffffffffu, cur_lo.z, j); lo.w = __shfl_sync(0xffffffffu, cur_lo.w, j);
+                hi.x = __shfl_sync(0xffffffffu, cur_hi.x, j); hi.y = __shfl_sync(0xffffffffu, cur_hi.y, j);
+                hi.z = __shfl_sync(0xffffffffu, cur_hi.z, j); hi.w = __shfl_sync(0xffffffffu, cur_hi.w, j);
+                if (lane == 0) {
+                    vb_mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* sa = smem + stage * VB_SYM_STAGE;
+                    const uint32_t wc2 = lo.w & 0xffffu;
+                    const uint32_t bytes_x = wc2 * 16u;
+                    const uint32_t bytes_a = bytes_x * VB_SYM_R;
+                    reinterpret_cast<uint4*>(&slot[stage])[0] = lo;
+                    reinterpret_cast<uint4*>(&slot[stage])[1] = hi;
+                    vb_mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_x + VB_SYM_STAGE_XR);
+                    vb_bulk_g2s(sa, reinterpret_cast<const unsigned char*>(mat) + (size_t)lo.x * 16,
+                                bytes_a, &full[stage], pol_stream);
+                    vb_bulk_g2s(sa + VB_SYM_STAGE_A, x + (size_t)lo.y * 2, bytes_x, &full[stage], pol_keep);
+                    vb_bulk_g2s(sa + VB_SYM_STAGE_A + VB_SYM_STAGE_X, x + (size_t)lo.z * 2,
+                                VB_SYM_STAGE_XR, &full[stage], pol_keep);
+                }
+                if (++stage == VB_SYM_STAGES) { stage = 0; phase ^= 1; }
+            }
+            g = ng; grp = ngrp; boff = nboff;
+            cur_lo = nxt_lo; cur_hi = nxt_hi;
+        }
+        if (lane == 0) {
+            vb_mbar_wait(&empty[stage], phase ^ 1);
+            slot[stage].flags = 0;
+            vb_mbar_arrive(&full[stage]);
+            const uint32_t done = atomicAdd(&sched[1], 1u);
+            if (done == gridDim.x - 1) {
+                sched[0] = 0;
+                sched[1] = 0;
+            }
+        }
+#else
     if (warp == VB_LD_CONSUMER_WARPS) {
         if (lane == 0) {
             const uint64_t pol_stream = vb_policy_evict_first();
@@ -291,9 +446,9 @@ vb_ld_sym_kernel(const double* __restrict__ mat, const VbSymItem* __restrict__ i
                 sched[1] = 0;
             }
         }
+#endif
     } else {
         uint32_t stage = 0, phase = 0;
-        int par = 0;
         double rowacc[VB_SYM_R], xr[VB_SYM_R];
 #pragma unroll
         for (int i = 0; i < VB_SYM_R; ++i) { rowacc[i] = 0.0; xr[i] = 0.0; }
@@ -318,24 +473,29 @@ vb_ld_sym_kernel(const double* __restrict__ mat, const VbSymItem* __restrict__ i
                 }
             }
             const int wc2 = item.wc2;
-            double2 cacc = make_double2(0.0, 0.0);
+            double2 cacc = make_double2(0.0, 0.0), cacc2 = make_double2(0.0, 0.0);
             if (cp < wc2) {
                 const double2 xc = sx[cp];
 #pragma unroll
-                for (int i = 0; i < VB_SYM_R; ++i) {
+                for (int i = 0; i < VB_SYM_R; i += 2) {
                     const double2 a = sa[i * wc2 + cp];
+                    const double2 b = sa[(i + 1) * wc2 + cp];
                     rowacc[i] = fma(a.x, xc.x, rowacc[i]);
                     rowacc[i] = fma(a.y, xc.y, rowacc[i]);
+                    rowacc[i + 1] = fma(b.x, xc.x, rowacc[i + 1]);
+                    rowacc[i + 1] = fma(b.y, xc.y, rowacc[i + 1]);
                     cacc.x = fma(a.x, xr[i], cacc.x);
                     cacc.y = fma(a.y, xr[i], cacc.y);
+                    cacc2.x = fma(b.x, xr[i + 1], cacc2.x);
+                    cacc2.y = fma(b.y, xr[i + 1], cacc2.y);
                 }
             }
             __syncwarp();
             if (lane == 0) vb_mbar_arrive(&empty[stage]);
             if (cp < item.elig2) {
                 double2 v = acccol2[item.c0_2 + cp];
-                v.x += cacc.x;
-                v.y += cacc.y;
+                v.x += cacc.x + cacc2.x;
+                v.y += cacc.y + cacc2.y;
                 acccol2[item.c0_2 + cp] = v;
             }
             if (item.flags & VB_SYM_LASTPANEL) {
@@ -362,24 +522,22 @@ vb_ld_sym_kernel(const double* __restrict__ mat, const VbSymItem* __restrict__ i
                 t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
                 t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
                 const int row = (hi16 ? 4 : 0) + (hi8 ? 2 : 0) + (hi4 ? 1 : 0);
-                if ((lane & 3) == 0) rowpart[(par * 8 + warp) * 8 + row] = t1;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (warp == 0 && lane < VB_SYM_R) {
-                    double s = 0.0;
-#pragma unroll
-                    for (int w = 0; w < VB_LD_CONSUMER_WARPS; ++w) s += rowpart[(par * 8 + w) * 8 + lane];
-                    accrow[item.r0 + lane] = s;
-                }
-                par ^= 1;
+                // this warp's share of the 8 row sums; the 8 warps are added at the end of the group
+                if ((lane & 3) == 0)
+                    rowpart[warp * VB_SYM_GROUP_ROWS + (item.r0 - item.grow0) + row] = t1;
             }
             if (item.flags & VB_SYM_LASTGROUP) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
+                const uint32_t grow0 = item.grow0;
                 for (uint32_t j = threadIdx.x; j < item.out_len; j += VB_LD_CONSUMER_WARPS * 32) {
-                    ypart[(size_t)item.out_off + j] = acccol[j] + accrow[j];
-                }
-                for (uint32_t j = threadIdx.x; j < item.out_len + VB_SYM_R; j += VB_LD_CONSUMER_WARPS * 32) {
+                    double v = acccol[j];
+                    if (j >= grow0) {
+#pragma unroll
+                        for (int w = 0; w < VB_LD_CONSUMER_WARPS; ++w)
+                            v += rowpart[w * VB_SYM_GROUP_ROWS + (j - grow0)];
+                    }
+                    ypart[(size_t)item.out_off + j] = v;
                     acccol[j] = 0.0;
-                    accrow[j] = 0.0;
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }

@@ -389,6 +389,7 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
             b.g0 = (uint32_t)sgroups.size();
             const int64_t n = b.n, npan = (n + VB_SYM_R - 1) / VB_SYM_R;
             size_t group_bytes = 0;
+            int64_t grow0 = 0;
             VbSymGroup cur;
             cur.first_item = (uint32_t)sitems.size();
             cur.n_items = 0;
@@ -412,14 +413,16 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
                     it.flags = VB_SYM_VALID;
                     if (c0 == 0) it.flags |= VB_SYM_FIRST;
                     if (c0 + VB_SYM_CC >= W) it.flags |= VB_SYM_LASTPANEL;
-                    it.r0 = (uint32_t)r0;
+                    it.r0 = (uint16_t)r0;
+                    it.grow0 = (uint16_t)grow0;
                     it.out_off = 0;
                     it.out_len = 0;
                     sitems.push_back(it);
                     cur.n_items++;
                     group_bytes += (size_t)wc * VB_SYM_R * 8;
                 }
-                if (group_bytes >= VB_SYM_GROUP_BYTES || p == npan - 1) {
+                if (group_bytes >= VB_SYM_GROUP_BYTES || p == npan - 1 ||
+                    r0 + 2 * VB_SYM_R - grow0 > VB_SYM_GROUP_ROWS) {
                     VbSymItem& last = sitems.back();
                     last.flags |= VB_SYM_LASTGROUP;
                     last.out_off = (uint32_t)ypart_len;
@@ -434,6 +437,7 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
                     cur.first_item = (uint32_t)sitems.size();
                     cur.n_items = 0;
                     group_bytes = 0;
+                    grow0 = r0 + VB_SYM_R;
                 }
             }
             b.ng = (uint32_t)sgroups.size() - b.g0;
