@@ -132,6 +132,35 @@ int vb_fit_pm_mark(vb_ctx* ctx, int which);
 /* vi_sigma[k0:k1][P][P][M] in the reference layout -> host  (:712-724) */
 int vb_fit_vi_sigma(vb_ctx* ctx, int k0, int k1, double* out_host);
 
+/* ---- native control loop --------------------------------------------------------------
+ * One outer iteration of optimize() without leaving C++: VIScheme._nat_grad_step
+ * (variational_inference.py:419-450: beta line search :762-802, hyper step :825-860, tau step
+ * :441-448/:472-486) followed by the convergence bookkeeping (:376-377), with the reference's
+ * thresholds.  Multi-GPU: vb_nccl_unique_id (rank 0) + vb_comm_init (every rank) create a NCCL
+ * communicator; the statistics of every evaluated state are then summed with ncclAllReduce.
+ * vb_fit_iteration returns 0, 1 (error) or 2 ("Encountered a numerical error.", :793/:797). */
+typedef struct vb_step_io {
+    double L[5];               /* in/out */
+    double line_search_rate;   /* in  (2.0 in optimize()) */
+    double running_elbo_delta; /* in  (ignored unless has_running) */
+    double obj;                /* in: objective of the accepted state; out: after the iteration */
+    double elbo_delta;         /* out: accumulated change of the ELBO */
+    double atol, rtol;         /* in: tolerances of the posterior-mean convergence test */
+    double diff[10];           /* out: see vb_fit_pm_diff */
+    int32_t has_running;       /* in */
+    int32_t trials;            /* out: line-search trials executed */
+    int32_t evals;             /* out: parameter states evaluated */
+    int32_t do_diff;           /* in: run the convergence bookkeeping */
+} vb_step_io;
+int vb_nccl_unique_id(char* out128);
+int vb_comm_init(vb_ctx* ctx, int nranks, int rank, const char* id128);
+int vb_fit_set_constants(vb_ctx* ctx, const double* chi_stat_host, const double* ld_ranks_host,
+                         const double* annotation_counts_host, const double* log_det_host,
+                         int scale_se);
+/* tau_io [P], hyper_io [A][K], stats_io [3P+3] (statistics of the accepted state) are host in/out */
+int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, double* hyper_io,
+                     double* stats_io);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,22 @@ def test_trajectory(name):
     assert np.isclose(vi.elbo(params), tr['elbo'][-1], rtol=1e-9)
 
 
+@pytest.mark.parametrize('name', ['vischeme_linked_a2_s1_t1', 'syn_p1_dense', 'syn_p3'])
+def test_trajectory_python_loop(name):
+    """The Python control loop (used with INFO logging) takes the same decisions as the C++ one."""
+    fx = load_case(name)
+    vi = make_product(fx)
+    vi.use_native_loop = False
+    np.random.seed(int(fx['seed']))
+    params = vi.optimize(None)
+    tr = vi.trajectory
+    assert tr['trials'] == fx['traj_trials'].tolist()
+    assert np.array_equal(np.array(tr['L0']), fx['traj_L0'])
+    assert np.allclose(tr['elbo'], fx['traj_elbo_out'], rtol=1e-8, atol=0)
+    assert np.allclose(params[0], fx['final_vi_mu'], rtol=1e-6, atol=1e-9)
+    assert np.allclose(vi.error_scaling, fx['final_error_scaling'], rtol=1e-8)
+
+
 @pytest.mark.parametrize('name', [n for n in VI_CASES if 'resume_ckpt_vi_mu' in load_case(n)])
 def test_resume(name):
     fx = load_case(name)

@@ -49,6 +49,23 @@ SIGNATURES = {
 }
 
 
+class StepIO(C.Structure):
+    """vb_step_io of include/vilma_b200.h"""
+    _fields_ = [('L', C.c_double * 5), ('line_search_rate', C.c_double),
+                ('running_elbo_delta', C.c_double), ('obj', C.c_double),
+                ('elbo_delta', C.c_double), ('atol', C.c_double), ('rtol', C.c_double),
+                ('diff', C.c_double * 10), ('has_running', C.c_int32), ('trials', C.c_int32),
+                ('evals', C.c_int32), ('do_diff', C.c_int32)]
+
+
+SIGNATURES.update({
+    'vb_nccl_unique_id': (C.c_int, [C.c_char_p]),
+    'vb_comm_init': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    'vb_fit_set_constants': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    'vb_fit_iteration': (C.c_int, [C.c_void_p, C.POINTER(StepIO), C.c_void_p, C.c_void_p, C.c_void_p]),
+})
+
+
 class VilmaB200Error(RuntimeError):
     pass
 

@@ -236,7 +236,8 @@ __global__ void vb_ld_slab_sum_kernel(const double* __restrict__ src, int64_t le
 __global__ void vb_ld_finish_kernel(const double* __restrict__ yb, int64_t len, int nslab,
                                     const double* __restrict__ xb, const int32_t* __restrict__ pos,
                                     const int32_t* __restrict__ snp, int64_t nreal,
-                                    double* __restrict__ y_snp, double* __restrict__ partial) {
+                                    double* __restrict__ y_snp, double* __restrict__ partial,
+                                    const VbFinalArgs fa) {
     __shared__ double scratch[32];
     double acc = 0.0;
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < nreal;
@@ -247,8 +248,7 @@ __global__ void vb_ld_finish_kernel(const double* __restrict__ yb, int64_t len, 
         y_snp[snp[j]] = v;
         acc = fma(xb[q], v, acc);
     }
-    acc = vb_block_sum(acc, scratch);
-    if (threadIdx.x == 0 && partial) partial[blockIdx.x] = acc;
+    vb_finish_epilogue(acc, partial, fa, scratch);
 }
 
 // =====================================================================================
@@ -581,7 +581,8 @@ __global__ void vb_ld_finish_sym_kernel(const double* __restrict__ yb, int64_t l
                                         const VbSymGroupOut* __restrict__ gout,
                                         const double* __restrict__ xb, const int32_t* __restrict__ pos,
                                         const int32_t* __restrict__ snp, int64_t nreal,
-                                        double* __restrict__ y_snp, double* __restrict__ partial) {
+                                        double* __restrict__ y_snp, double* __restrict__ partial,
+                                        const VbFinalArgs fa) {
     __shared__ double scratch[32];
     double acc = 0.0;
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < nreal;
@@ -604,6 +605,5 @@ __global__ void vb_ld_finish_sym_kernel(const double* __restrict__ yb, int64_t l
         y_snp[snp[j]] = v;
         acc = fma(xb[q], v, acc);
     }
-    acc = vb_block_sum(acc, scratch);
-    if (threadIdx.x == 0 && partial) partial[blockIdx.x] = acc;
+    vb_finish_epilogue(acc, partial, fa, scratch);
 }

@@ -21,8 +21,6 @@
 
 enum { VB_MODE_TRIAL = 0, VB_MODE_REFRESH = 1, VB_MODE_EVAL = 2 };
 
-// Number of doubles each CTA of the SNP kernel contributes: A_p[P], C_p[P], KL_delta, KL_quad, KL_sigma
-#define VB_NSNPSTAT(P) (2 * (P) + 3)
 
 struct VbSnpArgs {
     int K, A;
@@ -48,8 +46,11 @@ struct VbSnpArgs {
     double* mu_out;              // [K][P][M]  (TRIAL)
     double* delta_out;           // [K][M]     (TRIAL, REFRESH)
     double* pm_out;              // [P][M]
-    double* z_out;               // [P][M]     pm / se
     double* pv_out;              // [P][M] or null
+    // z = pm / se goes straight into each cohort's block-order mat-vec input: xb[p][xbpos[p][i]]
+    // (xbpos < 0: SNP i is not in cohort p's LD).  Null xbpos[p] = do not emit z.
+    const int32_t* xbpos[VB_MAXP];
+    double* xb[VB_MAXP];
     double* partial;             // [gridDim.x][VB_NSNPSTAT(P)]
 };
 
@@ -267,7 +268,10 @@ __global__ void __launch_bounds__(128) vb_snp_kernel(const VbSnpArgs a) {
             const double pm = spm[p] * inv_den;
             const double pv = sm2[p] * inv_den - pm * pm;
             a.pm_out[(size_t)p * M + i] = pm;
-            a.z_out[(size_t)p * M + i] = pm / a.se[(size_t)p * M + i];
+            if (a.xbpos[p]) {
+                const int32_t q = a.xbpos[p][i];
+                if (q >= 0) a.xb[p][q] = pm / a.se[(size_t)p * M + i];
+            }
             if (a.pv_out) a.pv_out[(size_t)p * M + i] = pv;
             tA[p] = fma(pm, a.adj[(size_t)p * M + i], tA[p]);
             tC[p] = fma(sld[p], pv, tC[p]);
@@ -289,28 +293,6 @@ __global__ void __launch_bounds__(128) vb_snp_kernel(const VbSnpArgs a) {
     if (threadIdx.x == 0) out[2 * P + 1] = v;
     v = vb_block_sum(tKs, scratch);
     if (threadIdx.x == 0) out[2 * P + 2] = v;
-}
-
-// Final fixed-order reduction of all partials of one evaluation into the stats vector:
-//   stats[0..P)   A_p = sum_i pm adj          stats[P..2P)  C_p = sum_i sld pv
-//   stats[2P..3P) B_p = sum_i z (R z)         stats[3P..3P+3) KL_delta, KL_quad, KL_sigma
-__global__ void vb_stats_finalize_kernel(const double* __restrict__ part_snp, int n_part_snp, int P,
-                                         const double* __restrict__ part_fin, int n_part_fin,
-                                         double* __restrict__ stats) {
-    __shared__ double scratch[32];
-    const int NS = VB_NSNPSTAT(P);
-    for (int s = 0; s < NS; ++s) {
-        double acc = 0.0;
-        for (int b = threadIdx.x; b < n_part_snp; b += blockDim.x) acc += part_snp[(size_t)b * NS + s];
-        acc = vb_block_sum(acc, scratch);
-        if (threadIdx.x == 0) stats[s < 2 * P ? s : s + P] = acc;
-    }
-    for (int p = 0; p < P; ++p) {
-        double acc = 0.0;
-        for (int b = threadIdx.x; b < n_part_fin; b += blockDim.x) acc += part_fin[(size_t)p * n_part_fin + b];
-        acc = vb_block_sum(acc, scratch);
-        if (threadIdx.x == 0) stats[2 * P + p] = acc;
-    }
 }
 
 // Per-annotation column sums of delta (numerics.py:118-129 sum_annotations), deterministic.

@@ -101,3 +101,60 @@ __device__ __forceinline__ double vb_block_max(double v, double* scratch) {
     }
     return r;
 }
+
+// ---------------------------------------------------------------- evaluation statistics
+// Number of doubles each CTA of the per-SNP kernel contributes: A_p[P], C_p[P], KL_delta, KL_quad, KL_sigma
+#define VB_NSNPSTAT(P) (2 * (P) + 3)
+
+// Final fixed-order reduction of all partials of one evaluation into the stats vector:
+//   stats[0..P)   A_p = sum_i pm adj          stats[P..2P)  C_p = sum_i sld pv
+//   stats[2P..3P) B_p = sum_i z (R z)         stats[3P..3P+3) KL_delta, KL_quad, KL_sigma
+// It runs in the last block of the last cohort's mat-vec finish kernel (no extra launch).
+struct VbFinalArgs {
+    const double* part_snp;   // [n_part_snp][2P+3] from the per-SNP kernel
+    const double* part_fin;   // [P][n_part_fin]    sum z (R z) partials of every cohort
+    double* stats;            // [3P+3] out
+    uint32_t* counter;        // zero on entry; the last block to finish does the final sums
+    int n_part_snp, n_part_fin, P;
+    int do_final;             // only the last cohort's finish launch reduces
+};
+// Called by every thread of the LAST block (fixed summation order => deterministic).
+__device__ __forceinline__ void vb_final_reduce(const VbFinalArgs& fa, double* scratch) {
+    const int P = fa.P, NS = VB_NSNPSTAT(P);
+    for (int s = 0; s < NS; ++s) {
+        double acc = 0.0;
+        for (int b = threadIdx.x; b < fa.n_part_snp; b += blockDim.x) acc += __ldcg(&fa.part_snp[(size_t)b * NS + s]);
+        acc = vb_block_sum(acc, scratch);
+        if (threadIdx.x == 0) fa.stats[s < 2 * P ? s : s + P] = acc;
+    }
+    for (int p = 0; p < P; ++p) {
+        double acc = 0.0;
+        for (int b = threadIdx.x; b < fa.n_part_fin; b += blockDim.x) acc += __ldcg(&fa.part_fin[(size_t)p * fa.n_part_fin + b]);
+        acc = vb_block_sum(acc, scratch);
+        if (threadIdx.x == 0) fa.stats[2 * P + p] = acc;
+    }
+}
+// Block epilogue shared by the finish kernels: publish this block's partial, elect the last block.
+__device__ __forceinline__ void vb_finish_epilogue(double acc, double* partial, const VbFinalArgs& fa,
+                                                   double* scratch) {
+    __shared__ int s_last;
+    acc = vb_block_sum(acc, scratch);
+    if (threadIdx.x == 0) {
+        if (partial) partial[blockIdx.x] = acc;
+        s_last = 0;
+        if (fa.counter) {
+            __threadfence();
+            const uint32_t t = atomicAdd(fa.counter, 1u);
+            if (t == gridDim.x - 1) {
+                *fa.counter = 0;
+                s_last = 1;
+            }
+        }
+    }
+    __syncthreads();
+    if (s_last && fa.do_final) {
+        __threadfence();
+        vb_final_reduce(fa, scratch);
+    }
+}
+

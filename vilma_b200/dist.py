@@ -25,6 +25,9 @@ class SingleComm:
     def barrier(self):
         pass
 
+    def broadcast_bytes(self, data):
+        return data
+
 
 def _to_numpy(t):
     if isinstance(t, np.ndarray):
@@ -77,6 +80,11 @@ class TorchComm(SingleComm):
 
     def barrier(self):
         self._dist.barrier()
+
+    def broadcast_bytes(self, data):
+        box = [data]
+        self._dist.broadcast_object_list(box, src=0)
+        return box[0]
 
 
 def default_comm():

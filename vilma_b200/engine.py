@@ -194,6 +194,7 @@ class CudaEngine:
         self._ann = torch.zeros(A * K, dtype=torch.float64, device=dev)
         self._diff = torch.zeros(self.N_DIFF, dtype=torch.float64, device=dev)
         self.ld_bytes = sum(ld_.bytes for ld_ in self.lds)
+        self.native_ready = False
 
     # ---- small inputs
     def set_hyper(self, hyper):
@@ -267,6 +268,33 @@ class CudaEngine:
         out = np.empty((k1 - k0, self.P, self.P, self.M))
         _lib.check(self.lib.vb_fit_vi_sigma(self.ctx.handle, k0, k1, _lib.np_ptr(out)))
         return out
+
+    # ---- native control loop (one outer iteration per call)
+    def set_constants(self, chi_stat, ld_ranks, annotation_counts, log_det, scale_se):
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        c, r, n, ld = f64(chi_stat), f64(ld_ranks), f64(annotation_counts), f64(log_det)
+        _lib.check(self.lib.vb_fit_set_constants(self.ctx.handle, _lib.np_ptr(c), _lib.np_ptr(r),
+                                                 _lib.np_ptr(n), _lib.np_ptr(ld),
+                                                 1 if scale_se else 0))
+        self.native_ready = True
+
+    def init_comm(self, comm):
+        """Create the library's own NCCL communicator over the ranks of `comm` (TorchComm)."""
+        if comm.world <= 1:
+            return
+        buf = C.create_string_buffer(128)
+        if comm.rank == 0:
+            _lib.check(self.lib.vb_nccl_unique_id(buf))
+        ident = comm.broadcast_bytes(buf.raw)
+        _lib.check(self.lib.vb_comm_init(self.ctx.handle, comm.world, comm.rank, ident))
+
+    def iteration(self, io, tau, hyper, stats):
+        """vb_fit_iteration: `io` is a _lib.StepIO; tau/hyper/stats are float64 arrays updated in place."""
+        rc = self.lib.vb_fit_iteration(self.ctx.handle, C.byref(io), _lib.np_ptr(tau),
+                                       _lib.np_ptr(hyper), _lib.np_ptr(stats))
+        if rc == 2:
+            raise RuntimeError('Encountered a numerical error.')
+        _lib.check(rc)
 
     def close(self):
         self.lib.vb_fit_destroy(self.ctx.handle)

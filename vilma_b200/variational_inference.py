@@ -114,6 +114,7 @@ class VIScheme():
             raise ValueError('annotations dimension does not match GWAS marginal effect '
                              'size shape.')
 
+        self.use_native_loop = True      # C++ outer iteration (vb_fit_iteration) when possible
         self._comm = comm if comm is not None else default_comm()
         self._device = device
         self._engine_factory = engine_factory
@@ -254,6 +255,10 @@ class VIScheme():
         L, elbo, running_elbo_delta = state['L'], state['elbo'], state['running']
         num_its, converged = state['num_its'], state['converged']
         want_info = logging.getLogger().isEnabledFor(logging.INFO)
+        native = (self.use_native_loop and not want_info
+                  and hasattr(eng, 'iteration') and self._engine_factory is None)
+        if native:
+            return self._run_loop_native(state, max_its, fresh)
         while num_its < max_its and not converged:
             if num_its % self.checkpoint_freq == 0 and self.checkpoint:
                 eng.pm_mark(1)
@@ -283,6 +288,69 @@ class VIScheme():
             num_its += 1
         return {'elbo': elbo, 'running': running_elbo_delta, 'num_its': num_its, 'L': L,
                 'converged': converged}
+
+    def _run_loop_native(self, state, max_its, fresh):
+        """run_loop with each outer iteration executed by the library's C++ loop
+        (vb_fit_iteration): same thresholds and decisions, one ctypes call per iteration."""
+        from ._lib import StepIO
+        eng = self._eng
+        if not eng.native_ready:
+            eng.set_constants(self.chi_stat, self.ld_ranks, self.annotation_counts,
+                              self.log_det, self.scale_se)
+        L, elbo, running = state['L'], state['elbo'], state['running']
+        num_its, converged = state['num_its'], state['converged']
+        tau = np.ascontiguousarray(self.error_scaling, dtype=np.float64).copy()
+        hyper = np.ascontiguousarray(self._hyper, dtype=np.float64).copy()
+        stats = np.ascontiguousarray(self._res_stats, dtype=np.float64).copy()
+        io = StepIO()
+        io.line_search_rate = 2.
+        io.atol, io.rtol = ABS_TOL, REL_TOL
+        io.do_diff = 1
+        io.obj = self._res_obj
+        for i in range(5):
+            io.L[i] = L[i]
+        while num_its < max_its and not converged:
+            if num_its % self.checkpoint_freq == 0 and self.checkpoint:
+                eng.pm_mark(1)
+                self._sync_from_native(tau, hyper, stats, io)
+                fname = '{}.{}'.format(self.checkpoint_path, num_its)
+                dump_dict = self.create_dump_dict(self._download())
+                if self._comm.rank == 0:
+                    np.savez(fname, **dump_dict)
+            io.has_running = 0 if running is None else 1
+            io.running_elbo_delta = 0. if running is None else running
+            eng.iteration(io, tau, hyper, stats)
+            self._resident = None
+            elbo_change = io.elbo_delta
+            elbo = elbo + elbo_change                       # reference :405
+            if running is None:
+                running = elbo_change
+            running *= ELBO_MOMENTUM
+            running += (1 - ELBO_MOMENTUM) * np.maximum(elbo_change, 0)
+            self.n_trials += io.trials
+            self.n_evals += io.evals
+            converged = io.diff[0] == 0
+            converged = converged or bool(np.isclose(running, 0, atol=ELBO_TOL, rtol=0))
+            if num_its < 10 and fresh:
+                converged = False
+            self.trajectory['elbo'].append(float(elbo))
+            self.trajectory['L0'].append(float(io.L[0]))
+            self.trajectory['trials'].append(int(io.trials))
+            self.trajectory['running'].append(float(running))
+            num_its += 1
+        self._sync_from_native(tau, hyper, stats, io)
+        return {'elbo': elbo, 'running': running, 'num_its': num_its,
+                'L': np.array([io.L[i] for i in range(5)]), 'converged': converged}
+
+    def _sync_from_native(self, tau, hyper, stats, io):
+        """Mirror the state the C++ loop advanced back into the Python object."""
+        self.error_scaling = tau.copy()
+        self._hyper = hyper.copy()
+        self._gtable = numerics.vi_delta_grad_table(self._hyper, self.log_det)
+        self._res_stats = stats.copy()
+        self._res_obj = float(io.obj)
+        self._res_valid = True
+        self._resident = None
 
     def _optimize_step_dev(self, L, curr_elbo, line_search_rate, running_elbo_delta):
         logging.info('Current ELBO = %f and L = %f,%f,%f,%f,%f',
@@ -436,6 +504,7 @@ class MultiPopVI(VIScheme):
                     ids, perm_local = local_blocks(ld, snps, M)
                     lds.append(DeviceLD(ctx, len(snps), ld.device_blocks(ids), perm_local))
             self._eng = CudaEngine(ctx, lds, **pieces)
+            self._eng.init_comm(self._comm)
         self._eng.set_tau(self.error_scaling)
 
     # ------------------------------------------------------------------ hidden state
