@@ -258,6 +258,8 @@ def run_ours(args):
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+        os.environ['NCCL_DEBUG'] = 'WARN'       # keep NCCL's version banner off stdout (one JSON line)
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)

@@ -38,6 +38,8 @@ const char* vb_last_error(void);
 /* process-wide options read when an LD operator is created:
  *   "ld_symmetric" (default 1): store dense blocks of n <= 4096 symmetric-packed (half the bytes) */
 int vb_set_option(const char* name, int64_t value);
+/* largest dense block (rows) that is stored symmetric-packed; larger ones are stored in full */
+int64_t vb_ld_sym_nmax(void);
 /* device: CUDA ordinal; stream: cudaStream_t (may be NULL). */
 int vb_ctx_create(int device, void* stream, vb_ctx** out);
 int vb_ctx_destroy(vb_ctx* ctx);

@@ -155,6 +155,7 @@ struct vb_ld {
 extern "C" int vb_abi_version(void) { return VB_ABI_VERSION; }
 // Process-wide options read when an LD operator is created.
 //   "ld_symmetric" (default 1): store dense blocks with n <= 4096 symmetric-packed.
+extern "C" int64_t vb_ld_sym_nmax(void) { return VB_SYM_NMAX; }
 extern "C" int vb_set_option(const char* name, int64_t value) {
     if (name && std::strcmp(name, "ld_symmetric") == 0) {
         g_disable_sym = (value == 0);
@@ -186,6 +187,7 @@ extern "C" int vb_ctx_create(int device, void* stream, vb_ctx** out) {
                             VB_LD_SMEM));
     CK(cudaFuncSetAttribute(vb_ld_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             VB_SYM_SMEM));
+    CK(cudaFuncSetAttribute(vb_ld_sym_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     *out = c;
     return 0;
 }
@@ -681,7 +683,7 @@ static int ld_apply(vb_ctx* ctx, LdPop& L, const double* x_snp, double* y_snp, d
     }
     if (L.n_sgroups > 0) {
         prof_begin(ctx, 0);
-        vb_ld_sym_kernel<<<ctx->num_sms, VB_LD_THREADS, VB_SYM_SMEM, st>>>(
+        vb_ld_sym_kernel<<<ctx->num_sms * VB_SYM_CTAS_PER_SM, VB_LD_THREADS, VB_SYM_SMEM, st>>>(
             L.mat, L.sitems, L.sgroups, (uint32_t)L.n_sgroups, L.sched + 4, L.xall, L.ypart);
         prof_end(ctx, 0);
         CK_LAUNCH(ctx);

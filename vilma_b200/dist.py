@@ -67,16 +67,32 @@ class TorchComm(SingleComm):
         return self._reduce(t, self._dist.ReduceOp.MAX)
 
     def gather_snp_axis(self, local, snps, M, axis):
-        parts = [None] * self.world
-        self._dist.all_gather_object(parts, (np.asarray(snps), np.asarray(local)))
-        shape = list(local.shape)
-        shape[axis] = M
-        out = np.zeros(shape, dtype=local.dtype)
-        for idx, arr in parts:
-            sl = [slice(None)] * out.ndim
-            sl[axis] = idx
-            out[tuple(sl)] = arr
-        return out
+        """All-gather per-rank shards (padded to a common length) as tensors -- device tensors
+        over NCCL, host tensors over gloo -- and scatter them into the global array."""
+        import torch
+        dev = torch.device('cuda', torch.cuda.current_device()) if self._backend == 'nccl' \
+            else torch.device('cpu')
+        local = np.moveaxis(np.asarray(local), axis, 0)
+        rest = local.shape[1:]
+        flat = np.ascontiguousarray(local.reshape(local.shape[0], -1))
+        n_loc = torch.tensor([flat.shape[0]], dtype=torch.int64, device=dev)
+        sizes = [torch.zeros_like(n_loc) for _ in range(self.world)]
+        self._dist.all_gather(sizes, n_loc)
+        sizes = [int(t.item()) for t in sizes]
+        n_max = max(sizes)
+        pad = torch.zeros((n_max, flat.shape[1]), dtype=torch.from_numpy(flat).dtype, device=dev)
+        pad[:flat.shape[0]] = torch.from_numpy(flat).to(dev)
+        idx = torch.full((n_max,), -1, dtype=torch.int64, device=dev)
+        idx[:flat.shape[0]] = torch.from_numpy(np.asarray(snps, dtype=np.int64)).to(dev)
+        all_pad = [torch.empty_like(pad) for _ in range(self.world)]
+        all_idx = [torch.empty_like(idx) for _ in range(self.world)]
+        self._dist.all_gather(all_pad, pad)
+        self._dist.all_gather(all_idx, idx)
+        out = np.zeros((M, flat.shape[1]), dtype=flat.dtype)
+        for r in range(self.world):
+            k = sizes[r]
+            out[all_idx[r][:k].cpu().numpy()] = all_pad[r][:k].cpu().numpy()
+        return np.moveaxis(out.reshape((M,) + rest), 0, axis)
 
     def barrier(self):
         self._dist.barrier()

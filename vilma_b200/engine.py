@@ -60,12 +60,14 @@ class DeviceContext:
         return {'ld_matvec': (ms[0], cnt[0]), 'snp': (ms[1], cnt[1])}
 
 
-SYM_NMAX = 4096     # csrc/ld_kernels.cuh VB_SYM_NMAX
+def sym_nmax():
+    """Largest block stored symmetric-packed (csrc/ld_kernels.cuh VB_SYM_NMAX)."""
+    return int(_lib.load().vb_ld_sym_nmax())
 
 
 def dense_bytes(n):
-    """Bytes one mat-vec streams for a dense block: symmetric-packed up to SYM_NMAX, else full."""
-    return 4 * n * (n + 1) if n <= SYM_NMAX else 8 * n * n
+    """Bytes one mat-vec streams for a dense block: symmetric-packed up to sym_nmax(), else full."""
+    return 4 * n * (n + 1) if n <= sym_nmax() else 8 * n * n
 
 
 def choose_storage(n, r):

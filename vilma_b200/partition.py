@@ -10,7 +10,7 @@ import numpy as np
 
 def block_cost(n, r):
     """Bytes one mat-vec reads for a block (packed dense vs two factor passes)."""
-    dense = 4 * n * (n + 1) if n <= 4096 else 8 * n * n
+    dense = 4 * n * (n + 1) if n <= 2816 else 8 * n * n
     return float(min(dense, 16 * n * r))
 
 
