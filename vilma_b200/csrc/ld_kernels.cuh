@@ -604,9 +604,20 @@ __global__ void vb_ld_finish_sym_kernel(const double* __restrict__ yb, int64_t l
             const VbSymBlockRef br = bref[b];
             const uint32_t l = (uint32_t)loc[j];
             v = 0.0;
-            for (uint32_t g = br.g0; g < br.g0 + br.ng; ++g) {
+            uint32_t g = br.g0;
+            const uint32_t gend = br.g0 + br.ng;
+            // four independent loads in flight per step; summation order stays g-ascending
+            for (; g + 4 <= gend; g += 4) {
+                const VbSymGroupOut o0 = gout[g], o1 = gout[g + 1], o2 = gout[g + 2], o3 = gout[g + 3];
+                const double t0 = l < o0.len ? __ldg(&ypart[(size_t)o0.off + l]) : 0.0;
+                const double t1 = l < o1.len ? __ldg(&ypart[(size_t)o1.off + l]) : 0.0;
+                const double t2 = l < o2.len ? __ldg(&ypart[(size_t)o2.off + l]) : 0.0;
+                const double t3 = l < o3.len ? __ldg(&ypart[(size_t)o3.off + l]) : 0.0;
+                v += t0; v += t1; v += t2; v += t3;
+            }
+            for (; g < gend; ++g) {
                 const VbSymGroupOut go = gout[g];
-                if (l < go.len) v += ypart[(size_t)go.off + l];
+                if (l < go.len) v += __ldg(&ypart[(size_t)go.off + l]);
             }
         } else {
             v = yb[q];

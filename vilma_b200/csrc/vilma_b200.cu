@@ -742,7 +742,7 @@ extern "C" int vb_fit_create(vb_ctx* ctx, int K, int P, int64_t M, int A, vb_ld*
     CK(cudaMemsetAsync(f.pm_prev, 0, PM * 8, ctx->stream));
     CK(cudaMemsetAsync(f.pm_ckpt, 0, PM * 8, ctx->stream));
     f.grid_snp = (int)std::min<int64_t>((M + 127) / 128, (int64_t)ctx->num_sms * 16);
-    f.grid_fin = 2 * ctx->num_sms;
+    f.grid_fin = 8 * ctx->num_sms;
     f.grid_ann = (int)std::min<int64_t>((M + 255) / 256, (int64_t)ctx->num_sms);
     f.grid_diff = (int)std::min<int64_t>((int64_t)(PM + 255) / 256, (int64_t)ctx->num_sms * 4);
     CK(cudaMalloc(&f.part_snp, (size_t)f.grid_snp * VB_NSNPSTAT(P) * 8));
