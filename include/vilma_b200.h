@@ -91,6 +91,9 @@ int64_t vb_ld_bytes(const vb_ld* ld);
  */
 int vb_fit_create(vb_ctx* ctx, int K, int P, int64_t M, int A, vb_ld* const* lds);
 int vb_fit_destroy(vb_ctx* ctx);
+/* fuse_ann != 0: evaluations also return the per-annotation sums of delta (see below); used on
+ * multi-GPU runs where a separate pass + reduction per hyper step costs more than it saves */
+int vb_fit_set_fusion(vb_ctx* ctx, int fuse_ann);
 int vb_fit_set_snp_data(vb_ctx* ctx, const double* adj_host, const double* se_host,
                         const double* sld_host, const double* scalings_host,
                         const int32_t* ann_host);
@@ -101,7 +104,9 @@ int vb_fit_set_tau(vb_ctx* ctx, const double* tau_host);
 int vb_fit_set_params(vb_ctx* ctx, const double* vi_mu_host, const double* vi_delta_mk_host);
 int vb_fit_get_params(vb_ctx* ctx, double* vi_mu_host, double* vi_delta_mk_host);
 
-/* ---- evaluations: each fills stats_dev[0 .. 3P+3) for ONE parameter state -------------
+/* ---- evaluations: each fills stats_dev[0 .. 3P+3) for ONE parameter state; stats_dev must hold
+ * 3P+3+58 doubles: with vb_fit_set_fusion(ctx, 1) and A*K <= 48, entries [3P+3, 3P+3+A*K) receive
+ * the per-annotation sums of that state's delta (index a*K+k) ------------------------------
  *   [0,P)   A_p = sum_i pm adj      [P,2P)  C_p = sum_i sld pv      [2P,3P) B_p = sum_i z (R z)
  *   3P KL_delta  3P+1 KL_quad  3P+2 KL_sigma
  * from which  loglik = sum_p [(-(C_p+B_p)/2 + A_p - chi_p/2)/tau_p - rank_p log(tau_p)/2]

@@ -587,6 +587,7 @@ struct VbSymGroupOut {
 __global__ void vb_ld_finish_sym_kernel(const double* __restrict__ yb, int64_t len, int nslab,
                                         const double* __restrict__ ypart,
                                         const int32_t* __restrict__ blk, const int32_t* __restrict__ loc,
+                                        const int32_t* __restrict__ gfirst,
                                         const VbSymBlockRef* __restrict__ bref,
                                         const VbSymGroupOut* __restrict__ gout,
                                         const double* __restrict__ xb, const int32_t* __restrict__ pos,
@@ -604,15 +605,15 @@ __global__ void vb_ld_finish_sym_kernel(const double* __restrict__ yb, int64_t l
             const VbSymBlockRef br = bref[b];
             const uint32_t l = (uint32_t)loc[j];
             v = 0.0;
-            uint32_t g = br.g0;
+            uint32_t g = (uint32_t)gfirst[j];          // groups before it do not reach row l
             const uint32_t gend = br.g0 + br.ng;
             // four independent loads in flight per step; summation order stays g-ascending
             for (; g + 4 <= gend; g += 4) {
                 const VbSymGroupOut o0 = gout[g], o1 = gout[g + 1], o2 = gout[g + 2], o3 = gout[g + 3];
                 const double t0 = l < o0.len ? __ldg(&ypart[(size_t)o0.off + l]) : 0.0;
-                const double t1 = l < o1.len ? __ldg(&ypart[(size_t)o1.off + l]) : 0.0;
-                const double t2 = l < o2.len ? __ldg(&ypart[(size_t)o2.off + l]) : 0.0;
-                const double t3 = l < o3.len ? __ldg(&ypart[(size_t)o3.off + l]) : 0.0;
+                const double t1 = __ldg(&ypart[(size_t)o1.off + l]);
+                const double t2 = __ldg(&ypart[(size_t)o2.off + l]);
+                const double t3 = __ldg(&ypart[(size_t)o3.off + l]);
                 v += t0; v += t1; v += t2; v += t3;
             }
             for (; g < gend; ++g) {

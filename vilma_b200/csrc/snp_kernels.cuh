@@ -20,6 +20,8 @@
 #include "vb_common.cuh"
 
 enum { VB_MODE_TRIAL = 0, VB_MODE_REFRESH = 1, VB_MODE_EVAL = 2 };
+#define VB_FUSE_ANN_MAX 48     // A*K up to which annotation sums ride along with every evaluation
+#define VB_SNP_THREADS 128
 
 
 struct VbSnpArgs {
@@ -51,6 +53,10 @@ struct VbSnpArgs {
     // (xbpos < 0: SNP i is not in cohort p's LD).  Null xbpos[p] = do not emit z.
     const int32_t* xbpos[VB_MAXP];
     double* xb[VB_MAXP];
+    // fused extras (no extra launches / reductions per evaluation):
+    //  fuse_ann : accumulate the per-annotation sums of this state's delta (A*K <= VB_FUSE_ANN_MAX)
+    int fuse_ann;
+    int nsp;                     // row stride of `partial`
     double* partial;             // [gridDim.x][VB_NSNPSTAT(P)]
 };
 
@@ -132,20 +138,29 @@ __device__ __forceinline__ void vb_sym_matvec(const double (&A)[P * (P + 1) / 2]
 }
 
 template <int P, int MODE>
-__global__ void __launch_bounds__(128) vb_snp_kernel(const VbSnpArgs a) {
+__global__ void __launch_bounds__(VB_SNP_THREADS) vb_snp_kernel(const VbSnpArgs a) {
     constexpr int NT = P * (P + 1) / 2;
     constexpr int NS = VB_NSNPSTAT(P);
     __shared__ double scratch[32];
+    extern __shared__ double s_ann[];        // [warps][A*K] per-warp annotation sums of delta
     const int K = a.K;
     const int64_t M = a.M;
     const size_t PM = (size_t)P * M;
+    const int AKf = a.fuse_ann ? a.A * K : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* my_ann = s_ann + warp * AKf;     // written by lane 0 of this warp only
+    for (int j = threadIdx.x; j < AKf * (VB_SNP_THREADS / 32); j += VB_SNP_THREADS) s_ann[j] = 0.0;
+    if (AKf) __syncthreads();
 
     double tA[P], tC[P], tKd = 0.0, tKq = 0.0, tKs = 0.0;
 #pragma unroll
     for (int p = 0; p < P; ++p) { tA[p] = 0.0; tC[p] = 0.0; }
 
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    // warp-uniform trip count (lanes past M are clamped and masked) so that warp collectives are legal
+    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < M;
+         base += (int64_t)gridDim.x * blockDim.x) {
+        const bool valid = base + lane < M;
+        const int64_t i = valid ? base + lane : M - 1;
         double dt[P], sld[P], g[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) {
@@ -199,6 +214,12 @@ __global__ void __launch_bounds__(128) vb_snp_kernel(const VbSnpArgs a) {
             double lk = 0.0;
             if constexpr (MODE == VB_MODE_EVAL) {
                 w = a.delta_in[(size_t)k * M + i];
+                if (AKf) {
+                    for (int aa = 0; aa < a.A; ++aa) {
+                        const double sv = vb_warp_sum((valid && an == aa) ? w : 0.0);
+                        if (lane == 0) my_ann[aa * K + k] += sv;
+                    }
+                }
             } else {
                 vb_sym_matvec<P>(lam, mu, eta);            // eta_old = Lambda mu
                 if constexpr (MODE == VB_MODE_TRIAL) {
@@ -206,15 +227,17 @@ __global__ void __launch_bounds__(128) vb_snp_kernel(const VbSnpArgs a) {
                     for (int p = 0; p < P; ++p)
                         eta[p] = a.step * g[p] + (1.0 - a.step) * eta[p];
                     vb_sym_matvec<P>(S, eta, mu);          // mu' = S eta
+                    if (valid) {
 #pragma unroll
-                    for (int p = 0; p < P; ++p)
-                        a.mu_out[(size_t)k * PM + (size_t)p * M + i] = mu[p];
+                        for (int p = 0; p < P; ++p)
+                            a.mu_out[(size_t)k * PM + (size_t)p * M + i] = mu[p];
+                    }
                 }
                 double dot = 0.0;
 #pragma unroll
                 for (int p = 0; p < P; ++p) dot += mu[p] * eta[p];
                 lk = 0.5 * (c + dot) + gfull[k];
-                a.delta_out[(size_t)k * M + i] = lk;       // logits parked; normalised below
+                if (valid) a.delta_out[(size_t)k * M + i] = lk;   // logits parked; normalised below
                 if (lk > mx) {
                     const double r = exp(mx - lk);
                     s0 *= r; sKd *= r; sKq *= r; sKs *= r;
@@ -252,10 +275,18 @@ __global__ void __launch_bounds__(128) vb_snp_kernel(const VbSnpArgs a) {
             // second pass: delta_k = max(exp(l_k - mx) / denom, EPSILON)   (numerics.py:188-194)
             for (int k = 0; k < K; ++k) {
                 const double lk = a.delta_out[(size_t)k * M + i];
-                a.delta_out[(size_t)k * M + i] = fmax(exp(lk - mx) * inv_den, VB_EPSILON);
+                const double d = fmax(exp(lk - mx) * inv_den, VB_EPSILON);
+                if (valid) a.delta_out[(size_t)k * M + i] = d;
+                if (AKf) {
+                    for (int aa = 0; aa < a.A; ++aa) {
+                        const double sv = vb_warp_sum((valid && an == aa) ? d : 0.0);
+                        if (lane == 0) my_ann[aa * K + k] += sv;
+                    }
+                }
             }
         }
         // moments and per-SNP objective pieces
+        if (!valid) continue;          // (after the last warp collective of this trip)
         if constexpr (MODE == VB_MODE_EVAL) {
             tKd += sKd;
         } else {
@@ -278,21 +309,32 @@ __global__ void __launch_bounds__(128) vb_snp_kernel(const VbSnpArgs a) {
         }
     }
 
-    // deterministic block reduction -> partial[blockIdx][NS]
-    double* out = a.partial + (size_t)blockIdx.x * NS;
+    // deterministic block reduction -> partial[stat][blockIdx]  (stat-major: the final reduction
+    // reads each statistic's partials as one coalesced run)
+    double* out = a.partial + blockIdx.x;
+    const size_t ps = gridDim.x;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         double v = vb_block_sum(tA[p], scratch);
-        if (threadIdx.x == 0) out[p] = v;
+        if (threadIdx.x == 0) out[p * ps] = v;
         v = vb_block_sum(tC[p], scratch);
-        if (threadIdx.x == 0) out[P + p] = v;
+        if (threadIdx.x == 0) out[(P + p) * ps] = v;
     }
     double v = vb_block_sum(tKd, scratch);
-    if (threadIdx.x == 0) out[2 * P] = v;
+    if (threadIdx.x == 0) out[(2 * P) * ps] = v;
     v = vb_block_sum(tKq, scratch);
-    if (threadIdx.x == 0) out[2 * P + 1] = v;
+    if (threadIdx.x == 0) out[(2 * P + 1) * ps] = v;
     v = vb_block_sum(tKs, scratch);
-    if (threadIdx.x == 0) out[2 * P + 2] = v;
+    if (threadIdx.x == 0) out[(2 * P + 2) * ps] = v;
+    if (AKf) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < AKf; j += VB_SNP_THREADS) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < VB_SNP_THREADS / 32; ++w) t += s_ann[w * AKf + j];
+            out[(NS + j) * ps] = t;
+        }
+    }
 }
 
 // Per-annotation column sums of delta (numerics.py:118-129 sum_annotations), deterministic.
@@ -337,9 +379,11 @@ __global__ void vb_sum_annotations_final_kernel(const double* __restrict__ parti
 //   sums[0] = #violations of |new-old| <= atol + rtol*|old|;  sums[1] = sum|new-old|; sums[2] = sum (new-old)^2
 //   sums[3] = sum|new-ckpt|; sums[4] = sum (new-ckpt)^2
 //   maxs[0] = max|new|; maxs[1] = max rel(prev); maxs[2] = max abs(prev); maxs[3] = max rel(ckpt); maxs[4] = max abs(ckpt)
+// The new scaled mean is written to `next` (== prev for an in-place update).
 __global__ void vb_pm_diff_kernel(const double* __restrict__ pm, const double* __restrict__ scal,
-                                  double* __restrict__ prev, const double* __restrict__ ckpt, int64_t n,
-                                  double atol, double rtol, double* __restrict__ part /*[grid][10]*/) {
+                                  const double* prev, const double* __restrict__ ckpt, double* next,
+                                  int64_t n, double atol, double rtol,
+                                  double* __restrict__ part /*[grid][10]*/) {
     __shared__ double scratch[32];
     double viol = 0, sab = 0, ssq = 0, cab = 0, csq = 0, mnew = 0, mrel = 0, mabs = 0, crel = 0, cabs = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
@@ -353,7 +397,7 @@ __global__ void vb_pm_diff_kernel(const double* __restrict__ pm, const double* _
         mabs = fmax(mabs, d); cabs = fmax(cabs, dc);
         mrel = fmax(mrel, fabs((v - o) / (o + VB_EPSILON)));
         crel = fmax(crel, fabs((v - c) / (c + VB_EPSILON)));
-        prev[i] = v;
+        next[i] = v;
     }
     double* out = part + (size_t)blockIdx.x * 10;
     double r;

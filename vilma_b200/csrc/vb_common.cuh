@@ -111,21 +111,30 @@ __device__ __forceinline__ double vb_block_max(double v, double* scratch) {
 //   stats[2P..3P) B_p = sum_i z (R z)         stats[3P..3P+3) KL_delta, KL_quad, KL_sigma
 // It runs in the last block of the last cohort's mat-vec finish kernel (no extra launch).
 struct VbFinalArgs {
-    const double* part_snp;   // [n_part_snp][2P+3] from the per-SNP kernel
+    const double* part_snp;   // [2P+3 (+akf)][n_part_snp] from the per-SNP kernel (stat-major)
     const double* part_fin;   // [P][n_part_fin]    sum z (R z) partials of every cohort
     double* stats;            // [3P+3] out
     uint32_t* counter;        // zero on entry; the last block to finish does the final sums
     int n_part_snp, n_part_fin, P;
     int do_final;             // only the last cohort's finish launch reduces
+    int nsp;                  // row stride of part_snp
+    int akf;                  // fused annotation sums per row (0: none) -> stats[3P+3 .. 3P+3+akf)
 };
 // Called by every thread of the LAST block (fixed summation order => deterministic).
 __device__ __forceinline__ void vb_final_reduce(const VbFinalArgs& fa, double* scratch) {
     const int P = fa.P, NS = VB_NSNPSTAT(P);
     for (int s = 0; s < NS; ++s) {
         double acc = 0.0;
-        for (int b = threadIdx.x; b < fa.n_part_snp; b += blockDim.x) acc += __ldcg(&fa.part_snp[(size_t)b * NS + s]);
+        for (int b = threadIdx.x; b < fa.n_part_snp; b += blockDim.x) acc += __ldcg(&fa.part_snp[(size_t)s * fa.n_part_snp + b]);
         acc = vb_block_sum(acc, scratch);
         if (threadIdx.x == 0) fa.stats[s < 2 * P ? s : s + P] = acc;
+    }
+    const int n_sum = fa.akf;
+    for (int s = 0; s < n_sum; ++s) {
+        double acc = 0.0;
+        for (int b = threadIdx.x; b < fa.n_part_snp; b += blockDim.x) acc += __ldcg(&fa.part_snp[(size_t)(NS + s) * fa.n_part_snp + b]);
+        acc = vb_block_sum(acc, scratch);
+        if (threadIdx.x == 0) fa.stats[3 * P + 3 + s] = acc;
     }
     for (int p = 0; p < P; ++p) {
         double acc = 0.0;

@@ -45,6 +45,14 @@ static int vb_fail(const char* fmt, ...) {
     } while (0)
 
 static inline int64_t even_up(int64_t v) { return (v + 1) & ~int64_t(1); }
+// Measured on C2 (tools/ld_bench.py): claiming groups in natural (memory) order beats largest-first
+// (0.696 vs 0.736 ms) and capping the groups per block does not pay either.
+#ifndef VB_SYM_MAX_GROUPS
+#define VB_SYM_MAX_GROUPS 1000000
+#endif
+#ifndef VB_SYM_LPT
+#define VB_SYM_LPT 0
+#endif
 static bool g_disable_sym = false;   // vb_set_option("ld_symmetric", 0): store dense blocks in full
 
 // ------------------------------------------------------------------------------------
@@ -91,7 +99,8 @@ struct LdPop {
     VbSymBlockRef* bref = nullptr;
     int64_t n_sgroups = 0;
     double* ypart = nullptr;
-    int32_t *blk = nullptr, *loc = nullptr;
+    int32_t *blk = nullptr, *loc = nullptr, *gfirst = nullptr;
+    std::vector<VbSymGroupOut> gout_host;
     int64_t bytes = 0;             // algorithmic bytes per mat-vec
 };
 
@@ -109,7 +118,8 @@ struct Fit {
     int cur_mu = 0, cur_delta = 0, cur_vec = 0;
     int trial_kind = -1;           // -1 none, 0 beta trial (new mu+delta), 1 refresh (new delta)
     double* scratch3 = nullptr;    // [3][P][M]
-    double *pm_prev = nullptr, *pm_ckpt = nullptr;
+    double *pm_prev = nullptr, *pm_ckpt = nullptr, *pm_next = nullptr;
+    int akf = 0, nsp = 0;          // fused annotation sums per evaluation; partial row stride
     double* part_snp = nullptr;
     int grid_snp = 0;
     double* part_fin = nullptr;
@@ -197,7 +207,7 @@ static void free_ld(LdPop& L) {
     cudaFree(L.items1); cudaFree(L.items2); cudaFree(L.sched);
     cudaFree(L.pos); cudaFree(L.snp); cudaFree(L.xbpos); cudaFree(L.fin_counter);
     cudaFree(L.sitems); cudaFree(L.sgroups); cudaFree(L.gout); cudaFree(L.bref); cudaFree(L.ypart);
-    cudaFree(L.blk); cudaFree(L.loc);
+    cudaFree(L.blk); cudaFree(L.loc); cudaFree(L.gfirst);
     L = LdPop();
 }
 static void free_fit(Fit& f) {
@@ -207,7 +217,7 @@ static void free_fit(Fit& f) {
         cudaFree(f.mu[s]); cudaFree(f.delta[s]); cudaFree(f.pm[s]);
         cudaFree(f.linked[s]);
     }
-    cudaFree(f.scratch3); cudaFree(f.pm_prev); cudaFree(f.pm_ckpt);
+    cudaFree(f.scratch3); cudaFree(f.pm_prev); cudaFree(f.pm_ckpt); cudaFree(f.pm_next);
     cudaFree(f.part_snp); cudaFree(f.part_fin); cudaFree(f.part_ann); cudaFree(f.part_diff);
     f = Fit();
 }
@@ -380,6 +390,7 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
     L.bytes = 0;
     std::vector<VbSymItem> sitems;
     std::vector<VbSymGroup> sgroups;
+    std::vector<size_t> sgroup_bytes;
     std::vector<VbSymGroupOut> gout;
     std::vector<VbSymBlockRef> bref(L.blocks.size());
     size_t ypart_len = 0;
@@ -394,6 +405,9 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
             const int64_t n = b.n, npan = (n + VB_SYM_R - 1) / VB_SYM_R;
             size_t group_bytes = 0;
             int64_t grow0 = 0;
+            // at most ~12 byte-limited groups per block: the finish kernel walks a block's groups
+            const size_t block_bytes = (size_t)4 * n * (n + 1);
+            const size_t group_target = std::max<size_t>(VB_SYM_GROUP_BYTES, block_bytes / VB_SYM_MAX_GROUPS);
             VbSymGroup cur;
             cur.first_item = (uint32_t)sitems.size();
             cur.n_items = 0;
@@ -425,7 +439,7 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
                     cur.n_items++;
                     group_bytes += (size_t)wc * VB_SYM_R * 8;
                 }
-                if (group_bytes >= VB_SYM_GROUP_BYTES || p == npan - 1 ||
+                if (group_bytes >= group_target || p == npan - 1 ||
                     r0 + 2 * VB_SYM_R - grow0 > VB_SYM_GROUP_ROWS) {
                     VbSymItem& last = sitems.back();
                     last.flags |= VB_SYM_LASTGROUP;
@@ -438,6 +452,7 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
                     ypart_len += go.len;
                     gout.push_back(go);
                     sgroups.push_back(cur);
+                    sgroup_bytes.push_back(group_bytes);
                     cur.first_item = (uint32_t)sitems.size();
                     cur.n_items = 0;
                     group_bytes = 0;
@@ -471,8 +486,18 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
     if (L.n_sgroups > 0) {
         CK(cudaMalloc(&L.sitems, sitems.size() * sizeof(VbSymItem)));
         CK(cudaMemcpy(L.sitems, sitems.data(), sitems.size() * sizeof(VbSymItem), cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&L.sgroups, sgroups.size() * sizeof(VbSymGroup)));
-        CK(cudaMemcpy(L.sgroups, sgroups.data(), sgroups.size() * sizeof(VbSymGroup), cudaMemcpyHostToDevice));
+        // claim order: largest groups first (LPT), so the tail of the dynamic schedule is made of
+        // the smallest groups; group *indices* (gout / bref) keep the block order
+        std::vector<uint32_t> order(sgroups.size());
+        for (size_t g = 0; g < order.size(); ++g) order[g] = (uint32_t)g;
+        if (VB_SYM_LPT)
+            std::stable_sort(order.begin(), order.end(),
+                             [&](uint32_t x, uint32_t y) { return sgroup_bytes[x] > sgroup_bytes[y]; });
+        std::vector<VbSymGroup> sched(sgroups.size());
+        for (size_t g = 0; g < order.size(); ++g) sched[g] = sgroups[order[g]];
+        CK(cudaMalloc(&L.sgroups, sched.size() * sizeof(VbSymGroup)));
+        CK(cudaMemcpy(L.sgroups, sched.data(), sched.size() * sizeof(VbSymGroup), cudaMemcpyHostToDevice));
+        L.gout_host = gout;
         CK(cudaMalloc(&L.gout, gout.size() * sizeof(VbSymGroupOut)));
         CK(cudaMemcpy(L.gout, gout.data(), gout.size() * sizeof(VbSymGroupOut), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&L.bref, bref.size() * sizeof(VbSymBlockRef)));
@@ -608,12 +633,19 @@ extern "C" int vb_ld_finalize(vb_ld* h, const int64_t* perm_host, int64_t nperm)
     std::vector<int32_t> pos(std::max<int64_t>(nperm, 1)), snp(std::max<int64_t>(nperm, 1));
     std::vector<char> seen(L.M, 0);
     std::vector<int32_t> blk(std::max<int64_t>(nperm, 1)), loc(std::max<int64_t>(nperm, 1));
+    std::vector<int32_t> gfirst(std::max<int64_t>(nperm, 1), 0);
     int64_t j = 0;
     for (size_t bi = 0; bi < L.blocks.size(); ++bi) {
         LdBlock& b = L.blocks[bi];
         for (int64_t t = 0; t < b.n; ++t, ++j) {
             blk[j] = b.sym ? (int32_t)bi : -1;
             loc[j] = (int32_t)t;
+            if (b.sym) {
+                // first group of the block whose partial vector covers row t (lengths increase)
+                uint32_t g = b.g0;
+                while (g + 1 < b.g0 + b.ng && L.gout_host[g].len <= (uint32_t)t) ++g;
+                gfirst[j] = (int32_t)g;
+            }
             const int64_t i = perm_host[j];
             if (i < 0 || i >= L.M) return vb_fail("vb_ld_finalize: perm[%lld]=%lld out of range", (long long)j, (long long)i);
             if (seen[i]) return vb_fail("vb_ld_finalize: SNP %lld appears twice in perm", (long long)i);
@@ -636,6 +668,8 @@ extern "C" int vb_ld_finalize(vb_ld* h, const int64_t* perm_host, int64_t nperm)
         CK(cudaMalloc(&L.loc, loc.size() * sizeof(int32_t)));
         CK(cudaMemcpy(L.blk, blk.data(), blk.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(L.loc, loc.data(), loc.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&L.gfirst, gfirst.size() * sizeof(int32_t)));
+        CK(cudaMemcpy(L.gfirst, gfirst.data(), gfirst.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
     CK(cudaMalloc(&L.pos, pos.size() * sizeof(int32_t)));
     CK(cudaMalloc(&L.snp, snp.size() * sizeof(int32_t)));
@@ -688,7 +722,7 @@ static int ld_apply(vb_ctx* ctx, LdPop& L, const double* x_snp, double* y_snp, d
         prof_end(ctx, 0);
         CK_LAUNCH(ctx);
         vb_ld_finish_sym_kernel<<<grid_fin, 256, 0, st>>>(L.yb, L.xb_len, L.nslab2, L.ypart, L.blk,
-                                                          L.loc, L.bref, L.gout, L.xall, L.pos, L.snp,
+                                                          L.loc, L.gfirst, L.bref, L.gout, L.xall, L.pos, L.snp,
                                                           L.nreal, y_snp, partial, fa);
         CK_LAUNCH(ctx);
     } else {
@@ -739,13 +773,17 @@ extern "C" int vb_fit_create(vb_ctx* ctx, int K, int P, int64_t M, int A, vb_ld*
     }
     CK(cudaMalloc(&f.scratch3, 3 * PM * 8));
     CK(cudaMalloc(&f.pm_prev, PM * 8)); CK(cudaMalloc(&f.pm_ckpt, PM * 8));
+    CK(cudaMalloc(&f.pm_next, PM * 8));
+    CK(cudaMemsetAsync(f.pm_next, 0, PM * 8, ctx->stream));
+    f.akf = 0;                                        // see vb_fit_set_fusion
+    f.nsp = VB_NSNPSTAT(P) + VB_FUSE_ANN_MAX;
     CK(cudaMemsetAsync(f.pm_prev, 0, PM * 8, ctx->stream));
     CK(cudaMemsetAsync(f.pm_ckpt, 0, PM * 8, ctx->stream));
     f.grid_snp = (int)std::min<int64_t>((M + 127) / 128, (int64_t)ctx->num_sms * 16);
     f.grid_fin = 8 * ctx->num_sms;
     f.grid_ann = (int)std::min<int64_t>((M + 255) / 256, (int64_t)ctx->num_sms);
     f.grid_diff = (int)std::min<int64_t>((int64_t)(PM + 255) / 256, (int64_t)ctx->num_sms * 4);
-    CK(cudaMalloc(&f.part_snp, (size_t)f.grid_snp * VB_NSNPSTAT(P) * 8));
+    CK(cudaMalloc(&f.part_snp, (size_t)f.grid_snp * f.nsp * 8));
     CK(cudaMalloc(&f.part_fin, (size_t)P * f.grid_fin * 8));
     CK(cudaMemsetAsync(f.part_fin, 0, (size_t)P * f.grid_fin * 8, ctx->stream));
     CK(cudaMalloc(&f.part_ann, (size_t)f.grid_ann * K * A * 8));
@@ -761,6 +799,15 @@ extern "C" int vb_fit_create(vb_ctx* ctx, int K, int P, int64_t M, int A, vb_ld*
         if (!lds[p]->L.finalized) return vb_fail("vb_fit_create: LD operator %d is not finalized", p);
         if (lds[p]->L.M != M) return vb_fail("vb_fit_create: LD operator %d has M=%lld, fit has M=%lld", p, (long long)lds[p]->L.M, (long long)M);
     }
+    return 0;
+}
+// fuse_ann != 0: every evaluation also accumulates the per-annotation sums of that state's delta
+// (needs A*K <= 48 and A <= 4, silently off otherwise).  Worth it when a separate pass + reduction
+// per hyper step costs more than ~5 % extra per-SNP kernel time, i.e. on multi-GPU runs.
+extern "C" int vb_fit_set_fusion(vb_ctx* ctx, int fuse_ann) {
+    if (!ctx || !ctx->fit.created) return vb_fail("fit state not created");
+    Fit& f = ctx->fit;
+    f.akf = (fuse_ann && f.A * f.K <= VB_FUSE_ANN_MAX && f.A <= 4) ? f.A * f.K : 0;
     return 0;
 }
 extern "C" int vb_fit_destroy(vb_ctx* ctx) {
@@ -853,14 +900,15 @@ extern "C" int vb_fit_get_params(vb_ctx* ctx, double* mu, double* delta_mk) {
 template <int MODE>
 static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
     cudaStream_t st = ctx->stream;
+    const size_t sm = a.fuse_ann ? (size_t)a.A * a.K * (VB_SNP_THREADS / 32) * sizeof(double) : 0;
     prof_begin(ctx, 1);
     switch (P) {
-        case 1: vb_snp_kernel<1, MODE><<<grid, 128, 0, st>>>(a); break;
-        case 2: vb_snp_kernel<2, MODE><<<grid, 128, 0, st>>>(a); break;
-        case 3: vb_snp_kernel<3, MODE><<<grid, 128, 0, st>>>(a); break;
-        case 4: vb_snp_kernel<4, MODE><<<grid, 128, 0, st>>>(a); break;
-        case 5: vb_snp_kernel<5, MODE><<<grid, 128, 0, st>>>(a); break;
-        case 6: vb_snp_kernel<6, MODE><<<grid, 128, 0, st>>>(a); break;
+        case 1: vb_snp_kernel<1, MODE><<<grid, VB_SNP_THREADS, sm, st>>>(a); break;
+        case 2: vb_snp_kernel<2, MODE><<<grid, VB_SNP_THREADS, sm, st>>>(a); break;
+        case 3: vb_snp_kernel<3, MODE><<<grid, VB_SNP_THREADS, sm, st>>>(a); break;
+        case 4: vb_snp_kernel<4, MODE><<<grid, VB_SNP_THREADS, sm, st>>>(a); break;
+        case 5: vb_snp_kernel<5, MODE><<<grid, VB_SNP_THREADS, sm, st>>>(a); break;
+        case 6: vb_snp_kernel<6, MODE><<<grid, VB_SNP_THREADS, sm, st>>>(a); break;
         default: return vb_fail("unsupported cohort count %d", P);
     }
     prof_end(ctx, 1);
@@ -875,6 +923,8 @@ static void base_args(const Fit& f, VbSnpArgs& a) {
     a.prec = f.prec; a.logdet = f.logdet; a.logh = f.logh; a.gfull = f.gfull;
     for (int p = 0; p < VB_MAXP; ++p) a.inv_tau[p] = f.inv_tau[p];
     a.partial = f.part_snp;
+    a.fuse_ann = f.akf > 0;
+    a.nsp = f.nsp;
 }
 // route z = pm/se of every cohort into its LD operator's block-order input
 static void route_z(const vb_ctx* ctx, VbSnpArgs& a) {
@@ -898,6 +948,8 @@ static int finish_eval(vb_ctx* ctx, int v, double* stats_dev) {
     fa.n_part_snp = f.grid_snp;
     fa.n_part_fin = f.grid_fin;
     fa.P = f.P;
+    fa.nsp = f.nsp;
+    fa.akf = f.akf;
     for (int p = 0; p < f.P; ++p) {
         LdPop& L = ctx->fit_ld[p]->L;
         fa.do_final = (p == f.P - 1);
@@ -985,6 +1037,7 @@ extern "C" int vb_fit_posterior(vb_ctx* ctx, double* pm_host, double* pv_host) {
     a.delta_in = f.delta[f.cur_delta];
     a.pm_out = f.scratch3;
     a.pv_out = f.scratch3 + 2 * PM;
+    a.fuse_ann = 0;
     if (launch_snp<VB_MODE_EVAL>(ctx, a, f.P, f.grid_snp)) return 1;
     if (pm_host) CK(cudaMemcpyAsync(pm_host, f.scratch3, PM * 8, cudaMemcpyDeviceToHost, ctx->stream));
     if (pv_host) CK(cudaMemcpyAsync(pv_host, f.scratch3 + 2 * PM, PM * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -996,7 +1049,8 @@ extern "C" int vb_fit_pm_diff(vb_ctx* ctx, double atol, double rtol, double* out
     NEED_FIT(ctx);
     const int64_t n = (int64_t)f.P * f.M;
     vb_pm_diff_kernel<<<f.grid_diff, 256, 0, ctx->stream>>>(f.pm[f.cur_vec], f.scal, f.pm_prev,
-                                                            f.pm_ckpt, n, atol, rtol, f.part_diff);
+                                                            f.pm_ckpt, f.pm_prev, n, atol, rtol,
+                                                            f.part_diff);
     CK_LAUNCH(ctx);
     vb_pm_diff_final_kernel<<<1, 256, 0, ctx->stream>>>(f.part_diff, f.grid_diff, out_dev);
     CK_LAUNCH(ctx);
@@ -1142,14 +1196,14 @@ extern "C" int vb_fit_set_constants(vb_ctx* ctx, const double* chi_stat, const d
     nl->counts.assign(annotation_counts, annotation_counts + f.A);
     nl->logdet.assign(log_det, log_det + f.K);
     nl->scale_se = scale_se;
-    const size_t need = std::max<size_t>(std::max<size_t>(3 * f.P + 3, (size_t)f.A * f.K), 16);
+    const size_t need = std::max<size_t>(3 * f.P + 3 + VB_FUSE_ANN_MAX + 10, (size_t)f.A * f.K) + 16;
     if (nl->pinned_len < need) {
         if (nl->pinned) cudaFreeHost(nl->pinned);
         CK(cudaHostAlloc(&nl->pinned, need * sizeof(double), cudaHostAllocDefault));
         nl->pinned_len = need;
     }
     cudaFree(nl->stats_dev); cudaFree(nl->ann_dev); cudaFree(nl->diff_dev);
-    CK(cudaMalloc(&nl->stats_dev, (3 * f.P + 3) * sizeof(double)));
+    CK(cudaMalloc(&nl->stats_dev, (3 * f.P + 3 + VB_FUSE_ANN_MAX + 10) * sizeof(double)));
     CK(cudaMalloc(&nl->ann_dev, (size_t)f.A * f.K * sizeof(double)));
     CK(cudaMalloc(&nl->diff_dev, 16 * sizeof(double)));
     nl->ready = true;
@@ -1157,14 +1211,15 @@ extern "C" int vb_fit_set_constants(vb_ctx* ctx, const double* chi_stat, const d
 }
 
 // device vector -> (all-reduced) host values
-static int reduce_to_host(vb_ctx* ctx, NativeLoop* nl, double* dev, int n, double* out) {
+// n values are summed over ranks; `tail` further values are copied rank-local (maxima, logging only)
+static int reduce_to_host(vb_ctx* ctx, NativeLoop* nl, double* dev, int n, double* out, int tail = 0) {
     if (nl->comm) {
         int rc = g_nccl.AllReduce(dev, dev, (size_t)n, kNcclDouble, kNcclSum, nl->comm, ctx->stream);
         if (rc) return vb_fail("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     }
-    CK(cudaMemcpyAsync(nl->pinned, dev, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(nl->pinned, dev, (n + tail) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    std::memcpy(out, nl->pinned, n * sizeof(double));
+    std::memcpy(out, nl->pinned, (n + tail) * sizeof(double));
     return 0;
 }
 
@@ -1179,13 +1234,26 @@ static double objective_of(const NativeLoop* nl, int P, const double* s, const d
 static inline bool close_to_zero(double a, double atol) { return std::fabs(a) <= atol; }     // np.isclose(a, 0, atol, rtol=0)
 static inline bool np_isclose(double a, double b) { return std::fabs(a - b) <= 1e-8 + 1e-5 * std::fabs(b); }
 
+// delta refresh + evaluation of the resulting state; the convergence bookkeeping of the new state
+// (against prev / ckpt, written to pm_next) is queued behind it so that ONE all-reduce + copy +
+// synchronisation returns everything.  stats: [3P+3 | akf annotation sums | 10 diff statistics]
 static int native_refresh(vb_ctx* ctx, NativeLoop* nl, Fit& f, double* stats, const double* tau,
                           double* obj, vb_step_io* io) {
     if (vb_fit_refresh_delta(ctx, nl->stats_dev)) return 1;
-    if (reduce_to_host(ctx, nl, nl->stats_dev, 3 * f.P + 3, stats)) return 1;
+    const int nbase = 3 * f.P + 3 + f.akf;
+    const int64_t n = (int64_t)f.P * f.M;
+    // the trial slot holds the refreshed state's posterior mean
+    vb_pm_diff_kernel<<<f.grid_diff, 256, 0, ctx->stream>>>(f.pm[1 - f.cur_vec], f.scal, f.pm_prev,
+                                                            f.pm_ckpt, f.pm_next, n, io->atol, io->rtol,
+                                                            f.part_diff);
+    CK_LAUNCH(ctx);
+    vb_pm_diff_final_kernel<<<1, 256, 0, ctx->stream>>>(f.part_diff, f.grid_diff, nl->stats_dev + nbase);
+    CK_LAUNCH(ctx);
+    if (reduce_to_host(ctx, nl, nl->stats_dev, nbase + 5, stats, 5)) return 1;
     io->evals++;
     if (vb_fit_accept(ctx)) return 1;
     *obj = objective_of(nl, f.P, stats, tau);
+    std::memcpy(io->diff, stats + nbase, 10 * sizeof(double));
     return 0;
 }
 
@@ -1195,13 +1263,15 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
     NEED_FIT(ctx);
     NativeLoop* nl = loop_of(ctx, false);
     if (!nl || !nl->ready) return vb_fail("vb_fit_iteration: call vb_fit_set_constants first");
-    const int P = f.P, K = f.K, A = f.A, NS = 3 * P + 3;
+    const int P = f.P, K = f.K, A = f.A, NS = 3 * P + 3, NSX = NS + f.akf + 10;
     const double conv_tol = io->has_running ? 0.1 * io->running_elbo_delta : INFINITY;
     double new_elbo_delta = 0.0;
     double obj = io->obj;
     io->trials = 0;
     io->evals = 0;
-    std::vector<double> stats(stats_io, stats_io + NS), trial(NS);
+    std::vector<double> stats(NSX, 0.0), trial(NSX, 0.0);
+    std::memcpy(stats.data(), stats_io, NS * sizeof(double));
+    bool ann_valid = false;          // stats[NS..NS+akf) hold the accepted state's annotation sums
     double* L = io->L;
 
     // ---- idx 0: beta (natural-gradient step with backtracking on 1/L)
@@ -1216,7 +1286,7 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
             while (true) {
                 const double step = 1.0 / L[0];
                 if (vb_fit_beta_trial(ctx, step, nl->stats_dev)) return 1;
-                if (reduce_to_host(ctx, nl, nl->stats_dev, NS, trial.data())) return 1;
+                if (reduce_to_host(ctx, nl, nl->stats_dev, NS + f.akf, trial.data())) return 1;
                 io->trials++;
                 io->evals++;
                 new_obj = objective_of(nl, P, trial.data(), tau_io);
@@ -1235,6 +1305,7 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
             if (accepted) {
                 if (vb_fit_accept(ctx)) return 1;
                 stats = trial;
+                ann_valid = f.akf > 0;
                 obj = new_obj;
             } else if (bail) {
                 new_obj = orig_obj;
@@ -1249,9 +1320,14 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
         for (int it = 0; it < VB_MAX_NUM_ITERS; ++it) {
             L[1] = std::max(1.0, L[1] / 1.25);
             const double orig_obj = obj;
-            if (vb_fit_sum_annotations(ctx, nl->ann_dev)) return 1;
             std::vector<double> sums((size_t)A * K);
-            if (reduce_to_host(ctx, nl, nl->ann_dev, A * K, sums.data())) return 1;
+            if (ann_valid) {
+                // rode along with the evaluation of the accepted state (index a*K + k)
+                std::memcpy(sums.data(), stats.data() + NS, (size_t)A * K * sizeof(double));
+            } else {
+                if (vb_fit_sum_annotations(ctx, nl->ann_dev)) return 1;
+                if (reduce_to_host(ctx, nl, nl->ann_dev, A * K, sums.data())) return 1;
+            }
             std::vector<double> g((size_t)A * std::max(K - 1, 1));
             for (int a = 0; a < A; ++a) {
                 double tot = 0.0;
@@ -1271,6 +1347,7 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
             if (K > 1 && vb_fit_set_delta_grad(ctx, g.data())) return 1;
             double new_obj;
             if (native_refresh(ctx, nl, f, stats.data(), tau_io, &new_obj, io)) return 1;
+            ann_valid = f.akf > 0;
             obj = new_obj;
             new_elbo_delta += new_obj - orig_obj;
             if (close_to_zero(new_obj - orig_obj, conv_tol) || L[1] == 1.0 || L[1] > VB_L_MAX) break;
@@ -1294,11 +1371,8 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
     io->elbo_delta = new_elbo_delta;
     std::memcpy(stats_io, stats.data(), NS * sizeof(double));
 
-    if (io->do_diff) {
-        if (vb_fit_pm_diff(ctx, io->atol, io->rtol, nl->diff_dev)) return 1;
-        // sums are all-reduced; the five maxima stay rank-local (they are only logged)
-        if (reduce_to_host(ctx, nl, nl->diff_dev, 5, io->diff)) return 1;
-        CK(cudaMemcpy(io->diff + 5, nl->diff_dev + 5, 5 * sizeof(double), cudaMemcpyDeviceToHost));
-    }
+    // the last refresh of the iteration compared the new posterior mean with prev / ckpt and wrote
+    // it to pm_next: it becomes prev now
+    std::swap(f.pm_prev, f.pm_next);
     return 0;
 }

@@ -191,7 +191,7 @@ class CudaEngine:
         prec, ld = f64(mixture_prec).reshape(K, P, P), f64(log_det)
         _lib.check(self.lib.vb_fit_set_mixture(ctx.handle, _lib.np_ptr(prec), _lib.np_ptr(ld)))
         dev = torch.device('cuda', ctx.device)
-        self.n_stats = 3 * P + 3
+        self.n_stats = 3 * P + 3 + 48 + 10     # + fused annotation sums and convergence slots
         self._stats = torch.zeros(self.n_stats, dtype=torch.float64, device=dev)
         self._ann = torch.zeros(A * K, dtype=torch.float64, device=dev)
         self._diff = torch.zeros(self.N_DIFF, dtype=torch.float64, device=dev)
@@ -289,6 +289,8 @@ class CudaEngine:
             _lib.check(self.lib.vb_nccl_unique_id(buf))
         ident = comm.broadcast_bytes(buf.raw)
         _lib.check(self.lib.vb_comm_init(self.ctx.handle, comm.world, comm.rank, ident))
+        # with several ranks every reduction is a rendezvous: let the annotation sums ride along
+        _lib.check(self.lib.vb_fit_set_fusion(self.ctx.handle, 1))
 
     def iteration(self, io, tau, hyper, stats):
         """vb_fit_iteration: `io` is a _lib.StepIO; tau/hyper/stats are float64 arrays updated in place."""
