@@ -388,6 +388,8 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
     L.nslab2 = ns2;
     int dummy1 = 1, dummy2 = 1;
     L.bytes = 0;
+    // groups of ~0.5 MB: smaller groups for small (multi-GPU) shards were measured slower (flush cost)
+    const size_t group_bytes_base = VB_SYM_GROUP_BYTES;
     std::vector<VbSymItem> sitems;
     std::vector<VbSymGroup> sgroups;
     std::vector<size_t> sgroup_bytes;
@@ -407,7 +409,7 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
             int64_t grow0 = 0;
             // at most ~12 byte-limited groups per block: the finish kernel walks a block's groups
             const size_t block_bytes = (size_t)4 * n * (n + 1);
-            const size_t group_target = std::max<size_t>(VB_SYM_GROUP_BYTES, block_bytes / VB_SYM_MAX_GROUPS);
+            const size_t group_target = std::max<size_t>(group_bytes_base, block_bytes / VB_SYM_MAX_GROUPS);
             VbSymGroup cur;
             cur.first_item = (uint32_t)sitems.size();
             cur.n_items = 0;
