@@ -160,6 +160,14 @@ typedef struct vb_step_io {
     int32_t do_diff;           /* in: run the convergence bookkeeping */
 } vb_step_io;
 int vb_nccl_unique_id(char* out128);
+/* optional faster rendezvous for one node: every rank creates a mailbox (vb_xr_create returns its
+ * 64-byte CUDA IPC handle), the handles are exchanged by the caller and opened with vb_xr_open
+ * (nranks x 64 bytes, rank order).  The last CTA of every evaluation then sums the statistics over
+ * the ranks through NVLink peer stores and publishes them to mapped pinned memory the host polls:
+ * no NCCL launch, copy or stream synchronisation per evaluation.  With nranks == 1 it just replaces
+ * the copy + synchronisation by the polled flag. */
+int vb_xr_create(vb_ctx* ctx, char* handle_out64);
+int vb_xr_open(vb_ctx* ctx, int nranks, int rank, const char* handles);
 int vb_comm_init(vb_ctx* ctx, int nranks, int rank, const char* id128);
 int vb_fit_set_constants(vb_ctx* ctx, const double* chi_stat_host, const double* ld_ranks_host,
                          const double* annotation_counts_host, const double* log_det_host,

@@ -63,6 +63,8 @@ class StepIO(C.Structure):
 SIGNATURES.update({
     'vb_nccl_unique_id': (C.c_int, [C.c_char_p]),
     'vb_comm_init': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
+    'vb_xr_create': (C.c_int, [C.c_void_p, C.c_char_p]),
+    'vb_xr_open': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     'vb_fit_set_constants': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     'vb_fit_iteration': (C.c_int, [C.c_void_p, C.POINTER(StepIO), C.c_void_p, C.c_void_p, C.c_void_p]),
 })

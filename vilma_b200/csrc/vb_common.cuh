@@ -110,6 +110,83 @@ __device__ __forceinline__ double vb_block_max(double v, double* scratch) {
 //   stats[0..P)   A_p = sum_i pm adj          stats[P..2P)  C_p = sum_i sld pv
 //   stats[2P..3P) B_p = sum_i z (R z)         stats[3P..3P+3) KL_delta, KL_quad, KL_sigma
 // It runs in the last block of the last cohort's mat-vec finish kernel (no extra launch).
+#define VB_XR_MAXRANKS 8
+#define VB_XR_MAXVALS 64
+// Cross-rank exchange fused into the last CTA of an evaluation (one rank per GPU, one node):
+// every rank stores its statistics vector into every peer's mailbox over NVLink (peer memory mapped
+// with CUDA IPC), raises a per-sender flag carrying the evaluation's epoch, waits for the peers'
+// flags, adds the nranks vectors in rank order (identical bits on every rank) and publishes the
+// result to host-mapped pinned memory, where the host polls a flag: no NCCL launch, no copy, no
+// stream synchronisation on the critical path.  Two mailbox slots (epoch parity) make it safe for a
+// rank to run one evaluation ahead of a peer that is still reading.
+struct VbXrank {
+    double* peer_box[VB_XR_MAXRANKS];      // peer r's mailbox base: [2 slots][MAXRANKS][MAXVALS]
+    uint32_t* peer_flag[VB_XR_MAXRANKS];   // peer r's flags:        [2 slots][MAXRANKS]
+    double* host_out;                      // host-mapped: [MAXVALS] result
+    uint32_t* host_flag;                   // host-mapped: epoch of the last published result
+    uint32_t* dev_err;                     // device: set to 1 if a peer never showed up
+    uint32_t epoch;
+    int nranks, rank;
+    int n_sum, n_max;                      // first n_sum entries are summed, the next n_max are max-ed
+    int enabled;
+};
+__device__ __forceinline__ unsigned long long vb_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// All threads of the last block call this after the local statistics are in stats[0 .. n_sum+n_max).
+__device__ __forceinline__ void vb_xrank_exchange(const VbXrank& xr, double* stats) {
+    const int n = xr.n_sum + xr.n_max;
+    const int slot = xr.epoch & 1;
+    __syncthreads();
+    if (xr.nranks > 1) {
+        // 1. my vector -> every rank's mailbox (own included, so the summation order is uniform)
+        for (int idx = threadIdx.x; idx < n * xr.nranks; idx += blockDim.x) {
+            const int r = idx / n, t = idx % n;
+            xr.peer_box[r][((size_t)slot * VB_XR_MAXRANKS + xr.rank) * VB_XR_MAXVALS + t] = __ldcg(&stats[t]);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < xr.nranks) {
+            volatile uint32_t* fl = xr.peer_flag[threadIdx.x] + slot * VB_XR_MAXRANKS + xr.rank;
+            *fl = xr.epoch;
+        }
+        // 2. wait for every sender's flag in my own mailbox (bounded: ~20 s, then flag an error)
+        if (threadIdx.x < xr.nranks) {
+            volatile uint32_t* fl = xr.peer_flag[xr.rank] + slot * VB_XR_MAXRANKS + threadIdx.x;
+            const unsigned long long t0 = vb_globaltimer();
+            while (*fl != xr.epoch) {
+                if (vb_globaltimer() - t0 > 20000000000ull) {
+                    *xr.dev_err = 1;
+                    break;
+                }
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        // 3. combine in rank order
+        if (threadIdx.x < n) {
+            const volatile double* box = xr.peer_box[xr.rank] + (size_t)slot * VB_XR_MAXRANKS * VB_XR_MAXVALS;
+            double v = box[threadIdx.x];
+            for (int r = 1; r < xr.nranks; ++r) {
+                const double w = box[(size_t)r * VB_XR_MAXVALS + threadIdx.x];
+                v = threadIdx.x < xr.n_sum ? v + w : fmax(v, w);
+            }
+            stats[threadIdx.x] = v;
+            xr.host_out[threadIdx.x] = v;
+        }
+    } else if (threadIdx.x < n) {
+        xr.host_out[threadIdx.x] = __ldcg(&stats[threadIdx.x]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile uint32_t* hf = xr.host_flag;
+        *hf = (xr.nranks > 1 && *xr.dev_err) ? 0xffffffffu : xr.epoch;
+    }
+}
+
 struct VbFinalArgs {
     const double* part_snp;   // [2P+3 (+akf)][n_part_snp] from the per-SNP kernel (stat-major)
     const double* part_fin;   // [P][n_part_fin]    sum z (R z) partials of every cohort
@@ -119,6 +196,9 @@ struct VbFinalArgs {
     int do_final;             // only the last cohort's finish launch reduces
     int nsp;                  // row stride of part_snp
     int akf;                  // fused annotation sums per row (0: none) -> stats[3P+3 .. 3P+3+akf)
+    const double* part_diff;  // [n_part_diff][10] convergence partials, or null -> stats[3P+3+akf .. +10)
+    int n_part_diff;
+    VbXrank xr;
 };
 // Called by every thread of the LAST block (fixed summation order => deterministic).
 __device__ __forceinline__ void vb_final_reduce(const VbFinalArgs& fa, double* scratch) {
@@ -142,6 +222,21 @@ __device__ __forceinline__ void vb_final_reduce(const VbFinalArgs& fa, double* s
         acc = vb_block_sum(acc, scratch);
         if (threadIdx.x == 0) fa.stats[2 * P + p] = acc;
     }
+    if (fa.part_diff) {
+        // 5 sums then 5 maxima (vb_pm_diff_kernel partial rows)
+        for (int s = 0; s < 10; ++s) {
+            double acc = 0.0;
+            if (s < 5) {
+                for (int b = threadIdx.x; b < fa.n_part_diff; b += blockDim.x) acc += __ldcg(&fa.part_diff[(size_t)b * 10 + s]);
+                acc = vb_block_sum(acc, scratch);
+            } else {
+                for (int b = threadIdx.x; b < fa.n_part_diff; b += blockDim.x) acc = fmax(acc, __ldcg(&fa.part_diff[(size_t)b * 10 + s]));
+                acc = vb_block_max(acc, scratch);
+            }
+            if (threadIdx.x == 0) fa.stats[3 * P + 3 + fa.akf + s] = acc;
+        }
+    }
+    if (fa.xr.enabled) vb_xrank_exchange(fa.xr, fa.stats);
 }
 // Block epilogue shared by the finish kernels: publish this block's partial, elect the last block.
 __device__ __forceinline__ void vb_finish_epilogue(double acc, double* partial, const VbFinalArgs& fa,

@@ -159,6 +159,86 @@ struct vb_ld {
     LdPop L;
 };
 
+#include <dlfcn.h>
+#include <atomic>
+#include <chrono>
+
+#define VB_L_MAX 1e12
+#define VB_REL_TOL 1e-6
+#define VB_ABS_TOL 1e-6
+#define VB_EM_TOL 10.0
+#define VB_MAX_NUM_ITERS 20
+
+namespace {
+typedef struct { char internal[128]; } vbNcclUniqueId;
+typedef void* vbNcclComm;
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(vbNcclUniqueId*) = nullptr;
+    int (*CommInitRank)(vbNcclComm*, int, vbNcclUniqueId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, vbNcclComm, cudaStream_t) = nullptr;
+    int (*CommDestroy)(vbNcclComm) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+const int kNcclDouble = 8, kNcclSum = 0, kNcclMax = 2;   // ncclFloat64 / ncclSum / ncclMax
+
+int load_nccl() {
+    if (g_nccl.handle) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) return vb_fail("NCCL not found (dlopen libnccl.so.2): %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(vbNcclUniqueId*))dlsym(g_nccl.handle, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(vbNcclComm*, int, vbNcclUniqueId, int))dlsym(g_nccl.handle, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, vbNcclComm, cudaStream_t))dlsym(g_nccl.handle, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(vbNcclComm))dlsym(g_nccl.handle, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.handle, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce)
+        return vb_fail("NCCL symbols missing in the loaded libnccl");
+    return 0;
+}
+}  // namespace
+
+struct NativeLoop {
+    bool ready = false;
+    std::vector<double> chi, ranks, counts, logdet, tau, hyper;
+    int scale_se = 0;
+    double* pinned = nullptr;     // host staging
+    size_t pinned_len = 0;
+    double *stats_dev = nullptr, *ann_dev = nullptr, *diff_dev = nullptr;
+    vbNcclComm comm = nullptr;
+    int nranks = 1;
+    // cross-rank mailbox exchange (vb_common.cuh VbXrank)
+    bool xr_ready = false;        // mailboxes exchanged (or single rank): host-flag signalling usable
+    bool xr_active = false;       // set by vb_fit_iteration while it drives the evaluations
+    bool want_diff = false;       // next evaluation also reduces the convergence partials
+    double diff_atol = 0.0, diff_rtol = 0.0;
+    int xr_nranks = 1, xr_rank = 0;
+    unsigned char* xr_box = nullptr;                 // my mailbox (device): data + flags
+    double* xr_peer_box[VB_XR_MAXRANKS] = {nullptr};
+    uint32_t* xr_peer_flag[VB_XR_MAXRANKS] = {nullptr};
+    double *xr_host_out = nullptr, *xr_host_out_dev = nullptr;
+    uint32_t *xr_host_flag = nullptr, *xr_host_flag_dev = nullptr;
+    uint32_t* xr_dev_err = nullptr;
+    uint32_t epoch = 0;
+};
+#define VB_XR_DATA_BYTES (2 * VB_XR_MAXRANKS * VB_XR_MAXVALS * sizeof(double))
+#define VB_XR_BOX_BYTES (VB_XR_DATA_BYTES + 2 * VB_XR_MAXRANKS * sizeof(uint32_t) + 64)
+static std::vector<std::pair<vb_ctx*, NativeLoop*>> g_loops;
+static NativeLoop* loop_of(vb_ctx* ctx, bool create) {
+    for (auto& pr : g_loops)
+        if (pr.first == ctx) return pr.second;
+    if (!create) return nullptr;
+    NativeLoop* nl = new NativeLoop();
+    g_loops.emplace_back(ctx, nl);
+    return nl;
+}
+
+
+
 // ------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------
@@ -229,6 +309,20 @@ extern "C" int vb_ctx_destroy(vb_ctx* ctx) {
     free_fit(ctx->fit);
     for (int cat = 0; cat < 2; ++cat)
         for (auto& e : ctx->ev[cat]) cudaEventDestroy(e);
+    for (size_t i = 0; i < g_loops.size(); ++i) {
+        if (g_loops[i].first != ctx) continue;
+        NativeLoop* nl = g_loops[i].second;
+        if (nl->pinned) cudaFreeHost(nl->pinned);
+        cudaFree(nl->stats_dev); cudaFree(nl->ann_dev); cudaFree(nl->diff_dev);
+        for (int r = 0; r < nl->xr_nranks; ++r)
+            if (nl->xr_ready && r != nl->xr_rank && nl->xr_peer_box[r]) cudaIpcCloseMemHandle(nl->xr_peer_box[r]);
+        cudaFree(nl->xr_box);
+        if (nl->xr_host_out) cudaFreeHost(nl->xr_host_out);
+        if (nl->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(nl->comm);
+        delete nl;
+        g_loops.erase(g_loops.begin() + i);
+        break;
+    }
     delete ctx;
     return 0;
 }
@@ -692,6 +786,7 @@ static int ld_apply(vb_ctx* ctx, LdPop& L, const double* x_snp, double* y_snp, d
     std::memset(&fa, 0, sizeof(fa));
     if (final_args) fa = *final_args;
     fa.counter = L.fin_counter;
+    if (!fa.do_final) fa.xr.enabled = 0;
     if (L.nreal > 0 && x_snp) {
         const int g = (int)std::min<int64_t>((L.nreal + 255) / 256, 1184);
         vb_ld_gather_kernel<<<g, 256, 0, st>>>(x_snp, L.pos, L.snp, L.nreal, L.xall);
@@ -942,6 +1037,7 @@ static void route_z(const vb_ctx* ctx, VbSnpArgs& a) {
 // the fixed-order final reduction into stats_dev.
 static int finish_eval(vb_ctx* ctx, int v, double* stats_dev) {
     Fit& f = ctx->fit;
+    NativeLoop* nl = loop_of(ctx, false);
     VbFinalArgs fa;
     std::memset(&fa, 0, sizeof(fa));
     fa.part_snp = f.part_snp;
@@ -952,6 +1048,33 @@ static int finish_eval(vb_ctx* ctx, int v, double* stats_dev) {
     fa.P = f.P;
     fa.nsp = f.nsp;
     fa.akf = f.akf;
+    const bool native = nl && nl->xr_active;
+    if (native && nl->want_diff) {
+        // convergence partials of the state being evaluated, reduced together with everything else
+        const int64_t n = (int64_t)f.P * f.M;
+        vb_pm_diff_kernel<<<f.grid_diff, 256, 0, ctx->stream>>>(f.pm[v], f.scal, f.pm_prev, f.pm_ckpt,
+                                                                f.pm_next, n, nl->diff_atol,
+                                                                nl->diff_rtol, f.part_diff);
+        CK_LAUNCH(ctx);
+        fa.part_diff = f.part_diff;
+        fa.n_part_diff = f.grid_diff;
+    }
+    if (native && nl->xr_ready) {
+        VbXrank& xr = fa.xr;
+        xr.enabled = 1;
+        xr.nranks = nl->xr_nranks;
+        xr.rank = nl->xr_rank;
+        xr.epoch = nl->epoch;
+        for (int r = 0; r < nl->xr_nranks; ++r) {
+            xr.peer_box[r] = nl->xr_peer_box[r];
+            xr.peer_flag[r] = nl->xr_peer_flag[r];
+        }
+        xr.host_out = nl->xr_host_out_dev;
+        xr.host_flag = nl->xr_host_flag_dev;
+        xr.dev_err = nl->xr_dev_err;
+        xr.n_sum = 3 * f.P + 3 + f.akf + (fa.part_diff ? 5 : 0);
+        xr.n_max = fa.part_diff ? 5 : 0;
+    }
     for (int p = 0; p < f.P; ++p) {
         LdPop& L = ctx->fit_ld[p]->L;
         fa.do_final = (p == f.P - 1);
@@ -1104,67 +1227,6 @@ extern "C" int vb_fit_vi_sigma(vb_ctx* ctx, int k0, int k1, double* out_host) {
 // Multi-GPU: statistics are summed with ncclAllReduce on the context's stream (NCCL is resolved
 // at run time from the libnccl already loaded in the process).
 // ====================================================================================
-#include <dlfcn.h>
-
-#define VB_L_MAX 1e12
-#define VB_REL_TOL 1e-6
-#define VB_ABS_TOL 1e-6
-#define VB_EM_TOL 10.0
-#define VB_MAX_NUM_ITERS 20
-
-namespace {
-typedef struct { char internal[128]; } vbNcclUniqueId;
-typedef void* vbNcclComm;
-struct NcclApi {
-    void* handle = nullptr;
-    int (*GetUniqueId)(vbNcclUniqueId*) = nullptr;
-    int (*CommInitRank)(vbNcclComm*, int, vbNcclUniqueId, int) = nullptr;
-    int (*AllReduce)(const void*, void*, size_t, int, int, vbNcclComm, cudaStream_t) = nullptr;
-    int (*CommDestroy)(vbNcclComm) = nullptr;
-    const char* (*GetErrorString)(int) = nullptr;
-};
-NcclApi g_nccl;
-const int kNcclDouble = 8, kNcclSum = 0, kNcclMax = 2;   // ncclFloat64 / ncclSum / ncclMax
-
-int load_nccl() {
-    if (g_nccl.handle) return 0;
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* nm : names) {
-        g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
-        if (g_nccl.handle) break;
-    }
-    if (!g_nccl.handle) return vb_fail("NCCL not found (dlopen libnccl.so.2): %s", dlerror());
-    g_nccl.GetUniqueId = (int (*)(vbNcclUniqueId*))dlsym(g_nccl.handle, "ncclGetUniqueId");
-    g_nccl.CommInitRank = (int (*)(vbNcclComm*, int, vbNcclUniqueId, int))dlsym(g_nccl.handle, "ncclCommInitRank");
-    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, vbNcclComm, cudaStream_t))dlsym(g_nccl.handle, "ncclAllReduce");
-    g_nccl.CommDestroy = (int (*)(vbNcclComm))dlsym(g_nccl.handle, "ncclCommDestroy");
-    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.handle, "ncclGetErrorString");
-    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce)
-        return vb_fail("NCCL symbols missing in the loaded libnccl");
-    return 0;
-}
-}  // namespace
-
-struct NativeLoop {
-    bool ready = false;
-    std::vector<double> chi, ranks, counts, logdet, tau, hyper;
-    int scale_se = 0;
-    double* pinned = nullptr;     // host staging
-    size_t pinned_len = 0;
-    double *stats_dev = nullptr, *ann_dev = nullptr, *diff_dev = nullptr;
-    vbNcclComm comm = nullptr;
-    int nranks = 1;
-};
-static std::vector<std::pair<vb_ctx*, NativeLoop*>> g_loops;
-static NativeLoop* loop_of(vb_ctx* ctx, bool create) {
-    for (auto& pr : g_loops)
-        if (pr.first == ctx) return pr.second;
-    if (!create) return nullptr;
-    NativeLoop* nl = new NativeLoop();
-    g_loops.emplace_back(ctx, nl);
-    return nl;
-}
-
 extern "C" int vb_nccl_unique_id(char* out128) {
     if (load_nccl()) return 1;
     vbNcclUniqueId id;
@@ -1185,6 +1247,70 @@ extern "C" int vb_comm_init(vb_ctx* ctx, int nranks, int rank, const char* id128
     int rc = g_nccl.CommInitRank(&nl->comm, nranks, id, rank);
     if (rc) return vb_fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
     nl->nranks = nranks;
+    return 0;
+}
+
+// Allocate this rank's mailbox and return its CUDA IPC handle (64 bytes).
+extern "C" int vb_xr_create(vb_ctx* ctx, char* handle_out64) {
+    if (!ctx) return vb_fail("null ctx");
+    CK(cudaSetDevice(ctx->device));
+    NativeLoop* nl = loop_of(ctx, true);
+    if (!nl->xr_box) {
+        CK(cudaMalloc(&nl->xr_box, VB_XR_BOX_BYTES + sizeof(uint32_t) * 16));
+        CK(cudaMemset(nl->xr_box, 0, VB_XR_BOX_BYTES + sizeof(uint32_t) * 16));
+        nl->xr_dev_err = reinterpret_cast<uint32_t*>(nl->xr_box + VB_XR_BOX_BYTES);
+        CK(cudaHostAlloc(&nl->xr_host_out, VB_XR_MAXVALS * sizeof(double) + 64, cudaHostAllocMapped));
+        std::memset(nl->xr_host_out, 0, VB_XR_MAXVALS * sizeof(double) + 64);
+        nl->xr_host_flag = reinterpret_cast<uint32_t*>(nl->xr_host_out + VB_XR_MAXVALS);
+        CK(cudaHostGetDevicePointer(&nl->xr_host_out_dev, nl->xr_host_out, 0));
+        nl->xr_host_flag_dev = reinterpret_cast<uint32_t*>(nl->xr_host_out_dev + VB_XR_MAXVALS);
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, nl->xr_box));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle_out64, &h, 64);
+    return 0;
+}
+// handles: nranks x 64 bytes, in rank order (every rank passes the same array).
+extern "C" int vb_xr_open(vb_ctx* ctx, int nranks, int rank, const char* handles) {
+    if (!ctx) return vb_fail("null ctx");
+    if (nranks < 1 || nranks > VB_XR_MAXRANKS || rank < 0 || rank >= nranks)
+        return vb_fail("vb_xr_open: %d ranks unsupported (1..%d)", nranks, VB_XR_MAXRANKS);
+    CK(cudaSetDevice(ctx->device));
+    NativeLoop* nl = loop_of(ctx, true);
+    if (!nl->xr_box) return vb_fail("vb_xr_open: call vb_xr_create first");
+    for (int r = 0; r < nranks; ++r) {
+        void* base = nl->xr_box;
+        if (r != rank) {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, handles + (size_t)r * 64, 64);
+            CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        }
+        nl->xr_peer_box[r] = reinterpret_cast<double*>(base);
+        nl->xr_peer_flag[r] = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(base) + VB_XR_DATA_BYTES);
+    }
+    nl->xr_nranks = nranks;
+    nl->xr_rank = rank;
+    nl->xr_ready = true;
+    return 0;
+}
+// host side of the rendezvous: poll the mapped flag until the evaluation `epoch` has been published
+static int xr_wait(NativeLoop* nl, uint32_t epoch, double* out, int n) {
+    volatile uint32_t* hf = nl->xr_host_flag;
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (true) {
+        const uint32_t v = *hf;
+        if (v == epoch) break;
+        if (v == 0xffffffffu) return vb_fail("cross-rank exchange timed out waiting for a peer");
+        if ((++spins & 0xfffff) == 0) {
+            if (cudaPeekAtLastError() != cudaSuccess) return vb_fail("CUDA error while waiting: %s", cudaGetErrorString(cudaGetLastError()));
+            if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 60.0)
+                return vb_fail("timed out waiting for an evaluation to finish");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    std::memcpy(out, nl->xr_host_out, n * sizeof(double));
     return 0;
 }
 
@@ -1236,22 +1362,36 @@ static double objective_of(const NativeLoop* nl, int P, const double* s, const d
 static inline bool close_to_zero(double a, double atol) { return std::fabs(a) <= atol; }     // np.isclose(a, 0, atol, rtol=0)
 static inline bool np_isclose(double a, double b) { return std::fabs(a - b) <= 1e-8 + 1e-5 * std::fabs(b); }
 
-// delta refresh + evaluation of the resulting state; the convergence bookkeeping of the new state
-// (against prev / ckpt, written to pm_next) is queued behind it so that ONE all-reduce + copy +
-// synchronisation returns everything.  stats: [3P+3 | akf annotation sums | 10 diff statistics]
+// Bring the statistics of the evaluation just queued to the host (summed over ranks): through the
+// mailbox exchange fused into the evaluation's last CTA when available, else NCCL + copy + sync.
+static int fetch_stats(vb_ctx* ctx, NativeLoop* nl, int n_sum, int n_tail, double* out) {
+    if (nl->xr_ready) return xr_wait(nl, nl->epoch, out, n_sum + n_tail);
+    return reduce_to_host(ctx, nl, nl->stats_dev, n_sum, out, n_tail);
+}
+// delta refresh + evaluation of the resulting state, with the convergence bookkeeping of the new
+// state (against prev / ckpt, written to pm_next) reduced in the same rendezvous.
+// stats: [3P+3 | akf annotation sums | 10 diff statistics]
 static int native_refresh(vb_ctx* ctx, NativeLoop* nl, Fit& f, double* stats, const double* tau,
                           double* obj, vb_step_io* io) {
-    if (vb_fit_refresh_delta(ctx, nl->stats_dev)) return 1;
     const int nbase = 3 * f.P + 3 + f.akf;
-    const int64_t n = (int64_t)f.P * f.M;
-    // the trial slot holds the refreshed state's posterior mean
-    vb_pm_diff_kernel<<<f.grid_diff, 256, 0, ctx->stream>>>(f.pm[1 - f.cur_vec], f.scal, f.pm_prev,
-                                                            f.pm_ckpt, f.pm_next, n, io->atol, io->rtol,
-                                                            f.part_diff);
-    CK_LAUNCH(ctx);
-    vb_pm_diff_final_kernel<<<1, 256, 0, ctx->stream>>>(f.part_diff, f.grid_diff, nl->stats_dev + nbase);
-    CK_LAUNCH(ctx);
-    if (reduce_to_host(ctx, nl, nl->stats_dev, nbase + 5, stats, 5)) return 1;
+    nl->want_diff = nl->xr_ready;
+    nl->diff_atol = io->atol;
+    nl->diff_rtol = io->rtol;
+    nl->epoch++;
+    const int rc = vb_fit_refresh_delta(ctx, nl->stats_dev);
+    nl->want_diff = false;
+    if (rc) return 1;
+    if (!nl->xr_ready) {
+        // fallback: queue the convergence kernels behind the evaluation, then one NCCL rendezvous
+        const int64_t n = (int64_t)f.P * f.M;
+        vb_pm_diff_kernel<<<f.grid_diff, 256, 0, ctx->stream>>>(f.pm[1 - f.cur_vec], f.scal, f.pm_prev,
+                                                                f.pm_ckpt, f.pm_next, n, io->atol,
+                                                                io->rtol, f.part_diff);
+        CK_LAUNCH(ctx);
+        vb_pm_diff_final_kernel<<<1, 256, 0, ctx->stream>>>(f.part_diff, f.grid_diff, nl->stats_dev + nbase);
+        CK_LAUNCH(ctx);
+    }
+    if (fetch_stats(ctx, nl, nbase + 5, 5, stats)) return 1;
     io->evals++;
     if (vb_fit_accept(ctx)) return 1;
     *obj = objective_of(nl, f.P, stats, tau);
@@ -1273,6 +1413,11 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
     io->evals = 0;
     std::vector<double> stats(NSX, 0.0), trial(NSX, 0.0);
     std::memcpy(stats.data(), stats_io, NS * sizeof(double));
+    struct ActiveGuard {          // evaluations queued from here use the fused rendezvous
+        NativeLoop* n;
+        explicit ActiveGuard(NativeLoop* p) : n(p) { n->xr_active = true; }
+        ~ActiveGuard() { n->xr_active = false; }
+    } guard(nl);
     bool ann_valid = false;          // stats[NS..NS+akf) hold the accepted state's annotation sums
     double* L = io->L;
 
@@ -1287,8 +1432,9 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
             bool accepted = false, bail = false;
             while (true) {
                 const double step = 1.0 / L[0];
+                nl->epoch++;
                 if (vb_fit_beta_trial(ctx, step, nl->stats_dev)) return 1;
-                if (reduce_to_host(ctx, nl, nl->stats_dev, NS + f.akf, trial.data())) return 1;
+                if (fetch_stats(ctx, nl, NS + f.akf, 0, trial.data())) return 1;
                 io->trials++;
                 io->evals++;
                 new_obj = objective_of(nl, P, trial.data(), tau_io);

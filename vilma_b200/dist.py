@@ -28,6 +28,9 @@ class SingleComm:
     def broadcast_bytes(self, data):
         return data
 
+    def allgather_bytes(self, data):
+        return [data]
+
 
 def _to_numpy(t):
     if isinstance(t, np.ndarray):
@@ -101,6 +104,11 @@ class TorchComm(SingleComm):
         box = [data]
         self._dist.broadcast_object_list(box, src=0)
         return box[0]
+
+    def allgather_bytes(self, data):
+        out = [None] * self.world
+        self._dist.all_gather_object(out, data)
+        return out
 
 
 def default_comm():

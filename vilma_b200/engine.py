@@ -281,16 +281,22 @@ class CudaEngine:
         self.native_ready = True
 
     def init_comm(self, comm):
-        """Create the library's own NCCL communicator over the ranks of `comm` (TorchComm)."""
-        if comm.world <= 1:
-            return
-        buf = C.create_string_buffer(128)
-        if comm.rank == 0:
-            _lib.check(self.lib.vb_nccl_unique_id(buf))
-        ident = comm.broadcast_bytes(buf.raw)
-        _lib.check(self.lib.vb_comm_init(self.ctx.handle, comm.world, comm.rank, ident))
-        # with several ranks every reduction is a rendezvous: let the annotation sums ride along
-        _lib.check(self.lib.vb_fit_set_fusion(self.ctx.handle, 1))
+        """Rank plumbing of the native loop: the library's own NCCL communicator over the ranks of
+        `comm` plus (one node, <= 8 ranks) the NVLink mailbox rendezvous (vb_xr_*)."""
+        import os
+        if comm.world > 1:
+            buf = C.create_string_buffer(128)
+            if comm.rank == 0:
+                _lib.check(self.lib.vb_nccl_unique_id(buf))
+            ident = comm.broadcast_bytes(buf.raw)
+            _lib.check(self.lib.vb_comm_init(self.ctx.handle, comm.world, comm.rank, ident))
+            # with several ranks every reduction is a rendezvous: let the annotation sums ride along
+            _lib.check(self.lib.vb_fit_set_fusion(self.ctx.handle, 1))
+        if os.environ.get('VILMA_B200_NO_XRANK', '0') != '1' and comm.world <= 8:
+            h = C.create_string_buffer(64)
+            _lib.check(self.lib.vb_xr_create(self.ctx.handle, h))
+            handles = b''.join(comm.allgather_bytes(h.raw))
+            _lib.check(self.lib.vb_xr_open(self.ctx.handle, comm.world, comm.rank, handles))
 
     def iteration(self, io, tau, hyper, stats):
         """vb_fit_iteration: `io` is a _lib.StepIO; tau/hyper/stats are float64 arrays updated in place."""
