@@ -306,6 +306,9 @@ def run_ours(args):
     launches0 = ctx.launch_count()
     trials0 = vi.n_trials
     evals0 = vi.n_evals
+    import ctypes as C
+    tm0 = (C.c_double * 4)()
+    ctx.lib.vb_fit_timing(ctx.handle, tm0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     state = vi.run_loop(state, args.warmup + args.steps, fresh=True)
@@ -316,6 +319,10 @@ def run_ours(args):
     ms = float(comm.max(np.array([ms]))[0])
     clocks = sampler.stop() if comm.rank == 0 else {}
     prof = ctx.profile_read()
+    tm1 = (C.c_double * 4)()
+    ctx.lib.vb_fit_timing(ctx.handle, tm1)
+    log('[rank %d] native loop host time in region: enqueue %.3f ms, wait %.3f ms over %d rendezvous; region %.3f ms' % (
+        comm.rank, (tm1[0] - tm0[0]) * 1e3, (tm1[1] - tm0[1]) * 1e3, int(tm1[2] - tm0[2]), ms))
     ctx.profile(False)
     trials = vi.n_trials - trials0
     evals = vi.n_evals - evals0
@@ -327,6 +334,10 @@ def run_ours(args):
     mv_ms, mv_n = prof['ld_matvec']
     snp_ms, snp_n = prof['snp']
     mv_avg = mv_ms / max(mv_n, 1)
+    # per-rank kernel averages (rank skew: every evaluation ends in a rendezvous of all ranks)
+    per_rank = np.zeros((comm.world, 3))
+    per_rank[comm.rank] = [mv_avg, snp_ms / max(snp_n, 1), len(vi._snps)]
+    per_rank = comm.sum(per_rank) if comm.world > 1 else per_rank
     achieved = info['ld_bytes_rank'] / (mv_avg * 1e-3) / 1e9 if mv_n else 0.0
     traffic = None
     if comm.world == 1 and M == M_TOTAL:
@@ -387,6 +398,9 @@ def run_ours(args):
                      'launches_timed': int(mv_n),
                      'share_of_step': mv_ms / ms if ms else None,
                      'snp_kernel_avg_ms': snp_ms / max(snp_n, 1),
+                     'per_rank_ld_ms': [round(float(v), 4) for v in per_rank[:, 0]],
+                     'per_rank_snp_ms': [round(float(v), 4) for v in per_rank[:, 1]],
+                     'per_rank_snps': [int(v) for v in per_rank[:, 2]],
                      'whole_trial_frac': (bytes_trial / comm.world) * evals / (ms * 1e-3) / 1e9 / hbm_peak},
     }
     if comm.rank == 0 and comm.world == 1 and not args.no_cpu:

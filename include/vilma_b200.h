@@ -175,6 +175,9 @@ int vb_fit_set_constants(vb_ctx* ctx, const double* chi_stat_host, const double*
 /* tau_io [P], hyper_io [A][K], stats_io [3P+3] (statistics of the accepted state) are host in/out */
 int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, double* hyper_io,
                      double* stats_io);
+/* host-side time of the native loop so far: {s enqueueing evaluations, s waiting for their
+ * statistics, number of rendezvous, 0} */
+int vb_fit_timing(vb_ctx* ctx, double* out4);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,7 @@ SIGNATURES.update({
     'vb_xr_create': (C.c_int, [C.c_void_p, C.c_char_p]),
     'vb_xr_open': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p]),
     'vb_fit_set_constants': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    'vb_fit_timing': (C.c_int, [C.c_void_p, c_dp]),
     'vb_fit_iteration': (C.c_int, [C.c_void_p, C.POINTER(StepIO), C.c_void_p, C.c_void_p, C.c_void_p]),
 })
 

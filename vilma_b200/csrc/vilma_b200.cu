@@ -224,6 +224,9 @@ struct NativeLoop {
     uint32_t *xr_host_flag = nullptr, *xr_host_flag_dev = nullptr;
     uint32_t* xr_dev_err = nullptr;
     uint32_t epoch = 0;
+    // host-side timing of the native loop (seconds): enqueueing evaluations / waiting for results
+    double t_enqueue = 0.0, t_wait = 0.0;
+    int64_t n_wait = 0;
 };
 #define VB_XR_DATA_BYTES (2 * VB_XR_MAXRANKS * VB_XR_MAXVALS * sizeof(double))
 #define VB_XR_BOX_BYTES (VB_XR_DATA_BYTES + 2 * VB_XR_MAXRANKS * sizeof(uint32_t) + 64)
@@ -1365,8 +1368,19 @@ static inline bool np_isclose(double a, double b) { return std::fabs(a - b) <= 1
 // Bring the statistics of the evaluation just queued to the host (summed over ranks): through the
 // mailbox exchange fused into the evaluation's last CTA when available, else NCCL + copy + sync.
 static int fetch_stats(vb_ctx* ctx, NativeLoop* nl, int n_sum, int n_tail, double* out) {
-    if (nl->xr_ready) return xr_wait(nl, nl->epoch, out, n_sum + n_tail);
-    return reduce_to_host(ctx, nl, nl->stats_dev, n_sum, out, n_tail);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = nl->xr_ready ? xr_wait(nl, nl->epoch, out, n_sum + n_tail)
+                                : reduce_to_host(ctx, nl, nl->stats_dev, n_sum, out, n_tail);
+    nl->t_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    nl->n_wait++;
+    return rc;
+}
+// {seconds enqueueing, seconds waiting, rendezvous count, reserved} of the native loop so far
+extern "C" int vb_fit_timing(vb_ctx* ctx, double* out4) {
+    NativeLoop* nl = loop_of(ctx, false);
+    if (!nl) return vb_fail("no native loop state");
+    out4[0] = nl->t_enqueue; out4[1] = nl->t_wait; out4[2] = (double)nl->n_wait; out4[3] = 0.0;
+    return 0;
 }
 // delta refresh + evaluation of the resulting state, with the convergence bookkeeping of the new
 // state (against prev / ckpt, written to pm_next) reduced in the same rendezvous.
@@ -1378,7 +1392,9 @@ static int native_refresh(vb_ctx* ctx, NativeLoop* nl, Fit& f, double* stats, co
     nl->diff_atol = io->atol;
     nl->diff_rtol = io->rtol;
     nl->epoch++;
+    const auto te0 = std::chrono::steady_clock::now();
     const int rc = vb_fit_refresh_delta(ctx, nl->stats_dev);
+    nl->t_enqueue += std::chrono::duration<double>(std::chrono::steady_clock::now() - te0).count();
     nl->want_diff = false;
     if (rc) return 1;
     if (!nl->xr_ready) {
@@ -1433,7 +1449,9 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
             while (true) {
                 const double step = 1.0 / L[0];
                 nl->epoch++;
+                const auto te0 = std::chrono::steady_clock::now();
                 if (vb_fit_beta_trial(ctx, step, nl->stats_dev)) return 1;
+                nl->t_enqueue += std::chrono::duration<double>(std::chrono::steady_clock::now() - te0).count();
                 if (fetch_stats(ctx, nl, NS + f.akf, 0, trial.data())) return 1;
                 io->trials++;
                 io->evals++;
