@@ -204,3 +204,30 @@ def test_fails_loudly_on_bad_input():
     ctx = DeviceContext.get()
     with pytest.raises(VilmaB200Error):
         DeviceLD(ctx, 4, [{'n': 3, 'kind': 'dense', 'R': np.eye(3)}], np.array([0, 1, 1]))
+
+
+def test_sym_and_full_storage_agree():
+    """The symmetric-packed and the full dense stores are the same operator (to rounding)."""
+    import torch
+    from vilma_b200.engine import DeviceContext, DeviceLD, set_option
+    rng = np.random.default_rng(9)
+    sizes = [700, 64, 1500, 333]
+    mats = []
+    for n in sizes:
+        a = rng.standard_normal((n, n))
+        mats.append(a @ a.T / n)
+    M = sum(sizes)
+    blocks = [{'n': n, 'kind': 'dense', 'R': R} for n, R in zip(sizes, mats)]
+    ctx = DeviceContext.get()
+    packed = DeviceLD(ctx, M, blocks, np.arange(M))
+    set_option('ld_symmetric', 0)
+    try:
+        full = DeviceLD(ctx, M, blocks, np.arange(M))
+    finally:
+        set_option('ld_symmetric', 1)
+    x = rng.standard_normal(M)
+    yp, yf = packed.dot(x), full.dot(x)
+    assert packed.bytes < 0.55 * full.bytes
+    assert np.allclose(yp, yf, rtol=1e-13, atol=1e-13 * np.abs(yf).max())
+    packed.close()
+    full.close()
