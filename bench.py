@@ -161,7 +161,28 @@ def build_cpu_sample(n_blocks=SAMPLE_BLOCKS):
 
 
 def time_cpu(steps, warmup):
-    """Oracle port of the reference loop on the sample: returns (value, seconds, trials, M, info)."""
+    """Oracle port of the reference loop on the sample: returns (value, seconds, trials, M, info).
+    Uses every host core for BLAS (torchrun exports OMP_NUM_THREADS=1, which would otherwise
+    silently make the baseline single-threaded)."""
+    cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=cores)
+    except Exception:
+        limiter = None
+    try:
+        import torch
+        torch.set_num_threads(cores)
+    except Exception:
+        pass
+    try:
+        return _time_cpu(steps, warmup, cores)
+    finally:
+        if limiter is not None:
+            limiter.restore_original_limits()
+
+
+def _time_cpu(steps, warmup, cores):
     t_setup = time.time()
     vi, M, nb = build_cpu_sample()
     np.random.seed(42)
@@ -184,7 +205,6 @@ def time_cpu(steps, warmup):
         params = tuple(params)
     dt = time.perf_counter() - t0
     trials = vi.counters['trials'] - tr0
-    cores = os.cpu_count() or 1
     sample = ('first %d of the %d LD blocks of the same generator (M=%d SNPs), %d warm-up + %d '
               'timed outer iterations, %d trials, %d LD mat-vecs; NumPy/OpenBLAS oracle port of '
               'the reference loop' % (nb, N_BLOCKS, M, warmup, steps, trials,
