@@ -36,7 +36,8 @@ typedef struct vb_ld vb_ld; /* one cohort's block-diagonal LD operator, resident
 int vb_abi_version(void);
 const char* vb_last_error(void);
 /* process-wide options read when an LD operator is created:
- *   "ld_symmetric" (default 1): store dense blocks of n <= 4096 symmetric-packed (half the bytes) */
+ *   "ld_symmetric" (default 1): store dense blocks of n <= vb_ld_sym_nmax() symmetric-packed
+ *   "snp_three_pass" (default 1): one- and two-cohort updates use the three-pass softmax kernel */
 int vb_set_option(const char* name, int64_t value);
 /* largest dense block (rows) that is stored symmetric-packed; larger ones are stored in full */
 int64_t vb_ld_sym_nmax(void);

@@ -337,6 +337,232 @@ __global__ void __launch_bounds__(VB_SNP_THREADS) vb_snp_kernel(const VbSnpArgs 
     }
 }
 
+// Three-pass variant for P <= 2 (TRIAL / REFRESH): exact-maximum softmax with ONE exp per (k, SNP).
+//   pass 1  logits l_k (one log, one reciprocal), mu' stored, running maximum
+//   pass 2  w_k = exp(l_k - max); moments and KL sums; log|S| is recovered from the logit itself,
+//           c = 2 (l_k - g_k) - mu'^T Lambda mu'  (no second log), S from a second reciprocal
+//   pass 3  delta_k = max(w_k / denom, 1e-100)
+// Logits, w_k and mu' make their round trips through L1/L2 (the CTA's slice is K*(P+1)*1 KB).
+// The online single-pass kernel above executes its rescale branch for almost every k once any lane
+// of a warp raises its maximum (~3 exp per pair); this one is ~40 % fewer instructions.  Closed-form
+// inverses only, hence P <= 2.
+template <int P>
+__device__ __forceinline__ void vb_small_inverse(const double (&lam)[P * (P + 1) / 2],
+                                                 double (&S)[P * (P + 1) / 2], double& det) {
+    static_assert(P <= 2, "closed form only");
+    if constexpr (P == 1) {
+        det = lam[0];
+        S[0] = 1.0 / lam[0];
+    } else {
+        det = lam[0] * lam[2] - lam[1] * lam[1];
+        const double idet = 1.0 / det;
+        S[0] = lam[2] * idet;
+        S[2] = lam[0] * idet;
+        S[1] = -lam[1] * idet;
+    }
+}
+
+// CTAs per SM requested from the compiler: the kernel is latency-bound, 8 CTAs (64 registers) beat
+// 6 (78) and 10 (48, spills) on C2: 0.212 vs 0.234 vs 0.220 ms
+#ifndef VB_SNP3_MINBLOCKS
+#define VB_SNP3_MINBLOCKS 8
+#endif
+#ifndef VB_SNP3_UNROLL
+#define VB_SNP3_UNROLL 1
+#endif
+template <int P, int MODE>
+__global__ void __launch_bounds__(VB_SNP_THREADS, (P == 1) ? VB_SNP3_MINBLOCKS : 4) vb_snp3_kernel(const VbSnpArgs a) {
+    static_assert(MODE != VB_MODE_EVAL, "EVAL has no softmax: use vb_snp_kernel");
+    constexpr int UNR = VB_SNP3_UNROLL;
+    constexpr int NT = P * (P + 1) / 2;
+    constexpr int NS = VB_NSNPSTAT(P);
+    __shared__ double scratch[32];
+    extern __shared__ double s_ann[];
+    const int K = a.K;
+    const int64_t M = a.M;
+    const size_t PM = (size_t)P * M;
+    const int AKf = a.fuse_ann ? a.A * K : 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* my_ann = s_ann + warp * AKf;
+    for (int j = threadIdx.x; j < AKf * (VB_SNP_THREADS / 32); j += VB_SNP_THREADS) s_ann[j] = 0.0;
+    if (AKf) __syncthreads();
+
+    double tA[P], tC[P], tKd = 0.0, tKq = 0.0, tKs = 0.0;
+#pragma unroll
+    for (int p = 0; p < P; ++p) { tA[p] = 0.0; tC[p] = 0.0; }
+    const double* mu_cur = (MODE == VB_MODE_TRIAL) ? a.mu_out : a.mu_in;   // the state's mu in pass 2
+    // kernel arguments used in the inner loops, copied to registers once (pointer bumping below
+    // replaces per-access 64-bit index arithmetic, which was ~40 % of the executed instructions)
+    const double* const g_mu_in = a.mu_in;
+    double* const g_mu_out = a.mu_out;
+    double* const g_delta = a.delta_out;
+    const double* const g_prec = a.prec;
+    const double* const g_logdet = a.logdet;
+    const double step = a.step, one_minus_step = 1.0 - a.step;
+
+    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x & ~31); base < M;
+         base += (int64_t)gridDim.x * blockDim.x) {
+        const bool valid = base + lane < M;
+        const int64_t i = valid ? base + lane : M - 1;
+        double dt[P], sld[P], g[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            sld[p] = a.sld[(size_t)p * M + i];
+            dt[p] = sld[p] * a.inv_tau[p];
+            g[p] = 0.0;
+        }
+        if constexpr (MODE == VB_MODE_TRIAL) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const double se = a.se[(size_t)p * M + i];
+                const double lk = a.linked_in[(size_t)p * M + i] / se -
+                                  a.pm_in[(size_t)p * M + i] * sld[p];
+                g[p] = (a.adj[(size_t)p * M + i] - lk) * a.inv_tau[p];
+            }
+        }
+        const int an = a.ann[i];
+        const double* logh = a.logh + (size_t)an * K;
+        const double* gfull = a.gfull + (size_t)an * K;
+
+        // ---- pass 1: logits
+        double mx = -1.0e300;
+#pragma unroll UNR
+        const double* pmu_in = g_mu_in + i;
+        double* pmu_out = g_mu_out + i;
+        double* pdl = g_delta + i;
+        const double* prec = g_prec;
+        for (int k = 0; k < K; ++k, pmu_in += PM, pmu_out += PM, pdl += M, prec += P * P) {
+            double lam[NT], S[NT], mu[P], eta[P], det;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+#pragma unroll
+                for (int q = 0; q <= p; ++q) lam[VB_TRI(p, q)] = prec[p * P + q];
+                lam[VB_TRI(p, p)] += dt[p];
+                mu[p] = pmu_in[(size_t)p * M];
+            }
+            vb_small_inverse<P>(lam, S, det);
+            const double c = -log(det);
+            vb_sym_matvec<P>(lam, mu, eta);
+            if constexpr (MODE == VB_MODE_TRIAL) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) eta[p] = step * g[p] + one_minus_step * eta[p];
+                vb_sym_matvec<P>(S, eta, mu);
+                if (valid) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) pmu_out[(size_t)p * M] = mu[p];
+                }
+            }
+            double dot = 0.0;
+#pragma unroll
+            for (int p = 0; p < P; ++p) dot += mu[p] * eta[p];
+            const double lk = 0.5 * (c + dot) + gfull[k];
+            if (valid) *pdl = lk;
+            mx = fmax(mx, lk);
+        }
+        // ---- pass 2: weights, moments, KL pieces
+        double s0 = 0.0, sKd = 0.0, sKq = 0.0, sKs = 0.0, spm[P], sm2[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) { spm[p] = 0.0; sm2[p] = 0.0; }
+#pragma unroll UNR
+        const double* pmu = mu_cur + i;
+        pdl = g_delta + i;
+        prec = g_prec;
+        for (int k = 0; k < K; ++k, pmu += PM, pdl += M, prec += P * P) {
+            double lam[NT], S[NT], mu[P], eta[P], det;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+#pragma unroll
+                for (int q = 0; q <= p; ++q) lam[VB_TRI(p, q)] = prec[p * P + q];
+                lam[VB_TRI(p, p)] += dt[p];
+                mu[p] = valid ? pmu[(size_t)p * M] : 0.0;
+            }
+            vb_small_inverse<P>(lam, S, det);
+            vb_sym_matvec<P>(lam, mu, eta);
+            double dot = 0.0, quad = 0.0, tr = 0.0;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                dot += mu[p] * eta[p];
+#pragma unroll
+                for (int q = 0; q < P; ++q) {
+                    quad += mu[p] * mu[q] * prec[q * P + p];
+                    tr += prec[p * P + q] * S[p >= q ? VB_TRI(p, q) : VB_TRI(q, p)];
+                }
+            }
+            const double lk = valid ? *pdl : mx;
+            const double c = 2.0 * (lk - gfull[k]) - dot;          // log|S_k| back from the logit
+            const double w = exp(lk - mx);
+            if (valid) *pdl = w;
+            s0 += w;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                spm[p] = fma(w, mu[p], spm[p]);
+                sm2[p] = fma(w, S[VB_TRI(p, p)] + mu[p] * mu[p], sm2[p]);
+            }
+            sKd = fma(w, lk - logh[k], sKd);
+            sKq = fma(w, quad, sKq);
+            sKs = fma(w, g_logdet[k] - c + tr, sKs);
+        }
+        const double inv_den = 1.0 / s0;
+        const double log_norm = mx + log(s0);
+        // ---- pass 3: normalise (floored, not renormalised: numerics.py:188-194)
+#pragma unroll UNR
+        pdl = g_delta + i;
+        for (int k = 0; k < K; ++k, pdl += M) {
+            const double w = valid ? *pdl : 0.0;
+            const double d = fmax(w * inv_den, VB_EPSILON);
+            if (valid) *pdl = d;
+            if (AKf) {
+                for (int aa = 0; aa < a.A; ++aa) {
+                    const double sv = vb_warp_sum((valid && an == aa) ? d : 0.0);
+                    if (lane == 0) my_ann[aa * K + k] += sv;
+                }
+            }
+        }
+        if (!valid) continue;
+        tKd += sKd * inv_den - log_norm;
+        tKq += 0.5 * sKq * inv_den;
+        tKs += 0.5 * sKs * inv_den;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const double pm = spm[p] * inv_den;
+            const double pv = sm2[p] * inv_den - pm * pm;
+            a.pm_out[(size_t)p * M + i] = pm;
+            if (a.xbpos[p]) {
+                const int32_t q = a.xbpos[p][i];
+                if (q >= 0) a.xb[p][q] = pm / a.se[(size_t)p * M + i];
+            }
+            if (a.pv_out) a.pv_out[(size_t)p * M + i] = pv;
+            tA[p] = fma(pm, a.adj[(size_t)p * M + i], tA[p]);
+            tC[p] = fma(sld[p], pv, tC[p]);
+        }
+    }
+
+    double* out = a.partial + blockIdx.x;
+    const size_t ps = gridDim.x;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        double v = vb_block_sum(tA[p], scratch);
+        if (threadIdx.x == 0) out[p * ps] = v;
+        v = vb_block_sum(tC[p], scratch);
+        if (threadIdx.x == 0) out[(P + p) * ps] = v;
+    }
+    double v = vb_block_sum(tKd, scratch);
+    if (threadIdx.x == 0) out[(2 * P) * ps] = v;
+    v = vb_block_sum(tKq, scratch);
+    if (threadIdx.x == 0) out[(2 * P + 1) * ps] = v;
+    v = vb_block_sum(tKs, scratch);
+    if (threadIdx.x == 0) out[(2 * P + 2) * ps] = v;
+    if (AKf) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < AKf; j += VB_SNP_THREADS) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < VB_SNP_THREADS / 32; ++w) t += s_ann[w * AKf + j];
+            out[(NS + j) * ps] = t;
+        }
+    }
+}
+
 // Per-annotation column sums of delta (numerics.py:118-129 sum_annotations), deterministic.
 // grid = (chunks, K).  partial[(chunk*K + k)*A + a]
 #define VB_ANN_TILE 8

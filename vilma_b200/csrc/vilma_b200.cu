@@ -53,7 +53,8 @@ static inline int64_t even_up(int64_t v) { return (v + 1) & ~int64_t(1); }
 #ifndef VB_SYM_LPT
 #define VB_SYM_LPT 0
 #endif
-static bool g_disable_sym = false;   // vb_set_option("ld_symmetric", 0): store dense blocks in full
+static bool g_disable_sym = false;
+static bool g_three_pass = true;     // vb_set_option("snp_three_pass", 0): always the online single-pass kernel   // vb_set_option("ld_symmetric", 0): store dense blocks in full
 
 // ------------------------------------------------------------------------------------
 // state
@@ -247,11 +248,16 @@ static NativeLoop* loop_of(vb_ctx* ctx, bool create) {
 // ------------------------------------------------------------------------------------
 extern "C" int vb_abi_version(void) { return VB_ABI_VERSION; }
 // Process-wide options read when an LD operator is created.
-//   "ld_symmetric" (default 1): store dense blocks with n <= 4096 symmetric-packed.
+//   "ld_symmetric" (default 1): store dense blocks with n <= VB_SYM_NMAX symmetric-packed.
+//   "snp_three_pass" (default 1): P <= 2 updates use the exact-max three-pass softmax kernel.
 extern "C" int64_t vb_ld_sym_nmax(void) { return VB_SYM_NMAX; }
 extern "C" int vb_set_option(const char* name, int64_t value) {
     if (name && std::strcmp(name, "ld_symmetric") == 0) {
         g_disable_sym = (value == 0);
+        return 0;
+    }
+    if (name && std::strcmp(name, "snp_three_pass") == 0) {
+        g_three_pass = (value != 0);
         return 0;
     }
     return vb_fail("vb_set_option: unknown option '%s'", name ? name : "(null)");
@@ -1002,6 +1008,15 @@ static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
     cudaStream_t st = ctx->stream;
     const size_t sm = a.fuse_ann ? (size_t)a.A * a.K * (VB_SNP_THREADS / 32) * sizeof(double) : 0;
     prof_begin(ctx, 1);
+    if constexpr (MODE != VB_MODE_EVAL) {
+        if (P <= 2 && g_three_pass) {       // exact-max softmax, one exp per (k, SNP)
+            if (P == 1) vb_snp3_kernel<1, MODE><<<grid, VB_SNP_THREADS, sm, st>>>(a);
+            else vb_snp3_kernel<2, MODE><<<grid, VB_SNP_THREADS, sm, st>>>(a);
+            prof_end(ctx, 1);
+            CK_LAUNCH(ctx);
+            return 0;
+        }
+    }
     switch (P) {
         case 1: vb_snp_kernel<1, MODE><<<grid, VB_SNP_THREADS, sm, st>>>(a); break;
         case 2: vb_snp_kernel<2, MODE><<<grid, VB_SNP_THREADS, sm, st>>>(a); break;
