@@ -145,3 +145,74 @@ def test_product_does_not_import_oracle():
         if fn.endswith('.py'):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), fn
+
+
+def test_constructor_validation_matches_reference_errors():
+    """VIScheme.__init__ argument checks (reference variational_inference.py:143-203, :606-613)."""
+    from _np_engine import NumpyShardEngine
+    from vilma_b200.matrix_structures import BlockDiagonalMatrix, LowRankMatrix
+    from vilma_b200.variational_inference import MultiPopVI
+    fx = load_case('vischeme_unlinked_a1_s0_t0')
+    lds = build_ld(fx, LowRankMatrix, BlockDiagonalMatrix)
+    base = dict(vi_kwargs(fx), ld_mats=lds, precomputed=precomputed(fx),
+                engine_factory=NumpyShardEngine)
+
+    def build(**over):
+        kw = dict(base)
+        kw.update(over)
+        return MultiPopVI(**kw)
+
+    build()                                            # the unmodified arguments are fine
+    for missing in ('init_hg', 'gwas_N', 'num_its', 'annotations', 'std_errs'):
+        with pytest.raises(ValueError):
+            build(**{missing: None})
+    bad = fx['betas'].copy()
+    bad[0, 3] = np.nan
+    with pytest.raises(ValueError):
+        build(marginal_effects=bad)
+    bad = fx['std_errs'].copy()
+    bad[1, 0] = np.inf
+    with pytest.raises(ValueError):
+        build(std_errs=bad)
+    with pytest.raises(ValueError):
+        build(ld_mats=lds[:1])                         # fewer LD matrices than populations
+    with pytest.raises(ValueError):
+        build(ld_mats=[lds[0], 'not an LD operator'])
+    ann = np.array(fx['annotations'], dtype=float)
+    ann[0, 0] = 0
+    with pytest.raises(ValueError):
+        build(annotations=ann)                         # a SNP without annotation
+    with pytest.raises(ValueError):
+        build(annotations=np.ones((7, 1)))             # wrong length
+    with pytest.raises(ValueError):
+        build(mixture_covs=[np.eye(3)])                # wrong shape
+    with pytest.raises(ValueError):
+        build(mixture_covs=[np.array([[1., 2.], [2., 1.]])])   # not positive definite
+
+
+def test_update_beta_requires_nat_grad():
+    """reference :770-772"""
+    fx = load_case('vischeme_unlinked_a1_s0_t0')
+    vi = make_host_vi(fx)
+    params = (fx['init_vi_mu'], fx['init_vi_delta'], fx['init_hyper_delta'])
+    with pytest.raises(RuntimeError):
+        vi._update_beta(*params, None, np.ones(5), 0, 2.)
+
+
+def test_checkpoint_files_written(tmp_path):
+    """-checkpoint.<it>.npz cadence and contents (reference :362-367), host loop."""
+    from _np_engine import NumpyShardEngine
+    from vilma_b200.matrix_structures import BlockDiagonalMatrix, LowRankMatrix
+    from vilma_b200.variational_inference import MultiPopVI
+    fx = load_case('vischeme_unlinked_a2_s0_t1')
+    kw = dict(vi_kwargs(fx), checkpoint=True, checkpoint_freq=4, output=str(tmp_path / 'run'))
+    vi = MultiPopVI(ld_mats=build_ld(fx, LowRankMatrix, BlockDiagonalMatrix),
+                    precomputed=precomputed(fx), engine_factory=NumpyShardEngine, **kw)
+    np.random.seed(int(fx['seed']))
+    vi.optimize(None)
+    its = len(fx['traj_L0'])
+    expect = ['run-checkpoint.%d.npz' % i for i in range(0, its, 4)]
+    assert sorted(os.listdir(tmp_path)) == sorted(expect)
+    z = np.load(tmp_path / expect[0])
+    assert sorted(z.files) == ['error_scaling', 'hyper_delta', 'scalings', 'vi_delta', 'vi_mu']
+    assert np.allclose(z['vi_mu'], fx['init_vi_mu'], rtol=1e-7, atol=1e-12)
