@@ -203,37 +203,77 @@ struct VbFinalArgs {
 // Called by every thread of the LAST block (fixed summation order => deterministic).
 __device__ __forceinline__ void vb_final_reduce(const VbFinalArgs& fa, double* scratch) {
     const int P = fa.P, NS = VB_NSNPSTAT(P);
-    for (int s = 0; s < NS; ++s) {
-        double acc = 0.0;
-        for (int b = threadIdx.x; b < fa.n_part_snp; b += blockDim.x) acc += __ldcg(&fa.part_snp[(size_t)s * fa.n_part_snp + b]);
-        acc = vb_block_sum(acc, scratch);
-        if (threadIdx.x == 0) fa.stats[s < 2 * P ? s : s + P] = acc;
+    // All statistics of a partial row are loaded together (independent loads in flight) -- summing one
+    // statistic at a time made this tail a chain of ~50 dependent L2 round trips (45 us).
+    {
+        constexpr int SMAX = 2 * VB_MAXP + 3;
+        double acc[SMAX];
+#pragma unroll
+        for (int s = 0; s < SMAX; ++s) acc[s] = 0.0;
+        for (int b = threadIdx.x; b < fa.n_part_snp; b += blockDim.x) {
+#pragma unroll
+            for (int s = 0; s < SMAX; ++s)
+                if (s < NS) acc[s] += __ldcg(&fa.part_snp[(size_t)s * fa.n_part_snp + b]);
+        }
+#pragma unroll
+        for (int s = 0; s < SMAX; ++s) {
+            if (s < NS) {
+                const double t = vb_block_sum(acc[s], scratch);
+                if (threadIdx.x == 0) fa.stats[s < 2 * P ? s : s + P] = t;
+            }
+        }
     }
     const int n_sum = fa.akf;
-    for (int s = 0; s < n_sum; ++s) {
-        double acc = 0.0;
-        for (int b = threadIdx.x; b < fa.n_part_snp; b += blockDim.x) acc += __ldcg(&fa.part_snp[(size_t)(NS + s) * fa.n_part_snp + b]);
-        acc = vb_block_sum(acc, scratch);
-        if (threadIdx.x == 0) fa.stats[3 * P + 3 + s] = acc;
+    for (int s0 = 0; s0 < n_sum; s0 += 8) {
+        double acc[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[t] = 0.0;
+        for (int b = threadIdx.x; b < fa.n_part_snp; b += blockDim.x) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                if (s0 + t < n_sum) acc[t] += __ldcg(&fa.part_snp[(size_t)(NS + s0 + t) * fa.n_part_snp + b]);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            if (s0 + t < n_sum) {
+                const double v = vb_block_sum(acc[t], scratch);
+                if (threadIdx.x == 0) fa.stats[3 * P + 3 + s0 + t] = v;
+            }
+        }
     }
-    for (int p = 0; p < P; ++p) {
-        double acc = 0.0;
-        for (int b = threadIdx.x; b < fa.n_part_fin; b += blockDim.x) acc += __ldcg(&fa.part_fin[(size_t)p * fa.n_part_fin + b]);
-        acc = vb_block_sum(acc, scratch);
-        if (threadIdx.x == 0) fa.stats[2 * P + p] = acc;
+    {
+        double acc[VB_MAXP];
+#pragma unroll
+        for (int p = 0; p < VB_MAXP; ++p) acc[p] = 0.0;
+        for (int b = threadIdx.x; b < fa.n_part_fin; b += blockDim.x) {
+#pragma unroll
+            for (int p = 0; p < VB_MAXP; ++p)
+                if (p < P) acc[p] += __ldcg(&fa.part_fin[(size_t)p * fa.n_part_fin + b]);
+        }
+#pragma unroll
+        for (int p = 0; p < VB_MAXP; ++p) {
+            if (p < P) {
+                const double t = vb_block_sum(acc[p], scratch);
+                if (threadIdx.x == 0) fa.stats[2 * P + p] = t;
+            }
+        }
     }
     if (fa.part_diff) {
-        // 5 sums then 5 maxima (vb_pm_diff_kernel partial rows)
-        for (int s = 0; s < 10; ++s) {
-            double acc = 0.0;
-            if (s < 5) {
-                for (int b = threadIdx.x; b < fa.n_part_diff; b += blockDim.x) acc += __ldcg(&fa.part_diff[(size_t)b * 10 + s]);
-                acc = vb_block_sum(acc, scratch);
-            } else {
-                for (int b = threadIdx.x; b < fa.n_part_diff; b += blockDim.x) acc = fmax(acc, __ldcg(&fa.part_diff[(size_t)b * 10 + s]));
-                acc = vb_block_max(acc, scratch);
+        // 5 sums then 5 maxima (vb_pm_diff_kernel partial rows), loaded together
+        double acc[10];
+#pragma unroll
+        for (int s = 0; s < 10; ++s) acc[s] = 0.0;
+        for (int b = threadIdx.x; b < fa.n_part_diff; b += blockDim.x) {
+#pragma unroll
+            for (int s = 0; s < 10; ++s) {
+                const double v = __ldcg(&fa.part_diff[(size_t)b * 10 + s]);
+                acc[s] = s < 5 ? acc[s] + v : fmax(acc[s], v);
             }
-            if (threadIdx.x == 0) fa.stats[3 * P + 3 + fa.akf + s] = acc;
+        }
+#pragma unroll
+        for (int s = 0; s < 10; ++s) {
+            const double t = s < 5 ? vb_block_sum(acc[s], scratch) : vb_block_max(acc[s], scratch);
+            if (threadIdx.x == 0) fa.stats[3 * P + 3 + fa.akf + s] = t;
         }
     }
     if (fa.xr.enabled) vb_xrank_exchange(fa.xr, fa.stats);

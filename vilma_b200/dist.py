@@ -91,10 +91,12 @@ class TorchComm(SingleComm):
         all_idx = [torch.empty_like(idx) for _ in range(self.world)]
         self._dist.all_gather(all_pad, pad)
         self._dist.all_gather(all_idx, idx)
-        out = np.zeros((M, flat.shape[1]), dtype=flat.dtype)
-        for r in range(self.world):
-            k = sizes[r]
-            out[all_idx[r][:k].cpu().numpy()] = all_pad[r][:k].cpu().numpy()
+        # scatter on the gathering device (one index_copy_), then a single copy to the host
+        rows = torch.cat([all_pad[r][:sizes[r]] for r in range(self.world)], dim=0)
+        where = torch.cat([all_idx[r][:sizes[r]] for r in range(self.world)], dim=0)
+        full = torch.zeros((M, flat.shape[1]), dtype=rows.dtype, device=dev)
+        full.index_copy_(0, where, rows)
+        out = full.cpu().numpy()
         return np.moveaxis(out.reshape((M,) + rest), 0, axis)
 
     def barrier(self):
