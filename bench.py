@@ -341,8 +341,8 @@ def run_ours(args):
     prof = ctx.profile_read()
     tm1 = (C.c_double * 4)()
     ctx.lib.vb_fit_timing(ctx.handle, tm1)
-    log('[rank %d] native loop host time in region: enqueue %.3f ms, wait %.3f ms over %d rendezvous; region %.3f ms' % (
-        comm.rank, (tm1[0] - tm0[0]) * 1e3, (tm1[1] - tm0[1]) * 1e3, int(tm1[2] - tm0[2]), ms))
+    log('[rank %d] native loop host time in region: enqueue %.3f ms, wait %.3f ms over %d rendezvous; region %.3f ms; speculative trials used.wasted %.6f' % (
+        comm.rank, (tm1[0] - tm0[0]) * 1e3, (tm1[1] - tm0[1]) * 1e3, int(tm1[2] - tm0[2]), ms, tm1[3] - tm0[3]))
     ctx.profile(False)
     trials = vi.n_trials - trials0
     evals = vi.n_evals - evals0

@@ -159,6 +159,9 @@ typedef struct vb_step_io {
     int32_t trials;            /* out: line-search trials executed */
     int32_t evals;             /* out: parameter states evaluated */
     int32_t do_diff;           /* in: run the convergence bookkeeping */
+    int32_t speculate;         /* in: queue the next iteration's first beta trial behind this one's
+                                *     last evaluation (discarded if the caller stops or touches the state) */
+    int32_t reserved;
 } vb_step_io;
 int vb_nccl_unique_id(char* out128);
 /* optional faster rendezvous for one node: every rank creates a mailbox (vb_xr_create returns its
@@ -177,7 +180,7 @@ int vb_fit_set_constants(vb_ctx* ctx, const double* chi_stat_host, const double*
 int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, double* hyper_io,
                      double* stats_io);
 /* host-side time of the native loop so far: {s enqueueing evaluations, s waiting for their
- * statistics, number of rendezvous, 0} */
+ * statistics, number of rendezvous, speculative trials used + 1e-6 * wasted} */
 int vb_fit_timing(vb_ctx* ctx, double* out4);
 
 #ifdef __cplusplus

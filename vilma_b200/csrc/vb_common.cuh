@@ -122,8 +122,8 @@ __device__ __forceinline__ double vb_block_max(double v, double* scratch) {
 struct VbXrank {
     double* peer_box[VB_XR_MAXRANKS];      // peer r's mailbox base: [2 slots][MAXRANKS][MAXVALS]
     uint32_t* peer_flag[VB_XR_MAXRANKS];   // peer r's flags:        [2 slots][MAXRANKS]
-    double* host_out;                      // host-mapped: [MAXVALS] result
-    uint32_t* host_flag;                   // host-mapped: epoch of the last published result
+    double* host_out;                      // host-mapped: [2 slots][MAXVALS] results (slot = epoch & 1)
+    uint32_t* host_flag;                   // host-mapped: [2] epoch of the result published in each slot
     uint32_t* dev_err;                     // device: set to 1 if a peer never showed up
     uint32_t epoch;
     int nranks, rank;
@@ -174,15 +174,15 @@ __device__ __forceinline__ void vb_xrank_exchange(const VbXrank& xr, double* sta
                 v = threadIdx.x < xr.n_sum ? v + w : fmax(v, w);
             }
             stats[threadIdx.x] = v;
-            xr.host_out[threadIdx.x] = v;
+            xr.host_out[slot * VB_XR_MAXVALS + threadIdx.x] = v;
         }
     } else if (threadIdx.x < n) {
-        xr.host_out[threadIdx.x] = __ldcg(&stats[threadIdx.x]);
+        xr.host_out[slot * VB_XR_MAXVALS + threadIdx.x] = __ldcg(&stats[threadIdx.x]);
     }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        volatile uint32_t* hf = xr.host_flag;
+        volatile uint32_t* hf = xr.host_flag + slot;
         *hf = (xr.nranks > 1 && *xr.dev_err) ? 0xffffffffu : xr.epoch;
     }
 }

@@ -121,6 +121,7 @@ struct Fit {
     double* scratch3 = nullptr;    // [3][P][M]
     double *pm_prev = nullptr, *pm_ckpt = nullptr, *pm_next = nullptr;
     int akf = 0, nsp = 0;          // fused annotation sums per evaluation; partial row stride
+    int64_t mutations = 0;         // bumped by every public vb_fit_* call (guards speculative work)
     double* part_snp = nullptr;
     int grid_snp = 0;
     double* part_fin = nullptr;
@@ -225,6 +226,12 @@ struct NativeLoop {
     uint32_t *xr_host_flag = nullptr, *xr_host_flag_dev = nullptr;
     uint32_t* xr_dev_err = nullptr;
     uint32_t epoch = 0;
+    // a trial evaluation queued speculatively behind the last refresh of the previous iteration
+    bool spec_pending = false;
+    uint32_t spec_epoch = 0;
+    double spec_step = 0.0;
+    int64_t spec_mutations = 0;
+    int64_t spec_used = 0, spec_wasted = 0;
     // host-side timing of the native loop (seconds): enqueueing evaluations / waiting for results
     double t_enqueue = 0.0, t_wait = 0.0;
     int64_t n_wait = 0;
@@ -928,7 +935,8 @@ extern "C" int vb_fit_destroy(vb_ctx* ctx) {
 #define NEED_FIT(ctx)                                                      \
     if (!(ctx) || !(ctx)->fit.created) return vb_fail("fit state not created"); \
     CK(cudaSetDevice((ctx)->device));                                      \
-    Fit& f = (ctx)->fit;
+    Fit& f = (ctx)->fit;                                                   \
+    f.mutations++;
 
 extern "C" int vb_fit_set_snp_data(vb_ctx* ctx, const double* adj, const double* se, const double* sld,
                                    const double* scal, const int32_t* ann) {
@@ -1277,11 +1285,11 @@ extern "C" int vb_xr_create(vb_ctx* ctx, char* handle_out64) {
         CK(cudaMalloc(&nl->xr_box, VB_XR_BOX_BYTES + sizeof(uint32_t) * 16));
         CK(cudaMemset(nl->xr_box, 0, VB_XR_BOX_BYTES + sizeof(uint32_t) * 16));
         nl->xr_dev_err = reinterpret_cast<uint32_t*>(nl->xr_box + VB_XR_BOX_BYTES);
-        CK(cudaHostAlloc(&nl->xr_host_out, VB_XR_MAXVALS * sizeof(double) + 64, cudaHostAllocMapped));
-        std::memset(nl->xr_host_out, 0, VB_XR_MAXVALS * sizeof(double) + 64);
-        nl->xr_host_flag = reinterpret_cast<uint32_t*>(nl->xr_host_out + VB_XR_MAXVALS);
+        CK(cudaHostAlloc(&nl->xr_host_out, 2 * VB_XR_MAXVALS * sizeof(double) + 64, cudaHostAllocMapped));
+        std::memset(nl->xr_host_out, 0, 2 * VB_XR_MAXVALS * sizeof(double) + 64);
+        nl->xr_host_flag = reinterpret_cast<uint32_t*>(nl->xr_host_out + 2 * VB_XR_MAXVALS);
         CK(cudaHostGetDevicePointer(&nl->xr_host_out_dev, nl->xr_host_out, 0));
-        nl->xr_host_flag_dev = reinterpret_cast<uint32_t*>(nl->xr_host_out_dev + VB_XR_MAXVALS);
+        nl->xr_host_flag_dev = reinterpret_cast<uint32_t*>(nl->xr_host_out_dev + 2 * VB_XR_MAXVALS);
     }
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, nl->xr_box));
@@ -1314,7 +1322,7 @@ extern "C" int vb_xr_open(vb_ctx* ctx, int nranks, int rank, const char* handles
 }
 // host side of the rendezvous: poll the mapped flag until the evaluation `epoch` has been published
 static int xr_wait(NativeLoop* nl, uint32_t epoch, double* out, int n) {
-    volatile uint32_t* hf = nl->xr_host_flag;
+    volatile uint32_t* hf = nl->xr_host_flag + (epoch & 1);
     const auto t0 = std::chrono::steady_clock::now();
     unsigned spins = 0;
     while (true) {
@@ -1328,7 +1336,7 @@ static int xr_wait(NativeLoop* nl, uint32_t epoch, double* out, int n) {
         }
     }
     std::atomic_thread_fence(std::memory_order_acquire);
-    std::memcpy(out, nl->xr_host_out, n * sizeof(double));
+    std::memcpy(out, nl->xr_host_out + (size_t)(epoch & 1) * VB_XR_MAXVALS, n * sizeof(double));
     return 0;
 }
 
@@ -1382,9 +1390,9 @@ static inline bool np_isclose(double a, double b) { return std::fabs(a - b) <= 1
 
 // Bring the statistics of the evaluation just queued to the host (summed over ranks): through the
 // mailbox exchange fused into the evaluation's last CTA when available, else NCCL + copy + sync.
-static int fetch_stats(vb_ctx* ctx, NativeLoop* nl, int n_sum, int n_tail, double* out) {
+static int fetch_stats(vb_ctx* ctx, NativeLoop* nl, int n_sum, int n_tail, double* out, uint32_t epoch = 0) {
     const auto t0 = std::chrono::steady_clock::now();
-    const int rc = nl->xr_ready ? xr_wait(nl, nl->epoch, out, n_sum + n_tail)
+    const int rc = nl->xr_ready ? xr_wait(nl, epoch ? epoch : nl->epoch, out, n_sum + n_tail)
                                 : reduce_to_host(ctx, nl, nl->stats_dev, n_sum, out, n_tail);
     nl->t_wait += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     nl->n_wait++;
@@ -1394,22 +1402,22 @@ static int fetch_stats(vb_ctx* ctx, NativeLoop* nl, int n_sum, int n_tail, doubl
 extern "C" int vb_fit_timing(vb_ctx* ctx, double* out4) {
     NativeLoop* nl = loop_of(ctx, false);
     if (!nl) return vb_fail("no native loop state");
-    out4[0] = nl->t_enqueue; out4[1] = nl->t_wait; out4[2] = (double)nl->n_wait; out4[3] = 0.0;
+    out4[0] = nl->t_enqueue; out4[1] = nl->t_wait; out4[2] = (double)nl->n_wait;
+    out4[3] = (double)nl->spec_used + 1e-6 * (double)nl->spec_wasted;
     return 0;
 }
 // delta refresh + evaluation of the resulting state, with the convergence bookkeeping of the new
 // state (against prev / ckpt, written to pm_next) reduced in the same rendezvous.
 // stats: [3P+3 | akf annotation sums | 10 diff statistics]
 static int native_refresh(vb_ctx* ctx, NativeLoop* nl, Fit& f, double* stats, const double* tau,
-                          double* obj, vb_step_io* io) {
+                          double* obj, vb_step_io* io, double speculate_step = 0.0) {
     const int nbase = 3 * f.P + 3 + f.akf;
     nl->want_diff = nl->xr_ready;
     nl->diff_atol = io->atol;
     nl->diff_rtol = io->rtol;
-    nl->epoch++;
+    const uint32_t e_refresh = ++nl->epoch;
     const auto te0 = std::chrono::steady_clock::now();
     const int rc = vb_fit_refresh_delta(ctx, nl->stats_dev);
-    nl->t_enqueue += std::chrono::duration<double>(std::chrono::steady_clock::now() - te0).count();
     nl->want_diff = false;
     if (rc) return 1;
     if (!nl->xr_ready) {
@@ -1422,9 +1430,22 @@ static int native_refresh(vb_ctx* ctx, NativeLoop* nl, Fit& f, double* stats, co
         vb_pm_diff_final_kernel<<<1, 256, 0, ctx->stream>>>(f.part_diff, f.grid_diff, nl->stats_dev + nbase);
         CK_LAUNCH(ctx);
     }
-    if (fetch_stats(ctx, nl, nbase + 5, 5, stats)) return 1;
-    io->evals++;
+    // the refreshed state is accepted unconditionally (reference :859): flip now
     if (vb_fit_accept(ctx)) return 1;
+    nl->spec_pending = false;
+    if (speculate_step > 0.0 && nl->xr_ready) {
+        // Speculation: the next outer iteration starts with a beta trial at a step size that is
+        // already known (L[0] / 1.25).  Queue it right behind the refresh so the GPU never idles
+        // while the host reads the refresh statistics; the next call consumes it if nothing touched
+        // the state in between, otherwise it is simply discarded.
+        nl->spec_epoch = ++nl->epoch;
+        if (vb_fit_beta_trial(ctx, speculate_step, nl->stats_dev)) return 1;
+        nl->spec_pending = true;
+        nl->spec_step = speculate_step;
+    }
+    nl->t_enqueue += std::chrono::duration<double>(std::chrono::steady_clock::now() - te0).count();
+    if (fetch_stats(ctx, nl, nbase + 5, 5, stats, e_refresh)) return 1;
+    io->evals++;
     *obj = objective_of(nl, f.P, stats, tau);
     std::memcpy(io->diff, stats + nbase, 10 * sizeof(double));
     return 0;
@@ -1436,7 +1457,11 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
     NEED_FIT(ctx);
     NativeLoop* nl = loop_of(ctx, false);
     if (!nl || !nl->ready) return vb_fail("vb_fit_iteration: call vb_fit_set_constants first");
+    const int64_t mut_entry = f.mutations;      // (already counts this call)
     const int P = f.P, K = f.K, A = f.A, NS = 3 * P + 3, NSX = NS + f.akf + 10;
+    bool spec_usable = nl->spec_pending && nl->spec_mutations + 1 == mut_entry && f.trial_kind == 0;
+    if (nl->spec_pending && !spec_usable) nl->spec_wasted++;
+    nl->spec_pending = false;
     const double conv_tol = io->has_running ? 0.1 * io->running_elbo_delta : INFINITY;
     double new_elbo_delta = 0.0;
     double obj = io->obj;
@@ -1463,11 +1488,19 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
             bool accepted = false, bail = false;
             while (true) {
                 const double step = 1.0 / L[0];
-                nl->epoch++;
-                const auto te0 = std::chrono::steady_clock::now();
-                if (vb_fit_beta_trial(ctx, step, nl->stats_dev)) return 1;
-                nl->t_enqueue += std::chrono::duration<double>(std::chrono::steady_clock::now() - te0).count();
-                if (fetch_stats(ctx, nl, NS + f.akf, 0, trial.data())) return 1;
+                if (spec_usable && step == nl->spec_step) {
+                    // the trial queued behind the previous iteration's refresh
+                    spec_usable = false;
+                    nl->spec_used++;
+                    if (fetch_stats(ctx, nl, NS + f.akf, 0, trial.data(), nl->spec_epoch)) return 1;
+                } else {
+                    if (spec_usable) { spec_usable = false; nl->spec_wasted++; }
+                    nl->epoch++;
+                    const auto te0 = std::chrono::steady_clock::now();
+                    if (vb_fit_beta_trial(ctx, step, nl->stats_dev)) return 1;
+                    nl->t_enqueue += std::chrono::duration<double>(std::chrono::steady_clock::now() - te0).count();
+                    if (fetch_stats(ctx, nl, NS + f.akf, 0, trial.data())) return 1;
+                }
                 io->trials++;
                 io->evals++;
                 new_obj = objective_of(nl, P, trial.data(), tau_io);
@@ -1527,7 +1560,11 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
             if (vb_fit_set_hyper(ctx, hyper_io)) return 1;
             if (K > 1 && vb_fit_set_delta_grad(ctx, g.data())) return 1;
             double new_obj;
-            if (native_refresh(ctx, nl, f, stats.data(), tau_io, &new_obj, io)) return 1;
+            // L[1] is always 1 here, so this is the iteration's last evaluation unless the error
+            // scaling is being learned: speculate the next iteration's first beta trial behind it
+            const double spec_step = (!nl->scale_se && L[1] == 1.0 && io->speculate)
+                                         ? 1.0 / std::max(1.0, L[0] / 1.25) : 0.0;
+            if (native_refresh(ctx, nl, f, stats.data(), tau_io, &new_obj, io, spec_step)) return 1;
             ann_valid = f.akf > 0;
             obj = new_obj;
             new_elbo_delta += new_obj - orig_obj;
@@ -1551,6 +1588,7 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
     io->obj = obj;
     io->elbo_delta = new_elbo_delta;
     std::memcpy(stats_io, stats.data(), NS * sizeof(double));
+    nl->spec_mutations = f.mutations;
 
     // the last refresh of the iteration compared the new posterior mean with prev / ckpt and wrote
     // it to pm_next: it becomes prev now

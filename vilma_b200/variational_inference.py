@@ -115,6 +115,7 @@ class VIScheme():
                              'size shape.')
 
         self.use_native_loop = True      # C++ outer iteration (vb_fit_iteration) when possible
+        self.speculate_next_trial = True  # queue the next iteration's first trial behind the refresh
         self._comm = comm if comm is not None else default_comm()
         self._device = device
         self._engine_factory = engine_factory
@@ -306,6 +307,7 @@ class VIScheme():
         io.line_search_rate = 2.
         io.atol, io.rtol = ABS_TOL, REL_TOL
         io.do_diff = 1
+        io.speculate = 1 if self.speculate_next_trial else 0
         io.obj = self._res_obj
         for i in range(5):
             io.L[i] = L[i]
@@ -317,6 +319,7 @@ class VIScheme():
                 dump_dict = self.create_dump_dict(self._download())
                 if self._comm.rank == 0:
                     np.savez(fname, **dump_dict)
+            io.speculate = 1 if (self.speculate_next_trial and num_its + 1 < max_its) else 0
             io.has_running = 0 if running is None else 1
             io.running_elbo_delta = 0. if running is None else running
             eng.iteration(io, tau, hyper, stats)
