@@ -104,6 +104,9 @@ int vb_fit_set_delta_grad(vb_ctx* ctx, const double* table_host);
 int vb_fit_set_tau(vb_ctx* ctx, const double* tau_host);
 int vb_fit_set_params(vb_ctx* ctx, const double* vi_mu_host, const double* vi_delta_mk_host);
 int vb_fit_get_params(vb_ctx* ctx, double* vi_mu_host, double* vi_delta_mk_host);
+/* the same with device buffers (multi-GPU: shards are gathered / scattered on the device) */
+int vb_fit_set_params_dev(vb_ctx* ctx, const double* vi_mu_dev, const double* vi_delta_mk_dev);
+int vb_fit_get_params_dev(vb_ctx* ctx, double* vi_mu_dev, double* vi_delta_mk_dev);
 
 /* ---- evaluations: each fills stats_dev[0 .. 3P+3) for ONE parameter state; stats_dev must hold
  * 3P+3+58 doubles: with vb_fit_set_fusion(ctx, 1) and A*K <= 48, entries [3P+3, 3P+3+A*K) receive

@@ -981,13 +981,13 @@ extern "C" int vb_fit_set_tau(vb_ctx* ctx, const double* tau) {
     // pageable source: cudaMemcpyAsync returns once the data is staged, so no stream sync is needed
     return 0;
 }
-extern "C" int vb_fit_set_params(vb_ctx* ctx, const double* mu, const double* delta_mk) {
+static int fit_set_params(vb_ctx* ctx, const double* mu, const double* delta_mk, cudaMemcpyKind kind) {
     NEED_FIT(ctx);
     const size_t KM = (size_t)f.K * f.M;
-    CK(cudaMemcpyAsync(f.mu[f.cur_mu], mu, KM * f.P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f.mu[f.cur_mu], mu, KM * f.P * 8, kind, ctx->stream));
     // vi_delta arrives in the reference layout [M][K]; stage it in the trial slot, transpose on device
     double* stage = f.delta[1 - f.cur_delta];
-    CK(cudaMemcpyAsync(stage, delta_mk, KM * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(stage, delta_mk, KM * 8, kind, ctx->stream));
     const int grid = (int)std::min<int64_t>((f.M + 255) / 256, 4096);
     vb_mk_to_km_kernel<<<grid, 256, 0, ctx->stream>>>(stage, f.M, f.K, f.delta[f.cur_delta]);
     CK_LAUNCH(ctx);
@@ -995,20 +995,34 @@ extern "C" int vb_fit_set_params(vb_ctx* ctx, const double* mu, const double* de
     f.trial_kind = -1;
     return 0;
 }
-extern "C" int vb_fit_get_params(vb_ctx* ctx, double* mu, double* delta_mk) {
+extern "C" int vb_fit_set_params(vb_ctx* ctx, const double* mu, const double* delta_mk) {
+    return fit_set_params(ctx, mu, delta_mk, cudaMemcpyHostToDevice);
+}
+// same, from device buffers (this rank's shard already gathered on the device)
+extern "C" int vb_fit_set_params_dev(vb_ctx* ctx, const double* mu_dev, const double* delta_mk_dev) {
+    return fit_set_params(ctx, mu_dev, delta_mk_dev, cudaMemcpyDeviceToDevice);
+}
+static int fit_get_params(vb_ctx* ctx, double* mu, double* delta_mk, cudaMemcpyKind kind) {
     NEED_FIT(ctx);
     const size_t KM = (size_t)f.K * f.M;
-    if (mu) CK(cudaMemcpyAsync(mu, f.mu[f.cur_mu], KM * f.P * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mu) CK(cudaMemcpyAsync(mu, f.mu[f.cur_mu], KM * f.P * 8, kind, ctx->stream));
     if (delta_mk) {
         double* stage = f.delta[1 - f.cur_delta];      // any pending trial is discarded
         const int grid = (int)std::min<int64_t>((f.M + 255) / 256, 4096);
         vb_km_to_mk_kernel<<<grid, 256, 0, ctx->stream>>>(f.delta[f.cur_delta], f.M, f.K, stage);
         CK_LAUNCH(ctx);
-        CK(cudaMemcpyAsync(delta_mk, stage, KM * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(delta_mk, stage, KM * 8, kind, ctx->stream));
         f.trial_kind = -1;
     }
     CK(cudaStreamSynchronize(ctx->stream));
     return 0;
+}
+extern "C" int vb_fit_get_params(vb_ctx* ctx, double* mu, double* delta_mk) {
+    return fit_get_params(ctx, mu, delta_mk, cudaMemcpyDeviceToHost);
+}
+// same, into device buffers (for a device-side gather of the ranks' shards)
+extern "C" int vb_fit_get_params_dev(vb_ctx* ctx, double* mu_dev, double* delta_mk_dev) {
+    return fit_get_params(ctx, mu_dev, delta_mk_dev, cudaMemcpyDeviceToDevice);
 }
 
 template <int MODE>

@@ -99,6 +99,36 @@ class TorchComm(SingleComm):
         out = full.cpu().numpy()
         return np.moveaxis(out.reshape((M,) + rest), 0, axis)
 
+    def gather_device(self, local, snps, M, axis):
+        """gather_snp_axis for a torch tensor that already lives on the gathering device; the
+        result is returned as a page-locked host array (one device->host copy)."""
+        import torch
+        local = local.movedim(axis, 0).contiguous()
+        rest = tuple(local.shape[1:])
+        flat = local.reshape(local.shape[0], -1)
+        dev = flat.device
+        n_loc = torch.tensor([flat.shape[0]], dtype=torch.int64, device=dev)
+        sizes = [torch.zeros_like(n_loc) for _ in range(self.world)]
+        self._dist.all_gather(sizes, n_loc)
+        sizes = [int(t.item()) for t in sizes]
+        n_max = max(sizes)
+        pad = torch.zeros((n_max, flat.shape[1]), dtype=flat.dtype, device=dev)
+        pad[:flat.shape[0]] = flat
+        idx = torch.full((n_max,), -1, dtype=torch.int64, device=dev)
+        idx[:flat.shape[0]] = torch.as_tensor(np.asarray(snps, dtype=np.int64), device=dev)
+        all_pad = [torch.empty_like(pad) for _ in range(self.world)]
+        all_idx = [torch.empty_like(idx) for _ in range(self.world)]
+        self._dist.all_gather(all_pad, pad)
+        self._dist.all_gather(all_idx, idx)
+        rows = torch.cat([all_pad[r][:sizes[r]] for r in range(self.world)], dim=0)
+        where = torch.cat([all_idx[r][:sizes[r]] for r in range(self.world)], dim=0)
+        full = torch.zeros((M, flat.shape[1]), dtype=rows.dtype, device=dev)
+        full.index_copy_(0, where, rows)
+        full = full.reshape((M,) + rest).movedim(0, axis).contiguous()
+        host = torch.empty(full.shape, dtype=full.dtype, pin_memory=dev.type == 'cuda')
+        host.copy_(full)
+        return host.numpy()
+
     def barrier(self):
         self._dist.barrier()
 

@@ -236,6 +236,22 @@ class CudaEngine:
         _lib.check(self.lib.vb_fit_get_params(self.ctx.handle, _lib.np_ptr(mu), _lib.np_ptr(dmk)))
         return mu, dmk
 
+    def get_params_device(self):
+        """(vi_mu [K,P,M], vi_delta [M,K]) of this rank as torch CUDA tensors."""
+        torch = _torch()
+        dev = torch.device('cuda', self.ctx.device)
+        mu = torch.empty((self.K, self.P, self.M), dtype=torch.float64, device=dev)
+        dmk = torch.empty((self.M, self.K), dtype=torch.float64, device=dev)
+        _lib.check(self.lib.vb_fit_get_params_dev(self.ctx.handle, C.c_void_p(mu.data_ptr()),
+                                                  C.c_void_p(dmk.data_ptr())))
+        return mu, dmk
+
+    def set_params_device(self, mu, dmk):
+        assert mu.is_cuda and dmk.is_cuda and mu.is_contiguous() and dmk.is_contiguous()
+        assert tuple(mu.shape) == (self.K, self.P, self.M) and tuple(dmk.shape) == (self.M, self.K)
+        _lib.check(self.lib.vb_fit_set_params_dev(self.ctx.handle, C.c_void_p(mu.data_ptr()),
+                                                  C.c_void_p(dmk.data_ptr())))
+
     # ---- evaluations (return the device stats tensor, valid until the next evaluation)
     def eval(self):
         _lib.check(self.lib.vb_fit_eval(self.ctx.handle, C.c_void_p(self._stats.data_ptr())))
