@@ -231,3 +231,22 @@ def test_sym_and_full_storage_agree():
     assert np.allclose(yp, yf, rtol=1e-13, atol=1e-13 * np.abs(yf).max())
     packed.close()
     full.close()
+
+
+def test_checkpointing_does_not_disturb_speculation(tmp_path):
+    """Periodic checkpoints download the state between iterations, which invalidates the trial
+    queued speculatively behind the previous iteration: the fit must fall back and reproduce the
+    same trajectory (syn_p5 has no error-scaling step, so speculation is active)."""
+    fx = load_case('syn_p5')
+    vi = make_product(fx, checkpoint=True, checkpoint_freq=3, output=str(tmp_path / 'ck'))
+    np.random.seed(int(fx['seed']))
+    params = vi.optimize(None)
+    tr = vi.trajectory
+    assert tr['trials'] == fx['traj_trials'].tolist()
+    assert np.allclose(tr['elbo'], fx['traj_elbo_out'], rtol=1e-8, atol=0)
+    assert np.allclose(params[0], fx['final_vi_mu'], rtol=1e-6, atol=1e-9)
+    import os
+    files = sorted(os.listdir(tmp_path))
+    assert files == sorted('ck-checkpoint.%d.npz' % i for i in range(0, len(tr['elbo']), 3))
+    first = np.load(tmp_path / 'ck-checkpoint.0.npz')
+    assert np.allclose(first['vi_mu'], fx['init_vi_mu'], rtol=1e-7, atol=1e-12)
