@@ -128,6 +128,138 @@ def build_gpu_problem(comm, device, M_total=M_TOTAL, n_blocks=N_BLOCKS, num_its=
     return vi, ctx, info
 
 
+# Other BASELINE.json configurations (not the default bench line; `--workload c3|c5`).  Same block
+# layout and sumstat model; P cohorts with their own LD (seed per cohort), shared causal SNPs with
+# cross-cohort effect correlation 0.8.
+WORKLOADS = {
+    'c3': dict(P=3, N=(3e5, 1e5, 5e4), n_ref=0.3, ldthresh=0.99, grid=('simple', 2),
+               name='BASELINE configs[2]: synthetic 3-cohort joint fit, per-cohort low-rank LD '
+                    '(reference panel of 0.3 n haplotypes, --ldthresh 0.99), -K 2 grid'),
+    'c5': dict(P=5, N=(3e5, 1e5, 5e4, 5e4, 2e4), n_ref=2.0, ldthresh=1.0, grid=('custom', 256),
+               name='BASELINE configs[4]: synthetic 5-cohort fit, dense per-cohort LD, custom grid of '
+                    '256 SPD covariance matrices'),
+}
+
+
+def mixture_grid_multi(beta_hat, se, P, spec):
+    """Covariance grid of a multi-cohort workload: the reference's _make_simple (vi_options.py:301-337,
+    positive-definite members only -- its own constructor rejects the rest, :610-613) or a custom grid
+    built the same way (log-spaced scales x 3 random rescalings) as --load-checkpoint's .pkl allows."""
+    from vilma_b200 import vi_options
+    mins, maxes = vi_options._grid_range(beta_hat, se, False)
+    np.random.seed(42)
+    kind, k = spec
+    if kind == 'simple':
+        covs = vi_options._make_simple(P, k, mins, maxes)
+    else:
+        levels = (k + 2) // 3
+        diag_vals = vi_options._make_diag_vals(P, levels - 2, mins, maxes)
+        covs = []
+        for idx, diag in enumerate(diag_vals):
+            rho = (0.0, 0.5, 0.9)[idx % 3]
+            mat = np.full((P, P), rho) + (1 - rho) * np.eye(P)
+            mat = mat * np.sqrt(diag)
+            mat = mat.T * np.sqrt(diag)
+            for _ in range(3):
+                scale = np.diag(np.sqrt(np.exp(np.random.uniform(-1, 1, P))))
+                covs.append(scale.dot(mat.dot(scale)))
+        covs = covs[:k]
+    return [c for c in covs if np.all(np.linalg.eigvalsh(c) > 0)]
+
+
+def build_gpu_problem_multi(comm, device, wl, M_total=M_TOTAL, n_blocks=N_BLOCKS, num_its=1000):
+    """Multi-cohort analogue of build_gpu_problem: every cohort's LD shard is generated in HBM."""
+    import torch
+    from vilma_b200 import synth
+    from vilma_b200.engine import DeviceContext, DeviceLD, choose_storage, dense_bytes
+    from vilma_b200.variational_inference import DeviceBlockDiagonalMatrix, MultiPopVI
+
+    dev = torch.device('cuda', device)
+    P, N = wl['P'], np.array(wl['N'], dtype=np.float64)
+    M_ld, n_all, starts = layout(M_total, n_blocks)
+    mine = synth.assign_blocks(n_all, comm.world)[comm.rank]
+    miss_all = np.arange(M_ld, M_total, dtype=np.int64)
+    snps_ld = np.concatenate([np.arange(starts[b], starts[b + 1]) for b in mine])
+    snps = np.sort(np.concatenate([snps_ld, miss_all[comm.rank::comm.world]]))
+    g2l = np.full(M_total, -1, dtype=np.int64)
+    g2l[snps] = np.arange(len(snps))
+    t0 = time.time()
+    low_rank = wl['ldthresh'] < 1.0 or wl['n_ref'] <= 1.0
+
+    def rank_of(n):
+        return max(2, int(np.ceil(wl['n_ref'] * n))) - 1 if low_rank else n
+
+    inv_se2 = np.zeros(P)
+    for b in mine:
+        for p in range(P):
+            inv_se2[p] += float((synth.block_se(int(n_all[b]), 42 + p, b, N[p], dev) ** -2).sum())
+    inv_se2 = comm.sum(inv_se2) + (M_total - M_ld) * 1.0
+    prior = 2 * N * INIT_HG / inv_se2
+
+    ctx = DeviceContext(device)
+    kinds = [choose_storage(int(n_all[b]), rank_of(int(n_all[b]))) if low_rank else 'dense' for b in mine]
+    ranks = np.array([-1 if k == 'dense' else rank_of(int(n_all[b])) for k, b in zip(kinds, mine)],
+                     dtype=np.int64)
+    lds = [DeviceLD(ctx, len(snps), n=n_all[mine], rank=ranks) for _ in range(P)]
+    beta_hat = np.zeros((P, M_total))
+    se = np.ones((P, M_total))
+    adj = np.zeros((P, M_total))
+    inv_betas = np.zeros((P, M_total))
+    ld_diags = np.zeros((P, M_total))
+    chi = np.zeros(P)
+    ld_ranks = np.zeros(P)
+    for j, b in enumerate(mine):
+        nb = int(n_all[b])
+        sl = slice(starts[b], starts[b + 1])
+        beta = synth.shared_effects(nb, 42, b, P, M_total, dev)
+        for p in range(P):
+            se_b = synth.block_se(nb, 42 + p, b, N[p], dev)
+            blk = synth.cohort_block(nb, 1000 + p, b, p, se_b, beta[p], dev, wl['n_ref'], wl['ldthresh'])
+            ib = synth.ridge_start(blk, se_b, float(prior[p]))
+            if kinds[j] == 'dense':
+                r = blk['R'] if blk['R'] is not None else (blk['U'] * blk['s'][None, :]) @ blk['U'].T
+                lds[p].set_dense(j, r.contiguous())
+            else:
+                if blk['rank'] != ranks[j]:
+                    raise RuntimeError('block %d cohort %d: rank %d, planned %d' % (b, p, blk['rank'], ranks[j]))
+                lds[p].set_factor(j, blk['U'], blk['s'])
+            chi[p] += blk['chi']
+            ld_ranks[p] += blk['rank']
+            beta_hat[p, sl] = blk['beta_hat'].cpu().numpy()
+            se[p, sl] = se_b.cpu().numpy()
+            adj[p, sl] = blk['adj'].cpu().numpy()
+            inv_betas[p, sl] = ib.cpu().numpy()
+            ld_diags[p, sl] = blk['ld_diag'].cpu().numpy()
+            del blk
+    for ld in lds:
+        ld.finalize(g2l[snps_ld])
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    if comm.world > 1:
+        beta_hat, adj, inv_betas, ld_diags = (comm.sum(x) for x in (beta_hat, adj, inv_betas, ld_diags))
+        se = comm.sum(se - 1.0) + 1.0
+    chi, ld_ranks = comm.sum(chi), comm.sum(ld_ranks)
+    covs = mixture_grid_multi(beta_hat, se, P, wl['grid'])
+    pre = dict(ld_diags=ld_diags, adj_marginal_effects=adj, chi_stat=chi, ld_ranks=ld_ranks,
+               inverse_betas=inv_betas)
+    vi = MultiPopVI(marginal_effects=beta_hat, std_errs=se,
+                    ld_mats=[DeviceBlockDiagonalMatrix(ld, (M_total, M_total)) for ld in lds],
+                    mixture_covs=covs, annotations=np.ones((M_total, 1)), checkpoint=False,
+                    checkpoint_freq=-1, output='bench', scaled=False, scale_se=False,
+                    gwas_N=N, init_hg=np.full(P, INIT_HG), num_its=num_its,
+                    comm=comm, device=device, precomputed=pre, local_snps=snps, context=ctx)
+    per_block = [dense_bytes(int(n)) if choose_storage(int(n), rank_of(int(n))) == 'dense' or not low_rank
+                 else 16 * int(n) * rank_of(int(n)) for n in n_all]
+    info = dict(M=M_total, M_ld=M_ld, blocks=int(n_blocks), K=len(covs), P=P,
+                ld_bytes_total=int(P * sum(per_block)), ld_bytes_rank=int(sum(ld.bytes for ld in lds)),
+                setup_s=time.time() - t0, n_max=int(n_all.max()),
+                ld_store='%d of %d blocks symmetric-packed dense, the rest as factors' % (
+                    sum(1 for n in n_all if not low_rank or choose_storage(int(n), rank_of(int(n))) == 'dense'),
+                    len(n_all)),
+                rank_total=float(ld_ranks.sum()), name=wl['name'])
+    return vi, ctx, info
+
+
 def build_cpu_sample(n_blocks=SAMPLE_BLOCKS):
     """The bounded CPU sample: the first `n_blocks` blocks of the same generator, as oracle
     objects (LowRankBlock does the reference's eigendecomposition, matrix_structures.py:15-28)."""
@@ -216,16 +348,58 @@ def _time_cpu(steps, warmup, cores):
 # clocks
 # --------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (one
+    sample every ~2 ms; the region of a default run is ~50 ms, too short for `nvidia-smi -lms`),
+    falling back to an nvidia-smi subprocess when NVML bindings are unavailable."""
     FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
               'clocks_event_reasons.sw_power_cap')
+    # nvmlClocksEventReason* bit masks
+    REASONS = {'sw_power_cap': 0x4, 'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20,
+               'hw_thermal_slowdown': 0x40}
 
     def __init__(self, device):
         self.device = device
         self.proc = None
         self.path = None
+        self.thread = None
+        self.samples = []
+        self.mask = 0
+        self.max_mhz = None
+        self._stop = False
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(self.device)
+        try:
+            bus = '%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.device)
+
+    def _poll(self, nv, h):
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(get_reasons(h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import threading
+            nv, h = self._nvml_handle()
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix='.csv')
             os.close(fd)
@@ -238,6 +412,14 @@ class ClockSampler:
 
     def stop(self):
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            if self.samples:
+                out.update(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.max_mhz,
+                           reasons=sorted(k for k, m in self.REASONS.items() if self.mask & m),
+                           samples=len(self.samples))
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -299,9 +481,16 @@ def run_ours(args):
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
 
-    vi, ctx, info = build_gpu_problem(comm, device, M_total=args.snps, n_blocks=args.blocks)
+    if args.workload == 'c2':
+        vi, ctx, info = build_gpu_problem(comm, device, M_total=args.snps, n_blocks=args.blocks)
+        info['name'] = 'BASELINE configs[1]: synthetic single cohort, dense LD, -K 12'
+        info['ld_store'] = ('dense fp64, symmetric-packed (lower triangle in 8-row panels): '
+                            '4 n (n+1) bytes per block per mat-vec')
+    else:
+        vi, ctx, info = build_gpu_problem_multi(comm, device, WORKLOADS[args.workload],
+                                                M_total=args.snps, n_blocks=args.blocks)
     log('[rank %d] problem built in %.1fs: %s' % (comm.rank, info['setup_s'], info))
-    M = info['M']
+    M, P, K = info['M'], info['P'], info['K']
 
     # initial parameters: host arrays in pinned memory (e2e uploads them)
     np.random.seed(42)
@@ -311,7 +500,7 @@ def run_ours(args):
     pin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in init]
     init = tuple(t.numpy() for t in pin)
     ckpt = {'vi_mu': init[0], 'vi_delta': init[1], 'hyper_delta': init[2],
-            'error_scaling': np.ones(1)}
+            'error_scaling': np.ones(P)}
 
     # ---------------- device-resident run: warm-up then timed ----------------
     vi._set_state(init)
@@ -358,14 +547,19 @@ def run_ours(args):
     per_rank = np.zeros((comm.world, 3))
     per_rank[comm.rank] = [mv_avg, snp_ms / max(snp_n, 1), len(vi._snps)]
     per_rank = comm.sum(per_rank) if comm.world > 1 else per_rank
-    achieved = info['ld_bytes_rank'] / (mv_avg * 1e-3) / 1e9 if mv_n else 0.0
+    achieved = info['ld_bytes_rank'] / P / (mv_avg * 1e-3) / 1e9 if mv_n else 0.0    # one launch per cohort
     traffic = None
-    if comm.world == 1 and M == M_TOTAL:
+    if comm.world == 1 and M == M_TOTAL and args.workload == 'c2':
         try:
             traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ld_matvec_traffic.json')))['bytes_per_launch']
         except Exception:
             pass
-    bytes_trial = info['ld_bytes_total'] + 16 * info['K'] * 2 * M + 64 * M
+    bytes_trial = info['ld_bytes_total'] + 16 * K * (P + 1) * M + 64 * P * M
+    # the per-SNP kernel's own floor: trials read mu and write mu', delta; refreshes read mu, write delta
+    n_loc = len(vi._snps)
+    snp_bytes = (trials * (16 * K * (P + 1) + 64 * P) + (evals - trials) * (8 * K * (P + 2) + 40 * P)) * n_loc
+    snp_achieved = snp_bytes / (snp_ms * 1e-3) / 1e9 if snp_ms else 0.0
+    ld_dominant = mv_ms >= snp_ms
 
     # ---------------- end-to-end: the public call with host buffers ----------------
     vi.num_its = args.steps
@@ -400,8 +594,8 @@ def run_ours(args):
     e2e_trials = vi.n_trials - tr0
     e2e_steps = vi.num_its_run
     n_local = len(vi._snps)
-    h2d = (info['K'] * n_local * 2 + info['K']) * 8 / max(e2e_steps, 1)
-    d2h = (info['K'] * n_local * 2) * 8 / max(e2e_steps, 1) + (3 + 3 + 10) * 8 * 2
+    h2d = (K * n_local * (P + 1) + K) * 8 / max(e2e_steps, 1)
+    d2h = (K * n_local * (P + 1)) * 8 / max(e2e_steps, 1) + (3 * P + 3 + 10) * 8 * 2
     e2e_value = M * e2e_trials / e2e_s
 
     result = {
@@ -411,39 +605,48 @@ def run_ours(args):
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
         'config': {
-            'workload': 'BASELINE configs[1]: synthetic single cohort, %d SNPs (1%% without LD) in '
-                        '%d dense LD blocks (lognormal sizes, CV 0.6, max n=%d), -K 12 -> %d '
-                        'mixture components, P=1' % (M, info['blocks'], info['n_max'], info['K']),
-            'M': M, 'blocks': info['blocks'], 'K': info['K'], 'P': 1,
-            'ld_store': 'dense fp64, symmetric-packed (lower triangle in 8-row panels): '
-                        '4 n (n+1) bytes per block per mat-vec',
+            'workload': '%s; %d SNPs (1%% without LD) in %d LD blocks (lognormal sizes, CV 0.6, max '
+                        'n=%d), %d mixture components, P=%d' % (info['name'], M, info['blocks'],
+                                                                info['n_max'], K, P),
+            'M': M, 'blocks': info['blocks'], 'K': K, 'P': P,
+            'ld_store': info['ld_store'],
             'ld_bytes': info['ld_bytes_total'], 'algorithmic_bytes_per_trial': bytes_trial,
             'trials': int(trials), 'state_evaluations': int(evals),
             'trials_per_step': trials / max(steps_done, 1),
             'l2': 'inputs larger than L2: the %.1f GB LD store is re-read from HBM by every '
                   'evaluation' % (info['ld_bytes_rank'] / 1e9),
             'parallelism': 'LD blocks sharded over %d rank(s), LPT by n^2; one all-reduce of '
-                           '%d doubles per evaluated state' % (comm.world, 6),
+                           '%d doubles per evaluated state' % (comm.world, 3 * P + 3),
             'setup_s': info['setup_s'],
         },
-        'clocks': {k: clocks.get(k) for k in ('sm_mhz', 'sm_max_mhz', 'reasons')},
+        'clocks': {k: clocks.get(k) for k in ('sm_mhz', 'sm_max_mhz', 'reasons', 'samples')},
         'e2e': {'value': e2e_value, 'unit': 'SNP-updates/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': d2h, 'steps': int(e2e_steps), 'seconds': e2e_s,
                 'call': 'MultiPopVI.optimize(checkpoint) with pinned host parameter arrays'},
         'gpu_launches': int(launches),
-        'roofline': {'bound': 'hbm', 'kernel': 'vb_ld_sym_kernel', 'achieved': achieved,
-                     'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-                     'traffic': traffic, 'peak_source': peak_src,
-                     'bytes_per_launch': info['ld_bytes_rank'], 'avg_launch_ms': mv_avg,
-                     'launches_timed': int(mv_n),
-                     'share_of_step': mv_ms / ms if ms else None,
+        # the dominant kernel by time in the region: the LD mat-vec (one launch per cohort) for
+        # single-cohort fits, the per-SNP update for large K (P+1) state streams
+        'roofline': {'bound': 'hbm',
+                     'kernel': 'vb_ld_sym_kernel' if ld_dominant else 'vb_snp_tile_kernel',
+                     'achieved': achieved if ld_dominant else snp_achieved,
+                     'peak': hbm_peak, 'unit': 'GB/s',
+                     'frac': (achieved if ld_dominant else snp_achieved) / hbm_peak,
+                     'traffic': traffic if ld_dominant else None, 'peak_source': peak_src,
+                     'bytes_per_launch': info['ld_bytes_rank'] / P if ld_dominant else snp_bytes / max(snp_n, 1),
+                     'avg_launch_ms': mv_avg if ld_dominant else snp_ms / max(snp_n, 1),
+                     'launches_timed': int(mv_n if ld_dominant else snp_n),
+                     'share_of_step': (mv_ms if ld_dominant else snp_ms) / ms if ms else None,
+                     'ld_kernel': {'achieved': achieved, 'frac': achieved / hbm_peak, 'avg_launch_ms': mv_avg,
+                                   'share_of_step': mv_ms / ms if ms else None},
+                     'snp_kernel': {'achieved': snp_achieved, 'frac': snp_achieved / hbm_peak,
+                                    'share_of_step': snp_ms / ms if ms else None},
                      'snp_kernel_avg_ms': snp_ms / max(snp_n, 1),
                      'per_rank_ld_ms': [round(float(v), 4) for v in per_rank[:, 0]],
                      'per_rank_snp_ms': [round(float(v), 4) for v in per_rank[:, 1]],
                      'per_rank_snps': [int(v) for v in per_rank[:, 2]],
                      'whole_trial_frac': (bytes_trial / comm.world) * evals / (ms * 1e-3) / 1e9 / hbm_peak},
     }
-    if comm.rank == 0 and comm.world == 1 and not args.no_cpu:
+    if comm.rank == 0 and comm.world == 1 and not args.no_cpu and args.workload == 'c2':
         v, dt, tr, Ms, extra = time_cpu(steps=3, warmup=1)
         result['cpu_baseline'] = {'value': v, 'unit': 'SNP-updates/s', 'cores': extra['cores'],
                                   'kind': 'port', 'sample': extra['sample'], 'seconds': dt}
@@ -486,6 +689,8 @@ def main():
     ap.add_argument('--snps', type=int, default=M_TOTAL)
     ap.add_argument('--blocks', type=int, default=N_BLOCKS)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--workload', default='c2', choices=['c2', 'c3', 'c5'],
+                    help='c2 = BASELINE configs[1] (the bench line of record); c3 / c5 = configs[2] / configs[4]')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

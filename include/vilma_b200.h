@@ -140,6 +140,13 @@ int vb_fit_posterior(vb_ctx* ctx, double* pm_host, double* pv_host);
  * Then prev := new.  vb_fit_pm_mark(which): 0 -> prev := current, 1 -> ckpt := current. */
 int vb_fit_pm_diff(vb_ctx* ctx, double atol, double rtol, double* out_dev);
 int vb_fit_pm_mark(vb_ctx* ctx, int which);
+/* MultiPopVI._initialize on the device (variational_inference.py:643-700), for problems whose
+ * [K,P,P,M] host intermediates do not fit: vb_fit_init_delta(fake_mu_host [P][M]) leaves the first
+ * delta (:660-667) in the current state; the caller forms hyper_delta from its annotation sums
+ * (vb_fit_sum_annotations; :668-674) and sets it; vb_fit_init_mu then writes mu (:675-678);
+ * vb_fit_refresh_delta + vb_fit_accept complete the start (:679). */
+int vb_fit_init_delta(vb_ctx* ctx, const double* fake_mu_host);
+int vb_fit_init_mu(vb_ctx* ctx);
 /* vi_sigma[k0:k1][P][P][M] in the reference layout -> host  (:712-724) */
 int vb_fit_vi_sigma(vb_ctx* ctx, int k0, int k1, double* out_host);
 

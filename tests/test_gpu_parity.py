@@ -67,6 +67,23 @@ def test_precompute_and_state_eval(name):
 
 
 @pytest.mark.parametrize('name', VI_CASES)
+def test_initialize_on_device(name):
+    """vb_init_delta_kernel / vb_init_mu_kernel (used when the host form's [K,P,P,M] arrays would not
+    fit) give the reference's starting point, and the state they leave resident is that point."""
+    fx = load_case(name)
+    vi = make_product(fx)
+    vi.init_on_device = True
+    np.random.seed(int(fx['seed']))
+    params = vi._initialize()
+    assert np.allclose(params[0], fx['init_vi_mu'], rtol=1e-7, atol=1e-12)
+    assert np.allclose(params[1], fx['init_vi_delta'], rtol=1e-7, atol=1e-300)
+    assert np.allclose(params[2], fx['init_hyper_delta'], rtol=1e-9)
+    assert np.allclose(vi.nat_grad_vi_delta, fx['init_nat_grad_vi_delta'], rtol=1e-9, atol=1e-12)
+    assert vi._same(params)
+    assert np.isclose(vi.elbo(params), float(fx['init_elbo']), rtol=1e-9)
+
+
+@pytest.mark.parametrize('name', VI_CASES)
 def test_trajectory(name):
     """Full optimize(): same decisions, same ELBO trajectory, same final parameters."""
     fx = load_case(name)
@@ -103,6 +120,33 @@ def test_trajectory_python_loop(name):
     assert np.allclose(tr['elbo'], fx['traj_elbo_out'], rtol=1e-8, atol=0)
     assert np.allclose(params[0], fx['final_vi_mu'], rtol=1e-6, atol=1e-9)
     assert np.allclose(vi.error_scaling, fx['final_error_scaling'], rtol=1e-8)
+
+
+@pytest.mark.parametrize('warps', [1, 2, 8])
+@pytest.mark.parametrize('name', ['vischeme_linked_a2_s1_t1', 'syn_p1_dense', 'syn_p1_scaled',
+                                  'syn_p2_lowrank', 'syn_p3', 'syn_p5'])
+def test_trajectory_tile_kernel(name, warps):
+    """The K-split tile kernel (csrc/snp_tile_kernel.cuh), forced with W warps per 32-SNP tile, takes
+    the reference's decisions too (by default it serves P >= 3 and K >= 32 only)."""
+    from vilma_b200.engine import set_option
+    fx = load_case(name)
+    set_option('snp_tile', warps)
+    try:
+        vi = make_product(fx)
+        np.random.seed(int(fx['seed']))
+        params = vi.optimize(None)
+    finally:
+        set_option('snp_tile', -1)
+    tr = vi.trajectory
+    assert tr['trials'] == fx['traj_trials'].tolist()
+    assert np.array_equal(np.array(tr['L0']), fx['traj_L0'])
+    assert np.allclose(tr['elbo'], fx['traj_elbo_out'], rtol=1e-8, atol=0)
+    assert np.allclose(vi.error_scaling, fx['final_error_scaling'], rtol=1e-8)
+    assert np.allclose(params[0], fx['final_vi_mu'], rtol=1e-6, atol=1e-9)
+    assert np.allclose(params[1], fx['final_vi_delta'], rtol=1e-6, atol=1e-12)
+    assert np.allclose(params[2], fx['final_hyper_delta'], rtol=1e-6, atol=1e-12)
+    assert np.allclose(vi.real_posterior_mean(*params), fx['final_post_mean'], rtol=1e-6, atol=1e-9)
+    assert np.allclose(vi.real_posterior_variance(*params), fx['final_post_var'], rtol=1e-6, atol=1e-12)
 
 
 @pytest.mark.parametrize('name', [n for n in VI_CASES if 'resume_ckpt_vi_mu' in load_case(n)])

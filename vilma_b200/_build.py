@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libvilma_b200.so')
 SOURCES = ['vilma_b200.cu']
-HEADERS = ['vb_common.cuh', 'ld_kernels.cuh', 'snp_kernels.cuh',
+HEADERS = ['vb_common.cuh', 'ld_kernels.cuh', 'snp_kernels.cuh', 'snp_tile_kernel.cuh',
            os.path.join('..', '..', 'include', 'vilma_b200.h')]
 
 

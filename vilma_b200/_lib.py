@@ -50,6 +50,8 @@ SIGNATURES = {
     'vb_fit_pm_diff': (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_void_p]),
     'vb_fit_pm_mark': (C.c_int, [C.c_void_p, C.c_int]),
     'vb_fit_vi_sigma': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    'vb_fit_init_delta': (C.c_int, [C.c_void_p, C.c_void_p]),
+    'vb_fit_init_mu': (C.c_int, [C.c_void_p]),
 }
 
 
@@ -96,6 +98,12 @@ def load():
     if lib.vb_abi_version() != 1:
         raise VilmaB200Error('libvilma_b200.so ABI version mismatch')
     _lib = lib
+    # VILMA_B200_OPTIONS="name=value,name=value": process-wide vb_set_option calls at load (kernel
+    # selection for experiments and for the worker processes of the multi-GPU tests)
+    for item in filter(None, os.environ.get('VILMA_B200_OPTIONS', '').split(',')):
+        name, _, value = item.partition('=')
+        if lib.vb_set_option(name.strip().encode(), int(value)) != 0:
+            raise VilmaB200Error(lib.vb_last_error().decode())
     return lib
 
 

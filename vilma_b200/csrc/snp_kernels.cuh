@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(VB_SNP_THREADS, (P == 1) ? VB_SNP3_MINBLOCKS :
             }
             const double lk = valid ? *pdl : mx;
             const double c = 2.0 * (lk - gfull[k]) - dot;          // log|S_k| back from the logit
-            const double w = exp(lk - mx);
+            const double w = vb_exp_nonpos(lk - mx);
             if (valid) *pdl = w;
             s0 += w;
 #pragma unroll
@@ -685,6 +685,111 @@ __global__ void vb_vi_sigma_kernel(const double* __restrict__ prec, const double
 #pragma unroll
             for (int q = 0; q < P; ++q)
                 out[(((size_t)(k - k0) * P + p) * P + q) * M + i] = S[p >= q ? VB_TRI(p, q) : VB_TRI(q, p)];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device form of MultiPopVI._initialize (variational_inference.py:643-700): the reference builds the
+// starting point from three host arrays of shape [K,P,P,M] (61 GB for 5 cohorts x 256 components x
+// 1.2M SNPs); here S_ki is recomputed per (k, SNP) in registers.  `fm` is the jittered ridge start
+// fake_mu [P][M] (drawn on the host from NumPy's legacy stream, as the reference does).
+//   kernel 1 (:660-667): delta0_ik = max(e_ik / sum_k e_ik, 1e-100),
+//       e_ik = exp(-(p_ik - min_k p_ik)/2), p_ik = 1.6^2 fm^T Prec_k fm + tr(Prec_k S_ki) - log|Sigma_k|
+//   (host: hyper_delta from the annotation sums of delta0, :668-674)
+//   kernel 2 (:675-678): mu_ki = S_ki (sum_k delta0_ik S_ki)^-1 fm
+// The final delta (:679, _nat_to_not_vi_delta) is the REFRESH mode of the update kernel.
+template <int P>
+__global__ void __launch_bounds__(VB_SNP_THREADS) vb_init_delta_kernel(
+    int K, int64_t M, const double* __restrict__ prec, const double* __restrict__ logdet,
+    const double* __restrict__ sld, const double* __restrict__ inv_tau_dev,
+    const double* __restrict__ fm, double* __restrict__ delta) {
+    constexpr int NT = P * (P + 1) / 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double dt[P], f[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            dt[p] = sld[(size_t)p * M + i] * inv_tau_dev[p];
+            f[p] = 1.6 * fm[(size_t)p * M + i];
+        }
+        double mn = 1.0e300;
+        for (int k = 0; k < K; ++k) {
+            const double* pr = prec + (size_t)k * P * P;
+            double lam[NT], S[NT], c;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+#pragma unroll
+                for (int q = 0; q <= p; ++q) lam[VB_TRI(p, q)] = pr[p * P + q];
+                lam[VB_TRI(p, p)] += dt[p];
+            }
+            vb_spd_inverse<P>(lam, S, c);
+            double v = -logdet[k];
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+#pragma unroll
+                for (int q = 0; q < P; ++q)
+                    v += pr[p * P + q] * (f[p] * f[q] + S[p >= q ? VB_TRI(p, q) : VB_TRI(q, p)]);
+            delta[(size_t)k * M + i] = v;
+            mn = fmin(mn, v);
+        }
+        double tot = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const double e = exp(-0.5 * (delta[(size_t)k * M + i] - mn));
+            delta[(size_t)k * M + i] = e;
+            tot += e;
+        }
+        for (int k = 0; k < K; ++k)
+            delta[(size_t)k * M + i] = fmax(delta[(size_t)k * M + i] / tot, VB_EPSILON);
+    }
+}
+template <int P>
+__global__ void __launch_bounds__(VB_SNP_THREADS) vb_init_mu_kernel(
+    int K, int64_t M, const double* __restrict__ prec, const double* __restrict__ sld,
+    const double* __restrict__ inv_tau_dev, const double* __restrict__ fm,
+    const double* __restrict__ delta, double* __restrict__ mu) {
+    constexpr int NT = P * (P + 1) / 2;
+    const size_t PM = (size_t)P * M;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double dt[P], f[P], avg[NT];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            dt[p] = sld[(size_t)p * M + i] * inv_tau_dev[p];
+            f[p] = fm[(size_t)p * M + i];
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) avg[t] = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const double* pr = prec + (size_t)k * P * P;
+            double lam[NT], S[NT], c;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+#pragma unroll
+                for (int q = 0; q <= p; ++q) lam[VB_TRI(p, q)] = pr[p * P + q];
+                lam[VB_TRI(p, p)] += dt[p];
+            }
+            vb_spd_inverse<P>(lam, S, c);
+            const double d = delta[(size_t)k * M + i];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) avg[t] = fma(d, S[t], avg[t]);
+        }
+        double inv_avg[NT], c0, nat[P];
+        vb_spd_inverse<P>(avg, inv_avg, c0);
+        vb_sym_matvec<P>(inv_avg, f, nat);
+        for (int k = 0; k < K; ++k) {
+            const double* pr = prec + (size_t)k * P * P;
+            double lam[NT], S[NT], c, m[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+#pragma unroll
+                for (int q = 0; q <= p; ++q) lam[VB_TRI(p, q)] = pr[p * P + q];
+                lam[VB_TRI(p, p)] += dt[p];
+            }
+            vb_spd_inverse<P>(lam, S, c);
+            vb_sym_matvec<P>(S, nat, m);
+#pragma unroll
+            for (int p = 0; p < P; ++p) mu[(size_t)k * PM + (size_t)p * M + i] = m[p];
+        }
     }
 }
 

@@ -1,0 +1,330 @@
+// Tile form of the fused per-SNP update (TRIAL / REFRESH) for sm_100a: a CTA owns 32 consecutive
+// SNPs at a time and its W warps split the K mixture components among themselves.
+//
+// Same arithmetic as vb_snp_kernel / vb_snp3_kernel (snp_kernels.cuh; reference numerics.py:11-15,
+// 49-115, 132-146, 179-213 and variational_inference.py:712-733, 804-823), different mapping:
+//
+//   * thread (warp w, lane l) handles SNP 32*tile + l and components k = w, w+W, w+2W, ...
+//     -> 32W threads per 32 SNPs: W times the parallelism of thread-per-SNP when a rank owns few SNPs,
+//        and W times shorter serial k-loops when K is large (K = 582 for two cohorts at the default -K 12);
+//   * logits stay in SHARED memory (slot-major, lane-minor: conflict-free) between the pass that
+//     produces them and the pass that normalises them.  Thread-per-SNP parks them in the output
+//     delta buffer, which for K*(P+1) KB per CTA >> L1 means two extra HBM round trips per (k, SNP);
+//     here every state element crosses HBM exactly once: read mu, write mu', write delta
+//     = the 16 K (P+1) M floor of SURVEY 8(d);
+//   * softmax moments are accumulated online per thread over its slice (one exp per component: the
+//     rescale factor and the weight are the same exponential), the W slices of a SNP are merged
+//     through shared memory in warp order, and each warp normalises its own slice;
+//   * P >= 3: Lambda = Prec_k + diag(sld/tau) is factored as L D L^T (no square roots, ONE log of
+//     the pivot product); tr(Prec_k S) = P - sum_p (sld_p/tau_p) S_pp and
+//     mu'^T Prec_k mu' = mu'.eta - sum_p (sld_p/tau_p) mu'_p^2 reuse what the update already has.
+//
+// Deterministic: every reduction has a fixed order (slice merge in warp order, per-CTA statistics by
+// warp 0 lanes then a shuffle tree, annotation sums per (k) by the warp that owns k).
+#pragma once
+#include "snp_kernels.cuh"
+
+#ifndef VB_TILE_UNROLL_A
+#define VB_TILE_UNROLL_A 2        // independent components in flight per thread (the chain log -> exp is ~100 dependent fp64 ops)
+#endif
+#ifndef VB_TILE_UNROLL_B
+#define VB_TILE_UNROLL_B 4
+#endif
+#define VB_TILE_SNPS 32
+#define VB_TILE_MAXW 16
+#define VB_TILE_NV(P) (5 + 2 * (P))        // mx, s0, sKd, sKq, sKs, spm[P], sm2[P]
+
+// L D L^T of a packed SPD matrix (P >= 3).  Nl = strictly-lower part of L^-1 (unit lower), inv = 1/D.
+template <int P>
+struct VbLdl {
+    static constexpr int NL = P * (P - 1) / 2;
+    double N[NL > 0 ? NL : 1];
+    double inv[P];
+    double det;
+    __device__ __forceinline__ static constexpr int sl(int i, int j) { return i * (i - 1) / 2 + j; }   // j < i
+
+    __device__ __forceinline__ void factor(const double (&lam)[P * (P + 1) / 2]) {
+        double L[NL > 0 ? NL : 1], U[NL > 0 ? NL : 1];      // U_ij = L_ij D_j
+        det = 1.0;
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+#pragma unroll
+            for (int i = j; i < P; ++i) {
+                double v = lam[VB_TRI(i, j)];
+#pragma unroll
+                for (int k = 0; k < j; ++k) v = fma(-U[sl(i, k)], L[sl(j, k)], v);
+                if (i == j) {
+                    det *= v;
+                    inv[j] = 1.0 / v;
+                } else {
+                    U[sl(i, j)] = v;
+                    L[sl(i, j)] = v * inv[j];
+                }
+            }
+        }
+        // N = L^-1: N_ij = -(L_ij + sum_{j<k<i} L_ik N_kj)
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+#pragma unroll
+            for (int i = j + 1; i < P; ++i) {
+                double v = L[sl(i, j)];
+#pragma unroll
+                for (int k = j + 1; k < i; ++k) v = fma(L[sl(i, k)], N[sl(k, j)], v);
+                N[sl(i, j)] = -v;
+            }
+    }
+    // x = Lambda^-1 b = N^T D^-1 N b
+    __device__ __forceinline__ void solve(const double (&b)[P], double (&x)[P]) const {
+        double y[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            double v = b[i];
+#pragma unroll
+            for (int j = 0; j < i; ++j) v = fma(N[sl(i, j)], b[j], v);
+            y[i] = v * inv[i];
+        }
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            double v = y[j];
+#pragma unroll
+            for (int i = j + 1; i < P; ++i) v = fma(N[sl(i, j)], y[i], v);
+            x[j] = v;
+        }
+    }
+    // diagonal of Lambda^-1: S_pp = inv_p + sum_{k>p} N_kp^2 inv_k
+    __device__ __forceinline__ void diag(double (&sd)[P]) const {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            double v = inv[p];
+#pragma unroll
+            for (int k = p + 1; k < P; ++k) v = fma(N[sl(k, p)] * inv[k], N[sl(k, p)], v);
+            sd[p] = v;
+        }
+    }
+};
+
+// registers per thread: P = 1 -> 64 (1024 threads / SM), P = 2, 3 -> 128, P >= 4 -> 255
+template <int P> struct VbTileCfg {
+    static constexpr int MAXT = (P <= 3) ? 512 : 256;
+    static constexpr int MINB = (P == 1) ? 2 : 1;
+    static constexpr int THREADS_PER_SM = (P == 1) ? 1024 : (P <= 3 ? 512 : 256);
+};
+
+template <int P, int MODE>
+__global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp_tile_kernel(const VbSnpArgs a) {
+    static_assert(MODE != VB_MODE_EVAL, "EVAL has no softmax: use vb_snp_kernel");
+    constexpr int NT = P * (P + 1) / 2;
+    constexpr int NS = VB_NSNPSTAT(P);
+    constexpr int NV = VB_TILE_NV(P);
+    constexpr int UNROLL_A = VB_TILE_UNROLL_A, UNROLL_B = VB_TILE_UNROLL_B;
+    extern __shared__ double s_tile[];
+    const int K = a.K;
+    const int64_t M = a.M;
+    const size_t PM = (size_t)P * M;
+    const int W = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kslots = (K + W - 1) / W;
+    const int AKf = a.fuse_ann ? a.A * K : 0;
+    // shared memory: logits [kslots][W][32] | merge scratch [W][NV][32] | annotation sums [A*K]
+    double* s_logit = s_tile + (size_t)warp * 32 + lane;                   // + slot * W * 32
+    double* s_merge = s_tile + (size_t)kslots * W * 32;
+    double* s_ann = s_merge + (size_t)W * NV * 32;
+    for (int j = threadIdx.x; j < AKf; j += blockDim.x) s_ann[j] = 0.0;
+    if (AKf) __syncthreads();
+
+    double tA[P], tC[P], tKd = 0.0, tKq = 0.0, tKs = 0.0;       // warp 0 only
+#pragma unroll
+    for (int p = 0; p < P; ++p) { tA[p] = 0.0; tC[p] = 0.0; }
+    const double step = a.step, one_minus_step = 1.0 - a.step;
+    const double* const g_prec = a.prec;
+    const double* const g_logdet = a.logdet;
+    const int64_t ntiles = (M + VB_TILE_SNPS - 1) / VB_TILE_SNPS;
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t i0 = tile * VB_TILE_SNPS + lane;
+        const bool valid = i0 < M;
+        const int64_t i = valid ? i0 : M - 1;
+        double dt[P], sld[P], g[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            sld[p] = a.sld[(size_t)p * M + i];
+            dt[p] = sld[p] * a.inv_tau[p];
+            g[p] = 0.0;
+        }
+        if constexpr (MODE == VB_MODE_TRIAL) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const double se = a.se[(size_t)p * M + i];
+                const double lk = a.linked_in[(size_t)p * M + i] / se - a.pm_in[(size_t)p * M + i] * sld[p];
+                g[p] = (a.adj[(size_t)p * M + i] - lk) * a.inv_tau[p];
+            }
+        }
+        const int an = a.ann[i];
+        const double* logh = a.logh + (size_t)an * K;
+        const double* gfull = a.gfull + (size_t)an * K;
+
+        // ---- pass A: this thread's slice, online softmax moments
+        double mx = -1.0e300, s0 = 0.0, sKd = 0.0, sKq = 0.0, sKs = 0.0, spm[P], sm2[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) { spm[p] = 0.0; sm2[p] = 0.0; }
+        const double* pmu_in = a.mu_in + (size_t)warp * PM + i;
+        double* pmu_out = (MODE == VB_MODE_TRIAL) ? a.mu_out + (size_t)warp * PM + i : nullptr;
+        const size_t kstride = (size_t)W * PM;
+        double* sl = s_logit;
+#pragma unroll UNROLL_A
+        for (int k = warp; k < K; k += W, pmu_in += kstride, sl += W * 32) {
+            const double* prec = g_prec + (size_t)k * P * P;
+            double lam[NT], mu[P], eta[P], sd[P], det;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+#pragma unroll
+                for (int q = 0; q <= p; ++q) lam[VB_TRI(p, q)] = prec[p * P + q];
+                lam[VB_TRI(p, p)] += dt[p];
+                mu[p] = __ldg(pmu_in + (size_t)p * M);
+            }
+            vb_sym_matvec<P>(lam, mu, eta);                        // eta_old = Lambda mu
+            if constexpr (MODE == VB_MODE_TRIAL) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) eta[p] = step * g[p] + one_minus_step * eta[p];
+            }
+            if constexpr (P <= 2) {
+                double S[NT];
+                vb_small_inverse<P>(lam, S, det);
+                if constexpr (MODE == VB_MODE_TRIAL) vb_sym_matvec<P>(S, eta, mu);     // mu' = S eta
+#pragma unroll
+                for (int p = 0; p < P; ++p) sd[p] = S[VB_TRI(p, p)];
+            } else {
+                VbLdl<P> f;
+                f.factor(lam);
+                det = f.det;
+                if constexpr (MODE == VB_MODE_TRIAL) f.solve(eta, mu);
+                f.diag(sd);
+            }
+            if constexpr (MODE == VB_MODE_TRIAL) {
+                if (valid) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) pmu_out[(size_t)p * M] = mu[p];
+                }
+                pmu_out += kstride;
+            }
+            const double c = -log(det);                            // log|S_k|
+            double dot = 0.0, dmm = 0.0, dss = 0.0;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                dot = fma(mu[p], eta[p], dot);
+                dmm = fma(dt[p] * mu[p], mu[p], dmm);
+                dss = fma(dt[p], sd[p], dss);
+            }
+            const double lk = 0.5 * (c + dot) + gfull[k];
+            *sl = lk;
+            const double quad = dot - dmm;                         // mu'^T Prec_k mu'
+            const double sigsum = g_logdet[k] - c + ((double)P - dss);   // log|Sigma_k| - log|S| + tr(Prec_k S)
+            // one exponential serves as rescale factor (new maximum) or as weight
+            const double d = lk - mx;
+            const double e = vb_exp_nonpos(-fabs(d));
+            double w = e;
+            if (d > 0.0) {
+                s0 *= e; sKd *= e; sKq *= e; sKs *= e;
+#pragma unroll
+                for (int p = 0; p < P; ++p) { spm[p] *= e; sm2[p] *= e; }
+                mx = lk;
+                w = 1.0;
+            }
+            s0 += w;
+            sKd = fma(w, lk - logh[k], sKd);
+            sKq = fma(w, quad, sKq);
+            sKs = fma(w, sigsum, sKs);
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                spm[p] = fma(w, mu[p], spm[p]);
+                sm2[p] = fma(w, fma(mu[p], mu[p], sd[p]), sm2[p]);
+            }
+        }
+        // ---- merge the W slices of each SNP (warp order)
+        if (W > 1) {
+            double* mine = s_merge + ((size_t)warp * NV) * 32 + lane;
+            mine[0] = mx; mine[32] = s0; mine[64] = sKd; mine[96] = sKq; mine[128] = sKs;
+#pragma unroll
+            for (int p = 0; p < P; ++p) { mine[(5 + p) * 32] = spm[p]; mine[(5 + P + p) * 32] = sm2[p]; }
+            __syncthreads();
+            const double* all = s_merge + lane;
+            double gmx = all[0];
+            for (int w2 = 1; w2 < W; ++w2) gmx = fmax(gmx, all[(size_t)w2 * NV * 32]);
+            s0 = 0.0; sKd = 0.0; sKq = 0.0; sKs = 0.0;
+#pragma unroll
+            for (int p = 0; p < P; ++p) { spm[p] = 0.0; sm2[p] = 0.0; }
+            for (int w2 = 0; w2 < W; ++w2) {
+                const double* o = all + (size_t)w2 * NV * 32;
+                const double r = vb_exp_nonpos(o[0] - gmx);       // empty slice: exp(-1e300) = 0
+                s0 = fma(r, o[32], s0); sKd = fma(r, o[64], sKd); sKq = fma(r, o[96], sKq); sKs = fma(r, o[128], sKs);
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    spm[p] = fma(r, o[(5 + p) * 32], spm[p]);
+                    sm2[p] = fma(r, o[(5 + P + p) * 32], sm2[p]);
+                }
+            }
+            mx = gmx;
+            __syncthreads();           // scratch is rewritten by the next tile
+        }
+        const double inv_den = 1.0 / s0;
+        // ---- pass B: normalise this thread's slice (floored, not renormalised: numerics.py:188-194)
+        {
+            double* pdl = a.delta_out + (size_t)warp * M + i;
+            sl = s_logit;
+#pragma unroll UNROLL_B
+            for (int k = warp; k < K; k += W, pdl += (size_t)W * M, sl += W * 32) {
+                const double dk = fmax(vb_exp_nonpos(*sl - mx) * inv_den, VB_EPSILON);
+                if (valid) *pdl = dk;
+                if (AKf) {
+                    for (int aa = 0; aa < a.A; ++aa) {
+                        const double sv = vb_warp_sum((valid && an == aa) ? dk : 0.0);
+                        if (lane == 0) s_ann[aa * K + k] += sv;       // k is owned by this warp only
+                    }
+                }
+            }
+        }
+        // ---- per-SNP outputs and objective pieces (warp 0)
+        if (warp == 0 && valid) {
+            const double log_norm = mx + log(s0);
+            tKd += sKd * inv_den - log_norm;
+            tKq += 0.5 * sKq * inv_den;
+            tKs += 0.5 * sKs * inv_den;
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const double pm = spm[p] * inv_den;
+                const double pv = sm2[p] * inv_den - pm * pm;
+                a.pm_out[(size_t)p * M + i] = pm;
+                if (a.xbpos[p]) {
+                    const int32_t q = a.xbpos[p][i];
+                    if (q >= 0) a.xb[p][q] = pm / a.se[(size_t)p * M + i];
+                }
+                if (a.pv_out) a.pv_out[(size_t)p * M + i] = pv;
+                tA[p] = fma(pm, a.adj[(size_t)p * M + i], tA[p]);
+                tC[p] = fma(sld[p], pv, tC[p]);
+            }
+        }
+    }
+
+    // per-CTA statistics: warp 0's lanes, fixed shuffle tree -> partial[stat][blockIdx]
+    double* out = a.partial + blockIdx.x;
+    const size_t ps = gridDim.x;
+    if (warp == 0) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const double va = vb_warp_sum(tA[p]), vc = vb_warp_sum(tC[p]);
+            if (lane == 0) { out[p * ps] = va; out[(P + p) * ps] = vc; }
+        }
+        const double v0 = vb_warp_sum(tKd), v1 = vb_warp_sum(tKq), v2 = vb_warp_sum(tKs);
+        if (lane == 0) { out[(2 * P) * ps] = v0; out[(2 * P + 1) * ps] = v1; out[(2 * P + 2) * ps] = v2; }
+    }
+    if (AKf) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < AKf; j += blockDim.x) out[(NS + j) * ps] = s_ann[j];
+    }
+}
+
+// Shared memory one CTA of the tile kernel needs (bytes).
+static inline size_t vb_tile_smem(int K, int P, int W, int akf) {
+    const size_t kslots = (size_t)(K + W - 1) / W;
+    return (kslots * W * 32 + (size_t)W * VB_TILE_NV(P) * 32 + (size_t)akf) * sizeof(double);
+}

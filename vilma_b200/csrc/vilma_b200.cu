@@ -12,6 +12,7 @@
 #include "../../include/vilma_b200.h"
 #include "ld_kernels.cuh"
 #include "snp_kernels.cuh"
+#include "snp_tile_kernel.cuh"
 
 static_assert(VB_MAX_POPS <= VB_MAXP, "header / kernel cohort limits disagree");
 
@@ -54,6 +55,7 @@ static inline int64_t even_up(int64_t v) { return (v + 1) & ~int64_t(1); }
 #define VB_SYM_LPT 0
 #endif
 static bool g_disable_sym = false;
+static int g_tile_mode = -1;         // vb_set_option("snp_tile", ...): see tile_plan()
 static bool g_three_pass = true;     // vb_set_option("snp_three_pass", 0): always the online single-pass kernel   // vb_set_option("ld_symmetric", 0): store dense blocks in full
 
 // ------------------------------------------------------------------------------------
@@ -124,6 +126,7 @@ struct Fit {
     int64_t mutations = 0;         // bumped by every public vb_fit_* call (guards speculative work)
     double* part_snp = nullptr;
     int grid_snp = 0;
+    int snp_grid_used = 0;         // CTAs of the last per-SNP launch (= rows of part_snp it wrote)
     double* part_fin = nullptr;
     int grid_fin = 0;
     double* part_ann = nullptr;
@@ -257,6 +260,8 @@ extern "C" int vb_abi_version(void) { return VB_ABI_VERSION; }
 // Process-wide options read when an LD operator is created.
 //   "ld_symmetric" (default 1): store dense blocks with n <= VB_SYM_NMAX symmetric-packed.
 //   "snp_three_pass" (default 1): P <= 2 updates use the exact-max three-pass softmax kernel.
+//   "snp_tile" (default -1 = automatic): the K-split tile kernel (snp_tile_kernel.cuh) with W warps per
+//       32-SNP tile; 0 = never, W > 0 = always with that many warps.
 extern "C" int64_t vb_ld_sym_nmax(void) { return VB_SYM_NMAX; }
 extern "C" int vb_set_option(const char* name, int64_t value) {
     if (name && std::strcmp(name, "ld_symmetric") == 0) {
@@ -265,6 +270,11 @@ extern "C" int vb_set_option(const char* name, int64_t value) {
     }
     if (name && std::strcmp(name, "snp_three_pass") == 0) {
         g_three_pass = (value != 0);
+        return 0;
+    }
+    if (name && std::strcmp(name, "snp_tile") == 0) {       // -1 auto, 0 never, W = 1,2,4,8,16 forced
+        if (value > VB_TILE_MAXW) return vb_fail("vb_set_option: snp_tile takes -1, 0 or W <= %d", VB_TILE_MAXW);
+        g_tile_mode = (int)value;
         return 0;
     }
     return vb_fail("vb_set_option: unknown option '%s'", name ? name : "(null)");
@@ -1025,9 +1035,69 @@ extern "C" int vb_fit_get_params_dev(vb_ctx* ctx, double* mu_dev, double* delta_
     return fit_get_params(ctx, mu_dev, delta_mk_dev, cudaMemcpyDeviceToDevice);
 }
 
+// Launch geometry of the tile kernel: W warps per 32-SNP tile and CTAs per SM, chosen to maximise
+// resident threads under the shared-memory (logits + merge scratch) and register limits; ties go to
+// the smaller W (shorter merge).  Returns W = 0 when the thread-per-SNP kernels should run.
+struct TilePlan { int W, grid; size_t smem; };
+static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf) {
+    TilePlan best{0, 0, 0};
+    if (g_tile_mode == 0) return best;
+    // automatic: large grids and P >= 3 (where thread-per-SNP parks K logits per SNP in HBM and pays
+    // three logs and square roots per component); the tuned three-pass kernel keeps small P <= 2 grids
+    if (g_tile_mode < 0 && f.P <= 2 && f.K < 32) return best;
+    const int target = f.P == 1 ? 1024 : (f.P <= 3 ? 512 : 256);
+    const int maxw = f.P <= 3 ? 16 : 8;
+    const size_t cap = 227 * 1024;
+    int best_threads = 0;
+    for (int W = 1; W <= maxw; W *= 2) {
+        if (g_tile_mode > 0 && W != g_tile_mode) continue;
+        const size_t sm = vb_tile_smem(f.K, f.P, W, akf);
+        if (sm > cap) continue;
+        int ctas = std::min<int>(std::min<int>(target / (32 * W), (int)(cap / (sm + 1024))), 16);
+        if (ctas < 1) continue;
+        const int threads = ctas * 32 * W;
+        if (threads > best_threads) {
+            best_threads = threads;
+            best.W = W;
+            best.smem = sm;
+            const int64_t tiles = (f.M + VB_TILE_SNPS - 1) / VB_TILE_SNPS;
+            best.grid = (int)std::min<int64_t>(std::min<int64_t>((int64_t)ctx->num_sms * ctas, tiles), f.grid_snp);
+        }
+    }
+    return best;
+}
+template <int P, int MODE>
+static void launch_tile_one(const VbSnpArgs& a, const TilePlan& tp, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(vb_snp_tile_kernel<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_set = true;
+    }
+    vb_snp_tile_kernel<P, MODE><<<tp.grid, 32 * tp.W, tp.smem, st>>>(a);
+}
 template <int MODE>
 static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
     cudaStream_t st = ctx->stream;
+    ctx->fit.snp_grid_used = grid;
+    if constexpr (MODE != VB_MODE_EVAL) {
+        const TilePlan tp = tile_plan(ctx, ctx->fit, a.fuse_ann ? a.A * a.K : 0);
+        if (tp.W > 0) {
+            ctx->fit.snp_grid_used = tp.grid;
+            prof_begin(ctx, 1);
+            switch (P) {
+                case 1: launch_tile_one<1, MODE>(a, tp, st); break;
+                case 2: launch_tile_one<2, MODE>(a, tp, st); break;
+                case 3: launch_tile_one<3, MODE>(a, tp, st); break;
+                case 4: launch_tile_one<4, MODE>(a, tp, st); break;
+                case 5: launch_tile_one<5, MODE>(a, tp, st); break;
+                case 6: launch_tile_one<6, MODE>(a, tp, st); break;
+                default: return vb_fail("unsupported cohort count %d", P);
+            }
+            prof_end(ctx, 1);
+            CK_LAUNCH(ctx);
+            return 0;
+        }
+    }
     const size_t sm = a.fuse_ann ? (size_t)a.A * a.K * (VB_SNP_THREADS / 32) * sizeof(double) : 0;
     prof_begin(ctx, 1);
     if constexpr (MODE != VB_MODE_EVAL) {
@@ -1083,7 +1153,7 @@ static int finish_eval(vb_ctx* ctx, int v, double* stats_dev) {
     fa.part_snp = f.part_snp;
     fa.part_fin = f.part_fin;
     fa.stats = stats_dev;
-    fa.n_part_snp = f.grid_snp;
+    fa.n_part_snp = f.snp_grid_used;
     fa.n_part_fin = f.grid_fin;
     fa.P = f.P;
     fa.nsp = f.nsp;
@@ -1252,6 +1322,51 @@ extern "C" int vb_fit_vi_sigma(vb_ctx* ctx, int k0, int k1, double* out_host) {
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(buf);
     if (e != cudaSuccess) return vb_fail("vb_fit_vi_sigma: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// Device initialisation (MultiPopVI._initialize, reference :643-700), in two steps around the host's
+// hyper_delta computation.  fake_mu_host: [P][M] jittered ridge start.
+extern "C" int vb_fit_init_delta(vb_ctx* ctx, const double* fake_mu_host) {
+    NEED_FIT(ctx);
+    if (!fake_mu_host) return vb_fail("vb_fit_init_delta: null argument");
+    const size_t PM = (size_t)f.P * f.M;
+    double* fm = f.scratch3 + PM;          // middle third: vb_fit_posterior uses the outer two
+    CK(cudaMemcpyAsync(fm, fake_mu_host, PM * 8, cudaMemcpyHostToDevice, ctx->stream));
+    double* d = f.delta[f.cur_delta];
+    const int g = f.grid_snp;
+    switch (f.P) {
+        case 1: vb_init_delta_kernel<1><<<g, VB_SNP_THREADS, 0, ctx->stream>>>(f.K, f.M, f.prec, f.logdet, f.sld, f.inv_tau_dev, fm, d); break;
+        case 2: vb_init_delta_kernel<2><<<g, VB_SNP_THREADS, 0, ctx->stream>>>(f.K, f.M, f.prec, f.logdet, f.sld, f.inv_tau_dev, fm, d); break;
+        case 3: vb_init_delta_kernel<3><<<g, VB_SNP_THREADS, 0, ctx->stream>>>(f.K, f.M, f.prec, f.logdet, f.sld, f.inv_tau_dev, fm, d); break;
+        case 4: vb_init_delta_kernel<4><<<g, VB_SNP_THREADS, 0, ctx->stream>>>(f.K, f.M, f.prec, f.logdet, f.sld, f.inv_tau_dev, fm, d); break;
+        case 5: vb_init_delta_kernel<5><<<g, VB_SNP_THREADS, 0, ctx->stream>>>(f.K, f.M, f.prec, f.logdet, f.sld, f.inv_tau_dev, fm, d); break;
+        case 6: vb_init_delta_kernel<6><<<g, VB_SNP_THREADS, 0, ctx->stream>>>(f.K, f.M, f.prec, f.logdet, f.sld, f.inv_tau_dev, fm, d); break;
+        default: return vb_fail("unsupported cohort count %d", f.P);
+    }
+    CK_LAUNCH(ctx);
+    f.trial_kind = -1;
+    CK(cudaStreamSynchronize(ctx->stream));      // fake_mu_host may be pageable and reused by the caller
+    return 0;
+}
+// mu of the current state from delta (as left by vb_fit_init_delta) and the fake_mu kept in scratch.
+extern "C" int vb_fit_init_mu(vb_ctx* ctx) {
+    NEED_FIT(ctx);
+    const double* d = f.delta[f.cur_delta];
+    const double* fm = f.scratch3 + (size_t)f.P * f.M;
+    double* mu = f.mu[f.cur_mu];
+    const int g = f.grid_snp;
+    switch (f.P) {
+        case 1: vb_init_mu_kernel<1><<<g, VB_SNP_THREADS, 0, ctx->stream>>>(f.K, f.M, f.prec, f.sld, f.inv_tau_dev, fm, d, mu); break;
+        case 2: vb_init_mu_kernel<2><<<g, VB_SNP_THREADS, 0, ctx->stream>>>(f.K, f.M, f.prec, f.sld, f.inv_tau_dev, fm, d, mu); break;
+        case 3: vb_init_mu_kernel<3><<<g, VB_SNP_THREADS, 0, ctx->stream>>>(f.K, f.M, f.prec, f.sld, f.inv_tau_dev, fm, d, mu); break;
+        case 4: vb_init_mu_kernel<4><<<g, VB_SNP_THREADS, 0, ctx->stream>>>(f.K, f.M, f.prec, f.sld, f.inv_tau_dev, fm, d, mu); break;
+        case 5: vb_init_mu_kernel<5><<<g, VB_SNP_THREADS, 0, ctx->stream>>>(f.K, f.M, f.prec, f.sld, f.inv_tau_dev, fm, d, mu); break;
+        case 6: vb_init_mu_kernel<6><<<g, VB_SNP_THREADS, 0, ctx->stream>>>(f.K, f.M, f.prec, f.sld, f.inv_tau_dev, fm, d, mu); break;
+        default: return vb_fail("unsupported cohort count %d", f.P);
+    }
+    CK_LAUNCH(ctx);
+    f.trial_kind = -1;
     return 0;
 }
 

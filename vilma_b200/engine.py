@@ -275,6 +275,14 @@ class CudaEngine:
                                                    C.c_void_p(self._ann.data_ptr())))
         return self._ann
 
+    def init_delta(self, fake_mu):
+        fm = np.ascontiguousarray(fake_mu, dtype=np.float64)
+        assert fm.shape == (self.P, self.M)
+        _lib.check(self.lib.vb_fit_init_delta(self.ctx.handle, _lib.np_ptr(fm)))
+
+    def init_mu(self):
+        _lib.check(self.lib.vb_fit_init_mu(self.ctx.handle))
+
     def posterior(self):
         pm = np.empty((self.P, self.M))
         pv = np.empty((self.P, self.M))

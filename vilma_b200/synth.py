@@ -123,3 +123,79 @@ def mixture_grid_single(betas, std_errs, K):
     mn = np.nanpercentile(betas[betas**2 > 0]**2, 2.5)
     diag = [mn * 1e-6] + [mn * np.exp(np.log(mx / mn) / K * k) for k in range(K + 1)]
     return [np.array([[d]]) for d in diag]
+
+
+# ------------------------------------------------------------------------------------------
+# multi-cohort / low-rank workloads (BASELINE.json configs[2] and configs[4])
+# ------------------------------------------------------------------------------------------
+def lowrank_factors(g, ldthresh):
+    """Eigen-factors (U [n,r], s [r]) of R = g^T g kept by LowRankMatrix(t=ldthresh)
+    (matrix_structures.py:15-28: eigenvalues > 1 - sqrt(t), and > 1e-12 max for t = 1), from the
+    small Gram matrix g g^T (n_ref x n_ref) instead of the n x n block."""
+    import torch
+    lam, w = torch.linalg.eigh(g @ g.T)
+    cut = max(1.0 - float(np.sqrt(ldthresh)), 1e-12 * float(lam.max()))
+    keep = lam > cut
+    lam, w = lam[keep], w[:, keep]
+    u = (g.T @ w) / torch.sqrt(lam)[None, :]
+    return u.contiguous(), lam.contiguous()
+
+
+def shared_effects(n, seed, b, P, M, device, h2=0.3, corr=0.8):
+    """True effects of block b for P cohorts: the 4-component scale mixture of sim.py:97-156 with a
+    shared causal indicator and cross-cohort correlation `corr`.  [P, n]."""
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed) * 15485863 + int(b) * 31 + 5)
+    u = torch.rand(n, generator=gen, device=device, dtype=torch.float64)
+    var = torch.zeros(n, device=device, dtype=torch.float64)
+    var = torch.where(u > 0.95, torch.full_like(var, 1e-6), var)
+    var = torch.where(u > 0.99, torch.full_like(var, 1e-5), var)
+    var = torch.where(u > 0.999, torch.full_like(var, 1e-4), var)
+    scale = h2 / (M * 0.3175 * (0.04 * 1e-6 + 0.009 * 1e-5 + 0.001 * 1e-4))
+    shared = torch.randn(n, generator=gen, device=device, dtype=torch.float64)
+    own = torch.randn((P, n), generator=gen, device=device, dtype=torch.float64)
+    return torch.sqrt(var * scale)[None, :] * (np.sqrt(corr) * shared[None, :] + np.sqrt(1 - corr) * own)
+
+
+def cohort_block(n, seed, b, p, se, beta, device, n_ref_factor, ldthresh):
+    """One cohort's view of block b: LD factors (or the dense block), GWAS estimates and the set-up
+    values of VIScheme.__init__ (:226-252) that need the block's (pseudo-)inverse.
+    Returns dict(R or (U, s), beta_hat, chi, adj, ld_diag, rank) -- torch tensors on `device`."""
+    import torch
+    r, g, gen = make_block(n, (seed * 1000003 + int(b)) * 8 + p, device, n_ref_factor=n_ref_factor)
+    xi = torch.randn(g.shape[0], generator=gen, device=device, dtype=torch.float64)
+    full_rank = g.shape[0] > n and ldthresh >= 1.0
+    if full_rank:
+        beta_hat = se * (r @ (beta / se)) + se * (g.T @ xi)
+        z = beta_hat / se
+        L = torch.linalg.cholesky(r)
+        chi = float(z @ torch.cholesky_solve(z[:, None], L)[:, 0])
+        return dict(R=r, U=None, s=None, beta_hat=beta_hat, chi=chi, adj=z / se,
+                    ld_diag=torch.ones_like(se), rank=n)
+    u, s = lowrank_factors(g, ldthresh)
+    rb = (u * s[None, :]) @ (u.T @ (beta / se))
+    beta_hat = se * rb + se * (g.T @ xi)
+    z = beta_hat / se
+    a = u.T @ z
+    chi = float((a * a / s).sum())
+    adj = (u @ a) / se                        # R R^+ z / se
+    ld_diag = (u * u) @ s
+    return dict(R=None, U=u, s=s, beta_hat=beta_hat, chi=chi, adj=adj, ld_diag=ld_diag,
+                rank=int(s.shape[0]))
+
+
+def ridge_start(blk, se, prior):
+    """inverse_betas of one block (reference :246-252 -> ridge_inverse_dot,
+    matrix_structures.py:349-387): (R + diag(se^2/prior))^-1 (adj se) * se."""
+    import torch
+    lam = se * se / prior
+    b = blk['adj'] * se
+    if blk['R'] is not None:
+        Lr = torch.linalg.cholesky(blk['R'] + torch.diag(lam))
+        return torch.cholesky_solve(b[:, None], Lr)[:, 0] * se
+    u, s = blk['U'], blk['s']
+    li = 1.0 / lam
+    c = torch.diag(1.0 / s) + (u.T * li[None, :]) @ u           # Woodbury core, r x r
+    t = torch.cholesky_solve((u.T @ (li * b))[:, None], torch.linalg.cholesky(c))[:, 0]
+    return (li * b - li * (u @ t)) * se

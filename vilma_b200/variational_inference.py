@@ -37,6 +37,7 @@ ELBO_TOL = 0.1      # (:21)
 EM_TOL = 10         # (:22)
 ELBO_MOMENTUM = 0.5  # (:23)
 MAX_NUM_ITERS = 20  # (:24)
+INIT_HOST_BYTES = 2**31   # _initialize runs on the device when its host arrays would exceed this
 
 
 class DeviceBlockDiagonalMatrix():
@@ -115,6 +116,7 @@ class VIScheme():
                              'size shape.')
 
         self.use_native_loop = True      # C++ outer iteration (vb_fit_iteration) when possible
+        self.init_on_device = None       # _initialize on the device: None = when the host form is too big
         self.speculate_next_trial = True  # queue the next iteration's first trial behind the refresh
         self._comm = comm if comm is not None else default_comm()
         self._device = device
@@ -674,6 +676,12 @@ class MultiPopVI(VIScheme):
             mu_fill = np.tile(np.nanmean(fake_mu, axis=0), [fake_mu.shape[0], 1])
         fake_mu[missing] = mu_fill[missing]
         fake_mu[np.isnan(fake_mu)] = 0.
+        on_device = self.init_on_device
+        if on_device is None:
+            # the host form below holds three [K,P,P,M] arrays at once
+            on_device = 24. * self.num_mix * self.num_pops**2 * self.num_loci > INIT_HOST_BYTES
+        if on_device and hasattr(self._eng, 'init_delta'):
+            return self._initialize_device(fake_mu)
         vi_sigma = self.vi_sigma
         matches = np.einsum('kpq,kqpi->ik', self.mixture_prec[..., 0], vi_sigma)
         probs = np.einsum('pi,oi,kpo->ik', 1.6 * fake_mu, 1.6 * fake_mu,
@@ -694,6 +702,25 @@ class MultiPopVI(VIScheme):
         vi_mu = np.einsum('kqpi,pi->kqi', vi_sigma, temp_nat_mu)
         _, vi_delta, _ = self._nat_to_not_vi_delta((vi_mu, vi_delta, real_hyper_delta))
         return vi_mu, vi_delta, real_hyper_delta
+
+    def _initialize_device(self, fake_mu):
+        """The rest of _initialize (reference :660-679) on the device: S_ki is recomputed per
+        (k, SNP) in registers by vb_init_delta_kernel / vb_init_mu_kernel instead of being held
+        as [K,P,P,M] host arrays.  The state stays resident; the host tuple is its download."""
+        eng = self._eng
+        eng.set_tau(self.error_scaling)
+        eng.init_delta(fake_mu[:, self._snps])
+        sums = np.array(self._comm.sum(eng.sum_annotations()), dtype=np.float64)
+        real_hyper_delta = sums.reshape(self.num_annotations, self.num_mix) + 1.
+        real_hyper_delta /= np.sum(real_hyper_delta, axis=1, keepdims=True)
+        real_hyper_delta = np.maximum(real_hyper_delta, numerics.EPSILON)
+        self._set_gtable(numerics.vi_delta_grad_table(real_hyper_delta, self.log_det))
+        self._hyper = np.array(real_hyper_delta)
+        eng.set_hyper(self._hyper)
+        eng.init_mu()
+        self._refresh_delta_dev()
+        self._resident = None
+        return self._download()
 
     def _set_state(self, params):
         """Set internal values given parameter values (reference :702-710)."""
