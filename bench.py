@@ -557,7 +557,7 @@ def run_ours(args):
     bytes_trial = info['ld_bytes_total'] + 16 * K * (P + 1) * M + 64 * P * M
     # the per-SNP kernel's own floor: trials read mu and write mu', delta; refreshes read mu, write delta
     n_loc = len(vi._snps)
-    snp_bytes = (trials * (16 * K * (P + 1) + 64 * P) + (evals - trials) * (8 * K * (P + 2) + 40 * P)) * n_loc
+    snp_bytes = (trials * (16 * K * (P + 1) + 64 * P) + (evals - trials) * (8 * K * (P + 1) + 40 * P)) * n_loc
     snp_achieved = snp_bytes / (snp_ms * 1e-3) / 1e9 if snp_ms else 0.0
     ld_dominant = mv_ms >= snp_ms
 
@@ -641,6 +641,8 @@ def run_ours(args):
                      'snp_kernel': {'achieved': snp_achieved, 'frac': snp_achieved / hbm_peak,
                                     'share_of_step': snp_ms / ms if ms else None},
                      'snp_kernel_avg_ms': snp_ms / max(snp_n, 1),
+                     'finish_kernel_avg_ms': prof['finish'][0] / max(prof['finish'][1], 1),
+                     'bookkeeping_ms_per_step': prof['bookkeeping'][0] / max(steps_done, 1),
                      'per_rank_ld_ms': [round(float(v), 4) for v in per_rank[:, 0]],
                      'per_rank_snp_ms': [round(float(v), 4) for v in per_rank[:, 1]],
                      'per_rank_snps': [int(v) for v in per_rank[:, 2]],

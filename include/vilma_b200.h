@@ -48,10 +48,12 @@ int vb_ctx_sync(vb_ctx* ctx);
 /* number of kernels launched by this context since creation (bench.py "gpu_launches") */
 int64_t vb_ctx_launch_count(const vb_ctx* ctx);
 /* per-kernel timing with CUDA events on the context's stream (bench.py roofline leg):
- * enable / reset, then read {total ms, launches} for category 0 = LD mat-vec kernel,
- * 1 = fused per-SNP kernel.  At most 4096 launches per category are timed between reads. */
+ * enable / reset, then read {total ms, launches} for the 4 categories 0 = LD mat-vec kernel,
+ * 1 = fused per-SNP kernel, 2 = mat-vec finish kernel (incl. the final reduction / rank exchange in
+ * its last CTA), 3 = bookkeeping kernels (annotation sums, convergence partials).  At most 4096
+ * launches per category are timed between reads. */
 int vb_ctx_profile(vb_ctx* ctx, int enable);
-int vb_ctx_profile_read(vb_ctx* ctx, double* total_ms2, int64_t* count2);
+int vb_ctx_profile_read(vb_ctx* ctx, double* total_ms4, int64_t* count4);
 
 /* ---- LD operator ---------------------------------------------------------------------
  * Replaces BlockDiagonalMatrix(matrices, perm, missing) and its .dot

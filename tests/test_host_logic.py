@@ -216,3 +216,21 @@ def test_checkpoint_files_written(tmp_path):
     z = np.load(tmp_path / expect[0])
     assert sorted(z.files) == ['error_scaling', 'hyper_delta', 'scalings', 'vi_delta', 'vi_mu']
     assert np.allclose(z['vi_mu'], fx['init_vi_mu'], rtol=1e-7, atol=1e-12)
+
+
+@pytest.mark.parametrize('src', ['exp_check.c', 'log_check.c'])
+def test_device_math_helpers_accuracy(src, tmp_path):
+    """vb_exp_nonpos / vb_log_pos / vb_rcp_pos (csrc/vb_common.cuh) restated in C with the same
+    operations (fma, Cody-Waite reduction, polynomial): <= 1 ulp from glibc over 2e7 arguments."""
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    exe = str(tmp_path / 'chk')
+    subprocess.run(['gcc', '-O2', '-ffp-contract=off', '-mfma', os.path.join(ROOT, 'tools', src),
+                    '-o', exe, '-lm'], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    assert 'BAD' not in out
+    import re
+    for m in re.finditer(r'max ulp ([0-9.]+)', out):
+        assert float(m.group(1)) <= 1.0, out

@@ -1,3 +1,4 @@
+/* Accuracy check of vb_exp_nonpos (csrc/vb_common.cuh) against glibc exp: gcc -O2 -ffp-contract=off -mfma tools/exp_check.c -lm */
 #include <math.h>
 #include <stdio.h>
 #include <stdint.h>
@@ -5,6 +6,7 @@
 #include <stdlib.h>
 static inline double vb_exp_nonpos(double x) {
     const double SHIFT = 6755399441055744.0;
+    x = x < -1000.0 ? -1000.0 : x;
     const double t = fma(x, 1.4426950408889634, SHIFT);
     int64_t tb; memcpy(&tb, &t, 8);
     const int n = (int)(uint32_t)tb;
@@ -40,6 +42,7 @@ int main() {
         if (ulp > maxulp) { maxulp = ulp; worst = x; }
     }
     printf("max ulp %.3f at %.17g\n", maxulp, worst);
-    printf("%g %g %g %g\n", vb_exp_nonpos(0.0), vb_exp_nonpos(-1e300), vb_exp_nonpos(-700.0) / exp(-700.0), vb_exp_nonpos(NAN));
+    printf("%g %g %g %g\n", vb_exp_nonpos(0.0), vb_exp_nonpos(-1e300), vb_exp_nonpos(-690.0) / exp(-690.0), vb_exp_nonpos(NAN));
+    for (double x = -1.0; x > -1e301; x *= 1.7) if (vb_exp_nonpos(x) > exp(x) * 1.0000001 || (x > -690 && vb_exp_nonpos(x) < exp(x) * 0.9999999)) { printf("BAD at %g: %g vs %g\n", x, vb_exp_nonpos(x), exp(x)); return 1; }
     return 0;
 }

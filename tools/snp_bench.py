@@ -84,7 +84,7 @@ def run_case(ctx, P, K, M, reps, A=1):
         ld.close()
     torch.cuda.empty_cache()
     floor_trial = (16 * K * (P + 1) + 64 * P) * M
-    floor_refresh = (8 * K * (P + 2) + 40 * P) * M
+    floor_refresh = (8 * K * (P + 1) + 40 * P) * M
     return out, floor_trial, floor_refresh, stats
 
 

@@ -239,6 +239,7 @@ __global__ void vb_ld_finish_kernel(const double* __restrict__ yb, int64_t len, 
                                     double* __restrict__ y_snp, double* __restrict__ partial,
                                     const VbFinalArgs fa) {
     __shared__ double scratch[32];
+    vb_reduce_rows(fa, scratch);
     double acc = 0.0;
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < nreal;
          j += (int64_t)gridDim.x * blockDim.x) {
@@ -584,30 +585,47 @@ struct VbSymBlockRef {
 struct VbSymGroupOut {
     uint32_t off, len;
 };
+// One 16-byte record per block-order position (one coalesced LDG.128 instead of four table loads and a
+// dependent block lookup): where its z sits, which SNP it is, and which groups' partial vectors cover
+// its row.  gfirst < 0: the position belongs to a slab-form block.
+struct __align__(16) VbFinRec {
+    int32_t pos, snp, gfirst;
+    uint32_t loc_ncover;     // row within the block | (number of covering groups << 16)
+};
 __global__ void vb_ld_finish_sym_kernel(const double* __restrict__ yb, int64_t len, int nslab,
                                         const double* __restrict__ ypart,
-                                        const int32_t* __restrict__ blk, const int32_t* __restrict__ loc,
-                                        const int32_t* __restrict__ gfirst,
-                                        const VbSymBlockRef* __restrict__ bref,
+                                        const VbFinRec* __restrict__ rec,
                                         const VbSymGroupOut* __restrict__ gout,
-                                        const double* __restrict__ xb, const int32_t* __restrict__ pos,
-                                        const int32_t* __restrict__ snp, int64_t nreal,
+                                        const double* __restrict__ xb, int64_t nreal,
                                         double* __restrict__ y_snp, double* __restrict__ partial,
                                         const VbFinalArgs fa) {
     __shared__ double scratch[32];
+    vb_reduce_rows(fa, scratch);
     double acc = 0.0;
     for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < nreal;
          j += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t q = pos[j];
-        const int32_t b = blk[j];
+        const VbFinRec r = rec[j];
+        const int32_t q = r.pos;
         double v;
-        if (b >= 0) {
-            const VbSymBlockRef br = bref[b];
-            const uint32_t l = (uint32_t)loc[j];
+        if (r.gfirst >= 0) {
+            const uint32_t l = r.loc_ncover & 0xffffu;
             v = 0.0;
-            uint32_t g = (uint32_t)gfirst[j];          // groups before it do not reach row l
-            const uint32_t gend = br.g0 + br.ng;
-            // four independent loads in flight per step; summation order stays g-ascending
+            uint32_t g = (uint32_t)r.gfirst;          // groups before it do not reach row l
+            const uint32_t gend = g + (r.loc_ncover >> 16);
+            // eight, then four independent loads in flight per step (the first rows of a 2816-row block
+            // are covered by ~60 groups: the longest chain sets the kernel's tail); the summation
+            // order stays g-ascending
+            for (; g + 8 <= gend; g += 8) {
+                VbSymGroupOut o[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) o[t] = gout[g + t];
+                double tv[8];
+                tv[0] = l < o[0].len ? __ldg(&ypart[(size_t)o[0].off + l]) : 0.0;
+#pragma unroll
+                for (int t = 1; t < 8; ++t) tv[t] = __ldg(&ypart[(size_t)o[t].off + l]);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) v += tv[t];
+            }
             for (; g + 4 <= gend; g += 4) {
                 const VbSymGroupOut o0 = gout[g], o1 = gout[g + 1], o2 = gout[g + 2], o3 = gout[g + 3];
                 const double t0 = l < o0.len ? __ldg(&ypart[(size_t)o0.off + l]) : 0.0;
@@ -624,7 +642,7 @@ __global__ void vb_ld_finish_sym_kernel(const double* __restrict__ yb, int64_t l
             v = yb[q];
             for (int s = 1; s < nslab; ++s) v += yb[(size_t)s * len + q];
         }
-        y_snp[snp[j]] = v;
+        y_snp[r.snp] = v;
         acc = fma(xb[q], v, acc);
     }
     vb_finish_epilogue(acc, partial, fa, scratch);

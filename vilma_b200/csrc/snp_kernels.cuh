@@ -21,6 +21,7 @@
 
 enum { VB_MODE_TRIAL = 0, VB_MODE_REFRESH = 1, VB_MODE_EVAL = 2 };
 #define VB_FUSE_ANN_MAX 48     // A*K up to which annotation sums ride along with every evaluation
+#define VB_FUSE_ANN_SLOTS 16   // A*K up to which vb_snp3_kernel keeps them in per-thread shared-memory slots
 #define VB_SNP_THREADS 128
 
 
@@ -55,7 +56,7 @@ struct VbSnpArgs {
     double* xb[VB_MAXP];
     // fused extras (no extra launches / reductions per evaluation):
     //  fuse_ann : accumulate the per-annotation sums of this state's delta (A*K <= VB_FUSE_ANN_MAX)
-    int fuse_ann;
+    int fuse_ann;                // 1: per-warp shuffle sums; 2 (vb_snp3_kernel only): per-thread shared-memory slots
     int nsp;                     // row stride of `partial`
     double* partial;             // [gridDim.x][VB_NSNPSTAT(P)]
 };
@@ -352,10 +353,10 @@ __device__ __forceinline__ void vb_small_inverse(const double (&lam)[P * (P + 1)
     static_assert(P <= 2, "closed form only");
     if constexpr (P == 1) {
         det = lam[0];
-        S[0] = 1.0 / lam[0];
+        S[0] = vb_rcp_pos(lam[0]);
     } else {
         det = lam[0] * lam[2] - lam[1] * lam[1];
-        const double idet = 1.0 / det;
+        const double idet = vb_rcp_pos(det);
         S[0] = lam[2] * idet;
         S[2] = lam[0] * idet;
         S[1] = -lam[1] * idet;
@@ -384,7 +385,11 @@ __global__ void __launch_bounds__(VB_SNP_THREADS, (P == 1) ? VB_SNP3_MINBLOCKS :
     const int AKf = a.fuse_ann ? a.A * K : 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* my_ann = s_ann + warp * AKf;
-    for (int j = threadIdx.x; j < AKf * (VB_SNP_THREADS / 32); j += VB_SNP_THREADS) s_ann[j] = 0.0;
+    // fuse_ann == 2: every thread owns slot [j][threadIdx.x] of s_ann (no shuffles: one shared-memory
+    // add per (k, SNP)); the block reduces the A*K columns once at the end
+    const bool ann_slots = a.fuse_ann == 2;
+    for (int j = threadIdx.x; j < AKf * (ann_slots ? VB_SNP_THREADS : VB_SNP_THREADS / 32); j += VB_SNP_THREADS)
+        s_ann[j] = 0.0;
     if (AKf) __syncthreads();
 
     double tA[P], tC[P], tKd = 0.0, tKq = 0.0, tKs = 0.0;
@@ -441,7 +446,7 @@ __global__ void __launch_bounds__(VB_SNP_THREADS, (P == 1) ? VB_SNP3_MINBLOCKS :
                 mu[p] = pmu_in[(size_t)p * M];
             }
             vb_small_inverse<P>(lam, S, det);
-            const double c = -log(det);
+            const double c = -vb_log_pos(det);
             vb_sym_matvec<P>(lam, mu, eta);
             if constexpr (MODE == VB_MODE_TRIAL) {
 #pragma unroll
@@ -511,7 +516,9 @@ __global__ void __launch_bounds__(VB_SNP_THREADS, (P == 1) ? VB_SNP3_MINBLOCKS :
             const double w = valid ? *pdl : 0.0;
             const double d = fmax(w * inv_den, VB_EPSILON);
             if (valid) *pdl = d;
-            if (AKf) {
+            if (ann_slots) {
+                if (valid) s_ann[(an * K + k) * VB_SNP_THREADS + threadIdx.x] += d;
+            } else if (AKf) {
                 for (int aa = 0; aa < a.A; ++aa) {
                     const double sv = vb_warp_sum((valid && an == aa) ? d : 0.0);
                     if (lane == 0) my_ann[aa * K + k] += sv;
@@ -552,7 +559,12 @@ __global__ void __launch_bounds__(VB_SNP_THREADS, (P == 1) ? VB_SNP3_MINBLOCKS :
     if (threadIdx.x == 0) out[(2 * P + 1) * ps] = v;
     v = vb_block_sum(tKs, scratch);
     if (threadIdx.x == 0) out[(2 * P + 2) * ps] = v;
-    if (AKf) {
+    if (ann_slots) {
+        for (int j = 0; j < AKf; ++j) {
+            const double t = vb_block_sum(s_ann[j * VB_SNP_THREADS + threadIdx.x], scratch);
+            if (threadIdx.x == 0) out[(NS + j) * ps] = t;
+        }
+    } else if (AKf) {
         __syncthreads();
         for (int j = threadIdx.x; j < AKf; j += VB_SNP_THREADS) {
             double t = 0.0;
@@ -566,6 +578,24 @@ __global__ void __launch_bounds__(VB_SNP_THREADS, (P == 1) ? VB_SNP3_MINBLOCKS :
 // Per-annotation column sums of delta (numerics.py:118-129 sum_annotations), deterministic.
 // grid = (chunks, K).  partial[(chunk*K + k)*A + a]
 #define VB_ANN_TILE 8
+// A == 1 (no annotations given: the common case): a plain column sum, four independent loads in
+// flight per thread (the generic kernel below was latency-bound at 61 us for 134 MB on C2).
+__global__ void vb_sum_columns_kernel(const double* __restrict__ delta, int64_t M, int K,
+                                      double* __restrict__ partial) {
+    __shared__ double scratch[32];
+    const int k = blockIdx.y;
+    const double* src = delta + (size_t)k * M;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < M; i += 4 * stride) {
+        a0 += __ldg(&src[i]); a1 += __ldg(&src[i + stride]);
+        a2 += __ldg(&src[i + 2 * stride]); a3 += __ldg(&src[i + 3 * stride]);
+    }
+    for (; i < M; i += stride) a0 += __ldg(&src[i]);
+    const double v = vb_block_sum((a0 + a1) + (a2 + a3), scratch);
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.x * K + k] = v;
+}
 __global__ void vb_sum_annotations_kernel(const double* __restrict__ delta, const int32_t* __restrict__ ann,
                                           int64_t M, int K, int A, double* __restrict__ partial) {
     __shared__ double scratch[32];
@@ -590,14 +620,17 @@ __global__ void vb_sum_annotations_kernel(const double* __restrict__ delta, cons
         }
     }
 }
+// One warp per (k, a): lanes stride over the chunks, fixed shuffle tree.
 __global__ void vb_sum_annotations_final_kernel(const double* __restrict__ partial, int nchunk, int K, int A,
                                                 double* __restrict__ out /*[A][K]*/) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (idx >= K * A) return;
     const int k = idx / A, a = idx % A;
     double acc = 0.0;
-    for (int c = 0; c < nchunk; ++c) acc += partial[((size_t)c * K + k) * A + a];
-    out[(size_t)a * K + k] = acc;
+    for (int c = lane; c < nchunk; c += 32) acc += __ldcg(&partial[((size_t)c * K + k) * A + a]);
+    acc = vb_warp_sum(acc);
+    if (lane == 0) out[(size_t)a * K + k] = acc;
 }
 
 // Convergence bookkeeping on the real posterior mean (variational_inference.py:376-377 allclose,

@@ -55,7 +55,7 @@ struct VbLdl {
                 for (int k = 0; k < j; ++k) v = fma(-U[sl(i, k)], L[sl(j, k)], v);
                 if (i == j) {
                     det *= v;
-                    inv[j] = 1.0 / v;
+                    inv[j] = vb_rcp_pos(v);
                 } else {
                     U[sl(i, j)] = v;
                     L[sl(i, j)] = v * inv[j];
@@ -104,10 +104,13 @@ struct VbLdl {
 };
 
 // registers per thread: P = 1 -> 64 (1024 threads / SM), P = 2, 3 -> 128, P >= 4 -> 255
+#ifndef VB_TILE_P1_THREADS
+#define VB_TILE_P1_THREADS 1024
+#endif
 template <int P> struct VbTileCfg {
-    static constexpr int MAXT = (P <= 3) ? 512 : 256;
+    static constexpr int THREADS_PER_SM = (P == 1) ? VB_TILE_P1_THREADS : (P <= 3 ? 512 : 256);
+    static constexpr int MAXT = (P == 1) ? THREADS_PER_SM / 2 : THREADS_PER_SM;     // P = 1: two CTAs per SM
     static constexpr int MINB = (P == 1) ? 2 : 1;
-    static constexpr int THREADS_PER_SM = (P == 1) ? 1024 : (P <= 3 ? 512 : 256);
 };
 
 template <int P, int MODE>
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
                 }
                 pmu_out += kstride;
             }
-            const double c = -log(det);                            // log|S_k|
+            const double c = -vb_log_pos(det);                     // log|S_k|
             double dot = 0.0, dmm = 0.0, dss = 0.0;
 #pragma unroll
             for (int p = 0; p < P; ++p) {

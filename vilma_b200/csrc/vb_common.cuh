@@ -66,10 +66,11 @@ __device__ __forceinline__ void vb_bulk_g2s(void* smem_dst, const void* gsrc, ui
 // overflow / special-case paths, ~25 instructions instead of the library's ~50.  Cody-Waite reduction
 // x = n ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial (truncation 4e-18 relative), 2^n patched
 // into the exponent.  Max error 1 ulp against glibc over 2e7 arguments in [-690, 0]
-// (tools/exp_check.c).  Results below 2^-1000 are flushed to 0: every use is either floored at 1e-100
+// (tools/exp_check.c).  Arguments below -1000 are clamped; results below 2^-1000 are flushed to 0: every use is either floored at 1e-100
 // (numerics.py:188-194) or added to a sum that is >= 1.  NaN propagates.
 __device__ __forceinline__ double vb_exp_nonpos(double x) {
     const double SHIFT = 6755399441055744.0;                 // 1.5 * 2^52: rounds to nearest integer
+    x = x < -1000.0 ? -1000.0 : x;       // keeps n within int range (logit gaps reach 1e9+); NaN passes through
     const double t = fma(x, 1.4426950408889634, SHIFT);
     const int n = __double2loint(t);
     const double nf = t - SHIFT;
@@ -91,6 +92,41 @@ __device__ __forceinline__ double vb_exp_nonpos(double x) {
     p = fma(p, r, 1.0);
     const double out = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
     return n < -1000 ? 0.0 : out;
+}
+
+// Reciprocal and logarithm of a POSITIVE, NORMAL, FINITE double (pivots / determinants of
+// Lambda = Prec_k + diag(sld/tau)): branch-free, so that the compiler can interleave the independent
+// dependency chains of two mixture components (the library versions carry slow-path calls that end
+// the basic block).  vb_rcp_pos: MUFU.RCP64H seed (~20 bits) + two Newton steps -> agrees with 1/x
+// on 1e7 samples; vb_log_pos: fdlibm's e_log.c reduction and minimax coefficients -> max 1 ulp
+// against glibc over 2e7 arguments in [1e-282, 1e282] (tools/log_check.c).
+__device__ __forceinline__ double vb_rcp_pos(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+__device__ __forceinline__ double vb_log_pos(double x) {
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;                 // mantissa in [1, 2)
+    const bool big = hi >= 0x3ff6a09f;                   // > sqrt(2): halve it
+    hi -= big ? 0x00100000 : 0;
+    e += big ? 1 : 0;
+    const double f = __hiloint2double(hi, lo) - 1.0;
+    const double s = f * vb_rcp_pos(2.0 + f);
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01),
+                                     2.857142874366239149e-01), 6.666666666666735130e-01);
+    const double R = t1 + t2;
+    const double hfsq = 0.5 * f * f;
+    const double k = (double)e;
+    return k * 6.93147180369123816490e-01 - ((hfsq - fma(s, hfsq + R, k * 1.90821492927058770002e-10)) - f);
 }
 
 // ---------------------------------------------------------------- reductions
@@ -232,47 +268,47 @@ struct VbFinalArgs {
     int n_part_diff;
     VbXrank xr;
 };
-// Called by every thread of the LAST block (fixed summation order => deterministic).
-__device__ __forceinline__ void vb_final_reduce(const VbFinalArgs& fa, double* scratch) {
+// The per-SNP kernel's partial rows (and the convergence partials) are complete before the finish kernel
+// starts, so their fixed-order sums are spread over its CTAs -- CTA r reduces row r straight into
+// stats[] -- instead of being a serial tail of ~30 dependent L2 round trips in the last CTA.
+// Rows: [0, NS) statistics, [NS, NS+akf) annotation sums, then 10 convergence rows (5 sums, 5 maxima).
+__device__ __forceinline__ void vb_reduce_row(const VbFinalArgs& fa, int row, double* scratch) {
     const int P = fa.P, NS = VB_NSNPSTAT(P);
-    // All statistics of a partial row are loaded together (independent loads in flight) -- summing one
-    // statistic at a time made this tail a chain of ~50 dependent L2 round trips (45 us).
-    {
-        constexpr int SMAX = 2 * VB_MAXP + 3;
-        double acc[SMAX];
-#pragma unroll
-        for (int s = 0; s < SMAX; ++s) acc[s] = 0.0;
-        for (int b = threadIdx.x; b < fa.n_part_snp; b += blockDim.x) {
-#pragma unroll
-            for (int s = 0; s < SMAX; ++s)
-                if (s < NS) acc[s] += __ldcg(&fa.part_snp[(size_t)s * fa.n_part_snp + b]);
+    if (row < NS + fa.akf) {
+        const double* src = fa.part_snp + (size_t)row * fa.n_part_snp;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int b = threadIdx.x;
+        for (; b + 3 * (int)blockDim.x < fa.n_part_snp; b += 4 * blockDim.x) {
+            a0 += __ldcg(&src[b]); a1 += __ldcg(&src[b + blockDim.x]);
+            a2 += __ldcg(&src[b + 2 * blockDim.x]); a3 += __ldcg(&src[b + 3 * blockDim.x]);
         }
-#pragma unroll
-        for (int s = 0; s < SMAX; ++s) {
-            if (s < NS) {
-                const double t = vb_block_sum(acc[s], scratch);
-                if (threadIdx.x == 0) fa.stats[s < 2 * P ? s : s + P] = t;
-            }
+        for (; b < fa.n_part_snp; b += blockDim.x) a0 += __ldcg(&src[b]);
+        const double t = vb_block_sum((a0 + a1) + (a2 + a3), scratch);
+        if (threadIdx.x == 0) {
+            const int dst = row < 2 * P ? row : (row < NS ? row + P : 3 * P + 3 + (row - NS));
+            fa.stats[dst] = t;
         }
+    } else {
+        const int s = row - NS - fa.akf;          // 0..9
+        double acc = 0.0;
+        for (int b = threadIdx.x; b < fa.n_part_diff; b += blockDim.x) {
+            const double v = __ldcg(&fa.part_diff[(size_t)b * 10 + s]);
+            acc = s < 5 ? acc + v : fmax(acc, v);
+        }
+        const double t = s < 5 ? vb_block_sum(acc, scratch) : vb_block_max(acc, scratch);
+        if (threadIdx.x == 0) fa.stats[3 * P + 3 + fa.akf + s] = t;
     }
-    const int n_sum = fa.akf;
-    for (int s0 = 0; s0 < n_sum; s0 += 8) {
-        double acc[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) acc[t] = 0.0;
-        for (int b = threadIdx.x; b < fa.n_part_snp; b += blockDim.x) {
-#pragma unroll
-            for (int t = 0; t < 8; ++t)
-                if (s0 + t < n_sum) acc[t] += __ldcg(&fa.part_snp[(size_t)(NS + s0 + t) * fa.n_part_snp + b]);
-        }
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            if (s0 + t < n_sum) {
-                const double v = vb_block_sum(acc[t], scratch);
-                if (threadIdx.x == 0) fa.stats[3 * P + 3 + s0 + t] = v;
-            }
-        }
-    }
+}
+// First thing a finish kernel does (the first few CTAs only), so it overlaps the other CTAs' work.
+__device__ __forceinline__ void vb_reduce_rows(const VbFinalArgs& fa, double* scratch) {
+    if (!fa.do_final) return;
+    const int nrows = VB_NSNPSTAT(fa.P) + fa.akf + (fa.part_diff ? 10 : 0);
+    for (int row = blockIdx.x; row < nrows; row += gridDim.x) vb_reduce_row(fa, row, scratch);
+}
+// Called by every thread of the LAST block (fixed summation order => deterministic): the mat-vec's own
+// partials, then the rank exchange.
+__device__ __forceinline__ void vb_final_reduce(const VbFinalArgs& fa, double* scratch) {
+    const int P = fa.P;
     {
         double acc[VB_MAXP];
 #pragma unroll
@@ -288,24 +324,6 @@ __device__ __forceinline__ void vb_final_reduce(const VbFinalArgs& fa, double* s
                 const double t = vb_block_sum(acc[p], scratch);
                 if (threadIdx.x == 0) fa.stats[2 * P + p] = t;
             }
-        }
-    }
-    if (fa.part_diff) {
-        // 5 sums then 5 maxima (vb_pm_diff_kernel partial rows), loaded together
-        double acc[10];
-#pragma unroll
-        for (int s = 0; s < 10; ++s) acc[s] = 0.0;
-        for (int b = threadIdx.x; b < fa.n_part_diff; b += blockDim.x) {
-#pragma unroll
-            for (int s = 0; s < 10; ++s) {
-                const double v = __ldcg(&fa.part_diff[(size_t)b * 10 + s]);
-                acc[s] = s < 5 ? acc[s] + v : fmax(acc[s], v);
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < 10; ++s) {
-            const double t = s < 5 ? vb_block_sum(acc[s], scratch) : vb_block_max(acc[s], scratch);
-            if (threadIdx.x == 0) fa.stats[3 * P + 3 + fa.akf + s] = t;
         }
     }
     if (fa.xr.enabled) vb_xrank_exchange(fa.xr, fa.stats);
@@ -333,4 +351,3 @@ __device__ __forceinline__ void vb_finish_epilogue(double acc, double* partial, 
         vb_final_reduce(fa, scratch);
     }
 }
-

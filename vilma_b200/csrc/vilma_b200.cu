@@ -102,7 +102,7 @@ struct LdPop {
     VbSymBlockRef* bref = nullptr;
     int64_t n_sgroups = 0;
     double* ypart = nullptr;
-    int32_t *blk = nullptr, *loc = nullptr, *gfirst = nullptr;
+    VbFinRec* finrec = nullptr;    // per block-order position: finish-kernel record
     std::vector<VbSymGroupOut> gout_host;
     int64_t bytes = 0;             // algorithmic bytes per mat-vec
 };
@@ -135,6 +135,7 @@ struct Fit {
     int grid_diff = 0;
 };
 
+#define VB_PROF_CATS 4
 struct vb_ld;
 struct vb_ctx {
     int device = 0;
@@ -145,8 +146,10 @@ struct vb_ctx {
     Fit fit;
     // optional per-kernel timing with CUDA events on `stream` (bench.py roofline leg)
     bool profiling = false;
-    std::vector<cudaEvent_t> ev[2];     // category 0: LD mat-vec, 1: per-SNP kernel; start/stop pairs
-    size_t ev_used[2] = {0, 0};
+    // category 0: LD mat-vec, 1: per-SNP kernel, 2: mat-vec finish (+ final reduction / rank exchange),
+    // 3: bookkeeping kernels (annotation sums, convergence partials); start/stop pairs
+    std::vector<cudaEvent_t> ev[VB_PROF_CATS];
+    size_t ev_used[VB_PROF_CATS] = {0, 0, 0, 0};
 };
 #define VB_PROF_PAIRS 4096
 static inline void prof_begin(vb_ctx* c, int cat) {
@@ -313,7 +316,7 @@ static void free_ld(LdPop& L) {
     cudaFree(L.items1); cudaFree(L.items2); cudaFree(L.sched);
     cudaFree(L.pos); cudaFree(L.snp); cudaFree(L.xbpos); cudaFree(L.fin_counter);
     cudaFree(L.sitems); cudaFree(L.sgroups); cudaFree(L.gout); cudaFree(L.bref); cudaFree(L.ypart);
-    cudaFree(L.blk); cudaFree(L.loc); cudaFree(L.gfirst);
+    cudaFree(L.finrec);
     L = LdPop();
 }
 static void free_fit(Fit& f) {
@@ -356,13 +359,13 @@ extern "C" int vb_ctx_profile(vb_ctx* ctx, int enable) {
     if (!ctx) return vb_fail("null ctx");
     CK(cudaSetDevice(ctx->device));
     if (enable && ctx->ev[0].empty()) {
-        for (int cat = 0; cat < 2; ++cat) {
+        for (int cat = 0; cat < VB_PROF_CATS; ++cat) {
             ctx->ev[cat].resize(2 * VB_PROF_PAIRS);
             for (auto& e : ctx->ev[cat]) CK(cudaEventCreate(&e));
         }
     }
     ctx->profiling = enable != 0;
-    ctx->ev_used[0] = ctx->ev_used[1] = 0;
+    for (int cat = 0; cat < VB_PROF_CATS; ++cat) ctx->ev_used[cat] = 0;
     return 0;
 }
 // total_ms[cat], count[cat] of the launches timed since profiling was (re-)enabled; resets.
@@ -370,7 +373,7 @@ extern "C" int vb_ctx_profile_read(vb_ctx* ctx, double* total_ms, int64_t* count
     if (!ctx) return vb_fail("null ctx");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    for (int cat = 0; cat < 2; ++cat) {
+    for (int cat = 0; cat < VB_PROF_CATS; ++cat) {
         double tot = 0.0;
         for (size_t i = 0; i + 1 < ctx->ev_used[cat]; i += 2) {
             float ms = 0.f;
@@ -754,19 +757,19 @@ extern "C" int vb_ld_finalize(vb_ld* h, const int64_t* perm_host, int64_t nperm)
                                      (long long)nperm, (long long)tot);
     std::vector<int32_t> pos(std::max<int64_t>(nperm, 1)), snp(std::max<int64_t>(nperm, 1));
     std::vector<char> seen(L.M, 0);
-    std::vector<int32_t> blk(std::max<int64_t>(nperm, 1)), loc(std::max<int64_t>(nperm, 1));
-    std::vector<int32_t> gfirst(std::max<int64_t>(nperm, 1), 0);
+    std::vector<VbFinRec> rec(std::max<int64_t>(nperm, 1));
     int64_t j = 0;
     for (size_t bi = 0; bi < L.blocks.size(); ++bi) {
         LdBlock& b = L.blocks[bi];
         for (int64_t t = 0; t < b.n; ++t, ++j) {
-            blk[j] = b.sym ? (int32_t)bi : -1;
-            loc[j] = (int32_t)t;
+            rec[j].gfirst = -1;
+            rec[j].loc_ncover = 0;
             if (b.sym) {
                 // first group of the block whose partial vector covers row t (lengths increase)
                 uint32_t g = b.g0;
                 while (g + 1 < b.g0 + b.ng && L.gout_host[g].len <= (uint32_t)t) ++g;
-                gfirst[j] = (int32_t)g;
+                rec[j].gfirst = (int32_t)g;
+                rec[j].loc_ncover = (uint32_t)t | ((b.g0 + b.ng - g) << 16);
             }
             const int64_t i = perm_host[j];
             if (i < 0 || i >= L.M) return vb_fail("vb_ld_finalize: perm[%lld]=%lld out of range", (long long)j, (long long)i);
@@ -774,6 +777,8 @@ extern "C" int vb_ld_finalize(vb_ld* h, const int64_t* perm_host, int64_t nperm)
             seen[i] = 1;
             pos[j] = (int32_t)(b.xpos + t);
             snp[j] = (int32_t)i;
+            rec[j].pos = pos[j];
+            rec[j].snp = snp[j];
         }
     }
     L.nreal = nperm;
@@ -786,12 +791,8 @@ extern "C" int vb_ld_finalize(vb_ld* h, const int64_t* perm_host, int64_t nperm)
         CK(cudaMemset(L.fin_counter, 0, sizeof(uint32_t)));
     }
     if (L.n_sgroups > 0) {
-        CK(cudaMalloc(&L.blk, blk.size() * sizeof(int32_t)));
-        CK(cudaMalloc(&L.loc, loc.size() * sizeof(int32_t)));
-        CK(cudaMemcpy(L.blk, blk.data(), blk.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(L.loc, loc.data(), loc.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&L.gfirst, gfirst.size() * sizeof(int32_t)));
-        CK(cudaMemcpy(L.gfirst, gfirst.data(), gfirst.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&L.finrec, rec.size() * sizeof(VbFinRec)));
+        CK(cudaMemcpy(L.finrec, rec.data(), rec.size() * sizeof(VbFinRec), cudaMemcpyHostToDevice));
     }
     CK(cudaMalloc(&L.pos, pos.size() * sizeof(int32_t)));
     CK(cudaMalloc(&L.snp, snp.size() * sizeof(int32_t)));
@@ -844,13 +845,16 @@ static int ld_apply(vb_ctx* ctx, LdPop& L, const double* x_snp, double* y_snp, d
             L.mat, L.sitems, L.sgroups, (uint32_t)L.n_sgroups, L.sched + 4, L.xall, L.ypart);
         prof_end(ctx, 0);
         CK_LAUNCH(ctx);
-        vb_ld_finish_sym_kernel<<<grid_fin, 256, 0, st>>>(L.yb, L.xb_len, L.nslab2, L.ypart, L.blk,
-                                                          L.loc, L.gfirst, L.bref, L.gout, L.xall, L.pos, L.snp,
-                                                          L.nreal, y_snp, partial, fa);
+        prof_begin(ctx, 2);
+        vb_ld_finish_sym_kernel<<<grid_fin, 256, 0, st>>>(L.yb, L.xb_len, L.nslab2, L.ypart, L.finrec,
+                                                          L.gout, L.xall, L.nreal, y_snp, partial, fa);
+        prof_end(ctx, 2);
         CK_LAUNCH(ctx);
     } else {
+        prof_begin(ctx, 2);
         vb_ld_finish_kernel<<<grid_fin, 256, 0, st>>>(L.yb, L.xb_len, L.nslab2, L.xall, L.pos, L.snp,
                                                       L.nreal, y_snp, partial, fa);
+        prof_end(ctx, 2);
         CK_LAUNCH(ctx);
     }
     return 0;
@@ -927,10 +931,17 @@ extern "C" int vb_fit_create(vb_ctx* ctx, int K, int P, int64_t M, int A, vb_ld*
 // fuse_ann != 0: every evaluation also accumulates the per-annotation sums of that state's delta
 // (needs A*K <= 48 and A <= 4, silently off otherwise).  Worth it when a separate pass + reduction
 // per hyper step costs more than ~5 % extra per-SNP kernel time, i.e. on multi-GPU runs.
+struct TilePlan { int W, grid; size_t smem; };
+static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf);
+// fuse_ann == 2: only where the sums are nearly free -- the three-pass kernel's per-thread
+// shared-memory slots (P <= 2, A*K <= 16), e.g. the single-cohort default grid on one GPU.
 extern "C" int vb_fit_set_fusion(vb_ctx* ctx, int fuse_ann) {
     if (!ctx || !ctx->fit.created) return vb_fail("fit state not created");
     Fit& f = ctx->fit;
-    f.akf = (fuse_ann && f.A * f.K <= VB_FUSE_ANN_MAX && f.A <= 4) ? f.A * f.K : 0;
+    bool on = fuse_ann && f.A * f.K <= VB_FUSE_ANN_MAX && f.A <= 4;
+    if (fuse_ann == 2)
+        on = on && f.P <= 2 && f.A * f.K <= VB_FUSE_ANN_SLOTS && g_three_pass && tile_plan(ctx, f, 0).W == 0;
+    f.akf = on ? f.A * f.K : 0;
     return 0;
 }
 extern "C" int vb_fit_destroy(vb_ctx* ctx) {
@@ -1038,15 +1049,14 @@ extern "C" int vb_fit_get_params_dev(vb_ctx* ctx, double* mu_dev, double* delta_
 // Launch geometry of the tile kernel: W warps per 32-SNP tile and CTAs per SM, chosen to maximise
 // resident threads under the shared-memory (logits + merge scratch) and register limits; ties go to
 // the smaller W (shorter merge).  Returns W = 0 when the thread-per-SNP kernels should run.
-struct TilePlan { int W, grid; size_t smem; };
 static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf) {
     TilePlan best{0, 0, 0};
     if (g_tile_mode == 0) return best;
     // automatic: large grids and P >= 3 (where thread-per-SNP parks K logits per SNP in HBM and pays
     // three logs and square roots per component); the tuned three-pass kernel keeps small P <= 2 grids
     if (g_tile_mode < 0 && f.P <= 2 && f.K < 32) return best;
-    const int target = f.P == 1 ? 1024 : (f.P <= 3 ? 512 : 256);
-    const int maxw = f.P <= 3 ? 16 : 8;
+    const int target = f.P == 1 ? VbTileCfg<1>::THREADS_PER_SM : (f.P <= 3 ? 512 : 256);
+    const int maxw = (f.P == 1 ? VbTileCfg<1>::MAXT : (f.P <= 3 ? 512 : 256)) / 32;
     const size_t cap = 227 * 1024;
     int best_threads = 0;
     for (int W = 1; W <= maxw; W *= 2) {
@@ -1102,8 +1112,14 @@ static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
     prof_begin(ctx, 1);
     if constexpr (MODE != VB_MODE_EVAL) {
         if (P <= 2 && g_three_pass) {       // exact-max softmax, one exp per (k, SNP)
-            if (P == 1) vb_snp3_kernel<1, MODE><<<grid, VB_SNP_THREADS, sm, st>>>(a);
-            else vb_snp3_kernel<2, MODE><<<grid, VB_SNP_THREADS, sm, st>>>(a);
+            VbSnpArgs a3 = a;
+            size_t sm3 = sm;
+            if (a.fuse_ann && a.A * a.K <= VB_FUSE_ANN_SLOTS) {
+                a3.fuse_ann = 2;
+                sm3 = (size_t)a.A * a.K * VB_SNP_THREADS * sizeof(double);
+            }
+            if (P == 1) vb_snp3_kernel<1, MODE><<<grid, VB_SNP_THREADS, sm3, st>>>(a3);
+            else vb_snp3_kernel<2, MODE><<<grid, VB_SNP_THREADS, sm3, st>>>(a3);
             prof_end(ctx, 1);
             CK_LAUNCH(ctx);
             return 0;
@@ -1162,9 +1178,11 @@ static int finish_eval(vb_ctx* ctx, int v, double* stats_dev) {
     if (native && nl->want_diff) {
         // convergence partials of the state being evaluated, reduced together with everything else
         const int64_t n = (int64_t)f.P * f.M;
+        prof_begin(ctx, 3);
         vb_pm_diff_kernel<<<f.grid_diff, 256, 0, ctx->stream>>>(f.pm[v], f.scal, f.pm_prev, f.pm_ckpt,
                                                                 f.pm_next, n, nl->diff_atol,
                                                                 nl->diff_rtol, f.part_diff);
+        prof_end(ctx, 3);
         CK_LAUNCH(ctx);
         fa.part_diff = f.part_diff;
         fa.n_part_diff = f.grid_diff;
@@ -1253,12 +1271,17 @@ extern "C" int vb_fit_accept(vb_ctx* ctx) {
 extern "C" int vb_fit_sum_annotations(vb_ctx* ctx, double* out_dev) {
     NEED_FIT(ctx);
     dim3 grid(f.grid_ann, f.K);
-    vb_sum_annotations_kernel<<<grid, 256, 0, ctx->stream>>>(f.delta[f.cur_delta], f.ann, f.M, f.K,
-                                                             f.A, f.part_ann);
+    prof_begin(ctx, 3);
+    if (f.A == 1)
+        vb_sum_columns_kernel<<<grid, 256, 0, ctx->stream>>>(f.delta[f.cur_delta], f.M, f.K, f.part_ann);
+    else
+        vb_sum_annotations_kernel<<<grid, 256, 0, ctx->stream>>>(f.delta[f.cur_delta], f.ann, f.M, f.K,
+                                                                 f.A, f.part_ann);
     CK_LAUNCH(ctx);
     const int tot = f.K * f.A;
-    vb_sum_annotations_final_kernel<<<(tot + 127) / 128, 128, 0, ctx->stream>>>(f.part_ann, f.grid_ann,
-                                                                                f.K, f.A, out_dev);
+    vb_sum_annotations_final_kernel<<<(tot * 32 + 127) / 128, 128, 0, ctx->stream>>>(f.part_ann, f.grid_ann,
+                                                                                     f.K, f.A, out_dev);
+    prof_end(ctx, 3);
     CK_LAUNCH(ctx);
     return 0;
 }
