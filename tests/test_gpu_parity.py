@@ -149,6 +149,30 @@ def test_trajectory_tile_kernel(name, warps):
     assert np.allclose(vi.real_posterior_variance(*params), fx['final_post_var'], rtol=1e-6, atol=1e-12)
 
 
+@pytest.mark.parametrize('option', ['snp3_park', 'snp_three_pass'])
+@pytest.mark.parametrize('name', ['vischeme_linked_a2_s1_t1', 'syn_p1_dense', 'syn_p1_scaled'])
+def test_trajectory_fallback_kernels(name, option):
+    """The per-SNP kernels that the defaults no longer reach on these fixtures: the three-pass kernel
+    parking its logits in the output buffers (snp3_park=0; used when K (P+1) KB exceeds 32 KB of
+    shared memory) and the online single-pass kernel (snp_three_pass=0)."""
+    from vilma_b200.engine import set_option
+    fx = load_case(name)
+    set_option(option, 0)
+    try:
+        vi = make_product(fx)
+        np.random.seed(int(fx['seed']))
+        params = vi.optimize(None)
+    finally:
+        set_option(option, 1)
+    tr = vi.trajectory
+    assert tr['trials'] == fx['traj_trials'].tolist()
+    assert np.array_equal(np.array(tr['L0']), fx['traj_L0'])
+    assert np.allclose(tr['elbo'], fx['traj_elbo_out'], rtol=1e-8, atol=0)
+    assert np.allclose(params[0], fx['final_vi_mu'], rtol=1e-6, atol=1e-9)
+    assert np.allclose(params[1], fx['final_vi_delta'], rtol=1e-6, atol=1e-12)
+    assert np.allclose(params[2], fx['final_hyper_delta'], rtol=1e-6, atol=1e-12)
+
+
 @pytest.mark.parametrize('name', [n for n in VI_CASES if 'resume_ckpt_vi_mu' in load_case(n)])
 def test_resume(name):
     fx = load_case(name)

@@ -368,18 +368,31 @@ __device__ __forceinline__ void vb_small_inverse(const double (&lam)[P * (P + 1)
 #ifndef VB_SNP3_MINBLOCKS
 #define VB_SNP3_MINBLOCKS 8
 #endif
+#ifndef VB_SNP3_PREFETCH
+#define VB_SNP3_PREFETCH 4      // components ahead whose mu is prefetched into L2 (pass 1)
+#endif
 #ifndef VB_SNP3_UNROLL
 #define VB_SNP3_UNROLL 1
 #endif
-template <int P, int MODE>
-__global__ void __launch_bounds__(VB_SNP_THREADS, (P == 1) ? VB_SNP3_MINBLOCKS : 4) vb_snp3_kernel(const VbSnpArgs a) {
+// PARK: logits / weights and mu' of the thread's SNP are parked in shared memory ([k][tid] and
+// [k][p][tid], conflict-free) between the passes instead of in the output buffers: global stores do
+// not allocate in L1, so every read-back was an L2 round trip (~3 per (k, SNP), the kernel's top
+// stall).  Needs K (P+1) KB of shared memory per CTA -- the host selects it when that is <= 32 KB
+// (P = 1: K <= 16, which covers the default 14-component grid; P = 2: K <= 10), 7 CTAs per SM for P = 1.
+#define VB_SNP3_PARK_MAX_BYTES (32 * 1024)
+template <int P, int MODE, bool PARK>
+__global__ void __launch_bounds__(VB_SNP_THREADS, (P == 1) ? (PARK ? 7 : VB_SNP3_MINBLOCKS) : 4) vb_snp3_kernel(const VbSnpArgs a) {
     static_assert(MODE != VB_MODE_EVAL, "EVAL has no softmax: use vb_snp_kernel");
     constexpr int UNR = VB_SNP3_UNROLL;
     constexpr int NT = P * (P + 1) / 2;
     constexpr int NS = VB_NSNPSTAT(P);
     __shared__ double scratch[32];
-    extern __shared__ double s_ann[];
+    extern __shared__ double s_dyn[];
     const int K = a.K;
+    // dynamic shared memory: [PARK: K logits/weights | K*P mu'] x 128 threads, then the annotation sums
+    double* const s_lw = s_dyn + threadIdx.x;                                   // + k * 128
+    double* const s_mu = s_dyn + (size_t)K * VB_SNP_THREADS + threadIdx.x;        // + (k * P + p) * 128
+    double* const s_ann = PARK ? s_dyn + (size_t)K * (P + 1) * VB_SNP_THREADS : s_dyn;
     const int64_t M = a.M;
     const size_t PM = (size_t)P * M;
     const int AKf = a.fuse_ann ? a.A * K : 0;
@@ -438,12 +451,16 @@ __global__ void __launch_bounds__(VB_SNP_THREADS, (P == 1) ? VB_SNP3_MINBLOCKS :
         const double* prec = g_prec;
         for (int k = 0; k < K; ++k, pmu_in += PM, pmu_out += PM, pdl += M, prec += P * P) {
             double lam[NT], S[NT], mu[P], eta[P], det;
+            if (VB_SNP3_PREFETCH > 0 && k + VB_SNP3_PREFETCH < K) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) vb_prefetch_l2(pmu_in + VB_SNP3_PREFETCH * PM + (size_t)p * M);
+            }
 #pragma unroll
             for (int p = 0; p < P; ++p) {
 #pragma unroll
                 for (int q = 0; q <= p; ++q) lam[VB_TRI(p, q)] = prec[p * P + q];
                 lam[VB_TRI(p, p)] += dt[p];
-                mu[p] = pmu_in[(size_t)p * M];
+                mu[p] = __ldg(pmu_in + (size_t)p * M);
             }
             vb_small_inverse<P>(lam, S, det);
             const double c = -vb_log_pos(det);
@@ -457,11 +474,16 @@ __global__ void __launch_bounds__(VB_SNP_THREADS, (P == 1) ? VB_SNP3_MINBLOCKS :
                     for (int p = 0; p < P; ++p) pmu_out[(size_t)p * M] = mu[p];
                 }
             }
+            if constexpr (PARK) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) s_mu[(k * P + p) * VB_SNP_THREADS] = mu[p];
+            }
             double dot = 0.0;
 #pragma unroll
             for (int p = 0; p < P; ++p) dot += mu[p] * eta[p];
             const double lk = 0.5 * (c + dot) + gfull[k];
-            if (valid) *pdl = lk;
+            if constexpr (PARK) s_lw[k * VB_SNP_THREADS] = lk;
+            else if (valid) *pdl = lk;
             mx = fmax(mx, lk);
         }
         // ---- pass 2: weights, moments, KL pieces
@@ -479,7 +501,8 @@ __global__ void __launch_bounds__(VB_SNP_THREADS, (P == 1) ? VB_SNP3_MINBLOCKS :
 #pragma unroll
                 for (int q = 0; q <= p; ++q) lam[VB_TRI(p, q)] = prec[p * P + q];
                 lam[VB_TRI(p, p)] += dt[p];
-                mu[p] = valid ? pmu[(size_t)p * M] : 0.0;
+                if constexpr (PARK) mu[p] = s_mu[(k * P + p) * VB_SNP_THREADS];
+                else mu[p] = valid ? pmu[(size_t)p * M] : 0.0;
             }
             vb_small_inverse<P>(lam, S, det);
             vb_sym_matvec<P>(lam, mu, eta);
@@ -493,10 +516,11 @@ __global__ void __launch_bounds__(VB_SNP_THREADS, (P == 1) ? VB_SNP3_MINBLOCKS :
                     tr += prec[p * P + q] * S[p >= q ? VB_TRI(p, q) : VB_TRI(q, p)];
                 }
             }
-            const double lk = valid ? *pdl : mx;
+            const double lk = PARK ? s_lw[k * VB_SNP_THREADS] : (valid ? *pdl : mx);
             const double c = 2.0 * (lk - gfull[k]) - dot;          // log|S_k| back from the logit
             const double w = vb_exp_nonpos(lk - mx);
-            if (valid) *pdl = w;
+            if constexpr (PARK) s_lw[k * VB_SNP_THREADS] = w;
+            else if (valid) *pdl = w;
             s0 += w;
 #pragma unroll
             for (int p = 0; p < P; ++p) {
@@ -513,7 +537,7 @@ __global__ void __launch_bounds__(VB_SNP_THREADS, (P == 1) ? VB_SNP3_MINBLOCKS :
 #pragma unroll UNR
         pdl = g_delta + i;
         for (int k = 0; k < K; ++k, pdl += M) {
-            const double w = valid ? *pdl : 0.0;
+            const double w = PARK ? s_lw[k * VB_SNP_THREADS] : (valid ? *pdl : 0.0);
             const double d = fmax(w * inv_den, VB_EPSILON);
             if (valid) *pdl = d;
             if (ann_slots) {

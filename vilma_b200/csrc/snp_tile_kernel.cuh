@@ -30,6 +30,9 @@
 #ifndef VB_TILE_UNROLL_B
 #define VB_TILE_UNROLL_B 4
 #endif
+#ifndef VB_TILE_PREFETCH
+#define VB_TILE_PREFETCH 4          // components ahead whose mu is prefetched into L2
+#endif
 #define VB_TILE_SNPS 32
 #define VB_TILE_MAXW 16
 #define VB_TILE_NV(P) (5 + 2 * (P))        // mx, s0, sKd, sKq, sKs, spm[P], sm2[P]
@@ -178,6 +181,10 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
         for (int k = warp; k < K; k += W, pmu_in += kstride, sl += W * 32) {
             const double* prec = g_prec + (size_t)k * P * P;
             double lam[NT], mu[P], eta[P], sd[P], det;
+            if (VB_TILE_PREFETCH > 0 && k + VB_TILE_PREFETCH * W < K) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) vb_prefetch_l2(pmu_in + VB_TILE_PREFETCH * kstride + (size_t)p * M);
+            }
 #pragma unroll
             for (int p = 0; p < P; ++p) {
 #pragma unroll

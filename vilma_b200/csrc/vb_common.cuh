@@ -61,6 +61,13 @@ __device__ __forceinline__ void vb_bulk_g2s(void* smem_dst, const void* gsrc, ui
         : "memory");
 }
 
+// L2 prefetch of a global address (no register, no scoreboard): the per-SNP kernels hold one 8-byte
+// load of the state per thread in flight, which caps them at ~threads x 8 B / HBM latency
+// (~1.2-2.4 TB/s); prefetching a few components ahead turns those loads into L2 hits.
+__device__ __forceinline__ void vb_prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // ---------------------------------------------------------------- exp for softmax weights
 // exp(x) for x <= 0, the only case the softmax kernels need (weights relative to a maximum): no
 // overflow / special-case paths, ~25 instructions instead of the library's ~50.  Cody-Waite reduction

@@ -56,6 +56,8 @@ static inline int64_t even_up(int64_t v) { return (v + 1) & ~int64_t(1); }
 #endif
 static bool g_disable_sym = false;
 static int g_tile_mode = -1;         // vb_set_option("snp_tile", ...): see tile_plan()
+static bool g_ann_slots = true;      // vb_set_option("snp_ann_slots", 0): fused annotation sums by warp shuffles only
+static bool g_snp3_park = true;      // vb_set_option("snp3_park", 0): three-pass kernel parks logits in the output buffers
 static bool g_three_pass = true;     // vb_set_option("snp_three_pass", 0): always the online single-pass kernel   // vb_set_option("ld_symmetric", 0): store dense blocks in full
 
 // ------------------------------------------------------------------------------------
@@ -263,6 +265,8 @@ extern "C" int vb_abi_version(void) { return VB_ABI_VERSION; }
 // Process-wide options read when an LD operator is created.
 //   "ld_symmetric" (default 1): store dense blocks with n <= VB_SYM_NMAX symmetric-packed.
 //   "snp_three_pass" (default 1): P <= 2 updates use the exact-max three-pass softmax kernel.
+//   "snp3_park" (default 1): the three-pass kernel keeps logits / weights / mu' in shared memory when
+//       K (P+1) KB fits 32 KB per CTA.
 //   "snp_tile" (default -1 = automatic): the K-split tile kernel (snp_tile_kernel.cuh) with W warps per
 //       32-SNP tile; 0 = never, W > 0 = always with that many warps.
 extern "C" int64_t vb_ld_sym_nmax(void) { return VB_SYM_NMAX; }
@@ -273,6 +277,14 @@ extern "C" int vb_set_option(const char* name, int64_t value) {
     }
     if (name && std::strcmp(name, "snp_three_pass") == 0) {
         g_three_pass = (value != 0);
+        return 0;
+    }
+    if (name && std::strcmp(name, "snp_ann_slots") == 0) {
+        g_ann_slots = (value != 0);
+        return 0;
+    }
+    if (name && std::strcmp(name, "snp3_park") == 0) {
+        g_snp3_park = (value != 0);
         return 0;
     }
     if (name && std::strcmp(name, "snp_tile") == 0) {       // -1 auto, 0 never, W = 1,2,4,8,16 forced
@@ -1114,12 +1126,24 @@ static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
         if (P <= 2 && g_three_pass) {       // exact-max softmax, one exp per (k, SNP)
             VbSnpArgs a3 = a;
             size_t sm3 = sm;
-            if (a.fuse_ann && a.A * a.K <= VB_FUSE_ANN_SLOTS) {
+            if (a.fuse_ann && a.A * a.K <= VB_FUSE_ANN_SLOTS && g_ann_slots) {
                 a3.fuse_ann = 2;
                 sm3 = (size_t)a.A * a.K * VB_SNP_THREADS * sizeof(double);
             }
-            if (P == 1) vb_snp3_kernel<1, MODE><<<grid, VB_SNP_THREADS, sm3, st>>>(a3);
-            else vb_snp3_kernel<2, MODE><<<grid, VB_SNP_THREADS, sm3, st>>>(a3);
+            const size_t park = (size_t)a.K * (P + 1) * VB_SNP_THREADS * sizeof(double);
+            if (g_snp3_park && park <= VB_SNP3_PARK_MAX_BYTES) {
+                static bool carve_set = false;
+                if (!carve_set) {       // all shared memory, no L1 needed: the kernel streams
+                    cudaFuncSetAttribute(vb_snp3_kernel<1, MODE, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                    cudaFuncSetAttribute(vb_snp3_kernel<2, MODE, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                    cudaFuncSetAttribute(vb_snp3_kernel<1, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+                    cudaFuncSetAttribute(vb_snp3_kernel<2, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+                    carve_set = true;
+                }
+                if (P == 1) vb_snp3_kernel<1, MODE, true><<<grid, VB_SNP_THREADS, park + sm3, st>>>(a3);
+                else vb_snp3_kernel<2, MODE, true><<<grid, VB_SNP_THREADS, park + sm3, st>>>(a3);
+            } else if (P == 1) vb_snp3_kernel<1, MODE, false><<<grid, VB_SNP_THREADS, sm3, st>>>(a3);
+            else vb_snp3_kernel<2, MODE, false><<<grid, VB_SNP_THREADS, sm3, st>>>(a3);
             prof_end(ctx, 1);
             CK_LAUNCH(ctx);
             return 0;
