@@ -347,13 +347,29 @@ def _time_cpu(steps, warmup, cores):
 # --------------------------------------------------------------------------------------
 # clocks
 # --------------------------------------------------------------------------------------
+_CLOCK_POLLER = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+bus, period = sys.argv[1], float(sys.argv[2])
+try:
+    h = nv.nvmlDeviceGetHandleByPciBusId(bus.encode())
+except Exception:
+    h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[3]))
+reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+print('max', nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+while True:
+    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), int(reasons(h)), flush=True)
+    time.sleep(period)
+"""
+
+
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (one
-    sample every ~2 ms; the region of a default run is ~50 ms, too short for `nvidia-smi -lms`),
-    falling back to an nvidia-smi subprocess when NVML bindings are unavailable."""
-    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-              'clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled DURING the timed region by a separate NVML polling
+    process (one sample every 5 ms; the region of a default run is ~45 ms, too short for
+    `nvidia-smi -lms`).  A polling THREAD in this process was measured to cost rank 0 ~0.4 ms of host
+    time per outer iteration (GIL / driver-lock hand-offs with the launch thread), hence the process:
+    it is started early, and only the samples stamped inside [mark_begin, mark_end] are used."""
     # nvmlClocksEventReason* bit masks
     REASONS = {'sw_power_cap': 0x4, 'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20,
                'hw_thermal_slowdown': 0x40}
@@ -362,64 +378,32 @@ class ClockSampler:
         self.device = device
         self.proc = None
         self.path = None
-        self.thread = None
-        self.samples = []
-        self.mask = 0
-        self.max_mhz = None
-        self._stop = False
-
-    def _nvml_handle(self):
-        import pynvml
-        import torch
-        pynvml.nvmlInit()
-        pr = torch.cuda.get_device_properties(self.device)
-        try:
-            bus = '%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
-            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
-        except Exception:
-            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.device)
-
-    def _poll(self, nv, h):
-        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
-            nv.nvmlDeviceGetCurrentClocksThrottleReasons
-        while not self._stop:
-            try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                self.mask |= int(get_reasons(h))
-            except Exception:
-                pass
-            time.sleep(0.002)
+        self.t0 = self.t1 = None
+        self.period = float(os.environ.get('BENCH_CLOCK_MS', '5')) * 1e-3
 
     def start(self):
-        try:
-            import threading
-            nv, h = self._nvml_handle()
-            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
-            self.thread.start()
+        if self.period <= 0:
             return
-        except Exception:
-            self.thread = None
         try:
-            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            import torch
+            pr = torch.cuda.get_device_properties(self.device)
+            bus = '%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            fd, self.path = tempfile.mkstemp(suffix='.clk')
             os.close(fd)
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.FIELDS,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
-                stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+            self.proc = subprocess.Popen([sys.executable, '-c', _CLOCK_POLLER, bus, str(self.period),
+                                          str(self.device)],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
     def stop(self):
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        if self.thread is not None:
-            self._stop = True
-            self.thread.join(timeout=2)
-            if self.samples:
-                out.update(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.max_mhz,
-                           reasons=sorted(k for k, m in self.REASONS.items() if self.mask & m),
-                           samples=len(self.samples))
-            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -427,34 +411,48 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        sm, mask, mx, nearest = [], 0, None, None
         try:
             for line in open(self.path):
-                parts = [p.strip() for p in line.split(',')]
-                if len(parts) < 7:
-                    continue
-                try:
-                    sm.append(float(parts[0]))
-                    mx.append(float(parts[1]))
-                except ValueError:
-                    continue
-                for nm, val in zip(names, parts[3:7]):
-                    if val.lower().startswith('active'):
-                        reasons.add(nm)
+                parts = line.split()
+                if len(parts) == 2 and parts[0] == 'max':
+                    mx = float(parts[1])
+                elif len(parts) == 3:
+                    t, c, m = float(parts[0]), float(parts[1]), int(parts[2])
+                    if self.t0 is not None and self.t0 <= t <= self.t1:
+                        sm.append(c)
+                        mask |= m
+                    elif self.t0 is not None and (nearest is None or abs(t - self.t0) < nearest[0]):
+                        nearest = (abs(t - self.t0), c, m)
             os.unlink(self.path)
         except Exception:
             pass
+        if not sm and nearest is not None and nearest[0] < 0.05:
+            sm, mask = [nearest[1]], nearest[2]        # region shorter than one polling period
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)),
-                       reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx,
+                       reasons=sorted(k for k, m in self.REASONS.items() if mask & m), samples=len(sm))
         return out
 
 
 # --------------------------------------------------------------------------------------
 # arms
 # --------------------------------------------------------------------------------------
+def claim_stdout():
+    """Route everything that writes to fd 1 (NCCL's version banner, library chatter) to stderr and
+    return a private handle on the real stdout: the bench prints exactly ONE JSON line there."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def emit(real_stdout, result):
+    os.write(real_stdout, (json.dumps(result) + '\n').encode())
+
+
 def run_ours(args):
+    real_stdout = claim_stdout()
     import torch
     from vilma_b200.dist import SingleComm, TorchComm
 
@@ -491,6 +489,11 @@ def run_ours(args):
                                                 M_total=args.snps, n_blocks=args.blocks)
     log('[rank %d] problem built in %.1fs: %s' % (comm.rank, info['setup_s'], info))
     M, P, K = info['M'], info['P'], info['K']
+    log('[rank %d] pinned to CPUs %s' % (comm.rank, getattr(vi._eng, 'cpus', None)))
+
+    sampler = ClockSampler(device)
+    if comm.rank == 0:
+        sampler.start()          # a separate process; it is polling long before the timed region
 
     # initial parameters: host arrays in pinned memory (e2e uploads them)
     np.random.seed(42)
@@ -508,9 +511,6 @@ def run_ours(args):
     state = vi.run_loop(state, args.warmup, fresh=True)
     comm.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(device)
-    if comm.rank == 0:
-        sampler.start()
     ctx.profile(True)
     launches0 = ctx.launch_count()
     trials0 = vi.n_trials
@@ -519,10 +519,12 @@ def run_ours(args):
     tm0 = (C.c_double * 4)()
     ctx.lib.vb_fit_timing(ctx.handle, tm0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     ev0.record()
     state = vi.run_loop(state, args.warmup + args.steps, fresh=True)
     ev1.record()
     torch.cuda.synchronize()
+    sampler.mark_end()
     comm.barrier()
     ms = ev0.elapsed_time(ev1)
     ms = float(comm.max(np.array([ms]))[0])
@@ -674,7 +676,7 @@ def run_ours(args):
         result['cpu_baseline'] = {'value': v, 'unit': 'SNP-updates/s', 'cores': extra['cores'],
                                   'kind': 'port', 'sample': extra['sample'], 'seconds': dt}
     if comm.rank == 0:
-        print(json.dumps(result), flush=True)
+        emit(real_stdout, result)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -685,6 +687,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    real_stdout = claim_stdout()
     v, dt, trials, M, extra = time_cpu(steps=args.steps, warmup=args.warmup)
     result = {
         'impl': 'reference',
@@ -700,7 +703,7 @@ def run_reference(args):
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(result), flush=True)
+    emit(real_stdout, result)
 
 
 def main():

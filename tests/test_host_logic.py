@@ -234,3 +234,22 @@ def test_device_math_helpers_accuracy(src, tmp_path):
     import re
     for m in re.finditer(r'max ulp ([0-9.]+)', out):
         assert float(m.group(1)) <= 1.0, out
+
+
+def test_rank_cpu_placement_plan():
+    """dist.plan_affinity: every rank of a NUMA node gets its own physical cores (all their SMT
+    threads), no overlap; too few cores -> leave the affinity alone."""
+    from vilma_b200.dist import _parse_cpulist, plan_affinity
+    assert _parse_cpulist('0-3,8,10-11') == [0, 1, 2, 3, 8, 10, 11]
+    # 2 sockets x 8 cores x 2 threads: cpu c and c+16 are siblings; node 0 = cores 0-7
+    topo = lambda c: (str((c % 16) // 8), str(c % 8))
+    node0 = [c for c in range(32) if (c % 16) < 8]
+    plans = [plan_affinity(range(32), node0, i, 4, topo) for i in range(4)]
+    assert plans[0] == [0, 1, 16, 17] and plans[3] == [6, 7, 22, 23]
+    flat = [c for p in plans for c in p]
+    assert len(flat) == len(set(flat)) == 16
+    # restricted cpuset: only what is allowed is used
+    assert plan_affinity([0, 1, 2, 3], node0, 1, 2, topo) == [2, 3]
+    # no overlap between node and cpuset -> fall back to the allowed set
+    assert plan_affinity([8, 9, 24, 25], node0, 0, 2, topo) == [8, 24]
+    assert plan_affinity(range(4), node0, 0, 8, topo) is None

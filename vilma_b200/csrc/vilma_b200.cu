@@ -333,7 +333,7 @@ static void free_ld(LdPop& L) {
 }
 static void free_fit(Fit& f) {
     cudaFree(f.adj); cudaFree(f.se); cudaFree(f.sld); cudaFree(f.scal); cudaFree(f.ann);
-    cudaFree(f.prec); cudaFree(f.logdet); cudaFree(f.logh); cudaFree(f.gfull); cudaFree(f.inv_tau_dev);
+    cudaFree(f.prec); cudaFree(f.logdet); cudaFree(f.logh); cudaFree(f.inv_tau_dev);   // gfull lives in logh's allocation
     for (int s = 0; s < 2; ++s) {
         cudaFree(f.mu[s]); cudaFree(f.delta[s]); cudaFree(f.pm[s]);
         cudaFree(f.linked[s]);
@@ -898,10 +898,10 @@ extern "C" int vb_fit_create(vb_ctx* ctx, int K, int P, int64_t M, int A, vb_ld*
     CK(cudaMalloc(&f.adj, PM * 8)); CK(cudaMalloc(&f.se, PM * 8)); CK(cudaMalloc(&f.sld, PM * 8));
     CK(cudaMalloc(&f.scal, PM * 8)); CK(cudaMalloc(&f.ann, (size_t)M * 4));
     CK(cudaMalloc(&f.prec, (size_t)K * P * P * 8)); CK(cudaMalloc(&f.logdet, (size_t)K * 8));
-    CK(cudaMalloc(&f.logh, (size_t)A * K * 8)); CK(cudaMalloc(&f.inv_tau_dev, VB_MAXP * 8));
-    CK(cudaMalloc(&f.gfull, (size_t)A * K * 8));
-    CK(cudaMemsetAsync(f.gfull, 0, (size_t)A * K * 8, ctx->stream));
-    CK(cudaMemsetAsync(f.logh, 0, (size_t)A * K * 8, ctx->stream));
+    // log hyper_delta and the delta-gradient table side by side: the hyper step uploads both at once
+    CK(cudaMalloc(&f.logh, (size_t)2 * A * K * 8)); CK(cudaMalloc(&f.inv_tau_dev, VB_MAXP * 8));
+    f.gfull = f.logh + (size_t)A * K;
+    CK(cudaMemsetAsync(f.logh, 0, (size_t)2 * A * K * 8, ctx->stream));
     for (int s = 0; s < 2; ++s) {
         CK(cudaMalloc(&f.mu[s], KM * P * 8));
         CK(cudaMalloc(&f.delta[s], KM * 8));
@@ -1004,6 +1004,18 @@ extern "C" int vb_fit_set_delta_grad(vb_ctx* ctx, const double* g) {
     for (int a = 0; a < f.A; ++a)
         for (int k = 0; k + 1 < f.K; ++k) full[(size_t)a * f.K + k] = g[(size_t)a * (f.K - 1) + k];
     CK(cudaMemcpyAsync(f.gfull, full.data(), full.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // pageable source: cudaMemcpyAsync returns once the data is staged, so no stream sync is needed
+    return 0;
+}
+// hyper_delta [A][K] and its gradient table g [A][K-1] in ONE host->device copy (native loop)
+static int fit_set_hyper_tables(vb_ctx* ctx, const double* hyper, const double* g) {
+    NEED_FIT(ctx);
+    const size_t AK = (size_t)f.A * f.K;
+    std::vector<double> both(2 * AK, 0.0);
+    for (size_t t = 0; t < AK; ++t) both[t] = std::log(hyper[t]);
+    for (int a = 0; a < f.A; ++a)
+        for (int k = 0; k + 1 < f.K; ++k) both[AK + (size_t)a * f.K + k] = g[(size_t)a * (f.K - 1) + k];
+    CK(cudaMemcpyAsync(f.logh, both.data(), both.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     // pageable source: cudaMemcpyAsync returns once the data is staged, so no stream sync is needed
     return 0;
 }
@@ -1131,7 +1143,8 @@ static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
                 sm3 = (size_t)a.A * a.K * VB_SNP_THREADS * sizeof(double);
             }
             const size_t park = (size_t)a.K * (P + 1) * VB_SNP_THREADS * sizeof(double);
-            if (g_snp3_park && park <= VB_SNP3_PARK_MAX_BYTES) {
+            // (not together with the fused annotation slots: 43 KB per CTA -> 5 CTAs / SM, measured 12 % slower)
+            if (g_snp3_park && park <= VB_SNP3_PARK_MAX_BYTES && !a.fuse_ann) {
                 static bool carve_set = false;
                 if (!carve_set) {       // all shared memory, no L1 needed: the kernel streams
                     cudaFuncSetAttribute(vb_snp3_kernel<1, MODE, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1733,8 +1746,7 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
                     g[(size_t)a * (K - 1) + k] =
                         (std::log(hyper_io[(size_t)a * K + k]) - 0.5 * nl->logdet[k]) - last;
             }
-            if (vb_fit_set_hyper(ctx, hyper_io)) return 1;
-            if (K > 1 && vb_fit_set_delta_grad(ctx, g.data())) return 1;
+            if (fit_set_hyper_tables(ctx, hyper_io, g.data())) return 1;
             double new_obj;
             // L[1] is always 1 here, so this is the iteration's last evaluation unless the error
             // scaling is being learned: speculate the next iteration's first beta trial behind it

@@ -318,6 +318,8 @@ class CudaEngine:
         `comm` plus (one node, <= 8 ranks) the NVLink mailbox rendezvous (vb_xr_*)."""
         import os
         if comm.world > 1:
+            from .dist import pin_rank
+            self.cpus = pin_rank(comm, self.ctx.device)
             buf = C.create_string_buffer(128)
             if comm.rank == 0:
                 _lib.check(self.lib.vb_nccl_unique_id(buf))
