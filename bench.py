@@ -36,6 +36,7 @@ K_GRID = 12
 N_GWAS = 3e5
 INIT_HG = 0.3
 SAMPLE_BLOCKS = 85          # CPU sample: 5 % of the blocks (~60k SNPs)
+SAMPLE_BLOCKS_MULTI = 12    # multi-cohort workloads: the oracle holds [K,P,P,M] arrays like the reference
 
 
 def log(*a):
@@ -292,7 +293,50 @@ def build_cpu_sample(n_blocks=SAMPLE_BLOCKS):
     return vi, M, n_blocks
 
 
-def time_cpu(steps, warmup):
+def build_cpu_sample_multi(wl, n_blocks):
+    """Bounded CPU sample of a multi-cohort workload: the first `n_blocks` blocks of the same
+    generator for every cohort, as oracle objects (the reference's set-up runs on them unchanged)."""
+    import torch
+    from oracle.ld_np import BlockDiagonalLD, LowRankBlock
+    from oracle.vi_np import OracleVI
+    from vilma_b200 import synth
+
+    P, N = wl['P'], np.array(wl['N'], dtype=np.float64)
+    _, n_all, _ = layout()
+    n = n_all[:n_blocks]
+    M_ld = int(n.sum())
+    n_miss = int(round(M_ld * MISSING_FRAC / (1 - MISSING_FRAC)))
+    M = M_ld + n_miss
+    dev = torch.device('cpu')
+    blocks = [[] for _ in range(P)]
+    beta_hat = np.zeros((P, M))
+    se = np.ones((P, M))
+    pos = 0
+    for b in range(n_blocks):
+        nb = int(n[b])
+        beta = synth.shared_effects(nb, 42, b, P, M_TOTAL, dev)
+        for p in range(P):
+            se_b = synth.block_se(nb, 42 + p, b, N[p], dev)
+            blk = synth.cohort_block(nb, 1000 + p, b, p, se_b, beta[p], dev, wl['n_ref'], wl['ldthresh'])
+            if blk['R'] is not None:
+                blocks[p].append(LowRankBlock(X=blk['R'].numpy(), t=1.0))
+            else:
+                u = blk['U'].numpy()
+                blocks[p].append(LowRankBlock(u=u, s=blk['s'].numpy(), v=u.T.copy(), D=np.zeros(nb),
+                                              t=wl['ldthresh']))
+            beta_hat[p, pos:pos + nb] = blk['beta_hat'].numpy()
+            se[p, pos:pos + nb] = se_b.numpy()
+        pos += nb
+    missing = np.arange(M_ld, M, dtype=np.int64)
+    lds = [BlockDiagonalLD(blocks[p], perm=np.arange(M), missing=missing) for p in range(P)]
+    covs = mixture_grid_multi(beta_hat, se, P, wl['grid'])
+    vi = OracleVI(marginal_effects=beta_hat, std_errs=se, ld_mats=lds, mixture_covs=covs,
+                  annotations=np.ones((M, 1)), scaled=False, scale_se=False, gwas_N=N,
+                  init_hg=np.full(P, INIT_HG), num_its=1000)
+    return vi, M, n_blocks
+
+
+def time_cpu(steps, warmup, workload='c2'):
     """Oracle port of the reference loop on the sample: returns (value, seconds, trials, M, info).
     Uses every host core for BLAS (torchrun exports OMP_NUM_THREADS=1, which would otherwise
     silently make the baseline single-threaded)."""
@@ -308,15 +352,18 @@ def time_cpu(steps, warmup):
     except Exception:
         pass
     try:
-        return _time_cpu(steps, warmup, cores)
+        return _time_cpu(steps, warmup, cores, workload)
     finally:
         if limiter is not None:
             limiter.restore_original_limits()
 
 
-def _time_cpu(steps, warmup, cores):
+def _time_cpu(steps, warmup, cores, workload='c2'):
     t_setup = time.time()
-    vi, M, nb = build_cpu_sample()
+    if workload == 'c2':
+        vi, M, nb = build_cpu_sample()
+    else:
+        vi, M, nb = build_cpu_sample_multi(WORKLOADS[workload], SAMPLE_BLOCKS_MULTI)
     np.random.seed(42)
     params = vi._initialize()
     elbo = vi.elbo(params)
@@ -671,10 +718,15 @@ def run_ours(args):
                                  'final_elbo': float(vi.trajectory['elbo'][-1]),
                                  'call': 'MultiPopVI.optimize(checkpoint) from the seeded start, host '
                                          'arrays in and out'}
-    if comm.rank == 0 and comm.world == 1 and not args.no_cpu and args.workload == 'c2':
-        v, dt, tr, Ms, extra = time_cpu(steps=3, warmup=1)
-        result['cpu_baseline'] = {'value': v, 'unit': 'SNP-updates/s', 'cores': extra['cores'],
-                                  'kind': 'port', 'sample': extra['sample'], 'seconds': dt}
+    if comm.rank == 0 and comm.world == 1 and not args.no_cpu:
+        try:
+            v, dt, tr, Ms, extra = time_cpu(steps=3 if args.workload == 'c2' else 2, warmup=1,
+                                            workload=args.workload)
+            result['cpu_baseline'] = {'value': v, 'unit': 'SNP-updates/s', 'cores': extra['cores'],
+                                      'kind': 'port', 'sample': extra['sample'], 'seconds': dt}
+        except Exception as exc:                 # the GPU numbers stand without it
+            log('cpu_baseline failed: %r' % (exc,))
+            result['cpu_baseline'] = None
     if comm.rank == 0:
         emit(real_stdout, result)
     if world > 1:
@@ -688,7 +740,7 @@ def run_reference(args):
     if rank != 0:
         return
     real_stdout = claim_stdout()
-    v, dt, trials, M, extra = time_cpu(steps=args.steps, warmup=args.warmup)
+    v, dt, trials, M, extra = time_cpu(steps=args.steps, warmup=args.warmup, workload=args.workload)
     result = {
         'impl': 'reference',
         'metric': 'CAVI SNP-updates/sec (1.2M SNPs, 1/2/4/8 B200)',
@@ -696,7 +748,8 @@ def run_reference(args):
         'warmup': args.warmup, 'ms_per_step': dt * 1e3 / max(args.steps, 1),
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
-        'config': {'workload': 'BASELINE configs[1] (bounded sample): ' + extra['sample']},
+        'config': {'workload': ('BASELINE configs[1]' if args.workload == 'c2' else WORKLOADS[args.workload]['name'])
+                               + ' (bounded sample): ' + extra['sample']},
         'cpu_baseline': {'value': v, 'unit': 'SNP-updates/s', 'cores': extra['cores'],
                          'kind': 'port', 'sample': extra['sample']},
         'e2e': {'value': v, 'unit': 'SNP-updates/s', 'h2d_bytes_per_step': 0,

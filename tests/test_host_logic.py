@@ -253,3 +253,54 @@ def test_rank_cpu_placement_plan():
     # no overlap between node and cpuset -> fall back to the allowed set
     assert plan_affinity([8, 9, 24, 25], node0, 0, 2, topo) == [8, 24]
     assert plan_affinity(range(4), node0, 0, 8, topo) is None
+
+
+def test_synth_lowrank_block_setup_values():
+    """vilma_b200.synth (bench scaffolding for configs[2]/[4]): the low-rank block's factors, the
+    set-up values computed from them and the Woodbury ridge start agree with dense NumPy algebra."""
+    import torch
+    from vilma_b200 import synth
+    dev = torch.device('cpu')
+    n = 96
+    se = synth.block_se(n, 42, 3, 1e5, dev)
+    beta = synth.shared_effects(n, 42, 3, 3, 1_200_000, dev)
+    blk = synth.cohort_block(n, 1001, 3, 1, se, beta[1], dev, 0.3, 0.99)
+    U, s = blk['U'].numpy(), blk['s'].numpy()
+    R = (U * s) @ U.T
+    assert blk['rank'] == int(np.ceil(0.3 * n)) - 1            # centred panel: one degree of freedom lost
+    assert np.allclose(U.T @ U, np.eye(len(s)), atol=1e-10)
+    assert np.allclose(np.diag(R), blk['ld_diag'].numpy(), rtol=1e-12)
+    z = (blk['beta_hat'] / se).numpy()
+    mle = np.linalg.pinv(R, rcond=1e-10) @ z
+    assert np.isclose(blk['chi'], z @ mle, rtol=1e-9)
+    assert np.allclose(blk['adj'].numpy(), (R @ mle) / se.numpy(), rtol=1e-8, atol=1e-8)
+    prior = 3e-7
+    ridge = synth.ridge_start(blk, se, prior).numpy()
+    ref = np.linalg.solve(R + np.diag(se.numpy()**2 / prior), blk['adj'].numpy() * se.numpy()) * se.numpy()
+    assert np.allclose(ridge, ref, rtol=1e-9, atol=1e-14)
+    # full-rank dense block: the same quantities through the Cholesky route
+    full = synth.cohort_block(n, 1000, 3, 0, se, beta[0], dev, 2.0, 1.0)
+    assert full['U'] is None and full['rank'] == n
+    Rf = full['R'].numpy()
+    zf = (full['beta_hat'] / se).numpy()
+    assert np.isclose(full['chi'], zf @ np.linalg.solve(Rf, zf), rtol=1e-9)
+
+
+def test_bench_multi_cohort_grid():
+    """bench.mixture_grid_multi: the reference's _make_simple with its indefinite members removed
+    (the reference's own constructor rejects them), and the 256-matrix custom grid, are SPD."""
+    sys.path.insert(0, ROOT)
+    import bench
+    rng = np.random.default_rng(0)
+    se = 10.0 ** rng.uniform(-3, -2, size=(3, 4000))
+    beta = rng.normal(size=(3, 4000)) * se * 2
+    covs = bench.mixture_grid_multi(beta, se, 3, ('simple', 2))
+    assert 60 < len(covs) <= 123
+    assert all(c.shape == (3, 3) and np.all(np.linalg.eigvalsh(c) > 0) for c in covs)
+    se5, beta5 = np.tile(se[:1], (5, 1)), np.tile(beta[:1], (5, 1))
+    covs = bench.mixture_grid_multi(beta5, se5, 5, ('custom', 256))
+    assert len(covs) == 256
+    assert all(np.all(np.linalg.eigvalsh(c) > 0) for c in covs)
+    # seeded: the same grid every time
+    again = bench.mixture_grid_multi(beta5, se5, 5, ('custom', 256))
+    assert all(np.array_equal(a, b) for a, b in zip(covs, again))
