@@ -9,8 +9,14 @@ VI_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN)
                   if f.endswith('.npz') and (f.startswith('syn_') or f.startswith('vischeme_')))
 
 
+# tests/golden/extra/: the reference's default two-cohort grid (582 components) and 4 / 6 cohorts
+EXTRA_CASES = sorted(f[:-4] for f in os.listdir(os.path.join(GOLDEN, 'extra')) if f.endswith('.npz')) \
+    if os.path.isdir(os.path.join(GOLDEN, 'extra')) else []
+
+
 def load_case(name):
-    return dict(np.load(os.path.join(GOLDEN, name + '.npz'), allow_pickle=False))
+    sub = 'extra' if name.startswith('xtr_') else ''
+    return dict(np.load(os.path.join(GOLDEN, sub, name + '.npz'), allow_pickle=False))
 
 
 def build_ld(fx, block_cls, bdm_cls):

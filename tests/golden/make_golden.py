@@ -522,8 +522,27 @@ SYN_CASES = {
 }
 
 
-def golden_synthetic(ref, outdir, only=None):
-    for name, c in SYN_CASES.items():
+# Further cases kept under tests/golden/extra/ (run by tests/test_gpu_extra.py): the reference's DEFAULT
+# two-cohort grid (-K 12 -> 582 components: the tile kernel at 16 warps per tile) and the cohort counts
+# no other fixture has (4 and 6: every P x P template instantiation then has a parity case).
+EXTRA_CASES = {
+    'xtr_p2_default_grid': dict(P=2, M=96, blocks=[30, 36, 28], K=12,
+                                ldthresh=1.0, lrf=None, A=1, miss=0.02, shuffle=False,
+                                scaled=False, scale_se=False, its=15, resume=None,
+                                n=[4e4, 1e4]),
+    'xtr_p4': dict(P=4, M=120, blocks=[34, 40, 44], K=1,
+                   ldthresh=1.0, lrf=None, A=1, miss=0.02, shuffle=True,
+                   scaled=False, scale_se=False, its=20, resume=None,
+                   n=[4e4, 2e4, 1e4, 1e4]),
+    'xtr_p6': dict(P=6, M=90, blocks=[28, 32, 28], K=1,
+                   ldthresh=0.99, lrf=0.6, A=2, miss=0.02, shuffle=False,
+                   scaled=False, scale_se=False, its=20, resume=None,
+                   n=[4e4, 2e4, 1e4, 1e4, 5e3, 5e3]),
+}
+
+
+def golden_synthetic(ref, outdir, only=None, cases=None):
+    for name, c in (cases or SYN_CASES).items():
         if only and name not in only:
             continue
         print(name)
@@ -559,3 +578,7 @@ if __name__ == '__main__':
         golden_vischeme(ref, HERE)
     if not sel or any(s.startswith('syn') for s in sel):
         golden_synthetic(ref, HERE, only=[s for s in (sel or []) if s.startswith('syn_')] or None)
+    if not sel or any(s.startswith('xtr') for s in sel):
+        os.makedirs(os.path.join(HERE, 'extra'), exist_ok=True)
+        golden_synthetic(ref, os.path.join(HERE, 'extra'),
+                         only=[s for s in (sel or []) if s.startswith('xtr_')] or None, cases=EXTRA_CASES)

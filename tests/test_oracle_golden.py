@@ -11,14 +11,14 @@ import pytest
 
 from oracle.ld_np import BlockDiagonalLD, LowRankBlock
 from oracle.vi_np import OracleVI
-from _fixtures import VI_CASES, build_ld, load_case, vi_kwargs
+from _fixtures import EXTRA_CASES, VI_CASES, build_ld, load_case, vi_kwargs
 
 
 def make_oracle(fx):
     return OracleVI(ld_mats=build_ld(fx, LowRankBlock, BlockDiagonalLD), **vi_kwargs(fx))
 
 
-@pytest.mark.parametrize('name', VI_CASES)
+@pytest.mark.parametrize('name', VI_CASES + EXTRA_CASES)
 def test_precompute_and_init(name):
     fx = load_case(name)
     vi = make_oracle(fx)
@@ -31,7 +31,9 @@ def test_precompute_and_init(name):
                        atol=1e-10 * np.abs(fx['pre_inverse_betas']).max())
     np.random.seed(int(fx['seed']))
     mu, delta, hyper = vi._initialize()
-    assert np.allclose(mu, fx['init_vi_mu'], rtol=1e-7, atol=1e-12)
+    # (elements that cancel to ~1e-8 of the array's scale carry the scale's rounding error)
+    assert np.allclose(mu, fx['init_vi_mu'], rtol=1e-7,
+                       atol=max(1e-12, 1e-13 * np.abs(fx['init_vi_mu']).max()))
     assert np.allclose(delta, fx['init_vi_delta'], rtol=1e-7, atol=1e-300)
     assert np.allclose(hyper, fx['init_hyper_delta'], rtol=1e-9)
     assert np.allclose(vi.nat_grad_vi_delta, fx['init_nat_grad_vi_delta'], rtol=1e-9, atol=1e-12)
@@ -43,7 +45,7 @@ def test_precompute_and_init(name):
     assert np.allclose(vi.real_posterior_variance(*params), fx['init_post_var'], rtol=1e-10, atol=1e-16)
 
 
-@pytest.mark.parametrize('name', VI_CASES)
+@pytest.mark.parametrize('name', VI_CASES + EXTRA_CASES)
 def test_trajectory(name):
     fx = load_case(name)
     vi = make_oracle(fx)
@@ -53,7 +55,11 @@ def test_trajectory(name):
     assert len(traj['elbo_out']) == len(fx['traj_elbo_out'])
     assert traj['trials'] == fx['traj_trials'].tolist()
     assert np.array_equal(np.array(traj['L0']), fx['traj_L0'])
-    assert np.allclose(traj['elbo_out'], fx['traj_elbo_out'], rtol=1e-9, atol=0)
+    # the tracked ELBO is an accumulation of deltas from the starting value (reference :405): where a
+    # fit starts six orders of magnitude below where it ends (xtr_p4: -9.3e8 -> -4.9e2) the late values
+    # carry the rounding of the early ones, hence the floor relative to the trajectory's scale
+    atol = 1e-14 * np.abs(fx['traj_elbo_out']).max() if name in EXTRA_CASES else 0
+    assert np.allclose(traj['elbo_out'], fx['traj_elbo_out'], rtol=1e-9, atol=atol)
     assert np.allclose(np.array(traj['tau']), fx['traj_tau'], rtol=1e-8)
     assert np.allclose(params[0], fx['final_vi_mu'], rtol=1e-6, atol=1e-9)
     assert np.allclose(params[1], fx['final_vi_delta'], rtol=1e-6, atol=1e-12)
