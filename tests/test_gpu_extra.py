@@ -2,18 +2,14 @@
 components: the tile kernel at 16 warps per tile) and 4 / 6 cohorts (the remaining P x P template
 instantiations).  Same checks and tolerances as test_gpu_parity.py.
 
-These fixtures were generated (and the oracle pinned on them, tests/test_oracle_golden.py) after the
-round's GPU budget was spent, so they have NOT run on a B200 yet: they are marked xfail(strict=False) --
-the run records XPASS / XFAIL for each without gating the suite -- and become ordinary tests once a GPU
-run has shown them green.
+The oracle is pinned on the same fixtures in tests/test_oracle_golden.py.
 """
 import numpy as np
 import pytest
 
 from _fixtures import EXTRA_CASES, build_ld, load_case, vi_kwargs
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason='new fixtures, not yet run on a GPU (round-1 budget spent)')]
+pytestmark = pytest.mark.gpu
 
 
 def make_product(fx):
