@@ -304,3 +304,56 @@ def test_bench_multi_cohort_grid():
     # seeded: the same grid every time
     again = bench.mixture_grid_multi(beta5, se5, 5, ('custom', 256))
     assert all(np.array_equal(a, b) for a, b in zip(covs, again))
+
+
+def test_setup_thread_pool_matches_serial(monkeypatch):
+    """vilma_b200._pool: per-block set-up work (eigh at load, pseudo-inverse, ridge solve, dense
+    reconstruction for upload) on the thread pool gives what the serial order gives, in block order,
+    and agrees with the oracle's operators."""
+    from oracle.ld_np import BlockDiagonalLD, LowRankBlock
+    from vilma_b200 import _pool
+    from vilma_b200.matrix_structures import BlockDiagonalMatrix, LowRankMatrix
+    rng = np.random.default_rng(3)
+    sizes = [40, 75, 33, 90, 61, 48, 57]
+    mats = []
+    for n in sizes:
+        g = rng.normal(size=(2 * n, n))
+        g -= g.mean(0)
+        g /= np.sqrt((g * g).sum(0))
+        mats.append(g.T @ g)
+    M = sum(sizes) + 5
+    perm = rng.permutation(M)
+    missing = perm[sum(sizes):]
+
+    def build(threads):
+        monkeypatch.setenv('VILMA_B200_SETUP_THREADS', str(threads))
+        pipe = _pool.OrderedPipeline(depth=2)
+        for m in mats:
+            pipe.submit(LowRankMatrix, m, 0.95)
+        return BlockDiagonalMatrix(pipe.results(), perm=perm, missing=missing)
+
+    serial, pooled = build(1), build(4)
+    assert [m.shape for m in pooled.matrices] == [m.shape for m in serial.matrices]
+    z = rng.normal(size=M)
+    reg = rng.uniform(0.05, 0.2, size=M)
+    monkeypatch.setenv('VILMA_B200_SETUP_THREADS', '4')
+    inv_p, ridge_p = pooled.inverse.dot(z), pooled.ridge_inverse_dot(z, reg)
+    blocks_p = pooled.device_blocks()
+    monkeypatch.setenv('VILMA_B200_SETUP_THREADS', '1')
+    inv_s, ridge_s = serial.inverse.dot(z), serial.ridge_inverse_dot(z, reg)
+    blocks_s = serial.device_blocks()
+    assert np.allclose(inv_p, inv_s, rtol=1e-10, atol=1e-12)
+    assert np.allclose(ridge_p, ridge_s, rtol=1e-10, atol=1e-12)
+    assert [b['kind'] for b in blocks_p] == [b['kind'] for b in blocks_s]
+    for bp, bs in zip(blocks_p, blocks_s):
+        key = 'R' if bp['kind'] == 'dense' else 'U'
+        assert np.allclose(bp[key], bs[key], rtol=1e-10, atol=1e-12)
+    # against the oracle's host operators
+    ora = BlockDiagonalLD([LowRankBlock(X=m, t=0.95) for m in mats], perm=perm, missing=missing)
+    assert np.allclose(inv_p, ora.inverse_dot(z) if hasattr(ora, 'inverse_dot') else ora.inverse.dot(z),
+                       rtol=1e-8, atol=1e-10)
+    assert np.allclose(ridge_p, ora.ridge_inverse_dot(z, reg), rtol=1e-8, atol=1e-10)
+    # an exception inside a worker reaches the caller
+    with pytest.raises(ValueError):
+        monkeypatch.setenv('VILMA_B200_SETUP_THREADS', '4')
+        _pool.map_blocks(lambda m: LowRankMatrix(m + np.triu(np.ones_like(m), 1), 1.0), mats)

@@ -170,7 +170,8 @@ def load_ld_from_schema(schema_path, variants, denylist, ldthresh, mmap=False):
     """Block-diagonal LD of a schema, matched and oriented to `variants` (load.py:237-354).
 
     Returns (BlockDiagonalMatrix in the order of `variants`, list of positions without LD)."""
-    svds = []
+    from ._pool import OrderedPipeline
+    svds = OrderedPipeline()        # one eigh per block, run concurrently (results in block order)
     perm = []
     var_reidx = variants.set_index('ID')
     var_reidx['old_idx'] = np.arange(var_reidx.shape[0])
@@ -209,8 +210,9 @@ def load_ld_from_schema(schema_path, variants, denylist, ldthresh, mmap=False):
         perm.append(idx[~mismatch])
         if mmap:
             _consume_mmap_rng()
-        svds.append(LowRankMatrix(accepted, ldthresh))
+        svds.submit(LowRankMatrix, accepted, ldthresh)
 
+    svds = svds.results()
     num = variants.shape[0]
     perm = np.concatenate(perm) if len(perm) > 0 else np.array([], dtype=np.int64)
     list_of_missing = sorted(set(range(num)) - set(perm.tolist()))

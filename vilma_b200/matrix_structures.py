@@ -140,29 +140,30 @@ class BlockDiagonalMatrix():
 
     # ---- device side -------------------------------------------------------------
     def device_blocks(self, block_ids=None):
-        """Describe blocks for upload: dense reconstruction when rank is close to n, else factor."""
-        from .engine import choose_storage
-        out = []
+        """Describe blocks for upload: dense reconstruction when rank is close to n, else factor.
+        The reconstructions (one GEMM per block) run on the set-up thread pool."""
+        from ._pool import map_blocks
+        from .engine import choose_storage, sym_nmax
+        sym_nmax()          # load the library on this thread before the workers ask for it
         ids = range(len(self.matrices)) if block_ids is None else block_ids
-        for b in ids:
-            m = self.matrices[b]
-            if not np.all(m.D == 0):
-                raise NotImplementedError('device LD blocks must have a zero diagonal part D')
-            n, r = m.u.shape
-            if m.s.shape[0] == 1 and m.s[0] == 0:
-                # rank-0 dummy block (matrix_structures.py:141-145): the zero matrix
-                out.append({'n': n, 'kind': 'factor', 'U': np.zeros((n, 1)), 's': np.zeros(1)})
-            elif choose_storage(n, r) == 'dense':
-                out.append({'n': n, 'kind': 'dense', 'R': (m.u * m.s).dot(m.v)})
-            else:
-                # the reference multiplies by v (= u^T for every block built from X); keep its
-                # semantics exactly for a caller-supplied v by folding v into the factor only
-                # when it is the transpose, else fall back to the dense product.
-                if m.v.shape == m.u.T.shape and np.array_equal(m.v, m.u.T):
-                    out.append({'n': n, 'kind': 'factor', 'U': m.u, 's': m.s})
-                else:
-                    out.append({'n': n, 'kind': 'dense', 'R': (m.u * m.s).dot(m.v)})
-        return out
+        return map_blocks(lambda b: self._device_block(self.matrices[b], choose_storage), ids)
+
+    @staticmethod
+    def _device_block(m, choose_storage):
+        if not np.all(m.D == 0):
+            raise NotImplementedError('device LD blocks must have a zero diagonal part D')
+        n, r = m.u.shape
+        if m.s.shape[0] == 1 and m.s[0] == 0:
+            # rank-0 dummy block (matrix_structures.py:141-145): the zero matrix
+            return {'n': n, 'kind': 'factor', 'U': np.zeros((n, 1)), 's': np.zeros(1)}
+        if choose_storage(n, r) == 'dense':
+            return {'n': n, 'kind': 'dense', 'R': (m.u * m.s).dot(m.v)}
+        # the reference multiplies by v (= u^T for every block built from X); keep its semantics
+        # exactly for a caller-supplied v by folding v into the factor only when it is the
+        # transpose, else fall back to the dense product.
+        if m.v.shape == m.u.T.shape and np.array_equal(m.v, m.u.T):
+            return {'n': n, 'kind': 'factor', 'U': m.u, 's': m.s}
+        return {'n': n, 'kind': 'dense', 'R': (m.u * m.s).dot(m.v)}
 
     def to_device(self, ctx=None):
         """Upload (once per context) and return the DeviceLD of the whole operator."""
@@ -186,9 +187,10 @@ class BlockDiagonalMatrix():
         """Matrix @ vector.  Non-inverted: GPU mat-vec.  Inverted: host pseudo-inverse (setup)."""
         vector = np.asarray(vector, dtype=np.float64)
         if self._inverted:
+            from ._pool import map_blocks
             xp = vector[self.perm]
-            parts = [m.inverse_dot(xp[lo:hi]) for m, lo, hi in
-                     zip(self.matrices, self.starts[:-1], self.starts[1:])]
+            parts = map_blocks(lambda t: t[0].inverse_dot(xp[t[1]:t[2]]),
+                               zip(self.matrices, self.starts[:-1], self.starts[1:]))
             parts.append(np.zeros([self.missing.shape[0]] + list(vector.shape[1:])))
             return np.concatenate(parts, axis=0)[self.inv_perm]
         dev = self.to_device(ctx)
@@ -206,10 +208,13 @@ class BlockDiagonalMatrix():
         reg[:] = regularizer
         reg = reg[self.perm]
         xp = vector[self.perm]
-        parts = []
-        for m, lo, hi in zip(self.matrices, self.starts[:-1], self.starts[1:]):
+        from ._pool import map_blocks
+
+        def one(t):
+            m, lo, hi = t
             shifted = LowRankMatrix(u=m.u, s=m.s, v=m.v, D=m.D + reg[lo:hi])
-            parts.append(shifted.inverse_dot(xp[lo:hi]))
+            return shifted.inverse_dot(xp[lo:hi])
+        parts = map_blocks(one, zip(self.matrices, self.starts[:-1], self.starts[1:]))
         parts.append(np.zeros(self.missing.shape[0]))
         return np.concatenate(parts, axis=0)[self.inv_perm]
 
