@@ -313,6 +313,7 @@ def test_setup_thread_pool_matches_serial(monkeypatch):
     from oracle.ld_np import BlockDiagonalLD, LowRankBlock
     from vilma_b200 import _pool
     from vilma_b200.matrix_structures import BlockDiagonalMatrix, LowRankMatrix
+    monkeypatch.setattr(_pool, 'MIN_BLOCKS', 1)
     rng = np.random.default_rng(3)
     sizes = [40, 75, 33, 90, 61, 48, 57]
     mats = []

@@ -44,11 +44,14 @@ class _SingleThreadBlas:
         return False
 
 
+MIN_BLOCKS = 16     # fewer items than this are not worth a pool (and keep small runs single-threaded)
+
+
 def map_blocks(fn, items, workers=None):
     """[fn(x) for x in items], evaluated on the pool; order preserved; exceptions propagate."""
     items = list(items)
     workers = setup_threads() if workers is None else workers
-    if workers <= 1 or len(items) <= 1:
+    if workers <= 1 or len(items) < max(MIN_BLOCKS, 2):
         return [fn(x) for x in items]
     with _SingleThreadBlas(), ThreadPoolExecutor(workers) as pool:
         return list(pool.map(fn, items))
