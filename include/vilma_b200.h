@@ -35,9 +35,14 @@ typedef struct vb_ld vb_ld; /* one cohort's block-diagonal LD operator, resident
 /* ---- context ------------------------------------------------------------------------ */
 int vb_abi_version(void);
 const char* vb_last_error(void);
-/* process-wide options read when an LD operator is created:
+/* process-wide options (kernel selection; the defaults are the measured best):
  *   "ld_symmetric" (default 1): store dense blocks of n <= vb_ld_sym_nmax() symmetric-packed
- *   "snp_three_pass" (default 1): one- and two-cohort updates use the three-pass softmax kernel */
+ *                  (read when an LD operator is created)
+ *   "snp_three_pass" (default 1): one- and two-cohort updates with K < 32 use the three-pass softmax kernel
+ *   "snp3_park" (default 1): that kernel keeps logits / weights / mu' in shared memory when they fit
+ *   "snp_tile" (default -1 = automatic: P >= 3 or K >= 32): the K-split tile kernel; 0 = never,
+ *                  W in {1,2,4,8,16} = always, with W warps per 32-SNP tile
+ *   "snp_ann_slots" (default 1): fused annotation sums in per-thread shared-memory slots (A*K <= 16) */
 int vb_set_option(const char* name, int64_t value);
 /* largest dense block (rows) that is stored symmetric-packed; larger ones are stored in full */
 int64_t vb_ld_sym_nmax(void);
