@@ -116,6 +116,66 @@ template <int P> struct VbTileCfg {
     static constexpr int MINB = (P == 1) ? 2 : 1;
 };
 
+// --- experimental (VB_TILE_PAIR=1, off by default; not yet measured on a GPU) -----------------------
+// `#pragma unroll 2` on the component loop leaves the two copies SEQUENTIAL in the SASS (the remainder
+// test between them ends the basic block), so a thread still walks one ~100-deep fp64 dependency chain
+// at a time with 4 warps per scheduler.  The paired loop computes two components in one straight-line
+// block (the second one clamped and masked when K runs out) and folds both into the online moments
+// without a branch, so the scheduler can interleave the two chains.
+#ifndef VB_TILE_PAIR
+#define VB_TILE_PAIR 0
+#endif
+template <int P>
+struct VbTileComp {
+    double lk, lkh, quad, sigsum, mu[P], sd[P];     // lkh = lk - log h_k
+};
+template <int P, int MODE>
+__device__ __forceinline__ VbTileComp<P> vb_tile_component(
+    const double* __restrict__ prec, const double* __restrict__ pmu, int64_t M, const double (&dt)[P],
+    const double (&g)[P], double step, double one_minus_step, double gk, double loghk, double logdetk) {
+    constexpr int NT = P * (P + 1) / 2;
+    VbTileComp<P> c;
+    double lam[NT], eta[P], det;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+#pragma unroll
+        for (int q = 0; q <= p; ++q) lam[VB_TRI(p, q)] = prec[p * P + q];
+        lam[VB_TRI(p, p)] += dt[p];
+        c.mu[p] = __ldg(pmu + (size_t)p * M);
+    }
+    vb_sym_matvec<P>(lam, c.mu, eta);
+    if constexpr (MODE == VB_MODE_TRIAL) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) eta[p] = step * g[p] + one_minus_step * eta[p];
+    }
+    if constexpr (P <= 2) {
+        double S[NT];
+        vb_small_inverse<P>(lam, S, det);
+        if constexpr (MODE == VB_MODE_TRIAL) vb_sym_matvec<P>(S, eta, c.mu);
+#pragma unroll
+        for (int p = 0; p < P; ++p) c.sd[p] = S[VB_TRI(p, p)];
+    } else {
+        VbLdl<P> f;
+        f.factor(lam);
+        det = f.det;
+        if constexpr (MODE == VB_MODE_TRIAL) f.solve(eta, c.mu);
+        f.diag(c.sd);
+    }
+    const double cl = -vb_log_pos(det);
+    double dot = 0.0, dmm = 0.0, dss = 0.0;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        dot = fma(c.mu[p], eta[p], dot);
+        dmm = fma(dt[p] * c.mu[p], c.mu[p], dmm);
+        dss = fma(dt[p], c.sd[p], dss);
+    }
+    c.lk = 0.5 * (cl + dot) + gk;
+    c.lkh = c.lk - loghk;
+    c.quad = dot - dmm;
+    c.sigsum = logdetk - cl + ((double)P - dss);
+    return c;
+}
+
 template <int P, int MODE>
 __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp_tile_kernel(const VbSnpArgs a) {
     static_assert(MODE != VB_MODE_EVAL, "EVAL has no softmax: use vb_snp_kernel");
@@ -177,6 +237,54 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
         double* pmu_out = (MODE == VB_MODE_TRIAL) ? a.mu_out + (size_t)warp * PM + i : nullptr;
         const size_t kstride = (size_t)W * PM;
         double* sl = s_logit;
+#if VB_TILE_PAIR
+        for (int k = warp; k < K; k += 2 * W, pmu_in += 2 * kstride, sl += 2 * W * 32) {
+            const bool has2 = k + W < K;
+            const int k2 = has2 ? k + W : k;                       // clamped: recomputes k, masked below
+            if (VB_TILE_PREFETCH > 0 && k + 2 * VB_TILE_PREFETCH * W < K) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    vb_prefetch_l2(pmu_in + 2 * VB_TILE_PREFETCH * kstride + (size_t)p * M);
+                    vb_prefetch_l2(pmu_in + (2 * VB_TILE_PREFETCH + 1) * kstride + (size_t)p * M);
+                }
+            }
+            const VbTileComp<P> c1 = vb_tile_component<P, MODE>(
+                g_prec + (size_t)k * P * P, pmu_in, M, dt, g, step, one_minus_step, gfull[k], logh[k], g_logdet[k]);
+            const VbTileComp<P> c2 = vb_tile_component<P, MODE>(
+                g_prec + (size_t)k2 * P * P, has2 ? pmu_in + kstride : pmu_in, M, dt, g, step, one_minus_step,
+                gfull[k2], logh[k2], g_logdet[k2]);
+            if constexpr (MODE == VB_MODE_TRIAL) {
+                if (valid) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) pmu_out[(size_t)p * M] = c1.mu[p];
+                    if (has2) {
+#pragma unroll
+                        for (int p = 0; p < P; ++p) pmu_out[kstride + (size_t)p * M] = c2.mu[p];
+                    }
+                }
+                pmu_out += 2 * kstride;
+            }
+            sl[0] = c1.lk;
+            if (has2) sl[W * 32] = c2.lk;
+            // branch-free online update with both: new maximum, one rescale of the running sums, two weights
+            const double lk2 = has2 ? c2.lk : -1.0e300;
+            const double nmx = fmax(mx, fmax(c1.lk, lk2));
+            const double r = vb_exp_nonpos(mx - nmx);
+            const double w1 = vb_exp_nonpos(c1.lk - nmx);
+            const double w2 = has2 ? vb_exp_nonpos(lk2 - nmx) : 0.0;
+            mx = nmx;
+            s0 = fma(s0, r, w1 + w2);
+            sKd = fma(sKd, r, fma(w1, c1.lkh, w2 * c2.lkh));
+            sKq = fma(sKq, r, fma(w1, c1.quad, w2 * c2.quad));
+            sKs = fma(sKs, r, fma(w1, c1.sigsum, w2 * c2.sigsum));
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                spm[p] = fma(spm[p], r, fma(w1, c1.mu[p], w2 * c2.mu[p]));
+                sm2[p] = fma(sm2[p], r, fma(w1, fma(c1.mu[p], c1.mu[p], c1.sd[p]),
+                                            w2 * fma(c2.mu[p], c2.mu[p], c2.sd[p])));
+            }
+        }
+#else
 #pragma unroll UNROLL_A
         for (int k = warp; k < K; k += W, pmu_in += kstride, sl += W * 32) {
             const double* prec = g_prec + (size_t)k * P * P;
@@ -250,6 +358,7 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
                 sm2[p] = fma(w, fma(mu[p], mu[p], sd[p]), sm2[p]);
             }
         }
+#endif
         // ---- merge the W slices of each SNP (warp order)
         if (W > 1) {
             double* mine = s_merge + ((size_t)warp * NV) * 32 + lane;
