@@ -360,7 +360,7 @@ def time_cpu(steps, warmup, workload='c2'):
 
 def _time_cpu(steps, warmup, cores, workload='c2'):
     t_setup = time.time()
-    if workload == 'c2':
+    if workload in ('c2', 'c4'):         # c4: same model and grid; the CPU sample keeps C2's block sizes
         vi, M, nb = build_cpu_sample()
     else:
         vi, M, nb = build_cpu_sample_multi(WORKLOADS[workload], SAMPLE_BLOCKS_MULTI)
@@ -526,11 +526,17 @@ def run_ours(args):
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
 
-    if args.workload == 'c2':
+    if args.workload in ('c2', 'c4'):
         vi, ctx, info = build_gpu_problem(comm, device, M_total=args.snps, n_blocks=args.blocks)
-        info['name'] = 'BASELINE configs[1]: synthetic single cohort, dense LD, -K 12'
-        info['ld_store'] = ('dense fp64, symmetric-packed (lower triangle in 8-row panels): '
-                            '4 n (n+1) bytes per block per mat-vec')
+        info['name'] = ('BASELINE configs[1]: synthetic single cohort, dense LD, -K 12' if args.workload == 'c2'
+                        else 'BASELINE configs[3]: synthetic single cohort, 6M SNPs genome-wide, dense LD '
+                             'sharded over the ranks, -K 12')
+        from vilma_b200.engine import sym_nmax
+        _, n_all, _ = layout(args.snps, args.blocks)
+        n_packed = int((n_all <= sym_nmax()).sum())
+        info['ld_store'] = ('dense fp64: %d of %d blocks symmetric-packed (lower triangle in 8-row panels, '
+                            '4 n (n+1) bytes per mat-vec), %d blocks above %d rows stored in full (8 n^2)'
+                            % (n_packed, len(n_all), len(n_all) - n_packed, sym_nmax()))
     else:
         vi, ctx, info = build_gpu_problem_multi(comm, device, WORKLOADS[args.workload],
                                                 M_total=args.snps, n_blocks=args.blocks)
@@ -598,7 +604,7 @@ def run_ours(args):
     per_rank = comm.sum(per_rank) if comm.world > 1 else per_rank
     achieved = info['ld_bytes_rank'] / P / (mv_avg * 1e-3) / 1e9 if mv_n else 0.0    # one launch per cohort
     traffic = None
-    if comm.world == 1 and M == M_TOTAL and args.workload == 'c2':
+    if comm.world == 1 and M == M_TOTAL and args.workload == 'c2':     # the ncu capture is of this exact launch
         try:
             traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ld_matvec_traffic.json')))['bytes_per_launch']
         except Exception:
@@ -748,7 +754,7 @@ def run_reference(args):
         'warmup': args.warmup, 'ms_per_step': dt * 1e3 / max(args.steps, 1),
         'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
-        'config': {'workload': ('BASELINE configs[1]' if args.workload == 'c2' else WORKLOADS[args.workload]['name'])
+        'config': {'workload': ('BASELINE configs[1]' if args.workload in ('c2', 'c4') else WORKLOADS[args.workload]['name'])
                                + ' (bounded sample): ' + extra['sample']},
         'cpu_baseline': {'value': v, 'unit': 'SNP-updates/s', 'cores': extra['cores'],
                          'kind': 'port', 'sample': extra['sample']},
@@ -770,9 +776,12 @@ def main():
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--converge', type=int, default=2000, metavar='MAX_ITS',
                     help='also run the fit to convergence (at most MAX_ITS iterations) and report the time')
-    ap.add_argument('--workload', default='c2', choices=['c2', 'c3', 'c5'],
-                    help='c2 = BASELINE configs[1] (the bench line of record); c3 / c5 = configs[2] / configs[4]')
+    ap.add_argument('--workload', default='c2', choices=['c2', 'c3', 'c4', 'c5'],
+                    help='c2 = BASELINE configs[1] (the bench line of record); c3 / c5 = configs[2] / configs[4]; '
+                         'c4 = configs[3]: 6M SNPs, 170 GB of LD -- needs --gpus 8 (21 GB per rank)')
     args = ap.parse_args()
+    if args.workload == 'c4' and args.snps == M_TOTAL:
+        args.snps = 6_000_000
     if args.impl == 'reference':
         run_reference(args)
     else:
