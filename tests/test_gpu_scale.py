@@ -102,3 +102,42 @@ def test_large_properties():
     assert np.all(params[1] >= 1e-100)
     pm = vi.real_posterior_mean(*params)
     assert np.all(pm[:, info['M_ld']:] == 0.0)         # no LD, BETA 0 -> posterior mean 0
+
+
+@pytest.mark.xfail(strict=False, reason='written after the round-1 GPU budget was spent: not yet run on a B200')
+def test_medium_multi_cohort_fit_matches_oracle():
+    """A ~4k-SNP slice of the three-cohort workload (bench.py --workload c3: low-rank panels, 87
+    components): device _initialize + the tile kernel against the oracle on identical inputs --
+    same line-search decisions, ELBO trajectory, posterior means."""
+    import bench
+    from vilma_b200.engine import DeviceContext, DeviceLD
+    from vilma_b200.variational_inference import DeviceBlockDiagonalMatrix, MultiPopVI
+    vi_o, M, _ = bench.build_cpu_sample_multi(bench.WORKLOADS['c3'], 6)
+    P = vi_o.num_pops
+    ctx = DeviceContext(0)
+    lds = []
+    for ld_o in vi_o.ld_mats:
+        blocks = [{'n': int(b.shape[0]), 'kind': 'dense', 'R': (b.u * b.s) @ b.v} for b in ld_o.matrices]
+        lds.append(DeviceLD(ctx, M, blocks, ld_o.perm[:int(ld_o.starts[-1])]))
+    pre = dict(ld_diags=vi_o.ld_diags, adj_marginal_effects=vi_o.adj_marginal_effects,
+               chi_stat=vi_o.chi_stat, ld_ranks=vi_o.ld_ranks, inverse_betas=vi_o.inverse_betas)
+    covs = [np.linalg.inv(vi_o.mixture_prec[k, :, :, 0]) for k in range(vi_o.num_mix)]
+    vi_p = MultiPopVI(marginal_effects=vi_o.marginal_effects, std_errs=vi_o.std_errs,
+                      ld_mats=[DeviceBlockDiagonalMatrix(ld, (M, M)) for ld in lds], mixture_covs=covs,
+                      annotations=np.ones((M, 1)), checkpoint=False, checkpoint_freq=-1, output='t',
+                      scaled=False, scale_se=False, gwas_N=np.array(bench.WORKLOADS['c3']['N']),
+                      init_hg=np.full(P, bench.INIT_HG), num_its=6, comm=None, device=0,
+                      precomputed=pre, context=ctx)
+    vi_p.init_on_device = True
+    vi_o.num_its = 6
+    traj = {}
+    np.random.seed(42)
+    res_o = vi_o.optimize(None, trajectory=traj)
+    np.random.seed(42)
+    res_p = vi_p.optimize(None)
+    assert vi_p.trajectory['trials'] == traj['trials']
+    assert np.array_equal(np.array(vi_p.trajectory['L0']), np.array(traj['L0']))
+    el = np.array(traj['elbo_out'])
+    assert np.allclose(vi_p.trajectory['elbo'], el, rtol=1e-8, atol=1e-13 * np.abs(el).max())
+    assert np.allclose(vi_p.real_posterior_mean(*res_p), vi_o.real_posterior_mean(*res_o), rtol=1e-6, atol=1e-9)
+    assert np.allclose(res_p[2], res_o[2], rtol=1e-6, atol=1e-12)
