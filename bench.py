@@ -35,7 +35,7 @@ MISSING_FRAC = 0.01
 K_GRID = 12
 N_GWAS = 3e5
 INIT_HG = 0.3
-SAMPLE_BLOCKS = 85          # CPU sample: 5 % of the blocks (~60k SNPs)
+SAMPLE_BLOCKS = int(os.environ.get('BENCH_SAMPLE_BLOCKS', '85'))   # CPU sample: 5 % of the blocks (~60k SNPs)
 SAMPLE_BLOCKS_MULTI = 12    # multi-cohort workloads: the oracle holds [K,P,P,M] arrays like the reference
 
 

@@ -358,3 +358,25 @@ def test_setup_thread_pool_matches_serial(monkeypatch):
     with pytest.raises(ValueError):
         monkeypatch.setenv('VILMA_B200_SETUP_THREADS', '4')
         _pool.map_blocks(lambda m: LowRankMatrix(m + np.triu(np.ones_like(m), 1), 1.0), mats)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the driver's CPU arm): exactly one line on stdout, the contract's
+    keys, metric / unit identical to the GPU arm's."""
+    import json
+    env = dict(os.environ, BENCH_SAMPLE_BLOCKS='6')
+    res = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
+                          '--steps', '1', '--warmup', '1'], capture_output=True, text=True, env=env,
+                         timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.split('\n') if l.strip()]
+    assert len(lines) == 1, res.stdout[:500]
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'SNP-updates/s' and d['higher_is_better'] is True
+    assert d['metric'].startswith('CAVI SNP-updates/sec')
+    for key in ('value', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'scaling', 'dtype', 'data', 'config',
+                'cpu_baseline', 'e2e'):
+        assert key in d
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+    assert d['value'] > 0
