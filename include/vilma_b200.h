@@ -44,6 +44,8 @@ const char* vb_last_error(void);
  *                  W in {1,2,4,8,16} = always, with W warps per 32-SNP tile
  *   "snp_ann_slots" (default 1): fused annotation sums in per-thread shared-memory slots (A*K <= 16) */
 int vb_set_option(const char* name, int64_t value);
+/* host-only: launch plan of the K-split tile kernel for a problem shape (W = 0: thread-per-SNP kernels) */
+int vb_debug_tile_plan(int P, int K, int64_t M, int akf, int num_sms, int* W, int* grid, int64_t* smem_bytes);
 /* largest dense block (rows) that is stored symmetric-packed; larger ones are stored in full */
 int64_t vb_ld_sym_nmax(void);
 /* device: CUDA ordinal; stream: cudaStream_t (may be NULL). */

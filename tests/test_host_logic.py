@@ -380,3 +380,38 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
     assert d['value'] > 0
+
+
+def test_tile_kernel_launch_plan():
+    """tile_plan (csrc/vilma_b200.cu) through vb_debug_tile_plan: which per-SNP kernel runs for the
+    shapes of BASELINE.json, with how many warps per 32-SNP tile, within the shared-memory limit."""
+    import ctypes as C
+    from vilma_b200 import _lib
+    lib = _lib.load()
+
+    def plan(P, K, M=1_200_000, akf=0, sms=148):
+        W, grid, smem = C.c_int(), C.c_int(), C.c_int64()
+        _lib.check(lib.vb_debug_tile_plan(P, K, M, akf, sms, C.byref(W), C.byref(grid), C.byref(smem)))
+        return W.value, grid.value, smem.value
+
+    assert plan(1, 14)[0] == 0 and plan(2, 8)[0] == 0          # single-cohort default grid: three-pass kernel
+    assert plan(2, 582)[0] == 16                                # two cohorts at -K 12: 512 threads on 188 KB
+    assert plan(3, 87)[0] == 4 and plan(3, 123)[0] == 4         # C3
+    assert plan(5, 256)[0] == 4                                 # C5 (255 registers: 256 threads per SM)
+    assert plan(6, 34)[0] == 1
+    assert plan(6, 2000)[0] == 0      # 250 logit slots x 8 warps do not fit: thread-per-SNP online kernel
+    for P, K in ((1, 40), (2, 42), (2, 582), (3, 123), (4, 31), (5, 256), (6, 34)):
+        W, grid, smem = plan(P, K)
+        assert W in (1, 2, 4, 8, 16) and 0 < smem <= 227 * 1024
+        assert 0 < grid <= 148 * 16
+    # a rank that owns few SNPs never launches more CTAs than tiles or partial rows
+    W, grid, smem = plan(3, 87, M=100)
+    assert grid == 1
+    # forced modes
+    _lib.check(lib.vb_set_option(b'snp_tile', 0))
+    try:
+        assert plan(3, 123)[0] == 0
+        _lib.check(lib.vb_set_option(b'snp_tile', 8))
+        assert plan(1, 14)[0] == 8
+    finally:
+        _lib.check(lib.vb_set_option(b'snp_tile', -1))

@@ -1100,6 +1100,20 @@ static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf) {
     }
     return best;
 }
+// The plan for a problem shape without a device (host logic only; tests/test_host_logic.py).
+extern "C" int vb_debug_tile_plan(int P, int K, int64_t M, int akf, int num_sms, int* W, int* grid,
+                                  int64_t* smem_bytes) {
+    if (P < 1 || P > VB_MAX_POPS || K < 1 || M < 1 || num_sms < 1 || !W || !grid || !smem_bytes)
+        return vb_fail("vb_debug_tile_plan: bad argument");
+    vb_ctx ctx;
+    ctx.num_sms = num_sms;
+    Fit f;
+    f.P = P; f.K = K; f.M = M;
+    f.grid_snp = (int)std::min<int64_t>((M + 127) / 128, (int64_t)num_sms * 16);
+    const TilePlan tp = tile_plan(&ctx, f, akf);
+    *W = tp.W; *grid = tp.grid; *smem_bytes = (int64_t)tp.smem;
+    return 0;
+}
 template <int P, int MODE>
 static void launch_tile_one(const VbSnpArgs& a, const TilePlan& tp, cudaStream_t st) {
     static bool attr_set = false;
