@@ -415,3 +415,36 @@ def test_tile_kernel_launch_plan():
         assert plan(1, 14)[0] == 8
     finally:
         _lib.check(lib.vb_set_option(b'snp_tile', -1))
+
+
+def test_setup_pool_releases_blas_limit_on_error(monkeypatch):
+    """A failing block (bad schema, asymmetric matrix) must not leave BLAS pinned to one thread or worker
+    threads behind."""
+    from threadpoolctl import threadpool_info
+    from vilma_b200 import _pool
+    monkeypatch.setenv('VILMA_B200_SETUP_THREADS', '4')
+    before = [(d.get('internal_api'), d.get('num_threads')) for d in threadpool_info()]
+
+    def boom(x):
+        if x == 3:
+            raise ValueError('bad block')
+        return x
+
+    pipe = _pool.OrderedPipeline(depth=2)
+    with pytest.raises(ValueError):
+        try:
+            for x in range(8):
+                pipe.submit(boom, x)
+            pipe.results()
+        finally:
+            pipe.close()
+    assert [(d.get('internal_api'), d.get('num_threads')) for d in threadpool_info()] == before
+    monkeypatch.setattr(_pool, 'MIN_BLOCKS', 1)
+    with pytest.raises(ValueError):
+        _pool.map_blocks(boom, range(8))
+    assert [(d.get('internal_api'), d.get('num_threads')) for d in threadpool_info()] == before
+    # and the happy path keeps order
+    pipe = _pool.OrderedPipeline(depth=2)
+    for x in range(20):
+        pipe.submit(lambda v: v * v, x)
+    assert pipe.results() == [v * v for v in range(20)]

@@ -171,48 +171,51 @@ def load_ld_from_schema(schema_path, variants, denylist, ldthresh, mmap=False):
 
     Returns (BlockDiagonalMatrix in the order of `variants`, list of positions without LD)."""
     from ._pool import OrderedPipeline
-    svds = OrderedPipeline()        # one eigh per block, run concurrently (results in block order)
+    pipe = OrderedPipeline()        # one eigh per block, run concurrently (results in block order)
     perm = []
     var_reidx = variants.set_index('ID')
     var_reidx['old_idx'] = np.arange(var_reidx.shape[0])
     var_a1 = variants['A1'].to_numpy()
     var_a2 = variants['A2'].to_numpy()
     total_flipped = 0
-    for snp_path, ld_path in schema_iterator(schema_path):
-        snp_metadata = _read_table(snp_path, header=None,
-                                   names=['ID', 'CHROM', 'BP', 'CM', 'A1', 'A2'])
-        logging.info('LD matrix shape: %s', ((snp_metadata.shape[0], snp_metadata.shape[0]),))
-        variant_indices = np.array(snp_metadata.ID.isin(variants.ID).to_numpy(), dtype=bool)
-        if np.sum(variant_indices) == 0:
-            continue
-        kept_ids = snp_metadata.ID[variant_indices]
-        idx = np.array(var_reidx.loc[kept_ids].old_idx.to_numpy()).flatten()
-        keep = np.isin(idx, denylist, invert=True)
-        to_change = np.where(variant_indices)[0][~keep]
-        variant_indices[to_change] = False
-        logging.info('Proportion of variant indices being used: %e', np.mean(variant_indices))
-        idx = idx[keep]
-        if len(idx) == 0:
-            continue
-        ld_a1 = snp_metadata['A1'].to_numpy()[variant_indices]
-        ld_a2 = snp_metadata['A2'].to_numpy()[variant_indices]
-        stay = np.array([(x1 == y1) and (x2 == y2) for x1, y1, x2, y2 in
-                         zip(var_a1[idx], ld_a1, var_a2[idx], ld_a2)], dtype=bool)
-        flip = np.array([(x1 == y2) and (x2 == y1) for x1, y1, x2, y2 in
-                         zip(var_a1[idx], ld_a1, var_a2[idx], ld_a2)], dtype=bool)
-        total_flipped += flip.sum()
-        mismatch = np.logical_and(~flip, ~stay)
-        if len(idx[~mismatch]) == 0:
-            continue
-        signs = np.ones(len(idx))
-        signs[flip] = -1
-        accepted = load_ld_mat(ld_path, variant_indices, mismatch, signs)
-        perm.append(idx[~mismatch])
-        if mmap:
-            _consume_mmap_rng()
-        svds.submit(LowRankMatrix, accepted, ldthresh)
+    try:
+        for snp_path, ld_path in schema_iterator(schema_path):
+            snp_metadata = _read_table(snp_path, header=None,
+                                       names=['ID', 'CHROM', 'BP', 'CM', 'A1', 'A2'])
+            logging.info('LD matrix shape: %s', ((snp_metadata.shape[0], snp_metadata.shape[0]),))
+            variant_indices = np.array(snp_metadata.ID.isin(variants.ID).to_numpy(), dtype=bool)
+            if np.sum(variant_indices) == 0:
+                continue
+            kept_ids = snp_metadata.ID[variant_indices]
+            idx = np.array(var_reidx.loc[kept_ids].old_idx.to_numpy()).flatten()
+            keep = np.isin(idx, denylist, invert=True)
+            to_change = np.where(variant_indices)[0][~keep]
+            variant_indices[to_change] = False
+            logging.info('Proportion of variant indices being used: %e', np.mean(variant_indices))
+            idx = idx[keep]
+            if len(idx) == 0:
+                continue
+            ld_a1 = snp_metadata['A1'].to_numpy()[variant_indices]
+            ld_a2 = snp_metadata['A2'].to_numpy()[variant_indices]
+            stay = np.array([(x1 == y1) and (x2 == y2) for x1, y1, x2, y2 in
+                             zip(var_a1[idx], ld_a1, var_a2[idx], ld_a2)], dtype=bool)
+            flip = np.array([(x1 == y2) and (x2 == y1) for x1, y1, x2, y2 in
+                             zip(var_a1[idx], ld_a1, var_a2[idx], ld_a2)], dtype=bool)
+            total_flipped += flip.sum()
+            mismatch = np.logical_and(~flip, ~stay)
+            if len(idx[~mismatch]) == 0:
+                continue
+            signs = np.ones(len(idx))
+            signs[flip] = -1
+            accepted = load_ld_mat(ld_path, variant_indices, mismatch, signs)
+            perm.append(idx[~mismatch])
+            if mmap:
+                _consume_mmap_rng()
+            pipe.submit(LowRankMatrix, accepted, ldthresh)
 
-    svds = svds.results()
+        svds = pipe.results()
+    finally:
+        pipe.close()               # also on a bad schema: workers and the BLAS thread limit are released
     num = variants.shape[0]
     perm = np.concatenate(perm) if len(perm) > 0 else np.array([], dtype=np.int64)
     list_of_missing = sorted(set(range(num)) - set(perm.tolist()))
