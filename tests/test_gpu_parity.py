@@ -318,3 +318,26 @@ def test_checkpointing_does_not_disturb_speculation(tmp_path):
     assert files == sorted('ck-checkpoint.%d.npz' % i for i in range(0, len(tr['elbo']), 3))
     first = np.load(tmp_path / 'ck-checkpoint.0.npz')
     assert np.allclose(first['vi_mu'], fx['init_vi_mu'], rtol=1e-7, atol=1e-12)
+
+
+def test_closed_form_covariances():
+    """The reference's hand-computed covariances for its unit fixture (tests/test.py:1297-1352) from the
+    device kernels: S_ki = diag(1/2, 4/5), diag(2/3, 4/3); log|S| = log(2/5), log(8/9);
+    tr(Prec_k S_ki) = 13/10, 1."""
+    fx = load_case('vischeme_linked_a2_s0_t1')
+    vi = make_product(fx)
+    M = fx['betas'].shape[1]
+    true_sigma = np.zeros((2, 2, 2, M))
+    true_sigma[0, 0, 0], true_sigma[0, 1, 1] = 1 / 2, 4 / 5
+    true_sigma[1, 0, 0], true_sigma[1, 1, 1] = 2 / 3, 4 / 3
+    assert np.allclose(vi.vi_sigma, true_sigma, rtol=1e-14, atol=1e-15)
+    true_nat = np.zeros((2, 2, 2, M))
+    true_nat[0, 0, 0], true_nat[0, 1, 1] = -1, -5 / 8
+    true_nat[1, 0, 0], true_nat[1, 1, 1] = -3 / 4, -3 / 8
+    assert np.allclose(vi.nat_sigma, true_nat)
+    true_ld = np.array([[np.log(2 / 5)] * M, [np.log(8 / 9)] * M])
+    assert np.allclose(vi.vi_sigma_log_det, true_ld)
+    true_matches = np.stack([np.full(M, 1 / 2 + 4 / 5), np.full(M, 1 / 3 + 2 / 3)], axis=1)
+    assert np.allclose(vi.vi_sigma_matches, true_matches)
+    assert np.allclose(vi.sigma_summary, np.array([0., 2 * np.log(2)]) - true_ld.T + true_matches)
+    assert vi.nat_grad_vi_delta is None

@@ -82,3 +82,40 @@ def test_resume(name):
     assert np.allclose(params[0], fx['resume_final_vi_mu'], rtol=1e-6, atol=1e-9)
     assert np.allclose(params[2], fx['resume_final_hyper_delta'], rtol=1e-6, atol=1e-12)
     assert np.allclose(vi.error_scaling, fx['resume_final_error_scaling'], rtol=1e-8)
+
+
+def test_closed_form_covariances():
+    """The reference's hand-computed values for its unit fixture (tests/test.py:1297-1411): betas =
+    arange(100), se = (1, 2), mixture covariances I and 2I, tau = 1  =>  S_ki = (Prec_k + diag(1/se^2))^-1
+    = diag(1/2, 4/5) and diag(2/3, 4/3), log|S| = log(2/5), log(8/9), tr(Prec_k S_ki) = 13/10 and 1."""
+    fx = load_case('vischeme_linked_a2_s0_t1')
+    vi = make_oracle(fx)
+    M = fx['betas'].shape[1]
+    true_sigma = np.zeros((2, 2, 2, M))
+    true_sigma[0, 0, 0], true_sigma[0, 1, 1] = 1 / 2, 4 / 5
+    true_sigma[1, 0, 0], true_sigma[1, 1, 1] = 2 / 3, 4 / 3
+    assert np.allclose(vi.vi_sigma, true_sigma)
+    true_nat = np.zeros((2, 2, 2, M))
+    true_nat[0, 0, 0], true_nat[0, 1, 1] = -1, -5 / 8
+    true_nat[1, 0, 0], true_nat[1, 1, 1] = -3 / 4, -3 / 8
+    assert np.allclose(vi.nat_sigma, true_nat)
+    true_ld = np.array([[np.log(2 / 5)] * M, [np.log(8 / 9)] * M])
+    assert np.allclose(vi.vi_sigma_log_det, true_ld)
+    true_matches = np.stack([np.full(M, 1 / 2 + 4 / 5), np.full(M, 1 / 3 + 2 / 3)], axis=1)
+    assert np.allclose(vi.vi_sigma_matches, true_matches)
+    assert np.allclose(vi.sigma_summary, np.array([0., 2 * np.log(2)]) - true_ld.T + true_matches)
+    assert np.allclose(vi.mixture_prec[0, :, :, 0], np.eye(2)) and np.allclose(vi.mixture_prec[1, :, :, 0], 0.5 * np.eye(2))
+    assert np.allclose(vi.log_det, [0., 2 * np.log(2)])
+    # set-up values from dense algebra (tests/test.py:1376-1411)
+    ld = build_ld(fx, LowRankBlock, BlockDiagonalLD)[0]
+    R = (ld.matrices[0].u * ld.matrices[0].s) @ ld.matrices[0].v
+    betas, se = fx['betas'], fx['std_errs']
+    for p in range(2):
+        z = betas[p] / se[p]
+        assert np.allclose(vi.adj_marginal_effects[p], np.linalg.solve(R, R @ z) / se[p])
+        assert np.isclose(vi.chi_stat[p], z @ np.linalg.solve(R, z))
+    assert np.allclose(vi.ld_ranks, M)
+    prior = 2 * fx['gwas_n'] * fx['init_hg'] / (se**-2).sum(axis=1)
+    for p in range(2):
+        want = np.linalg.solve(R + np.diag(se[p]**2) / prior[p], betas[p] / se[p]) * se[p]
+        assert np.allclose(vi.inverse_betas[p], want)
