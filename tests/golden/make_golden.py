@@ -564,6 +564,21 @@ def golden_synthetic(ref, outdir, only=None, cases=None):
         np.savez_compressed(os.path.join(outdir, name + '.npz'), **fx)
 
 
+def golden_cli_flags(ref, outdir):
+    """`vilma fit` flag surface (vi_options.py:9-84) as a table: tests/golden/cli_fit_flags.json."""
+    import json
+    top = argparse.ArgumentParser(prog='vilma')
+    parser = ref.vi_options.args(top.add_subparsers())
+    table = {}
+    for a in parser._actions:
+        if not a.option_strings or a.dest == 'help':
+            continue
+        table[a.dest] = dict(flags=sorted(a.option_strings), default=a.default, required=bool(a.required),
+                             nargs=a.nargs, type=getattr(a.type, '__name__', None), action=type(a).__name__)
+    with open(os.path.join(outdir, 'cli_fit_flags.json'), 'w') as fh:
+        json.dump(table, fh, indent=1, sort_keys=True)
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--only', nargs='*', default=None)
@@ -571,6 +586,7 @@ if __name__ == '__main__':
     ref = import_reference()
     sel = a.only
     if not sel or 'cli' in sel:
+        golden_cli_flags(ref, HERE)
         golden_cli_fit(ref, HERE)
         golden_example(ref, HERE)
         golden_cli_multi(ref, HERE)

@@ -4,6 +4,7 @@ Mirrors /root/reference/tests/test.py:486-706 (loaders) and the grid constructio
 vi_options.py:196-337; LD operators are checked through a dense reconstruction here (the
 `.dot` itself is a GPU test).
 """
+import os
 import numpy as np
 import pytest
 
@@ -106,3 +107,23 @@ def test_mixture_grid_matches_reference_pickles(data):
     mins, maxes = vi_options._grid_range(betas, ses, False)
     grid = vi_options._make_simple(2, 3, mins, maxes)
     assert np.allclose(np.array(grid), fx['run_covariance'], rtol=1e-12, atol=0)
+
+
+def test_cli_fit_flag_surface_matches_reference():
+    """`vilma fit` flags, defaults, types and required-ness, against the table recorded from the
+    reference's own parser (vi_options.py:9-84; tests/golden/cli_fit_flags.json, written by
+    introspecting the unmodified reference's argparse in the build container)."""
+    import argparse
+    import json
+    from vilma_b200 import vi_options
+    top = argparse.ArgumentParser(prog='vilma')
+    parser = vi_options.args(top.add_subparsers())
+    ours = {}
+    for a in parser._actions:
+        if not a.option_strings or a.dest == 'help':
+            continue
+        ours[a.dest] = dict(flags=sorted(a.option_strings), default=a.default, required=bool(a.required),
+                            nargs=a.nargs, type=getattr(a.type, '__name__', None), action=type(a).__name__)
+    ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
+                                      'cli_fit_flags.json')))
+    assert ours == ref
