@@ -713,14 +713,15 @@ def run_ours(args):
                                                     (vi.begin_loop, vi.run_loop, vi._download))
         comm.barrier()
         torch.cuda.synchronize()
-        tr0 = vi.n_trials
+        tr0, rj0 = vi.n_trials, vi.n_rejects
         t0 = time.perf_counter()
         vi.optimize(ckpt)
         torch.cuda.synchronize()
         conv_s = float(comm.max(np.array([time.perf_counter() - t0]))[0])
         result['convergence'] = {'seconds': conv_s, 'iterations': int(vi.num_its_run),
                                  'converged': bool(vi.num_its_run < args.converge),
-                                 'trials': int(vi.n_trials - tr0), 'max_iterations': args.converge,
+                                 'trials': int(vi.n_trials - tr0),
+                                 'rejected_trials': int(vi.n_rejects - rj0), 'max_iterations': args.converge,
                                  'final_elbo': float(vi.trajectory['elbo'][-1]),
                                  'call': 'MultiPopVI.optimize(checkpoint) from the seeded start, host '
                                          'arrays in and out'}

@@ -180,7 +180,7 @@ typedef struct vb_step_io {
     int32_t do_diff;           /* in: run the convergence bookkeeping */
     int32_t speculate;         /* in: queue the next iteration's first beta trial behind this one's
                                 *     last evaluation (discarded if the caller stops or touches the state) */
-    int32_t reserved;
+    int32_t rejects;                /* out: trials of this iteration whose step size was rejected (L doubled) */
 } vb_step_io;
 int vb_nccl_unique_id(char* out128);
 /* optional faster rendezvous for one node: every rank creates a mailbox (vb_xr_create returns its

@@ -64,7 +64,7 @@ class StepIO(C.Structure):
                 ('elbo_delta', C.c_double), ('atol', C.c_double), ('rtol', C.c_double),
                 ('diff', C.c_double * 10), ('has_running', C.c_int32), ('trials', C.c_int32),
                 ('evals', C.c_int32), ('do_diff', C.c_int32), ('speculate', C.c_int32),
-                ('reserved', C.c_int32)]
+                ('rejects', C.c_int32)]
 
 
 SIGNATURES.update({

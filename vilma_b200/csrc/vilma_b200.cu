@@ -1670,6 +1670,7 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
     double obj = io->obj;
     io->trials = 0;
     io->evals = 0;
+    io->rejects = 0;
     std::vector<double> stats(NSX, 0.0), trial(NSX, 0.0);
     std::memcpy(stats.data(), stats_io, NS * sizeof(double));
     struct ActiveGuard {          // evaluations queued from here use the fused rendezvous
@@ -1718,6 +1719,7 @@ extern "C" int vb_fit_iteration(vb_ctx* ctx, vb_step_io* io, double* tau_io, dou
                     break;
                 }
                 L[0] *= io->line_search_rate;
+                io->rejects++;
             }
             if (accepted) {
                 if (vb_fit_accept(ctx)) return 1;

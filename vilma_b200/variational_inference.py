@@ -334,6 +334,7 @@ class VIScheme():
             running += (1 - ELBO_MOMENTUM) * np.maximum(elbo_change, 0)
             self.n_trials += io.trials
             self.n_evals += io.evals
+            self.n_rejects += io.rejects
             converged = io.diff[0] == 0
             converged = converged or bool(np.isclose(running, 0, atol=ELBO_TOL, rtol=0))
             if num_its < 10 and fresh:
@@ -480,6 +481,7 @@ class MultiPopVI(VIScheme):
         self._hyper = None
         self.n_trials = 0
         self.n_evals = 0
+        self.n_rejects = 0              # line-search step sizes rejected (native loop)
         self._build_engine()
 
     # ------------------------------------------------------------------ engine
