@@ -34,6 +34,8 @@ typedef struct vb_ld vb_ld; /* one cohort's block-diagonal LD operator, resident
 
 /* ---- context ------------------------------------------------------------------------ */
 int vb_abi_version(void);
+/* SHA-256 (hex) of the sources this library was compiled from (vilma_b200/_build.py) */
+const char* vb_source_hash(void);
 const char* vb_last_error(void);
 /* process-wide options (kernel selection; the defaults are the measured best):
  *   "ld_symmetric" (default 1): store dense blocks of n <= vb_ld_sym_nmax() symmetric-packed

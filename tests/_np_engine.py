@@ -135,5 +135,13 @@ class NumpyShardEngine:
         else:
             self.ckpt = v.copy()
 
-    def vi_sigma(self, k0=0, k1=None):
-        return self._cov()[1][k0:k1]
+    def vi_sigma(self, k0=0, k1=None, out=None):
+        S = self._cov()[1][k0:k1]
+        if out is None:
+            return S
+        out[...] = S
+        return out
+
+    @staticmethod
+    def _host_array(shape):
+        return np.empty(shape)

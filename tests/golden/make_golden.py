@@ -538,7 +538,42 @@ EXTRA_CASES = {
                    ldthresh=0.99, lrf=0.6, A=2, miss=0.02, shuffle=False,
                    scaled=False, scale_se=False, its=20, resume=None,
                    n=[4e4, 2e4, 1e4, 1e4, 5e3, 5e3]),
+    # round 2: the shapes BASELINE.json configs[2] and [4] stress, and the multi-rank statistics vector at
+    # its largest.  `grid='custom:K'` = K SPD matrices built like the reference's grid (log-spaced scales x
+    # correlation levels x random rescalings), i.e. what --load-checkpoint's .pkl allows (vi_options.py:192-194).
+    # C5 shape: five cohorts, 256 components (the tile kernel's 4-warp plan with 64 slots per warp)
+    'xtr_p5_k256': dict(P=5, M=96, blocks=[30, 34, 28], K=None, grid='custom:256',
+                        ldthresh=1.0, lrf=None, A=1, miss=0.02, shuffle=False,
+                        scaled=False, scale_se=False, its=12, resume=None, slim=True,
+                        n=[3e5, 1e5, 5e4, 5e4, 2e4]),
+    # factor-stored LD: rank ~ n/10 (--ldthresh 0.8-like truncation), so 16 n r < 4 n (n+1) and the
+    # device keeps U, s instead of the dense block (csrc/ld_kernels.cuh factor path)
+    'xtr_p1_factor': dict(P=1, M=520, blocks=[120, 150, 100, 140], K=12, ldthresh=0.8, lrf=0.1,
+                          A=1, miss=0.02, shuffle=True, scaled=False, scale_se=True, its=30,
+                          resume=None, n=[5e4]),
+    # three cohorts, A*K = 48 fused annotation sums: 3P+3+48+10 = 70 exchanged values per evaluation
+    # (the multi-rank mailbox at its largest), 16 blocks so that 8 ranks all own LD
+    'xtr_p3_ann48': dict(P=3, M=480, blocks=[30, 26, 34, 28, 32, 24, 36, 30, 28, 26, 32, 30, 24, 34, 28, 30],
+                         K=None, grid='custom:16', ldthresh=1.0, lrf=None, A=3, miss=0.02, shuffle=True,
+                         scaled=False, scale_se=True, its=25, resume=None,
+                         n=[4e4, 2e4, 1e4]),
 }
+
+
+def custom_grid(P, K, betas, std_errs, seed):
+    """K SPD P x P covariance matrices spanning the data-driven range of vi_options.py:196-229."""
+    rng = np.random.default_rng(seed)
+    lo = max(np.nanpercentile(betas[betas != 0]**2, 2.5), 1e-10)
+    hi = max(np.max((np.abs(betas) - std_errs).clip(0)**2), 10 * lo)
+    scales = np.exp(np.linspace(np.log(lo), np.log(hi), (K + 2) // 3))
+    covs = []
+    for idx, sc in enumerate(scales):
+        rho = (0.0, 0.5, 0.9)[idx % 3]
+        base = np.full((P, P), rho) + (1 - rho) * np.eye(P)
+        for _ in range(3):
+            d = np.sqrt(sc * np.exp(rng.uniform(-1, 1, P)))
+            covs.append(base * d[:, None] * d[None, :])
+    return covs[:K]
 
 
 def golden_synthetic(ref, outdir, only=None, cases=None):
@@ -554,13 +589,19 @@ def golden_synthetic(ref, outdir, only=None, cases=None):
             grid_b, grid_s = betas / std_errs, np.ones_like(std_errs)
         else:
             grid_b, grid_s = betas, std_errs
-        covs = make_grid(ref, c['P'], c['K'], grid_b, grid_s, seed=11)
+        if c.get('grid', '').startswith('custom:'):
+            covs = custom_grid(c['P'], int(c['grid'].split(':')[1]), grid_b, grid_s, seed=11)
+        else:
+            covs = make_grid(ref, c['P'], c['K'], grid_b, grid_s, seed=11)
         fx = run_vi_case(ref, betas, std_errs, ld_mats, covs, ann, c['scaled'],
                          c['scale_se'], c['n'], [0.3] * c['P'], c['its'], seed=42,
                          resume_at=c['resume'])
         print('   K=%d its=%d trials=%s L0max=%.3g' % (
             len(covs), len(fx['traj_L0']), fx['traj_trials'].tolist(),
             fx['traj_L0'].max()))
+        if c.get('slim'):        # keep the committed file small: [K,P,P,M] is checked on the other cases
+            for k in ('final_vi_sigma',):
+                fx.pop(k, None)
         np.savez_compressed(os.path.join(outdir, name + '.npz'), **fx)
 
 

@@ -55,4 +55,5 @@ def test_trajectory(name):
     assert np.allclose(params[1], fx['final_vi_delta'], rtol=1e-6, atol=1e-12)
     assert np.allclose(params[2], fx['final_hyper_delta'], rtol=1e-6, atol=1e-12)
     assert np.allclose(vi.real_posterior_mean(*params), fx['final_post_mean'], rtol=1e-6, atol=1e-9)
-    assert np.allclose(vi.vi_sigma, fx['final_vi_sigma'], rtol=1e-8)
+    if 'final_vi_sigma' in fx:      # slim fixtures (K = 256) leave the [K,P,P,M] array out
+        assert np.allclose(vi.vi_sigma, fx['final_vi_sigma'], rtol=1e-8)

@@ -104,7 +104,6 @@ def test_large_properties():
     assert np.all(pm[:, info['M_ld']:] == 0.0)         # no LD, BETA 0 -> posterior mean 0
 
 
-@pytest.mark.xfail(strict=False, reason='written after the round-1 GPU budget was spent: not yet run on a B200')
 def test_medium_multi_cohort_fit_matches_oracle():
     """A ~4k-SNP slice of the three-cohort workload (bench.py --workload c3: low-rank panels, 87
     components): device _initialize + the tile kernel against the oracle on identical inputs --

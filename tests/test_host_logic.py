@@ -448,3 +448,115 @@ def test_setup_pool_releases_blas_limit_on_error(monkeypatch):
     for x in range(20):
         pipe.submit(lambda v: v * v, x)
     assert pipe.results() == [v * v for v in range(20)]
+
+
+def test_streamed_npz_equals_savez(tmp_path):
+    """outputs.save_fit_npz: the final `.npz` written slice by slice -- vi_sigma
+    never whole on the host -- is byte-compatible with the reference's np.savez call
+    (vi_options.py:263-265): same members, shapes, dtypes and values under np.load."""
+    from vilma_b200 import outputs
+    fx = load_case('syn_p3')
+    vi = make_host_vi(fx)
+    vi.num_its = 3
+    np.random.seed(int(fx['seed']))
+    params = vi.optimize(None)
+    K, P, M = vi.num_mix, vi.num_pops, vi.num_loci
+    plan = outputs.slice_plan(K, P, M, slice_bytes=5 * 8 * P * P * M)
+    assert plan[0] == (0, 5) and plan[-1][1] == K and all(a[1] == b[0] for a, b in zip(plan, plan[1:]))
+    stats = {}
+    path = outputs.save_fit_npz(str(tmp_path / 'streamed'), vi, params, slice_bytes=5 * 8 * P * P * M,
+                                stats=stats)
+    assert path.endswith('streamed.npz')
+    assert stats['slices'] == len(plan) > 3
+    assert stats['max_slice_bytes'] <= 5 * 8 * P * P * M          # never more than one slice per buffer
+    ref = vi.create_dump_dict(params)
+    ref['vi_sigma'] = vi.vi_sigma
+    np.savez(str(tmp_path / 'whole'), **ref)
+    a, b = np.load(path), np.load(str(tmp_path / 'whole.npz'))
+    assert a.files == b.files == ['vi_mu', 'vi_delta', 'hyper_delta', 'error_scaling', 'scalings', 'vi_sigma']
+    for k in b.files:
+        assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape
+        assert np.array_equal(a[k], b[k]), k
+    # a member larger than one slice (K = 1 per slice) and the degenerate single-slice plan
+    assert outputs.slice_plan(7, 2, 10, slice_bytes=1) == [(k, k + 1) for k in range(7)]
+    assert outputs.slice_plan(7, 2, 10, slice_bytes=1 << 40) == [(0, 7)]
+
+
+def _partition_reference(block_lists, M, world):
+    """The straightforward per-SNP formulation (union-find + one-by-one dealing) the vectorised
+    partition_snps must reproduce exactly."""
+    parent = list(range(M))
+
+    def find(i):
+        while parent[i] != i:
+            parent[i] = parent[parent[i]]
+            i = parent[i]
+        return i
+    for blocks in block_lists:
+        for snps, _ in blocks:
+            for i in snps[1:]:
+                a, b = find(int(snps[0])), find(int(i))
+                if a != b:
+                    parent[max(a, b)] = min(a, b)
+    roots = np.array([find(i) for i in range(M)])
+    cost = np.zeros(M)
+    in_block = np.zeros(M, dtype=bool)
+    for blocks in block_lists:
+        for snps, c in blocks:
+            if len(snps):
+                cost[roots[int(snps[0])]] += c
+                in_block[snps] = True
+    comp = np.unique(roots[in_block])
+    order = comp[np.argsort(-cost[comp], kind='stable')]
+    load = np.zeros(world)
+    owner = np.full(M, -1)
+    own_root = {}
+    for r in order:
+        k = int(np.argmin(load))
+        own_root[int(r)] = k
+        load[k] += cost[r]
+    for i in np.where(in_block)[0]:
+        owner[i] = own_root[int(roots[i])]
+    counts = np.array([(owner == r).sum() for r in range(world)])
+    for i in np.where(~in_block)[0]:
+        k = int(np.argmin(counts))
+        owner[i] = k
+        counts[k] += 1
+    return [np.where(owner == r)[0] for r in range(world)]
+
+
+def test_partition_vectorised_matches_per_snp_formulation():
+    from vilma_b200.partition import partition_snps
+    rng = np.random.default_rng(3)
+    for trial in range(6):
+        M = int(rng.integers(200, 900))
+        lists = []
+        for p in range(int(rng.integers(1, 4))):
+            # cohorts cut the (shuffled) SNPs at different places, and each leaves some SNPs out
+            order = rng.permutation(M) if trial % 2 else np.arange(M)
+            keep = order[rng.random(M) > 0.05]
+            cuts = np.sort(rng.choice(np.arange(1, len(keep)), size=int(rng.integers(3, 12)), replace=False))
+            blocks = [(b, float(len(b))**2) for b in np.split(keep, cuts)]
+            lists.append(blocks)
+        for world in (2, 3, 8):
+            got = partition_snps(lists, M, world)
+            want = _partition_reference(lists, M, world)
+            assert all(np.array_equal(a, b) for a, b in zip(got, want)), (trial, world)
+
+
+def test_partition_scales_to_benchmark_size():
+    """1.2M SNPs in 1700 blocks (BASELINE configs[1]) partitions in well under the per-SNP
+    interpreter loop's minutes."""
+    import time
+    from vilma_b200.partition import partition_snps
+    from vilma_b200 import synth
+    n = synth.block_sizes(1_188_000, 1700)
+    starts = np.concatenate([[0], np.cumsum(n)])
+    blocks = [(np.arange(starts[b], starts[b + 1]), float(n[b])**2) for b in range(len(n))]
+    t0 = time.time()
+    parts = partition_snps([blocks], 1_200_000, 8)
+    assert time.time() - t0 < 10
+    assert sum(len(p) for p in parts) == 1_200_000
+    loads = [sum(float(n[b])**2 for b in range(len(n)) if starts[b] in set_) for set_ in
+             [set(p[np.isin(p, starts[:-1])].tolist()) for p in parts]]
+    assert max(loads) / min(loads) < 1.02

@@ -66,7 +66,8 @@ def test_trajectory(name):
     assert np.allclose(params[2], fx['final_hyper_delta'], rtol=1e-6, atol=1e-12)
     assert np.allclose(vi.real_posterior_mean(*params), fx['final_post_mean'], rtol=1e-6, atol=1e-9)
     assert np.allclose(vi.real_posterior_variance(*params), fx['final_post_var'], rtol=1e-6, atol=1e-12)
-    assert np.allclose(vi.vi_sigma, fx['final_vi_sigma'], rtol=1e-8)
+    if 'final_vi_sigma' in fx:      # slim fixtures (K = 256) leave the [K,P,P,M] array out
+        assert np.allclose(vi.vi_sigma, fx['final_vi_sigma'], rtol=1e-8)
 
 
 @pytest.mark.parametrize('name', [n for n in VI_CASES if 'resume_ckpt_vi_mu' in load_case(n)])

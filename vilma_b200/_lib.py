@@ -13,6 +13,7 @@ c_i32p = C.POINTER(C.c_int32)
 # name -> (restype, argtypes); must list every symbol include/vilma_b200.h declares
 SIGNATURES = {
     'vb_abi_version': (C.c_int, []),
+    'vb_source_hash': (C.c_char_p, []),
     'vb_last_error': (C.c_char_p, []),
     'vb_set_option': (C.c_int, [C.c_char_p, C.c_int64]),
     'vb_ld_sym_nmax': (C.c_int64, []),

@@ -20,7 +20,7 @@
 #include "vb_common.cuh"
 
 enum { VB_MODE_TRIAL = 0, VB_MODE_REFRESH = 1, VB_MODE_EVAL = 2 };
-#define VB_FUSE_ANN_MAX 48     // A*K up to which annotation sums ride along with every evaluation
+// VB_FUSE_ANN_MAX (vb_common.cuh): A*K up to which annotation sums ride along with every evaluation
 #define VB_FUSE_ANN_SLOTS 16   // A*K up to which vb_snp3_kernel keeps them in per-thread shared-memory slots
 #define VB_SNP_THREADS 128
 

@@ -186,7 +186,13 @@ __device__ __forceinline__ double vb_block_max(double v, double* scratch) {
 //   stats[2P..3P) B_p = sum_i z (R z)         stats[3P..3P+3) KL_delta, KL_quad, KL_sigma
 // It runs in the last block of the last cohort's mat-vec finish kernel (no extra launch).
 #define VB_XR_MAXRANKS 8
-#define VB_XR_MAXVALS 64
+#ifndef VB_FUSE_ANN_MAX
+#define VB_FUSE_ANN_MAX 48     // A*K up to which annotation sums ride along with every evaluation
+#endif
+// One exchanged vector = 3P+3 statistics + fused annotation sums + 10 convergence values.
+#define VB_XR_MAXVALS 96
+static_assert(VB_XR_MAXVALS >= 3 * VB_MAXP + 3 + VB_FUSE_ANN_MAX + 10,
+              "mailbox rows must hold the largest statistics vector an evaluation can exchange");
 // Cross-rank exchange fused into the last CTA of an evaluation (one rank per GPU, one node):
 // every rank stores its statistics vector into every peer's mailbox over NVLink (peer memory mapped
 // with CUDA IPC), raises a per-sender flag carrying the evaluation's epoch, waits for the peers'

@@ -262,6 +262,11 @@ static NativeLoop* loop_of(vb_ctx* ctx, bool create) {
 // context
 // ------------------------------------------------------------------------------------
 extern "C" int vb_abi_version(void) { return VB_ABI_VERSION; }
+#ifndef VB_SOURCE_HASH
+#define VB_SOURCE_HASH "unknown"
+#endif
+static const char g_source_hash[] = "VB_SOURCE_HASH=" VB_SOURCE_HASH;
+extern "C" const char* vb_source_hash(void) { return g_source_hash + 15; }
 // Process-wide options read when an LD operator is created.
 //   "ld_symmetric" (default 1): store dense blocks with n <= VB_SYM_NMAX symmetric-packed.
 //   "snp_three_pass" (default 1): P <= 2 updates use the exact-max three-pass softmax kernel.
@@ -1253,6 +1258,9 @@ static int finish_eval(vb_ctx* ctx, int v, double* stats_dev) {
         xr.dev_err = nl->xr_dev_err;
         xr.n_sum = 3 * f.P + 3 + f.akf + (fa.part_diff ? 5 : 0);
         xr.n_max = fa.part_diff ? 5 : 0;
+        if (xr.n_sum + xr.n_max > VB_XR_MAXVALS)
+            return vb_fail("statistics vector of %d values exceeds the exchange mailbox (%d)",
+                           xr.n_sum + xr.n_max, VB_XR_MAXVALS);
     }
     for (int p = 0; p < f.P; ++p) {
         LdPop& L = ctx->fit_ld[p]->L;

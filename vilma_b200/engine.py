@@ -4,6 +4,7 @@ PyTorch appears here only as the owner of small device/pinned buffers (the stati
 vectors that may be all-reduced over NCCL); all compute is in libvilma_b200.so.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -31,8 +32,27 @@ class DeviceContext:
         torch.cuda.set_device(self.device)
         torch.cuda.init()
         self.handle = C.c_void_p()
+        self._lds = weakref.WeakSet()       # LD operators living in this context (closed before it)
         # stream 0 = the legacy default stream, which is also torch's default stream
         _lib.check(self.lib.vb_ctx_create(self.device, None, C.byref(self.handle)))
+
+    def close(self):
+        """Free everything the context owns on the device (fit state, mailbox, pinned staging) after
+        closing the LD operators that were created in it.  Idempotent."""
+        if self.handle:
+            for ld in list(self._lds):
+                ld.close()
+            self.lib.vb_ctx_destroy(self.handle)
+            self.handle = C.c_void_p()
+            for dev, inst in list(DeviceContext._instances.items()):
+                if inst is self:
+                    del DeviceContext._instances[dev]
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     @classmethod
     def get(cls, device=None):
@@ -102,6 +122,7 @@ class DeviceLD:
         rank = np.ascontiguousarray(rank, dtype=np.int64)
         self.handle = C.c_void_p()
         self.bytes = 0
+        ctx._lds.add(self)
         _lib.check(self.lib.vb_ld_create(
             ctx.handle, self.M, len(n), n.ctypes.data_as(_lib.c_i64p),
             rank.ctypes.data_as(_lib.c_i64p), C.byref(self.handle)))
@@ -154,7 +175,8 @@ class DeviceLD:
 
     def close(self):
         if self.handle:
-            self.lib.vb_ld_destroy(self.handle)
+            if self.ctx.handle:             # (a closed context has already closed its operators)
+                self.lib.vb_ld_destroy(self.handle)
             self.handle = C.c_void_p()
 
     def __del__(self):
@@ -298,9 +320,11 @@ class CudaEngine:
     def pm_mark(self, which):
         _lib.check(self.lib.vb_fit_pm_mark(self.ctx.handle, int(which)))
 
-    def vi_sigma(self, k0=0, k1=None):
+    def vi_sigma(self, k0=0, k1=None, out=None):
         k1 = self.K if k1 is None else k1
-        out = np.empty((k1 - k0, self.P, self.P, self.M))
+        if out is None:
+            out = np.empty((k1 - k0, self.P, self.P, self.M))
+        assert out.shape == (k1 - k0, self.P, self.P, self.M) and out.flags['C_CONTIGUOUS']
         _lib.check(self.lib.vb_fit_vi_sigma(self.ctx.handle, k0, k1, _lib.np_ptr(out)))
         return out
 
@@ -344,4 +368,6 @@ class CudaEngine:
         _lib.check(rc)
 
     def close(self):
-        self.lib.vb_fit_destroy(self.ctx.handle)
+        """Free the fit state (parameter buffers, scratch) of this engine's context."""
+        if self.ctx.handle:
+            self.lib.vb_fit_destroy(self.ctx.handle)

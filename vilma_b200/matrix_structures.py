@@ -177,6 +177,18 @@ class BlockDiagonalMatrix():
                                          self.perm[:nreal])
         return self._device[key]
 
+    def restrict(self, snps):
+        """The operator of the LD blocks that live entirely inside the sorted global SNP set `snps`
+        (one rank's shard), renumbered to positions in `snps`.  Blocks must not straddle the set."""
+        from .partition import local_blocks
+        snps = np.asarray(snps, dtype=np.int64)
+        ids, perm_local = local_blocks(self, snps, self.shape[0])
+        covered = np.zeros(len(snps), dtype=bool)
+        covered[perm_local] = True
+        missing = np.where(~covered)[0]
+        return BlockDiagonalMatrix([self.matrices[b] for b in ids], inverse=self._inverted,
+                                   perm=np.concatenate([perm_local, missing]), missing=missing)
+
     def release_device(self):
         for d in self._device.values():
             d.close()

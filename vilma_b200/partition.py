@@ -14,13 +14,37 @@ def block_cost(n, r):
     return float(min(dense, 16 * n * r))
 
 
-def _find(parent, i):
-    root = i
-    while parent[root] != root:
-        root = parent[root]
-    while parent[i] != root:
-        parent[i], i = root, parent[i]
-    return root
+def _components(block_lists, M):
+    """Connected components of the union of the cohorts' block partitions: root[i] = smallest SNP index
+    of i's component.  Min-label propagation, vectorised per sweep (np.minimum.reduceat over the
+    blocks of a cohort); cohorts that share a block file converge in two sweeps."""
+    root = np.arange(M, dtype=np.int64)
+    packed = []
+    for blocks in block_lists:
+        blocks = [np.asarray(s, dtype=np.int64) for s, _ in blocks if len(s)]
+        if not blocks:
+            continue
+        idx = np.concatenate(blocks)
+        starts = np.concatenate([[0], np.cumsum([len(b) for b in blocks])[:-1]]).astype(np.int64)
+        lens = np.array([len(b) for b in blocks], dtype=np.int64)
+        packed.append((idx, starts, lens))
+    while True:
+        changed = False
+        for idx, starts, lens in packed:
+            low = np.minimum.reduceat(root[idx], starts)
+            new = np.repeat(low, lens)
+            if np.any(new < root[idx]):
+                root[idx] = np.minimum(root[idx], new)
+                changed = True
+        # pointer jumping: labels always point at a SNP whose own label is <= theirs
+        while True:
+            nxt = root[root]
+            if np.array_equal(nxt, root):
+                break
+            root = nxt
+            changed = True
+        if not changed:
+            return root
 
 
 def partition_snps(block_lists, M, world):
@@ -30,42 +54,51 @@ def partition_snps(block_lists, M, world):
     """
     if world == 1:
         return [np.arange(M, dtype=np.int64)]
-    parent = np.arange(M, dtype=np.int64)
-    for blocks in block_lists:
-        for snps, _ in blocks:
-            if len(snps) == 0:
-                continue
-            r0 = _find(parent, int(snps[0]))
-            for i in snps[1:]:
-                ri = _find(parent, int(i))
-                if ri != r0:
-                    parent[ri] = r0
-    roots = np.array([_find(parent, i) for i in range(M)], dtype=np.int64)
+    roots = _components(block_lists, M)
     cost = np.zeros(M)
     in_block = np.zeros(M, dtype=bool)
     for blocks in block_lists:
-        for snps, c in blocks:
-            if len(snps):
-                cost[roots[int(snps[0])]] += c
-                in_block[snps] = True
+        firsts = np.array([int(s[0]) for s, _ in blocks if len(s)], dtype=np.int64)
+        costs = np.array([c for s, c in blocks if len(s)], dtype=np.float64)
+        np.add.at(cost, roots[firsts], costs)
+        for snps, _ in blocks:
+            in_block[np.asarray(snps, dtype=np.int64)] = True
     comp_roots = np.unique(roots[in_block])
     # LPT: heaviest component first onto the lightest rank (ties -> lowest rank, deterministic)
     order = comp_roots[np.argsort(-cost[comp_roots], kind='stable')]
     load = np.zeros(world)
-    owner_of_root = {}
+    owner_of_root = np.full(M, -1, dtype=np.int64)
     for root in order:
         r = int(np.argmin(load))
-        owner_of_root[int(root)] = r
+        owner_of_root[root] = r
         load[r] += cost[root]
-    owner = np.full(M, -1, dtype=np.int64)
-    for i in np.where(in_block)[0]:
-        owner[i] = owner_of_root[int(roots[i])]
-    counts = np.array([(owner == r).sum() for r in range(world)], dtype=np.int64)
-    for i in np.where(~in_block)[0]:
-        r = int(np.argmin(counts))
-        owner[i] = r
-        counts[r] += 1
+    owner = np.where(in_block, owner_of_root[roots], -1)
+    # SNPs in no block: dealt out to even up the SNP counts (lowest rank first on ties)
+    counts = np.bincount(owner[in_block], minlength=world).astype(np.int64)
+    free = np.where(~in_block)[0]
+    if len(free):
+        seq = _deal_sequence(counts, len(free))
+        owner[free] = seq
     return [np.where(owner == r)[0].astype(np.int64) for r in range(world)]
+
+
+def _deal_sequence(counts, n):
+    """Rank of each of n SNPs dealt one by one to the rank that currently has the fewest (ties ->
+    lowest rank): vectorised by levels instead of a Python loop per SNP."""
+    c = np.asarray(counts, dtype=np.int64).copy()
+    out = np.empty(n, dtype=np.int64)
+    pos = 0
+    while pos < n:
+        lo = c.min()
+        at_lo = np.where(c == lo)[0]
+        higher = c[c > lo]
+        levels = int(higher.min() - lo) if len(higher) else (n - pos + len(at_lo) - 1) // len(at_lo)
+        levels = max(1, min(levels, (n - pos + len(at_lo) - 1) // len(at_lo)))
+        chunk = np.tile(at_lo, levels)[:n - pos]
+        out[pos:pos + len(chunk)] = chunk
+        np.add.at(c, chunk, 1)
+        pos += len(chunk)
+    return out
 
 
 def host_block_lists(ld_mats):

@@ -122,6 +122,7 @@ class VIScheme():
         self._device = device
         self._engine_factory = engine_factory
         self._ctx = context
+        self._owns_ctx = False
 
         self.marginal_effects = np.copy(marginal_effects)
         if self.scaled:
@@ -153,32 +154,8 @@ class VIScheme():
                 [ld.diag().reshape((1, -1)) for ld in ld_mats], axis=0)
         self.scaled_ld_diags = self.std_errs**-2 * self.ld_diags
 
-        if precomputed is None:
-            # adjusted marginal effects S^-1 X X^+ S^-1 beta_hat, chi statistic, LD rank and the
-            # LDpred-inf style ridge start (reference :226-252).  Pseudo-inverse and ridge solve
-            # are one-off host LAPACK; the R @ mle product is the GPU operator.
-            self.adj_marginal_effects = np.zeros_like(self.marginal_effects)
-            self.chi_stat = np.zeros(self.num_pops)
-            self.ld_ranks = np.zeros(self.num_pops)
-            self.inverse_betas = np.zeros_like(self.marginal_effects)
-            for p in range(self.num_pops):
-                z_scores = self.marginal_effects[p] / self.std_errs[p]
-                mle = ld_mats[p].inverse.dot(z_scores)
-                self.chi_stat[p] = z_scores.dot(mle)
-                this_adj_marg = ld_mats[p].dot(np.copy(mle), ctx=self._context())
-                this_adj_marg = this_adj_marg / self.std_errs[p]
-                self.adj_marginal_effects[p, :] = this_adj_marg
-                self.ld_ranks[p] = ld_mats[p].get_rank()
-                prior = (2 * gwas_N[p] * init_hg[p] / (self.std_errs[p, :]**-2).sum())
-                inv_z_scores = ld_mats[p].ridge_inverse_dot(
-                    this_adj_marg * self.std_errs[p], self.std_errs[p, :]**2 / prior)
-                self.inverse_betas[p, :] = inv_z_scores * self.std_errs[p]
-
-        if not np.allclose(self.adj_marginal_effects[np.isclose(self.ld_diags, 0)], 0):
-            raise ValueError('Some SNPs that are missing in the LD matrix are not being '
-                             'treated as missing.')
-
-        # which SNPs this rank owns
+        # which SNPs this rank owns: decided BEFORE the set-up below, so that with several ranks each
+        # one factors, solves and uploads only its own LD blocks (1/N of the LAPACK work and of the HBM)
         if local_snps is not None:
             self._snps = np.asarray(local_snps, dtype=np.int64)
         elif self._comm.world == 1:
@@ -186,16 +163,75 @@ class VIScheme():
         else:
             parts = partition_snps(host_block_lists(ld_mats), self.num_loci, self._comm.world)
             self._snps = parts[self._comm.rank]
+        sharded = host_ld and len(self._snps) != self.num_loci
+        self._local_ld = [ld.restrict(self._snps) for ld in ld_mats] if sharded else list(ld_mats)
+
+        if precomputed is None:
+            # adjusted marginal effects S^-1 X X^+ S^-1 beta_hat, chi statistic, LD rank and the
+            # LDpred-inf style ridge start (reference :226-252) over this rank's blocks; the ranks'
+            # pieces are disjoint, so one sum assembles the global vectors.  Pseudo-inverse and ridge
+            # solve are one-off host LAPACK; the R @ mle product is the GPU operator.
+            snps = self._snps
+            self.adj_marginal_effects = np.zeros_like(self.marginal_effects)
+            self.chi_stat = np.zeros(self.num_pops)
+            self.ld_ranks = np.zeros(self.num_pops)
+            self.inverse_betas = np.zeros_like(self.marginal_effects)
+            for p in range(self.num_pops):
+                ld = self._local_ld[p]
+                se = self.std_errs[p, snps]
+                z_scores = self.marginal_effects[p, snps] / se
+                mle = ld.inverse.dot(z_scores)
+                self.chi_stat[p] = z_scores.dot(mle)
+                this_adj_marg = ld.dot(np.copy(mle), ctx=self._context())
+                this_adj_marg = this_adj_marg / se
+                self.adj_marginal_effects[p, snps] = this_adj_marg
+                self.ld_ranks[p] = ld.get_rank()
+                prior = (2 * gwas_N[p] * init_hg[p] / (self.std_errs[p, :]**-2).sum())
+                inv_z_scores = ld.ridge_inverse_dot(this_adj_marg * se, se**2 / prior)
+                self.inverse_betas[p, snps] = inv_z_scores * se
+            if sharded:
+                self.adj_marginal_effects = self._comm.sum(self.adj_marginal_effects)
+                self.inverse_betas = self._comm.sum(self.inverse_betas)
+                self.chi_stat = self._comm.sum(self.chi_stat)
+                self.ld_ranks = self._comm.sum(self.ld_ranks)
+
+        if not np.allclose(self.adj_marginal_effects[np.isclose(self.ld_diags, 0)], 0):
+            raise ValueError('Some SNPs that are missing in the LD matrix are not being '
+                             'treated as missing.')
 
     # ------------------------------------------------------------------ device plumbing
     def _context(self):
         if self._engine_factory is not None:
             return None
         if self._ctx is None:
+            # a vb_ctx holds ONE fit state, so every model gets its own context and frees it
+            # (close() / __del__) unless the caller passed one in with context=
             from .engine import DeviceContext
             self._ctx = DeviceContext(self._device if self._device is not None
                                       else _current_device())
+            self._owns_ctx = True
         return self._ctx
+
+    def close(self):
+        """Release the device memory of this model: the fit state and, when the model created its
+        own context, that context with the LD operators uploaded into it.  Idempotent; also run
+        when the object is garbage collected."""
+        eng = self.__dict__.get('_eng')
+        if eng is not None and hasattr(eng, 'close'):
+            eng.close()
+        if self.__dict__.get('_owns_ctx') and self._ctx is not None:
+            for ld in (self.__dict__.get('ld_mats') or []) + (self.__dict__.get('_local_ld') or []):
+                if hasattr(ld, 'release_device'):
+                    ld.release_device()
+            self._ctx.close()
+        self._eng = None
+        self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _dump_info(self, num_its, diff):
         """Log information about convergence (reference :292-331), from device reductions."""
@@ -234,13 +270,45 @@ class VIScheme():
                                 'to assume that the error scalings are 1.')
             self._set_state(params)
         state = self.begin_loop(params)
-        state = self.run_loop(state, self.num_its, fresh=loaded_checkpoint is None)
+        try:
+            state = self.run_loop(state, self.num_its, fresh=loaded_checkpoint is None)
+        finally:
+            self._finish_checkpoints()
         num_its = state['num_its']
         if num_its == self.num_its:
             logging.warning('Failed to converge')
         logging.info('Optimization ran for %d iterations', num_its)
         self.num_its_run = num_its
         return self._download()
+
+    # -- periodic checkpoints (reference :362-367) are snapshotted synchronously (device -> fresh host
+    # arrays) and written by a background thread while the next iterations run on the device; at most
+    # one write is in flight, so the host holds at most two snapshots.
+    def _write_checkpoint(self, fname, dump_dict):
+        if self._comm.rank != 0:
+            return
+        import threading
+        self._finish_checkpoints()
+        dump_dict = {k: np.array(v) if k in ('error_scaling',) else v for k, v in dump_dict.items()}
+        err = []
+
+        def work():
+            try:
+                np.savez(fname, **dump_dict)
+            except BaseException as exc:
+                err.append(exc)
+        th = threading.Thread(target=work, name='checkpoint-writer', daemon=True)
+        th.start()
+        self._ckpt_writer = (th, err)
+
+    def _finish_checkpoints(self):
+        pending = getattr(self, '_ckpt_writer', None)
+        if pending is None:
+            return
+        self._ckpt_writer = None
+        pending[0].join()
+        if pending[1]:
+            raise pending[1][0]
 
     def begin_loop(self, params):
         """Make `params` resident and set up the loop state of optimize() (reference :353-360)."""
@@ -261,14 +329,16 @@ class VIScheme():
         native = (self.use_native_loop and not want_info
                   and hasattr(eng, 'iteration') and self._engine_factory is None)
         if native:
-            return self._run_loop_native(state, max_its, fresh)
+            try:
+                return self._run_loop_native(state, max_its, fresh)
+            finally:
+                self._finish_checkpoints()
         while num_its < max_its and not converged:
             if num_its % self.checkpoint_freq == 0 and self.checkpoint:
                 eng.pm_mark(1)
                 fname = '{}.{}'.format(self.checkpoint_path, num_its)
                 dump_dict = self.create_dump_dict(self._download())
-                if self._comm.rank == 0:
-                    np.savez(fname, **dump_dict)
+                self._write_checkpoint(fname, dump_dict)
             trials0 = self.n_trials
             L, elbo, running_elbo_delta = self._optimize_step_dev(
                 L, elbo, 2., running_elbo_delta)
@@ -289,6 +359,7 @@ class VIScheme():
             self.trajectory['trials'].append(self.n_trials - trials0)
             self.trajectory['running'].append(float(running_elbo_delta))
             num_its += 1
+        self._finish_checkpoints()
         return {'elbo': elbo, 'running': running_elbo_delta, 'num_its': num_its, 'L': L,
                 'converged': converged}
 
@@ -319,8 +390,7 @@ class VIScheme():
                 self._sync_from_native(tau, hyper, stats, io)
                 fname = '{}.{}'.format(self.checkpoint_path, num_its)
                 dump_dict = self.create_dump_dict(self._download())
-                if self._comm.rank == 0:
-                    np.savez(fname, **dump_dict)
+                self._write_checkpoint(fname, dump_dict)
             io.speculate = 1 if (self.speculate_next_trial and num_its + 1 < max_its) else 0
             io.has_running = 0 if running is None else 1
             io.running_elbo_delta = 0. if running is None else running
@@ -465,6 +535,16 @@ class MultiPopVI(VIScheme):
         if not np.all(signs == 1):
             raise ValueError('Mixture component has a non-positive definite covariance '
                              'matrix.')
+        if num_pops >= 3:
+            # The reference only tests the determinant's sign (:610-613), which also lets through
+            # matrices with an even number of negative eigenvalues; it then inverts them with LAPACK
+            # and produces negative "variances".  The P >= 3 kernels factor Lambda = Prec_k + diag(.)
+            # as L D L^T and take logs of the pivots, so such a grid is rejected here, loudly, instead
+            # of being fitted to garbage (documented deviation).
+            evals = np.linalg.eigvalsh(np.array(mixture_covs, dtype=np.float64))
+            if not np.all(evals > 0):
+                raise ValueError('Mixture component has a non-positive definite covariance '
+                                 'matrix.')
         self.num_mix = len(mixture_covs)
         VIScheme.__init__(self, mixture_covs=mixture_covs, **kwargs)
         self.param_names = ['vi_mu', 'vi_delta', 'hyper_delta']
@@ -475,6 +555,7 @@ class MultiPopVI(VIScheme):
 
         self._gtable = None             # nat_grad_vi_delta as an [A,K-1] table
         self._resident = None           # host arrays the device state corresponds to
+        self._resident_fp = None
         self._res_valid = False
         self._res_obj = None
         self._res_stats = None
@@ -498,18 +579,15 @@ class MultiPopVI(VIScheme):
         if self._engine_factory is not None:
             self._eng = self._engine_factory(self, snps, pieces)
         else:
-            from .engine import CudaEngine, DeviceLD
+            from .engine import CudaEngine
             ctx = self._context()
             lds = []
-            for ld in self.ld_mats:
+            for ld in self._local_ld:
                 if isinstance(ld, DeviceBlockDiagonalMatrix):
                     lds.append(ld.device_ld)
-                elif self._comm.world == 1 and len(snps) == M:
-                    lds.append(ld.to_device(ctx))
                 else:
-                    ld.release_device()
-                    ids, perm_local = local_blocks(ld, snps, M)
-                    lds.append(DeviceLD(ctx, len(snps), ld.device_blocks(ids), perm_local))
+                    # (the rank's own blocks only; already resident if the set-up above used them)
+                    lds.append(ld.to_device(ctx))
             self._eng = CudaEngine(ctx, lds, **pieces)
             self._eng.init_comm(self._comm)
         self._eng.set_tau(self.error_scaling)
@@ -545,6 +623,13 @@ class MultiPopVI(VIScheme):
         """(vi_sigma [K,P,P,M], Lambda) on the host from the device kernel -- outputs/tests only."""
         return self._comm.gather_snp_axis(self._eng.vi_sigma(), self._snps, self.num_loci, 3)
 
+    def _covariance_slice(self, k0, k1, out=None):
+        """vi_sigma[k0:k1] (all SNPs) on the host; `out` = this rank's landing buffer.  The streamed
+        `.npz` writer (outputs.save_fit_npz) walks the components with this so that the [K,P,P,M] array
+        never exists whole."""
+        local = self._eng.vi_sigma(k0, k1, out=out)
+        return self._comm.gather_snp_axis(local, self._snps, self.num_loci, 3)
+
     @property
     def vi_sigma(self):
         """S_ki = (Prec_k + diag(sld_i/tau))^-1, [K,P,P,M]   (reference :712-724)."""
@@ -579,10 +664,23 @@ class MultiPopVI(VIScheme):
         self._res_valid = False
 
     # ------------------------------------------------------------------ host <-> device
+    @staticmethod
+    def _fingerprint(params):
+        """Cheap content check of a host state (a strided sample of every array): catches in-place
+        edits of arrays the identity-keyed cache would otherwise take for the resident state."""
+        out = []
+        for a in params:
+            flat = np.asarray(a).reshape(-1)
+            out.append(float(flat[::max(1, flat.size // 509)].sum()) if flat.size else 0.0)
+        return tuple(out)
+
     def _same(self, params):
         if self._resident is None or not self._res_valid:
             return False
-        return all(a is b for a, b in zip(params, self._resident))
+        if not all(a is b for a, b in zip(params, self._resident)):
+            return False
+        fp = self._fingerprint(params)
+        return all(x == y or (x != x and y != y) for x, y in zip(fp, self._resident_fp))
 
     def _make_resident(self, params):
         """Upload a host state (unless it is the resident one) and evaluate it."""
@@ -621,6 +719,7 @@ class MultiPopVI(VIScheme):
         ll, kl = self._objective(stats)
         self._res_obj = ll - kl
         self._resident = resident
+        self._resident_fp = self._fingerprint(resident) if resident is not None else None
         self._res_valid = True
 
     def _download(self):
@@ -637,6 +736,11 @@ class MultiPopVI(VIScheme):
             mu = self._comm.gather_snp_axis(mu, self._snps, self.num_loci, 2)
             delta = self._comm.gather_snp_axis(delta, self._snps, self.num_loci, 0)
         self._resident = (mu, delta, np.array(self._hyper))
+        for arr in self._resident:
+            # the cache is keyed on object identity (_same): an in-place edit by the caller would go
+            # unnoticed, so the arrays are handed out read-only (copy them to modify)
+            arr.setflags(write=False)
+        self._resident_fp = self._fingerprint(self._resident)
         return self._resident
 
     # ------------------------------------------------------------------ moments
@@ -751,6 +855,7 @@ class MultiPopVI(VIScheme):
         delta = self._comm.gather_snp_axis(delta, self._snps, self.num_loci, 0)
         out = (vi_mu, delta, hyper_delta)
         self._resident = out
+        self._resident_fp = self._fingerprint(out)
         return out
 
     def _update_beta_dev(self, orig_obj, L, idx, lsr):

@@ -136,8 +136,10 @@ def main(args):
         logging.info('Building cross-population covariances...')
         mins, maxes = _grid_range(betas, std_errs, args.scaled)
         cross_pop_covs = _make_simple(num_pops, num_components, mins, maxes)
-        with open('%s.covariance.pkl' % args.output, 'wb') as ofile:
-            pickle.dump([cross_pop_covs], ofile)
+        from .dist import default_comm
+        if default_comm().rank == 0:          # one writer when several ranks run the same command
+            with open('%s.covariance.pkl' % args.output, 'wb') as ofile:
+                pickle.dump([cross_pop_covs], ofile)
 
     logging.info('Fitting...')
     from .variational_inference import MultiPopVI
@@ -154,10 +156,10 @@ def main(args):
     params = elbo.optimize(checkpoint)
 
     rank0 = elbo._comm.rank == 0
-    to_save = elbo.create_dump_dict(params)
-    to_save['vi_sigma'] = elbo.vi_sigma
-    if rank0:
-        np.savez(args.output, **to_save)
+    # np.savez(args.output, vi_mu, vi_delta, hyper_delta, error_scaling, scalings, vi_sigma) of the
+    # reference (:263-265), with vi_sigma[K,P,P,M] streamed from the device slice by slice
+    from .outputs import save_fit_npz
+    save_fit_npz(args.output, elbo, params)
 
     for name, posterior in zip(names, elbo.real_posterior_mean(*params)):
         variants['posterior_' + name] = posterior
