@@ -13,8 +13,13 @@ as defined in SURVEY.md section 8(d).  The problem size is fixed as N grows (str
 `e2e`    : the public call -- MultiPopVI.optimize(checkpoint) with HOST parameter arrays:
            upload, K iterations, download of the fitted parameters, all inside the region.
 `roofline`: the LD mat-vec kernel, timed per launch with CUDA events inside the region.
-`cpu_baseline` / `--impl reference`: the NumPy oracle port of the reference loop on a
-           bounded sample of the same workload, on the host cores.
+`cpu_baseline` / `--impl reference`: the UNMODIFIED reference (numba + NumPy, installed in
+           oracle/_ref by oracle/build_ref.py; `kind: "reference"`) on a bounded sample of the same
+           workload on all host cores; the NumPy oracle port (`kind: "port"`) only if numba or
+           oracle/_ref is missing, with the reason on stderr and in `cpu_baseline.note`.
+`workloads`: after the headline, the other BASELINE.json configurations on the same build --
+           configs[2] (c3) and configs[4] (c5, with a checkpoint-every-5 + resume leg) at N = 1,
+           configs[3] (c4: 6M SNPs) at N = 8 -- each with value / roofline / convergence / cpu_baseline.
 """
 import argparse
 import json
@@ -35,8 +40,9 @@ MISSING_FRAC = 0.01
 K_GRID = 12
 N_GWAS = 3e5
 INIT_HG = 0.3
-SAMPLE_BLOCKS = int(os.environ.get('BENCH_SAMPLE_BLOCKS', '85'))   # CPU sample: 5 % of the blocks (~60k SNPs)
-SAMPLE_BLOCKS_MULTI = 12    # multi-cohort workloads: the oracle holds [K,P,P,M] arrays like the reference
+SAMPLE_BLOCKS = int(os.environ.get('BENCH_SAMPLE_BLOCKS', '170'))  # CPU sample: 10 % of the blocks (~120k SNPs)
+SAMPLE_BLOCKS_MULTI = 12    # multi-cohort workloads: the reference holds three [K,P,P,M] arrays
+T_START = time.time()
 
 
 def log(*a):
@@ -261,16 +267,86 @@ def build_gpu_problem_multi(comm, device, wl, M_total=M_TOTAL, n_blocks=N_BLOCKS
     return vi, ctx, info
 
 
-def build_cpu_sample(n_blocks=SAMPLE_BLOCKS):
-    """The bounded CPU sample: the first `n_blocks` blocks of the same generator, as oracle
-    objects (LowRankBlock does the reference's eigendecomposition, matrix_structures.py:15-28)."""
-    import torch
+def cpu_classes(kind='port'):
+    """(LowRank block class, block-diagonal class, VI class, extra VI kwargs, kind, note) of the CPU arm:
+    the unmodified reference from oracle/_ref when it imports here, else the NumPy oracle port."""
+    note = ''
+    if kind == 'reference':
+        try:
+            from oracle import ref_loader
+            ref = ref_loader.import_reference()
+            return (ref.matrix_structures.LowRankMatrix, ref.matrix_structures.BlockDiagonalMatrix,
+                    ref.variational_inference.MultiPopVI,
+                    dict(checkpoint=False, checkpoint_freq=-1, output='bench_ref'), 'reference', note)
+        except Exception as exc:
+            note = 'reference unavailable, timing the NumPy port instead: %s' % (exc,)
+            log('[cpu arm] ' + note)
     from oracle.ld_np import BlockDiagonalLD, LowRankBlock
     from oracle.vi_np import OracleVI
-    from vilma_b200 import synth
+    return LowRankBlock, BlockDiagonalLD, OracleVI, {}, 'port', note
 
-    M_ld_full, n_all, _ = layout()
-    n = n_all[:n_blocks]
+
+class TrialCounter:
+    """Counts _update_beta line-search trials and LD mat-vecs of a reference / oracle VI object the way
+    tests/golden/make_golden.py's Recorder does (objective evaluations inside _update_beta, minus the
+    one that evaluates the incoming state)."""
+
+    def __init__(self, vi):
+        self.trials = 0
+        self.matvec = 0
+        self.iterations = 0
+        me = self
+        orig_step = vi._optimize_step
+
+        def step(*a, **k):
+            me.iterations += 1
+            return orig_step(*a, **k)
+        vi._optimize_step = step
+        if hasattr(vi, 'counters'):          # the port counts trials / mat-vecs for itself
+            self._vi = vi
+            return
+        self._vi = None
+        orig_obj_fn, orig_update = vi._beta_objective, vi._update_beta
+
+        def beta_obj(params):
+            me.trials += 1
+            return orig_obj_fn(params)
+
+        def update_beta(vi_mu, vi_delta, hyper_delta, orig_obj, L, idx, lsr):
+            if orig_obj is None:
+                me.trials -= 1
+            return orig_update(vi_mu, vi_delta, hyper_delta, orig_obj, L, idx, lsr)
+        vi._beta_objective, vi._update_beta = beta_obj, update_beta
+        for ld in vi.ld_mats:
+            orig_dot = ld.dot
+
+            def dot(x, _f=orig_dot):
+                me.matvec += 1
+                return _f(x)
+            ld.dot = dot
+
+    def read(self):
+        if self._vi is not None:
+            return self._vi.counters['trials'], self._vi.counters['matvec']
+        return self.trials, self.matvec
+
+
+def build_cpu_sample(n_blocks=SAMPLE_BLOCKS, kind='port', sizes=None):
+    """The bounded CPU sample: the first `n_blocks` blocks of the same generator (or blocks of the
+    given `sizes`), as reference / oracle objects (LowRankMatrix(X=...) does the reference's
+    eigendecomposition, matrix_structures.py:15-28)."""
+    import torch
+    from vilma_b200 import synth
+    LowRankBlock, BlockDiagonalLD, OracleVI, vi_kw, kind, _ = cpu_classes(kind)
+
+    if sizes is None:
+        M_ld_full, n_all, _ = layout()
+        n = n_all[:n_blocks]
+        m_norm = M_TOTAL
+    else:
+        n = np.asarray(sizes, dtype=np.int64)
+        n_blocks = len(n)
+        m_norm = int(round(n.sum() / (1 - MISSING_FRAC)))
     M_ld = int(n.sum())
     n_miss = int(round(M_ld * MISSING_FRAC / (1 - MISSING_FRAC)))
     M = M_ld + n_miss
@@ -278,7 +354,7 @@ def build_cpu_sample(n_blocks=SAMPLE_BLOCKS):
     blocks, bh, se = [], [], []
     for b in range(n_blocks):
         s = synth.block_se(int(n[b]), 42, b, N_GWAS, dev)
-        r, beta_hat = synth.make_block_sumstats(int(n[b]), 42, b, s, M_TOTAL, dev)
+        r, beta_hat = synth.make_block_sumstats(int(n[b]), 42, b, s, m_norm, dev)
         blocks.append(LowRankBlock(X=r.numpy(), t=1.0))
         bh.append(beta_hat.numpy())
         se.append(s.numpy())
@@ -289,17 +365,17 @@ def build_cpu_sample(n_blocks=SAMPLE_BLOCKS):
     covs = synth.mixture_grid_single(beta_hat, std, K_GRID)
     vi = OracleVI(marginal_effects=beta_hat[None], std_errs=std[None], ld_mats=[ld],
                   mixture_covs=covs, annotations=np.ones((M, 1)), scaled=False, scale_se=False,
-                  gwas_N=np.array([N_GWAS]), init_hg=np.array([INIT_HG]), num_its=1000)
+                  gwas_N=np.array([N_GWAS]), init_hg=np.array([INIT_HG]), num_its=1000, **vi_kw)
     return vi, M, n_blocks
 
 
-def build_cpu_sample_multi(wl, n_blocks):
+def build_cpu_sample_multi(wl, n_blocks, kind='port'):
     """Bounded CPU sample of a multi-cohort workload: the first `n_blocks` blocks of the same
-    generator for every cohort, as oracle objects (the reference's set-up runs on them unchanged)."""
+    generator for every cohort, as reference / oracle objects (the reference's set-up runs on them
+    unchanged)."""
     import torch
-    from oracle.ld_np import BlockDiagonalLD, LowRankBlock
-    from oracle.vi_np import OracleVI
     from vilma_b200 import synth
+    LowRankBlock, BlockDiagonalLD, OracleVI, vi_kw, kind, _ = cpu_classes(kind)
 
     P, N = wl['P'], np.array(wl['N'], dtype=np.float64)
     _, n_all, _ = layout()
@@ -332,63 +408,105 @@ def build_cpu_sample_multi(wl, n_blocks):
     covs = mixture_grid_multi(beta_hat, se, P, wl['grid'])
     vi = OracleVI(marginal_effects=beta_hat, std_errs=se, ld_mats=lds, mixture_covs=covs,
                   annotations=np.ones((M, 1)), scaled=False, scale_se=False, gwas_N=N,
-                  init_hg=np.full(P, INIT_HG), num_its=1000)
+                  init_hg=np.full(P, INIT_HG), num_its=1000, **vi_kw)
     return vi, M, n_blocks
 
 
-def time_cpu(steps, warmup, workload='c2'):
-    """Oracle port of the reference loop on the sample: returns (value, seconds, trials, M, info).
-    Uses every host core for BLAS (torchrun exports OMP_NUM_THREADS=1, which would otherwise
-    silently make the baseline single-threaded)."""
+def _all_cores():
+    """Every host core for BLAS and numba (torchrun exports OMP_NUM_THREADS=1, which would otherwise
+    silently make the baseline single-threaded).  Returns (cores, restore callable)."""
     cores = os.cpu_count() or 1
+    for var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS', 'NUMBA_NUM_THREADS'):
+        os.environ[var] = str(cores)
+    limiter = None
     try:
         from threadpoolctl import threadpool_limits
         limiter = threadpool_limits(limits=cores)
     except Exception:
-        limiter = None
+        pass
     try:
         import torch
         torch.set_num_threads(cores)
     except Exception:
         pass
     try:
-        return _time_cpu(steps, warmup, cores, workload)
+        import numba
+        numba.set_num_threads(min(cores, numba.config.NUMBA_NUM_THREADS))
+    except Exception:
+        pass
+    return cores, (limiter.restore_original_limits if limiter is not None else (lambda: None))
+
+
+def time_cpu(steps, warmup, workload='c2', kind='reference', converge_20k=False):
+    """The reference's CPU fit (or the port) on the bounded sample: returns
+    (value, seconds, trials, M, info)."""
+    cores, restore = _all_cores()
+    try:
+        return _time_cpu(steps, warmup, cores, workload, kind, converge_20k)
     finally:
-        if limiter is not None:
-            limiter.restore_original_limits()
+        restore()
 
 
-def _time_cpu(steps, warmup, cores, workload='c2'):
+CONV20K_SIZES = [500] * 40      # BASELINE.md section 2: M = 20,000 in 40 dense blocks of 500, K = 14
+
+
+def cpu_convergence_20k(kind):
+    """Time to the reference's own stopping rule on the M = 20k problem BASELINE.md timed (38.4 s on 8
+    cores): the CPU arm's whole optimize() call from the seeded start."""
+    vi, M, _ = build_cpu_sample(kind=kind, sizes=CONV20K_SIZES)
+    vi.num_its = 2000
+    cnt = TrialCounter(vi)
+    np.random.seed(42)
+    t0 = time.perf_counter()
+    params = vi.optimize(None)
+    dt = time.perf_counter() - t0
+    trials, _ = cnt.read()
+    pm = vi.real_posterior_mean(*params)
+    return dict(seconds=dt, iterations=int(cnt.iterations), trials=int(trials), M=int(M),
+                final_elbo=float(vi.elbo(params)), pm_abs_sum=float(np.abs(pm).sum()))
+
+
+def _time_cpu(steps, warmup, cores, workload='c2', kind='reference', converge_20k=False):
     t_setup = time.time()
+    _, _, _, _, kind_used, note = cpu_classes(kind)
     if workload in ('c2', 'c4'):         # c4: same model and grid; the CPU sample keeps C2's block sizes
-        vi, M, nb = build_cpu_sample()
+        vi, M, nb = build_cpu_sample(kind=kind_used)
     else:
-        vi, M, nb = build_cpu_sample_multi(WORKLOADS[workload], SAMPLE_BLOCKS_MULTI)
+        vi, M, nb = build_cpu_sample_multi(WORKLOADS[workload], SAMPLE_BLOCKS_MULTI, kind=kind_used)
+    cnt = TrialCounter(vi)
     np.random.seed(42)
     params = vi._initialize()
     elbo = vi.elbo(params)
     L = np.ones(5)
     running = None
     t_setup = time.time() - t_setup
-    for _ in range(warmup):
+    for _ in range(warmup):            # (also absorbs what is left of the numba JIT)
         params, L, elbo, running = vi._optimize_step(params, L=L, curr_elbo=elbo,
                                                      line_search_rate=2.,
                                                      running_elbo_delta=running)
         params = tuple(params)
     t0 = time.perf_counter()
-    tr0, mv0 = vi.counters['trials'], vi.counters['matvec']
+    tr0, mv0 = cnt.read()
     for _ in range(steps):
         params, L, elbo, running = vi._optimize_step(params, L=L, curr_elbo=elbo,
                                                      line_search_rate=2.,
                                                      running_elbo_delta=running)
         params = tuple(params)
     dt = time.perf_counter() - t0
-    trials = vi.counters['trials'] - tr0
+    tr1, mv1 = cnt.read()
+    trials = tr1 - tr0
+    what = ('the unmodified reference (oracle/_ref: numba njit(parallel) kernels + NumPy/OpenBLAS)'
+            if kind_used == 'reference' else 'NumPy/OpenBLAS oracle port of the reference loop')
     sample = ('first %d of the %d LD blocks of the same generator (M=%d SNPs), %d warm-up + %d '
-              'timed outer iterations, %d trials, %d LD mat-vecs; NumPy/OpenBLAS oracle port of '
-              'the reference loop' % (nb, N_BLOCKS, M, warmup, steps, trials,
-                                      vi.counters['matvec'] - mv0))
-    return M * trials / dt, dt, trials, M, dict(cores=cores, sample=sample, setup_s=t_setup)
+              'timed outer iterations, %d trials, %d LD mat-vecs; %s' % (nb, N_BLOCKS, M, warmup, steps,
+                                                                         trials, mv1 - mv0, what))
+    extra = dict(cores=cores, sample=sample, setup_s=t_setup, kind=kind_used, note=note)
+    if converge_20k:
+        try:
+            extra['convergence_20k'] = cpu_convergence_20k(kind_used)
+        except Exception as exc:
+            log('cpu convergence_20k failed: %r' % (exc,))
+    return M * trials / dt, dt, trials, M, extra
 
 
 # --------------------------------------------------------------------------------------
@@ -498,26 +616,22 @@ def emit(real_stdout, result):
     os.write(real_stdout, (json.dumps(result) + '\n').encode())
 
 
-def run_ours(args):
-    real_stdout = claim_stdout()
+def setup_ranks():
     import torch
     from vilma_b200.dist import SingleComm, TorchComm
-
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
         os.environ['NCCL_DEBUG'] = 'WARN'       # keep NCCL's version banner off stdout (one JSON line)
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py needs a CUDA device; vilma_b200 has no CPU path')
+    torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
         comm = TorchComm()
     else:
         comm = SingleComm()
-    if not torch.cuda.is_available():
-        raise RuntimeError('bench.py needs a CUDA device; vilma_b200 has no CPU path')
-    device = local_rank
-    torch.cuda.set_device(device)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -525,35 +639,46 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s'
+    return comm, local_rank, hbm_peak, peak_src
 
-    if args.workload in ('c2', 'c4'):
-        vi, ctx, info = build_gpu_problem(comm, device, M_total=args.snps, n_blocks=args.blocks)
-        info['name'] = ('BASELINE configs[1]: synthetic single cohort, dense LD, -K 12' if args.workload == 'c2'
+
+def build_workload(workload, comm, device, snps=None, blocks=N_BLOCKS):
+    """(vi, ctx, info) of one BASELINE.json configuration, LD generated in HBM on this rank's shard."""
+    if snps is None:
+        snps = 6_000_000 if workload == 'c4' else M_TOTAL
+    if workload in ('c2', 'c4'):
+        vi, ctx, info = build_gpu_problem(comm, device, M_total=snps, n_blocks=blocks)
+        info['name'] = ('BASELINE configs[1]: synthetic single cohort, dense LD, -K 12' if workload == 'c2'
                         else 'BASELINE configs[3]: synthetic single cohort, 6M SNPs genome-wide, dense LD '
                              'sharded over the ranks, -K 12')
         from vilma_b200.engine import sym_nmax
-        _, n_all, _ = layout(args.snps, args.blocks)
+        _, n_all, _ = layout(snps, blocks)
         n_packed = int((n_all <= sym_nmax()).sum())
-        info['ld_store'] = ('dense fp64: %d of %d blocks symmetric-packed (lower triangle in 8-row panels, '
-                            '4 n (n+1) bytes per mat-vec), %d blocks above %d rows stored in full (8 n^2)'
-                            % (n_packed, len(n_all), len(n_all) - n_packed, sym_nmax()))
+        info['ld_store'] = ('dense fp64: %d of %d blocks symmetric-packed in one piece (lower triangle in 8-row '
+                            'panels), %d blocks above %d rows %s' % (
+                                n_packed, len(n_all), len(n_all) - n_packed, sym_nmax(), info.get('big_store', '')))
     else:
-        vi, ctx, info = build_gpu_problem_multi(comm, device, WORKLOADS[args.workload],
-                                                M_total=args.snps, n_blocks=args.blocks)
-    log('[rank %d] problem built in %.1fs: %s' % (comm.rank, info['setup_s'], info))
+        vi, ctx, info = build_gpu_problem_multi(comm, device, WORKLOADS[workload], M_total=snps,
+                                                n_blocks=blocks)
+    info['workload'] = workload
+    log('[rank %d] %s built in %.1fs: %s' % (comm.rank, workload, info['setup_s'], info))
+    return vi, ctx, info
+
+
+def measure(vi, ctx, info, comm, device, args, hbm_peak, peak_src, sampler=None, with_e2e=True,
+            converge=0):
+    """One workload on the device: warm-up, the timed region (CUDA events, max over ranks), per-kernel
+    roofline, the end-to-end public call and (optionally) the run to convergence."""
+    import ctypes as C
+    import torch
     M, P, K = info['M'], info['P'], info['K']
-    log('[rank %d] pinned to CPUs %s' % (comm.rank, getattr(vi._eng, 'cpus', None)))
-
-    sampler = ClockSampler(device)
-    if comm.rank == 0:
-        sampler.start()          # a separate process; it is polling long before the timed region
-
     # initial parameters: host arrays in pinned memory (e2e uploads them)
     np.random.seed(42)
     t0 = time.time()
     init = vi._initialize()
-    log('[rank %d] _initialize %.1fs' % (comm.rank, time.time() - t0))
-    pin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in init]
+    info['initialize_s'] = time.time() - t0
+    log('[rank %d] _initialize %.1fs' % (comm.rank, info['initialize_s']))
+    pin = [torch.from_numpy(np.array(a)).pin_memory() for a in init]
     init = tuple(t.numpy() for t in pin)
     ckpt = {'vi_mu': init[0], 'vi_delta': init[1], 'hyper_delta': init[2],
             'error_scaling': np.ones(P)}
@@ -566,22 +691,21 @@ def run_ours(args):
     torch.cuda.synchronize()
     ctx.profile(True)
     launches0 = ctx.launch_count()
-    trials0 = vi.n_trials
-    evals0 = vi.n_evals
-    import ctypes as C
+    trials0, evals0 = vi.n_trials, vi.n_evals
     tm0 = (C.c_double * 4)()
     ctx.lib.vb_fit_timing(ctx.handle, tm0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.mark_begin()
+    if sampler is not None:
+        sampler.mark_begin()
     ev0.record()
     state = vi.run_loop(state, args.warmup + args.steps, fresh=True)
     ev1.record()
     torch.cuda.synchronize()
-    sampler.mark_end()
+    if sampler is not None:
+        sampler.mark_end()
     comm.barrier()
     ms = ev0.elapsed_time(ev1)
     ms = float(comm.max(np.array([ms]))[0])
-    clocks = sampler.stop() if comm.rank == 0 else {}
     prof = ctx.profile_read()
     tm1 = (C.c_double * 4)()
     ctx.lib.vb_fit_timing(ctx.handle, tm1)
@@ -594,72 +718,30 @@ def run_ours(args):
     steps_done = state['num_its'] - args.warmup
     value = M * trials / (ms * 1e-3)
 
-    # roofline of the dominant kernel (LD mat-vec), this rank's launches
+    # roofline of the dominant kernel, this rank's launches
     mv_ms, mv_n = prof['ld_matvec']
     snp_ms, snp_n = prof['snp']
     mv_avg = mv_ms / max(mv_n, 1)
-    # per-rank kernel averages (rank skew: every evaluation ends in a rendezvous of all ranks)
     per_rank = np.zeros((comm.world, 3))
     per_rank[comm.rank] = [mv_avg, snp_ms / max(snp_n, 1), len(vi._snps)]
     per_rank = comm.sum(per_rank) if comm.world > 1 else per_rank
-    achieved = info['ld_bytes_rank'] / P / (mv_avg * 1e-3) / 1e9 if mv_n else 0.0    # one launch per cohort
+    launches_per_cohort = max(1, int(round(mv_n / max(evals * P, 1))))     # factor blocks: two passes
+    achieved = info['ld_bytes_rank'] / P / (mv_avg * launches_per_cohort * 1e-3) / 1e9 if mv_n else 0.0
     traffic = None
-    if comm.world == 1 and M == M_TOTAL and args.workload == 'c2':     # the ncu capture is of this exact launch
+    if comm.world == 1 and M == M_TOTAL and info['workload'] == 'c2':     # the ncu capture is of this exact launch
         try:
             traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ld_matvec_traffic.json')))['bytes_per_launch']
         except Exception:
             pass
     bytes_trial = info['ld_bytes_total'] + 16 * K * (P + 1) * M + 64 * P * M
-    # the per-SNP kernel's own floor: trials read mu and write mu', delta; refreshes read mu, write delta
     n_loc = len(vi._snps)
     snp_bytes = (trials * (16 * K * (P + 1) + 64 * P) + (evals - trials) * (8 * K * (P + 1) + 40 * P)) * n_loc
     snp_achieved = snp_bytes / (snp_ms * 1e-3) / 1e9 if snp_ms else 0.0
     ld_dominant = mv_ms >= snp_ms
-
-    # ---------------- end-to-end: the public call with host buffers ----------------
-    vi.num_its = args.steps
-    vi._resident = None
-    del_me = vi._download()      # warm the page-locked host allocator (first cudaHostAlloc is ~50 ms)
-    del del_me
-    vi._resident = None
-    comm.barrier()
-    torch.cuda.synchronize()
-    tr0 = vi.n_trials
-    # where the end-to-end time goes (stderr only)
-    marks = {}
-
-    def timed(name, fn):
-        def wrapper(*a, **k):
-            t = time.perf_counter()
-            r = fn(*a, **k)
-            torch.cuda.synchronize()
-            marks[name] = marks.get(name, 0.0) + time.perf_counter() - t
-            return r
-        wrapper.__wrapped__ = fn
-        return wrapper
-    vi.begin_loop = timed('upload+first evaluation', vi.begin_loop)
-    vi.run_loop = timed('iterations', vi.run_loop)
-    vi._download = timed('download', vi._download)
-    t0 = time.perf_counter()
-    out = vi.optimize(ckpt)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    log('[rank %d] e2e %.1f ms: %s' % (comm.rank, e2e_s * 1e3,
-                                       ', '.join('%s %.1f ms' % (k, v * 1e3) for k, v in marks.items())))
-    e2e_s = float(comm.max(np.array([e2e_s]))[0])
-    e2e_trials = vi.n_trials - tr0
-    e2e_steps = vi.num_its_run
-    n_local = len(vi._snps)
-    h2d = (K * n_local * (P + 1) + K) * 8 / max(e2e_steps, 1)
-    d2h = (K * n_local * (P + 1)) * 8 / max(e2e_steps, 1) + (3 * P + 3 + 10) * 8 * 2
-    e2e_value = M * e2e_trials / e2e_s
-
-    result = {
-        'metric': 'CAVI SNP-updates/sec (1.2M SNPs, 1/2/4/8 B200)',
-        'value': value, 'unit': 'SNP-updates/s', 'n_gpus': comm.world, 'steps': int(steps_done),
-        'warmup': args.warmup, 'ms_per_step': ms / max(steps_done, 1),
-        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic',
+    tile = vi.num_pops >= 3 or K >= 32
+    out = {
+        'value': value, 'unit': 'SNP-updates/s', 'steps': int(steps_done), 'ms_per_step': ms / max(steps_done, 1),
+        'gpu_launches': int(launches),
         'config': {
             'workload': '%s; %d SNPs (1%% without LD) in %d LD blocks (lognormal sizes, CV 0.6, max '
                         'n=%d), %d mixture components, P=%d' % (info['name'], M, info['blocks'],
@@ -673,22 +755,17 @@ def run_ours(args):
                   'evaluation' % (info['ld_bytes_rank'] / 1e9),
             'parallelism': 'LD blocks sharded over %d rank(s), LPT by n^2; one all-reduce of '
                            '%d doubles per evaluated state' % (comm.world, 3 * P + 3),
-            'setup_s': info['setup_s'],
+            'setup_s': info['setup_s'], 'initialize_s': info['initialize_s'],
         },
-        'clocks': {k: clocks.get(k) for k in ('sm_mhz', 'sm_max_mhz', 'reasons', 'samples')},
-        'e2e': {'value': e2e_value, 'unit': 'SNP-updates/s', 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': d2h, 'steps': int(e2e_steps), 'seconds': e2e_s,
-                'call': 'MultiPopVI.optimize(checkpoint) with pinned host parameter arrays'},
-        'gpu_launches': int(launches),
         # the dominant kernel by time in the region: the LD mat-vec (one launch per cohort) for
         # single-cohort fits, the per-SNP update for large K (P+1) state streams
         'roofline': {'bound': 'hbm',
-                     'kernel': 'vb_ld_sym_kernel' if ld_dominant else 'vb_snp_tile_kernel',
+                     'kernel': 'vb_ld_sym_kernel' if ld_dominant else ('vb_snp_tile_kernel' if tile else 'vb_snp3_kernel'),
                      'achieved': achieved if ld_dominant else snp_achieved,
                      'peak': hbm_peak, 'unit': 'GB/s',
                      'frac': (achieved if ld_dominant else snp_achieved) / hbm_peak,
                      'traffic': traffic if ld_dominant else None, 'peak_source': peak_src,
-                     'bytes_per_launch': info['ld_bytes_rank'] / P if ld_dominant else snp_bytes / max(snp_n, 1),
+                     'bytes_per_launch': info['ld_bytes_rank'] / P / launches_per_cohort if ld_dominant else snp_bytes / max(snp_n, 1),
                      'avg_launch_ms': mv_avg if ld_dominant else snp_ms / max(snp_n, 1),
                      'launches_timed': int(mv_n if ld_dominant else snp_n),
                      'share_of_step': (mv_ms if ld_dominant else snp_ms) / ms if ms else None,
@@ -704,36 +781,275 @@ def run_ours(args):
                      'per_rank_snps': [int(v) for v in per_rank[:, 2]],
                      'whole_trial_frac': (bytes_trial / comm.world) * evals / (ms * 1e-3) / 1e9 / hbm_peak},
     }
-    # time to ELBO convergence (the second half of BASELINE.json's metric): the same public call run
-    # until the reference's own stopping rule (variational_inference.py:376-382) fires
-    if args.converge:
-        vi.num_its = args.converge
+
+    # ---------------- end-to-end: the public call with host buffers ----------------
+    if with_e2e:
+        vi.num_its = args.steps
         vi._resident = None
-        vi.begin_loop, vi.run_loop, vi._download = (getattr(f, '__wrapped__', f) for f in
-                                                    (vi.begin_loop, vi.run_loop, vi._download))
+        del_me = vi._download()      # warm the page-locked host allocator (first cudaHostAlloc is ~50 ms)
+        del del_me
+        vi._resident = None
         comm.barrier()
         torch.cuda.synchronize()
-        tr0, rj0 = vi.n_trials, vi.n_rejects
+        tr0 = vi.n_trials
+        marks = {}
+
+        def timed(name, fn):
+            def wrapper(*a, **k):
+                t = time.perf_counter()
+                r = fn(*a, **k)
+                torch.cuda.synchronize()
+                marks[name] = marks.get(name, 0.0) + time.perf_counter() - t
+                return r
+            wrapper.__wrapped__ = fn
+            return wrapper
+        vi.begin_loop = timed('upload+first evaluation', vi.begin_loop)
+        vi.run_loop = timed('iterations', vi.run_loop)
+        vi._download = timed('download', vi._download)
+        t0 = time.perf_counter()
+        vi.optimize(ckpt)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        log('[rank %d] e2e %.1f ms: %s' % (comm.rank, e2e_s * 1e3,
+                                           ', '.join('%s %.1f ms' % (k, v * 1e3) for k, v in marks.items())))
+        vi.begin_loop, vi.run_loop, vi._download = (getattr(f, '__wrapped__', f) for f in
+                                                    (vi.begin_loop, vi.run_loop, vi._download))
+        e2e_s = float(comm.max(np.array([e2e_s]))[0])
+        e2e_trials = vi.n_trials - tr0
+        e2e_steps = vi.num_its_run
+        n_local = len(vi._snps)
+        h2d = (K * n_local * (P + 1) + K) * 8 / max(e2e_steps, 1)
+        d2h = (K * n_local * (P + 1)) * 8 / max(e2e_steps, 1) + (3 * P + 3 + 10) * 8 * 2
+        out['e2e'] = {'value': M * e2e_trials / e2e_s, 'unit': 'SNP-updates/s', 'h2d_bytes_per_step': h2d,
+                      'd2h_bytes_per_step': d2h, 'steps': int(e2e_steps), 'seconds': e2e_s,
+                      'call': 'MultiPopVI.optimize(checkpoint) with pinned host parameter arrays; every rank '
+                              'moves only its own shard across PCIe'}
+    # time to ELBO convergence (the second half of BASELINE.json's metric): the same public call run
+    # until the reference's own stopping rule (variational_inference.py:376-382) fires
+    if converge:
+        vi.num_its = converge
+        vi._resident = None
+        comm.barrier()
+        torch.cuda.synchronize()
+        tr0, rj0, ev0_ = vi.n_trials, vi.n_rejects, vi.n_evals
         t0 = time.perf_counter()
         vi.optimize(ckpt)
         torch.cuda.synchronize()
         conv_s = float(comm.max(np.array([time.perf_counter() - t0]))[0])
-        result['convergence'] = {'seconds': conv_s, 'iterations': int(vi.num_its_run),
-                                 'converged': bool(vi.num_its_run < args.converge),
-                                 'trials': int(vi.n_trials - tr0),
-                                 'rejected_trials': int(vi.n_rejects - rj0), 'max_iterations': args.converge,
-                                 'final_elbo': float(vi.trajectory['elbo'][-1]),
-                                 'call': 'MultiPopVI.optimize(checkpoint) from the seeded start, host '
-                                         'arrays in and out'}
-    if comm.rank == 0 and comm.world == 1 and not args.no_cpu:
+        ctrials = int(vi.n_trials - tr0)
+        out['convergence'] = {'seconds': conv_s, 'iterations': int(vi.num_its_run),
+                              'converged': bool(vi.num_its_run < converge),
+                              'trials': ctrials, 'state_evaluations': int(vi.n_evals - ev0_),
+                              'rejected_trials': int(vi.n_rejects - rj0), 'max_iterations': converge,
+                              'final_elbo': float(vi.trajectory['elbo'][-1]),
+                              'snp_updates_per_s': M * ctrials / conv_s,
+                              'call': 'MultiPopVI.optimize(checkpoint) from the seeded start, host '
+                                      'arrays in and out'}
+    return out, ckpt
+
+
+def checkpoint_resume_leg(vi, ckpt, comm, its=6, freq=5):
+    """BASELINE configs[4]: `--checkpoint-freq 5` and a mid-run resume from the `.npz` it wrote
+    (reference variational_inference.py:362-367 and :345-352): run `its` iterations with periodic
+    checkpoints, reload the last one, check that the resumed state's ELBO is the tracked one."""
+    import shutil
+    import torch
+    need = sum(np.asarray(v).nbytes for v in ckpt.values()) * 3
+    base = None
+    for cand in ('/dev/shm', tempfile.gettempdir()):
         try:
-            v, dt, tr, Ms, extra = time_cpu(steps=3 if args.workload == 'c2' else 2, warmup=1,
-                                            workload=args.workload)
-            result['cpu_baseline'] = {'value': v, 'unit': 'SNP-updates/s', 'cores': extra['cores'],
-                                      'kind': 'port', 'sample': extra['sample'], 'seconds': dt}
-        except Exception as exc:                 # the GPU numbers stand without it
-            log('cpu_baseline failed: %r' % (exc,))
-            result['cpu_baseline'] = None
+            st = os.statvfs(cand)
+            if st.f_bavail * st.f_frsize > need:
+                base = cand
+                break
+        except OSError:
+            pass
+    if base is None:
+        return {'skipped': 'no scratch space for %.1f GB of checkpoints' % (need / 1e9)}
+    d = tempfile.mkdtemp(prefix='vilma_b200_ckpt_', dir=base) if comm.rank == 0 else None
+    d = comm.broadcast_bytes((d or '').encode()).decode()
+    out = {'checkpoint_freq': freq, 'iterations': its, 'dir': base}
+    try:
+        vi.checkpoint, vi.checkpoint_freq = True, freq
+        vi.checkpoint_path = os.path.join(d, 'run-checkpoint')
+        vi.num_its = its
+        vi._resident = None
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        vi.optimize(ckpt)
+        torch.cuda.synchronize()
+        out['seconds_with_checkpoints'] = time.perf_counter() - t0
+        elbo_traj = list(vi.trajectory['elbo'])
+        comm.barrier()
+        files = sorted(f for f in os.listdir(d) if f.endswith('.npz'))
+        out['files'] = files
+        out['bytes_per_checkpoint'] = os.path.getsize(os.path.join(d, files[-1]))
+        last_it = max(int(f.split('.')[-2]) for f in files)
+        vi.checkpoint = False
+        t0 = time.perf_counter()
+        z = np.load(os.path.join(d, 'run-checkpoint.%d.npz' % last_it))
+        vi.num_its = 2
+        vi._resident = None
+        vi.optimize(z)
+        torch.cuda.synchronize()
+        out['resume_seconds'] = time.perf_counter() - t0
+        out['resumed_from_iteration'] = last_it
+        # the checkpoint at iteration `it` holds the state BEFORE that iteration: its ELBO is the
+        # tracked value after iteration it-1
+        params = [np.asarray(z[k]) for k in ('vi_mu', 'vi_delta', 'hyper_delta')]
+        vi._set_state(params)
+        e_resumed = float(vi.elbo(params))
+        e_tracked = float(elbo_traj[last_it - 1])
+        out['elbo_at_resume'] = e_resumed
+        out['elbo_tracked'] = e_tracked
+        out['resume_matches'] = bool(abs(e_resumed - e_tracked) <= 1e-8 * abs(e_tracked))
+    finally:
+        vi.checkpoint = False
+        comm.barrier()
+        if comm.rank == 0:
+            shutil.rmtree(d, ignore_errors=True)
+    return out
+
+
+def budget_left(args):
+    return args.budget_s - (time.time() - T_START)
+
+
+def cpu_baseline_leg(workload, converge_20k=False):
+    try:
+        v, dt, tr, Ms, extra = time_cpu(steps=3 if workload == 'c2' else 2, warmup=1, workload=workload,
+                                        kind='reference', converge_20k=converge_20k)
+        out = {'value': v, 'unit': 'SNP-updates/s', 'cores': extra['cores'], 'kind': extra['kind'],
+               'sample': extra['sample'], 'seconds': dt, 'setup_s': extra['setup_s']}
+        if extra.get('note'):
+            out['note'] = extra['note']
+        if 'convergence_20k' in extra:
+            out['convergence_20k'] = extra['convergence_20k']
+        return out
+    except Exception as exc:                 # the GPU numbers stand without it
+        log('cpu_baseline failed: %r' % (exc,))
+        return None
+
+
+def gpu_convergence_20k(comm, device):
+    """The M = 20k problem of BASELINE.md section 2 through the REAL constructor (host LowRankMatrix
+    objects: eigendecomposition, pseudo-inverse, ridge start -- nothing precomputed) and optimize()."""
+    import torch
+    from vilma_b200 import synth
+    from vilma_b200.matrix_structures import BlockDiagonalMatrix, LowRankMatrix
+    from vilma_b200.variational_inference import MultiPopVI
+    n = np.asarray(CONV20K_SIZES, dtype=np.int64)
+    M_ld = int(n.sum())
+    n_miss = int(round(M_ld * MISSING_FRAC / (1 - MISSING_FRAC)))
+    M = M_ld + n_miss
+    dev = torch.device('cpu')
+    blocks, bh, se = [], [], []
+    t0 = time.perf_counter()
+    for b in range(len(n)):
+        s = synth.block_se(int(n[b]), 42, b, N_GWAS, dev)
+        r, beta_hat = synth.make_block_sumstats(int(n[b]), 42, b, s, M, dev)
+        blocks.append(LowRankMatrix(X=r.numpy(), t=1.0))
+        bh.append(beta_hat.numpy())
+        se.append(s.numpy())
+    ld = BlockDiagonalMatrix(blocks, perm=np.arange(M), missing=np.arange(M_ld, M, dtype=np.int64))
+    beta_hat = np.concatenate(bh + [np.zeros(n_miss)])
+    std = np.concatenate(se + [np.ones(n_miss)])
+    covs = synth.mixture_grid_single(beta_hat, std, K_GRID)
+    vi = MultiPopVI(marginal_effects=beta_hat[None], std_errs=std[None], ld_mats=[ld], mixture_covs=covs,
+                    annotations=np.ones((M, 1)), checkpoint=False, checkpoint_freq=-1, output='bench20k',
+                    scaled=False, scale_se=False, gwas_N=np.array([N_GWAS]), init_hg=np.array([INIT_HG]),
+                    num_its=2000, comm=comm, device=device)
+    setup_s = time.perf_counter() - t0
+    np.random.seed(42)
+    t0 = time.perf_counter()
+    params = vi.optimize(None)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    pm = vi.real_posterior_mean(*params)
+    out = dict(seconds=dt, iterations=int(vi.num_its_run), trials=int(vi.n_trials), M=int(M),
+               final_elbo=float(vi.elbo(params)), pm_abs_sum=float(np.abs(pm).sum()), setup_s=setup_s,
+               call='MultiPopVI(...) real constructor + optimize(None) on host LowRankMatrix blocks')
+    vi.close()
+    return out
+
+
+def run_ours(args):
+    real_stdout = claim_stdout()
+    import torch
+    comm, device, hbm_peak, peak_src = setup_ranks()
+    world = comm.world
+    sampler = ClockSampler(device)
+    if comm.rank == 0:
+        sampler.start()          # a separate process; it is polling long before the timed region
+
+    vi, ctx, info = build_workload(args.workload, comm, device, snps=args.snps, blocks=args.blocks)
+    log('[rank %d] pinned to CPUs %s' % (comm.rank, getattr(vi._eng, 'cpus', None)))
+    head, ckpt = measure(vi, ctx, info, comm, device, args, hbm_peak, peak_src, sampler=sampler,
+                         with_e2e=True, converge=args.converge)
+    clocks = sampler.stop() if comm.rank == 0 else {}
+    result = {
+        'metric': 'CAVI SNP-updates/sec (1.2M SNPs, 1/2/4/8 B200)',
+        'value': head['value'], 'unit': 'SNP-updates/s', 'n_gpus': world, 'steps': head['steps'],
+        'warmup': args.warmup, 'ms_per_step': head['ms_per_step'],
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': head['config'],
+        'clocks': {k: clocks.get(k) for k in ('sm_mhz', 'sm_max_mhz', 'reasons', 'samples')},
+        'e2e': head.get('e2e'), 'gpu_launches': head['gpu_launches'], 'roofline': head['roofline'],
+    }
+    if 'convergence' in head:
+        result['convergence'] = head['convergence']
+    if args.workload == 'c5' and args.checkpoint_leg:
+        result['checkpoint_resume'] = checkpoint_resume_leg(vi, ckpt, comm)
+    vi.close()
+    ctx.close()
+    del vi, ctx, ckpt
+    torch.cuda.empty_cache()
+
+    # ---------------- CPU baseline: the reference on the host cores (rank 0, N = 1 only) ---------
+    if comm.rank == 0 and world == 1 and not args.no_cpu:
+        result['cpu_baseline'] = cpu_baseline_leg(args.workload, converge_20k=args.workload == 'c2')
+
+    # ---------------- the other BASELINE.json configurations on the same build -------------------
+    extras = [w for w in args.extra_workloads.split(',') if w and w != 'none']
+    if args.extra_workloads == 'auto':
+        extras = []
+        if args.workload == 'c2' and args.snps in (None, M_TOTAL):
+            extras = ['c3', 'c5'] if world == 1 else (['c4'] if world == 8 else [])
+    if extras:
+        result['workloads'] = {}
+    for w in extras:
+        if budget_left(args) < 60:
+            result['workloads'][w] = {'skipped': 'time budget of %d s spent' % args.budget_s}
+            continue
+        try:
+            vi, ctx, info = build_workload(w, comm, device)
+            conv = min(args.converge, 2000 if w == 'c4' else (600 if w == 'c3' else 150)) if args.converge else 0
+            wl, ckpt = measure(vi, ctx, info, comm, device, args, hbm_peak, peak_src, with_e2e=False,
+                               converge=conv if budget_left(args) > 120 else 0)
+            if w == 'c5' and args.checkpoint_leg and budget_left(args) > 90:
+                wl['checkpoint_resume'] = checkpoint_resume_leg(vi, ckpt, comm)
+            vi.close()
+            ctx.close()
+            del vi, ctx, ckpt
+            torch.cuda.empty_cache()
+            if comm.rank == 0 and world == 1 and not args.no_cpu and budget_left(args) > 90:
+                wl['cpu_baseline'] = cpu_baseline_leg(w)
+            wl['n_gpus'] = world
+            result['workloads'][w] = wl
+        except Exception as exc:
+            log('workload %s failed: %r' % (w, exc))
+            result['workloads'][w] = {'failed': repr(exc)}
+    # the M = 20k run to convergence next to the reference's (cpu_baseline.convergence_20k)
+    if world == 1 and args.workload == 'c2' and not args.no_cpu and args.converge and budget_left(args) > 30:
+        try:
+            result['convergence_20k'] = gpu_convergence_20k(comm, device)
+            ref = (result.get('cpu_baseline') or {}).get('convergence_20k')
+            if ref:
+                result['convergence_20k']['same_iterations_and_trials_as_cpu'] = bool(
+                    ref['iterations'] == result['convergence_20k']['iterations']
+                    and ref['trials'] == result['convergence_20k']['trials'])
+        except Exception as exc:
+            log('convergence_20k failed: %r' % (exc,))
     if comm.rank == 0:
         emit(real_stdout, result)
     if world > 1:
@@ -747,7 +1063,14 @@ def run_reference(args):
     if rank != 0:
         return
     real_stdout = claim_stdout()
-    v, dt, trials, M, extra = time_cpu(steps=args.steps, warmup=args.warmup, workload=args.workload)
+    v, dt, trials, M, extra = time_cpu(steps=args.steps, warmup=args.warmup, workload=args.workload,
+                                       kind='reference', converge_20k=bool(args.converge) and args.workload == 'c2')
+    cpu = {'value': v, 'unit': 'SNP-updates/s', 'cores': extra['cores'], 'kind': extra['kind'],
+           'sample': extra['sample'], 'setup_s': extra['setup_s']}
+    if extra.get('note'):
+        cpu['note'] = extra['note']
+    if 'convergence_20k' in extra:
+        cpu['convergence_20k'] = extra['convergence_20k']
     result = {
         'impl': 'reference',
         'metric': 'CAVI SNP-updates/sec (1.2M SNPs, 1/2/4/8 B200)',
@@ -757,8 +1080,7 @@ def run_reference(args):
         'data': 'synthetic',
         'config': {'workload': ('BASELINE configs[1]' if args.workload in ('c2', 'c4') else WORKLOADS[args.workload]['name'])
                                + ' (bounded sample): ' + extra['sample']},
-        'cpu_baseline': {'value': v, 'unit': 'SNP-updates/s', 'cores': extra['cores'],
-                         'kind': 'port', 'sample': extra['sample']},
+        'cpu_baseline': cpu,
         'e2e': {'value': v, 'unit': 'SNP-updates/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -772,7 +1094,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--snps', type=int, default=M_TOTAL)
+    ap.add_argument('--snps', type=int, default=None)
     ap.add_argument('--blocks', type=int, default=N_BLOCKS)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--converge', type=int, default=2000, metavar='MAX_ITS',
@@ -780,9 +1102,14 @@ def main():
     ap.add_argument('--workload', default='c2', choices=['c2', 'c3', 'c4', 'c5'],
                     help='c2 = BASELINE configs[1] (the bench line of record); c3 / c5 = configs[2] / configs[4]; '
                          'c4 = configs[3]: 6M SNPs, 170 GB of LD -- needs --gpus 8 (21 GB per rank)')
+    ap.add_argument('--extra-workloads', default='auto',
+                    help="other BASELINE.json configurations measured after the headline into `workloads`: "
+                         "'auto' (c3,c5 at N=1; c4 at N=8), 'none', or a comma list")
+    ap.add_argument('--no-checkpoint-leg', dest='checkpoint_leg', action='store_false',
+                    help='skip the checkpoint-every-5 + resume leg of c5')
+    ap.add_argument('--budget-s', type=int, default=int(os.environ.get('BENCH_BUDGET_S', '540')),
+                    help='wall-clock budget: optional legs are skipped once it is spent')
     args = ap.parse_args()
-    if args.workload == 'c4' and args.snps == M_TOTAL:
-        args.snps = 6_000_000
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -33,8 +33,16 @@
 #ifndef VB_TILE_PREFETCH
 #define VB_TILE_PREFETCH 4          // components ahead whose mu is prefetched into L2
 #endif
+#ifndef VB_TILE_SMEM_PREC
+#define VB_TILE_SMEM_PREC 1         // Prec_k (packed lower triangle) and log|Sigma_k| staged in shared memory once per CTA
+#endif
+#ifndef VB_TILE_REGPF
+#define VB_TILE_REGPF 1             // the next component's mu is loaded into registers one iteration ahead
+#endif
 #define VB_TILE_SNPS 32
 #define VB_TILE_MAXW 16
+// packed lower triangle of Prec_k padded to an even count (16-byte rows: LDS.128 broadcasts) + log|Sigma_k| slot
+#define VB_TILE_NTP(P) ((((P) * ((P) + 1) / 2) + 2) & ~1)
 #define VB_TILE_NV(P) (5 + 2 * (P))        // mx, s0, sKd, sKq, sKs, spm[P], sm2[P]
 
 // L D L^T of a packed SPD matrix (P >= 3).  Nl = strictly-lower part of L^-1 (unit lower), inv = 1/D.
@@ -110,8 +118,14 @@ struct VbLdl {
 #ifndef VB_TILE_P1_THREADS
 #define VB_TILE_P1_THREADS 1024
 #endif
+#ifndef VB_TILE_P23_THREADS
+#define VB_TILE_P23_THREADS 512
+#endif
+#ifndef VB_TILE_P456_THREADS
+#define VB_TILE_P456_THREADS 256
+#endif
 template <int P> struct VbTileCfg {
-    static constexpr int THREADS_PER_SM = (P == 1) ? VB_TILE_P1_THREADS : (P <= 3 ? 512 : 256);
+    static constexpr int THREADS_PER_SM = (P == 1) ? VB_TILE_P1_THREADS : (P <= 3 ? VB_TILE_P23_THREADS : VB_TILE_P456_THREADS);
     static constexpr int MAXT = (P == 1) ? THREADS_PER_SM / 2 : THREADS_PER_SM;     // P = 1: two CTAs per SM
     static constexpr int MINB = (P == 1) ? 2 : 1;
 };
@@ -129,20 +143,42 @@ template <int P>
 struct VbTileComp {
     double lk, lkh, quad, sigsum, mu[P], sd[P];     // lkh = lk - log h_k
 };
+// Lambda = Prec_k + diag(dt) as a packed lower triangle, from the shared-memory copy (packed, 16-byte
+// rows: the compiler fuses the uniform loads into LDS.128 broadcasts) or from the global [P][P] array.
+template <int P>
+__device__ __forceinline__ void vb_tile_load_lambda(const double* __restrict__ pk, const double (&dt)[P],
+                                                    double (&lam)[P * (P + 1) / 2]) {
+    constexpr int NT = P * (P + 1) / 2;
+#if VB_TILE_SMEM_PREC
+    const double2* pk2 = reinterpret_cast<const double2*>(pk);
+#pragma unroll
+    for (int t = 0; t < NT / 2; ++t) {
+        const double2 v = pk2[t];
+        lam[2 * t] = v.x;
+        lam[2 * t + 1] = v.y;
+    }
+    if constexpr (NT & 1) lam[NT - 1] = pk[NT - 1];
+#else
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+#pragma unroll
+        for (int q = 0; q <= p; ++q) lam[VB_TRI(p, q)] = pk[p * P + q];
+#endif
+#pragma unroll
+    for (int p = 0; p < P; ++p) lam[VB_TRI(p, p)] += dt[p];
+}
+// One mixture component of one SNP: Lambda, eta, mu' = S eta, logit and the KL pieces.  `mu` holds the
+// accepted mu on entry (already in registers: loaded one iteration ahead) and mu' on return (TRIAL).
 template <int P, int MODE>
 __device__ __forceinline__ VbTileComp<P> vb_tile_component(
-    const double* __restrict__ prec, const double* __restrict__ pmu, int64_t M, const double (&dt)[P],
+    const double* __restrict__ pk, const double (&mu_in)[P], const double (&dt)[P],
     const double (&g)[P], double step, double one_minus_step, double gk, double loghk, double logdetk) {
     constexpr int NT = P * (P + 1) / 2;
     VbTileComp<P> c;
     double lam[NT], eta[P], det;
+    vb_tile_load_lambda<P>(pk, dt, lam);
 #pragma unroll
-    for (int p = 0; p < P; ++p) {
-#pragma unroll
-        for (int q = 0; q <= p; ++q) lam[VB_TRI(p, q)] = prec[p * P + q];
-        lam[VB_TRI(p, p)] += dt[p];
-        c.mu[p] = __ldg(pmu + (size_t)p * M);
-    }
+    for (int p = 0; p < P; ++p) c.mu[p] = mu_in[p];
     vb_sym_matvec<P>(lam, c.mu, eta);
     if constexpr (MODE == VB_MODE_TRIAL) {
 #pragma unroll
@@ -192,36 +228,60 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
     const int kslots = (K + W - 1) / W;
     const int AKf = a.fuse_ann ? a.A * K : 0;
     // shared memory: logits [kslots][W][32] | merge scratch [W][NV][32] | annotation sums [A*K]
+    //                | Prec_k packed + log|Sigma_k| [K][NTP]
     double* s_logit = s_tile + (size_t)warp * 32 + lane;                   // + slot * W * 32
     double* s_merge = s_tile + (size_t)kslots * W * 32;
     double* s_ann = s_merge + (size_t)W * NV * 32;
+    constexpr int NTP = VB_TILE_NTP(P);
+#if VB_TILE_SMEM_PREC
+    double* s_prec = s_ann + ((AKf + 1) & ~1);
+    for (int j = threadIdx.x; j < K * NTP; j += blockDim.x) {
+        const int k = j / NTP, t = j - k * NTP;
+        double v = 0.0;
+        if (t < NT) {
+            int p = 0;
+            while ((p + 1) * (p + 2) / 2 <= t) ++p;                        // t = p (p+1)/2 + q
+            const int q = t - p * (p + 1) / 2;
+            v = a.prec[(size_t)k * P * P + p * P + q];
+        } else if (t == NTP - 1) {
+            v = a.logdet[k];
+        }
+        s_prec[j] = v;
+    }
+#endif
     for (int j = threadIdx.x; j < AKf; j += blockDim.x) s_ann[j] = 0.0;
-    if (AKf) __syncthreads();
+    __syncthreads();
 
     double tA[P], tC[P], tKd = 0.0, tKq = 0.0, tKs = 0.0;       // warp 0 only
 #pragma unroll
     for (int p = 0; p < P; ++p) { tA[p] = 0.0; tC[p] = 0.0; }
     const double step = a.step, one_minus_step = 1.0 - a.step;
-    const double* const g_prec = a.prec;
+#if VB_TILE_SMEM_PREC
+    const double* const k_prec = s_prec;
+    constexpr int KSTR = NTP;
+#else
+    const double* const k_prec = a.prec;
+    constexpr int KSTR = P * P;
     const double* const g_logdet = a.logdet;
+#endif
     const int64_t ntiles = (M + VB_TILE_SNPS - 1) / VB_TILE_SNPS;
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t i0 = tile * VB_TILE_SNPS + lane;
         const bool valid = i0 < M;
         const int64_t i = valid ? i0 : M - 1;
-        double dt[P], sld[P], g[P];
+        double dt[P], g[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            sld[p] = a.sld[(size_t)p * M + i];
-            dt[p] = sld[p] * a.inv_tau[p];
+            dt[p] = a.sld[(size_t)p * M + i] * a.inv_tau[p];
             g[p] = 0.0;
         }
         if constexpr (MODE == VB_MODE_TRIAL) {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const double se = a.se[(size_t)p * M + i];
-                const double lk = a.linked_in[(size_t)p * M + i] / se - a.pm_in[(size_t)p * M + i] * sld[p];
+                const double lk = a.linked_in[(size_t)p * M + i] / se -
+                                  a.pm_in[(size_t)p * M + i] * a.sld[(size_t)p * M + i];
                 g[p] = (a.adj[(size_t)p * M + i] - lk) * a.inv_tau[p];
             }
         }
@@ -238,9 +298,28 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
         const size_t kstride = (size_t)W * PM;
         double* sl = s_logit;
 #if VB_TILE_PAIR
+        double mu1[P], mu2[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            mu1[p] = (warp < K) ? __ldg(pmu_in + (size_t)p * M) : 0.0;
+            mu2[p] = (warp + W < K) ? __ldg(pmu_in + kstride + (size_t)p * M) : mu1[p];
+        }
         for (int k = warp; k < K; k += 2 * W, pmu_in += 2 * kstride, sl += 2 * W * 32) {
             const bool has2 = k + W < K;
             const int k2 = has2 ? k + W : k;                       // clamped: recomputes k, masked below
+            double nx1[P], nx2[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) { nx1[p] = mu1[p]; nx2[p] = mu2[p]; }
+#if VB_TILE_REGPF
+            if (k + 2 * W < K) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) nx1[p] = __ldg(pmu_in + 2 * kstride + (size_t)p * M);
+            }
+            if (k + 3 * W < K) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) nx2[p] = __ldg(pmu_in + 3 * kstride + (size_t)p * M);
+            }
+#endif
             if (VB_TILE_PREFETCH > 0 && k + 2 * VB_TILE_PREFETCH * W < K) {
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
@@ -248,11 +327,15 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
                     vb_prefetch_l2(pmu_in + (2 * VB_TILE_PREFETCH + 1) * kstride + (size_t)p * M);
                 }
             }
+#if VB_TILE_SMEM_PREC
+            const double ld1 = k_prec[(size_t)k * KSTR + NTP - 1], ld2 = k_prec[(size_t)k2 * KSTR + NTP - 1];
+#else
+            const double ld1 = g_logdet[k], ld2 = g_logdet[k2];
+#endif
             const VbTileComp<P> c1 = vb_tile_component<P, MODE>(
-                g_prec + (size_t)k * P * P, pmu_in, M, dt, g, step, one_minus_step, gfull[k], logh[k], g_logdet[k]);
+                k_prec + (size_t)k * KSTR, mu1, dt, g, step, one_minus_step, gfull[k], logh[k], ld1);
             const VbTileComp<P> c2 = vb_tile_component<P, MODE>(
-                g_prec + (size_t)k2 * P * P, has2 ? pmu_in + kstride : pmu_in, M, dt, g, step, one_minus_step,
-                gfull[k2], logh[k2], g_logdet[k2]);
+                k_prec + (size_t)k2 * KSTR, mu2, dt, g, step, one_minus_step, gfull[k2], logh[k2], ld2);
             if constexpr (MODE == VB_MODE_TRIAL) {
                 if (valid) {
 #pragma unroll
@@ -283,80 +366,82 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
                 sm2[p] = fma(sm2[p], r, fma(w1, fma(c1.mu[p], c1.mu[p], c1.sd[p]),
                                             w2 * fma(c2.mu[p], c2.mu[p], c2.sd[p])));
             }
+#if VB_TILE_REGPF
+#pragma unroll
+            for (int p = 0; p < P; ++p) { mu1[p] = nx1[p]; mu2[p] = nx2[p]; }
+#else
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                if (k + 2 * W < K) mu1[p] = __ldg(pmu_in + 2 * kstride + (size_t)p * M);
+                mu2[p] = (k + 3 * W < K) ? __ldg(pmu_in + 3 * kstride + (size_t)p * M) : mu1[p];
+            }
+#endif
         }
 #else
+        double mu_cur[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) mu_cur[p] = (warp < K) ? __ldg(pmu_in + (size_t)p * M) : 0.0;
 #pragma unroll UNROLL_A
         for (int k = warp; k < K; k += W, pmu_in += kstride, sl += W * 32) {
-            const double* prec = g_prec + (size_t)k * P * P;
-            double lam[NT], mu[P], eta[P], sd[P], det;
+            double mu_nx[P];
+#if VB_TILE_REGPF
+            // the next component's mu: issued now, consumed one iteration later (its latency hides
+            // behind this component's ~200-300 dependent fp64 instructions)
+#pragma unroll
+            for (int p = 0; p < P; ++p) mu_nx[p] = mu_cur[p];
+            if (k + W < K) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) mu_nx[p] = __ldg(pmu_in + kstride + (size_t)p * M);
+            }
+#endif
             if (VB_TILE_PREFETCH > 0 && k + VB_TILE_PREFETCH * W < K) {
 #pragma unroll
                 for (int p = 0; p < P; ++p) vb_prefetch_l2(pmu_in + VB_TILE_PREFETCH * kstride + (size_t)p * M);
             }
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-#pragma unroll
-                for (int q = 0; q <= p; ++q) lam[VB_TRI(p, q)] = prec[p * P + q];
-                lam[VB_TRI(p, p)] += dt[p];
-                mu[p] = __ldg(pmu_in + (size_t)p * M);
-            }
-            vb_sym_matvec<P>(lam, mu, eta);                        // eta_old = Lambda mu
-            if constexpr (MODE == VB_MODE_TRIAL) {
-#pragma unroll
-                for (int p = 0; p < P; ++p) eta[p] = step * g[p] + one_minus_step * eta[p];
-            }
-            if constexpr (P <= 2) {
-                double S[NT];
-                vb_small_inverse<P>(lam, S, det);
-                if constexpr (MODE == VB_MODE_TRIAL) vb_sym_matvec<P>(S, eta, mu);     // mu' = S eta
-#pragma unroll
-                for (int p = 0; p < P; ++p) sd[p] = S[VB_TRI(p, p)];
-            } else {
-                VbLdl<P> f;
-                f.factor(lam);
-                det = f.det;
-                if constexpr (MODE == VB_MODE_TRIAL) f.solve(eta, mu);
-                f.diag(sd);
-            }
+#if VB_TILE_SMEM_PREC
+            const double ldk = k_prec[(size_t)k * KSTR + NTP - 1];
+#else
+            const double ldk = g_logdet[k];
+#endif
+            const VbTileComp<P> c = vb_tile_component<P, MODE>(
+                k_prec + (size_t)k * KSTR, mu_cur, dt, g, step, one_minus_step, gfull[k], logh[k], ldk);
             if constexpr (MODE == VB_MODE_TRIAL) {
                 if (valid) {
 #pragma unroll
-                    for (int p = 0; p < P; ++p) pmu_out[(size_t)p * M] = mu[p];
+                    for (int p = 0; p < P; ++p) pmu_out[(size_t)p * M] = c.mu[p];
                 }
                 pmu_out += kstride;
             }
-            const double c = -vb_log_pos(det);                     // log|S_k|
-            double dot = 0.0, dmm = 0.0, dss = 0.0;
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                dot = fma(mu[p], eta[p], dot);
-                dmm = fma(dt[p] * mu[p], mu[p], dmm);
-                dss = fma(dt[p], sd[p], dss);
-            }
-            const double lk = 0.5 * (c + dot) + gfull[k];
-            *sl = lk;
-            const double quad = dot - dmm;                         // mu'^T Prec_k mu'
-            const double sigsum = g_logdet[k] - c + ((double)P - dss);   // log|Sigma_k| - log|S| + tr(Prec_k S)
+            *sl = c.lk;
             // one exponential serves as rescale factor (new maximum) or as weight
-            const double d = lk - mx;
+            const double d = c.lk - mx;
             const double e = vb_exp_nonpos(-fabs(d));
             double w = e;
             if (d > 0.0) {
                 s0 *= e; sKd *= e; sKq *= e; sKs *= e;
 #pragma unroll
                 for (int p = 0; p < P; ++p) { spm[p] *= e; sm2[p] *= e; }
-                mx = lk;
+                mx = c.lk;
                 w = 1.0;
             }
             s0 += w;
-            sKd = fma(w, lk - logh[k], sKd);
-            sKq = fma(w, quad, sKq);
-            sKs = fma(w, sigsum, sKs);
+            sKd = fma(w, c.lkh, sKd);
+            sKq = fma(w, c.quad, sKq);
+            sKs = fma(w, c.sigsum, sKs);
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                spm[p] = fma(w, mu[p], spm[p]);
-                sm2[p] = fma(w, fma(mu[p], mu[p], sd[p]), sm2[p]);
+                spm[p] = fma(w, c.mu[p], spm[p]);
+                sm2[p] = fma(w, fma(c.mu[p], c.mu[p], c.sd[p]), sm2[p]);
             }
+#if VB_TILE_REGPF
+#pragma unroll
+            for (int p = 0; p < P; ++p) mu_cur[p] = mu_nx[p];
+#else
+            if (k + W < K) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) mu_cur[p] = __ldg(pmu_in + kstride + (size_t)p * M);
+            }
+#endif
         }
 #endif
         // ---- merge the W slices of each SNP (warp order)
@@ -419,7 +504,7 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
                 }
                 if (a.pv_out) a.pv_out[(size_t)p * M + i] = pv;
                 tA[p] = fma(pm, a.adj[(size_t)p * M + i], tA[p]);
-                tC[p] = fma(sld[p], pv, tC[p]);
+                tC[p] = fma(a.sld[(size_t)p * M + i], pv, tC[p]);
             }
         }
     }
@@ -445,5 +530,9 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
 // Shared memory one CTA of the tile kernel needs (bytes).
 static inline size_t vb_tile_smem(int K, int P, int W, int akf) {
     const size_t kslots = (size_t)(K + W - 1) / W;
-    return (kslots * W * 32 + (size_t)W * VB_TILE_NV(P) * 32 + (size_t)akf) * sizeof(double);
+    size_t n = kslots * W * 32 + (size_t)W * VB_TILE_NV(P) * 32 + (size_t)((akf + 1) & ~1);
+#if VB_TILE_SMEM_PREC
+    n += (size_t)K * VB_TILE_NTP(P);
+#endif
+    return n * sizeof(double);
 }

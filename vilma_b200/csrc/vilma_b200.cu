@@ -1084,11 +1084,14 @@ static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf) {
     // automatic: large grids and P >= 3 (where thread-per-SNP parks K logits per SNP in HBM and pays
     // three logs and square roots per component); the tuned three-pass kernel keeps small P <= 2 grids
     if (g_tile_mode < 0 && f.P <= 2 && f.K < 32) return best;
-    const int target = f.P == 1 ? VbTileCfg<1>::THREADS_PER_SM : (f.P <= 3 ? 512 : 256);
-    const int maxw = (f.P == 1 ? VbTileCfg<1>::MAXT : (f.P <= 3 ? 512 : 256)) / 32;
+    const int target = f.P == 1 ? VbTileCfg<1>::THREADS_PER_SM
+                                : (f.P <= 3 ? VbTileCfg<3>::THREADS_PER_SM : VbTileCfg<5>::THREADS_PER_SM);
+    const int maxw = std::min(VB_TILE_MAXW, (f.P == 1 ? VbTileCfg<1>::MAXT : (f.P <= 3 ? VbTileCfg<3>::MAXT : VbTileCfg<5>::MAXT)) / 32);
     const size_t cap = 227 * 1024;
     int best_threads = 0;
-    for (int W = 1; W <= maxw; W *= 2) {
+    static const int kWidths[] = {1, 2, 3, 4, 6, 8, 12, 16};     // warps per tile (k is split round-robin: any W works)
+    for (int W : kWidths) {
+        if (W > maxw) break;
         if (g_tile_mode > 0 && W != g_tile_mode) continue;
         const size_t sm = vb_tile_smem(f.K, f.P, W, akf);
         if (sm > cap) continue;

@@ -32,6 +32,37 @@ class SingleComm:
         return [data]
 
 
+def index_runs(idx):
+    """Maximal runs of consecutive integers in the sorted index array `idx`:
+    [(global start, global stop, local start), ...]."""
+    idx = np.asarray(idx, dtype=np.int64)
+    if len(idx) == 0:
+        return []
+    cuts = np.where(np.diff(idx) != 1)[0] + 1
+    lo = np.concatenate([[0], cuts])
+    hi = np.concatenate([cuts, [len(idx)]])
+    return [(int(idx[a]), int(idx[b - 1]) + 1, int(a)) for a, b in zip(lo, hi)]
+
+
+def take_runs(arr, idx, axis):
+    """arr.take(idx, axis) for a sorted `idx`, as a few slice copies (whole LD blocks are contiguous
+    SNP ranges) instead of a gather."""
+    arr = np.asarray(arr)
+    runs = index_runs(idx)
+    if len(runs) > max(64, len(idx) // 16):          # scattered indices: a plain gather is as good
+        return np.ascontiguousarray(arr.take(idx, axis=axis))
+    sl = [slice(None)] * arr.ndim
+    shape = list(arr.shape)
+    shape[axis] = len(idx)
+    out = np.empty(shape, dtype=arr.dtype)
+    dst = [slice(None)] * arr.ndim
+    for g0, g1, l0 in runs:
+        sl[axis] = slice(g0, g1)
+        dst[axis] = slice(l0, l0 + (g1 - g0))
+        out[tuple(dst)] = arr[tuple(sl)]
+    return out
+
+
 def _to_numpy(t):
     if isinstance(t, np.ndarray):
         return np.array(t, dtype=np.float64)
@@ -128,6 +159,61 @@ class TorchComm(SingleComm):
         host = torch.empty(full.shape, dtype=full.dtype, pin_memory=dev.type == 'cuda')
         host.copy_(full)
         return host.numpy()
+
+    def gather_shared(self, locals_, snps, M, axes):
+        """Assemble several global arrays from per-rank shards along their SNP axes through ONE
+        node-shared host mapping (a file in /dev/shm mapped by every rank): each rank copies only its
+        own shard -- 1/N of the bytes -- and every rank ends up with the same zero-copy view.  Replaces
+        an all-gather to every GPU followed by N full device->host copies.  Returns None when the ranks
+        do not share a host or /dev/shm lacks the space (callers fall back to gather_snp_axis)."""
+        import mmap
+        import os
+        import socket
+        shapes, offs, total = [], [], 0
+        for a, ax in zip(locals_, axes):
+            shp = list(a.shape)
+            shp[ax] = M
+            shapes.append(tuple(shp))
+            offs.append(total)
+            total += int(np.prod(shp)) * 8
+            total = (total + 4095) & ~4095
+        hosts = self.allgather_bytes(socket.gethostname().encode())
+        ok = len(set(hosts)) == 1
+        name = b''
+        if self.rank == 0 and ok:
+            try:
+                st = os.statvfs('/dev/shm')
+                if st.f_bavail * st.f_frsize > total + (64 << 20):
+                    self._shm_seq = getattr(self, '_shm_seq', 0) + 1
+                    name = ('/dev/shm/vilma_b200_%d_%d' % (os.getpid(), self._shm_seq)).encode()
+                    fd = os.open(name.decode(), os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+                    os.ftruncate(fd, total)
+                    os.close(fd)
+            except OSError:
+                name = b''
+        name = self.broadcast_bytes(name)
+        if not name:
+            return None
+        fd = os.open(name.decode(), os.O_RDWR)
+        try:
+            mm = mmap.mmap(fd, total)
+        finally:
+            os.close(fd)
+        runs = index_runs(snps)
+        outs = []
+        for a, ax, shp, off in zip(locals_, axes, shapes, offs):
+            g = np.frombuffer(mm, dtype=np.float64, count=int(np.prod(shp)), offset=off).reshape(shp)
+            src = [slice(None)] * a.ndim
+            dst = [slice(None)] * a.ndim
+            for g0, g1, l0 in runs:
+                dst[ax] = slice(g0, g1)
+                src[ax] = slice(l0, l0 + (g1 - g0))
+                g[tuple(dst)] = a[tuple(src)]
+            outs.append(g)
+        self.barrier()                       # every shard is in place
+        if self.rank == 0:
+            os.unlink(name.decode())         # the mapping lives on until the last view is dropped
+        return outs
 
     def barrier(self):
         self._dist.barrier()

@@ -701,16 +701,11 @@ class MultiPopVI(VIScheme):
             self._eng.set_delta_grad(self._gtable)
         if len(snps) == self.num_loci:
             self._eng.set_params(vi_mu, vi_delta)
-        elif hasattr(self._eng, 'set_params_device'):
-            # this rank's shard is cut out on the device (one upload of the global arrays)
-            import torch
-            dev = torch.device('cuda', self._eng.ctx.device)
-            idx = torch.as_tensor(snps, device=dev)
-            mu = torch.as_tensor(np.ascontiguousarray(vi_mu)).to(dev).index_select(2, idx).contiguous()
-            dl = torch.as_tensor(np.ascontiguousarray(vi_delta)).to(dev).index_select(0, idx).contiguous()
-            self._eng.set_params_device(mu, dl)
         else:
-            self._eng.set_params(vi_mu[:, :, snps], vi_delta[snps])
+            # this rank's shard only crosses PCIe: whole LD blocks are contiguous SNP ranges, so the
+            # shard is cut out on the host with a few slice copies
+            from .dist import take_runs
+            self._eng.set_params(take_runs(vi_mu, snps, 2), take_runs(vi_delta, snps, 0))
 
     def _set_result(self, stats, resident):
         """Cache the reduced statistics / objective of the (new) accepted device state.
@@ -726,13 +721,13 @@ class MultiPopVI(VIScheme):
         """Resident state -> host tuple (new arrays, reference layouts)."""
         if self._resident is not None:
             return self._resident
-        if self._comm.world > 1 and hasattr(self._eng, 'get_params_device') \
-                and hasattr(self._comm, 'gather_device'):
-            mu_d, delta_d = self._eng.get_params_device()
-            mu = self._comm.gather_device(mu_d, self._snps, self.num_loci, 2)
-            delta = self._comm.gather_device(delta_d, self._snps, self.num_loci, 0)
+        mu, delta = self._eng.get_params()            # this rank's shard: 1/N of the bytes over PCIe
+        shared = None
+        if self._comm.world > 1 and hasattr(self._comm, 'gather_shared'):
+            shared = self._comm.gather_shared([mu, delta], self._snps, self.num_loci, [2, 0])
+        if shared is not None:
+            mu, delta = shared
         else:
-            mu, delta = self._eng.get_params()
             mu = self._comm.gather_snp_axis(mu, self._snps, self.num_loci, 2)
             delta = self._comm.gather_snp_axis(delta, self._snps, self.num_loci, 0)
         self._resident = (mu, delta, np.array(self._hyper))
