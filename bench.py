@@ -832,10 +832,18 @@ def measure(vi, ctx, info, comm, device, args, hbm_peak, peak_src, sampler=None,
         comm.barrier()
         torch.cuda.synchronize()
         tr0, rj0, ev0_ = vi.n_trials, vi.n_rejects, vi.n_evals
+        if args.profile_convergence:     # per-kernel CUDA events over the whole fit (adds ~1 % of event overhead)
+            ctx.profile(True)
+        tmc0 = (C.c_double * 4)()
+        ctx.lib.vb_fit_timing(ctx.handle, tmc0)
         t0 = time.perf_counter()
         vi.optimize(ckpt)
         torch.cuda.synchronize()
         conv_s = float(comm.max(np.array([time.perf_counter() - t0]))[0])
+        cprof = ctx.profile_read() if args.profile_convergence else {}
+        ctx.profile(False)
+        tmc1 = (C.c_double * 4)()
+        ctx.lib.vb_fit_timing(ctx.handle, tmc1)
         ctrials = int(vi.n_trials - tr0)
         out['convergence'] = {'seconds': conv_s, 'iterations': int(vi.num_its_run),
                               'converged': bool(vi.num_its_run < converge),
@@ -843,6 +851,10 @@ def measure(vi, ctx, info, comm, device, args, hbm_peak, peak_src, sampler=None,
                               'rejected_trials': int(vi.n_rejects - rj0), 'max_iterations': converge,
                               'final_elbo': float(vi.trajectory['elbo'][-1]),
                               'snp_updates_per_s': M * ctrials / conv_s,
+                              'kernel_ms': {k: round(v[0], 3) for k, v in cprof.items()},
+                              'kernel_launches': {k: int(v[1]) for k, v in cprof.items()},
+                              'host_enqueue_ms': (tmc1[0] - tmc0[0]) * 1e3,
+                              'host_wait_ms': (tmc1[1] - tmc0[1]) * 1e3,
                               'call': 'MultiPopVI.optimize(checkpoint) from the seeded start, host '
                                       'arrays in and out'}
     return out, ckpt
@@ -1107,6 +1119,8 @@ def main():
                          "'auto' (c3,c5 at N=1; c4 at N=8), 'none', or a comma list")
     ap.add_argument('--no-checkpoint-leg', dest='checkpoint_leg', action='store_false',
                     help='skip the checkpoint-every-5 + resume leg of c5')
+    ap.add_argument('--profile-convergence', action='store_true',
+                    help='time every kernel of the run to convergence with CUDA events (diagnosis)')
     ap.add_argument('--budget-s', type=int, default=int(os.environ.get('BENCH_BUDGET_S', '540')),
                     help='wall-clock budget: optional legs are skipped once it is spent')
     args = ap.parse_args()

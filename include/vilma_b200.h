@@ -59,7 +59,7 @@ int64_t vb_ctx_launch_count(const vb_ctx* ctx);
 /* per-kernel timing with CUDA events on the context's stream (bench.py roofline leg):
  * enable / reset, then read {total ms, launches} for the 4 categories 0 = LD mat-vec kernel,
  * 1 = fused per-SNP kernel, 2 = mat-vec finish kernel (incl. the final reduction / rank exchange in
- * its last CTA), 3 = bookkeeping kernels (annotation sums, convergence partials).  At most 4096
+ * its last CTA), 3 = bookkeeping kernels (annotation sums, convergence partials).  At most 32768
  * launches per category are timed between reads. */
 int vb_ctx_profile(vb_ctx* ctx, int enable);
 int vb_ctx_profile_read(vb_ctx* ctx, double* total_ms4, int64_t* count4);
@@ -87,6 +87,27 @@ int vb_ld_set_factor(vb_ld* ld, int64_t b, const double* U, const double* s, int
 int vb_ld_finalize(vb_ld* ld, const int64_t* perm_host, int64_t nperm);
 int vb_ld_dot(vb_ld* ld, const double* x_dev, double* y_dev);
 int64_t vb_ld_bytes(const vb_ld* ld);
+
+/* ---- set-up on the device ------------------------------------------------------------
+ * SURVEY 8(f) rows 1-2.  For DENSE blocks whose eigenvalues all exceed 1e-12 max -- where the
+ * reference's LowRankMatrix(X, t=1) keeps every eigenpair (matrix_structures.py:15-28, :119), so that
+ * its operator is X, its pseudo-inverse X^-1 and its rank n -- the per-block eigendecomposition
+ * (:17), pseudo-inverse product (inverse_dot, :159-196) and Woodbury ridge solve (ridge_inverse_dot,
+ * :349-387) of VIScheme.__init__ (variational_inference.py:236-252) reduce to two Cholesky
+ * factorisations, done here by one CTA per block.
+ *   n_host[b]          block sizes (<= vb_setup_nmax());  R_dev: the blocks back to back, each n x n
+ *                      row-major and exactly symmetric;  W_dev: workspace of the same size
+ *   z_dev, reg_dev     block-order vectors: z-scores and the ridge diagonal se^2 / prior
+ *   mle_dev            X^-1 z            rmle_dev   X (X^-1 z)          ridge_dev  (X + diag(reg))^-1 (X mle)
+ *   chi_dev[b]         z_b . mle_b       lam_dev[2b], [2b+1]  lambda_min estimate, ||X||_inf
+ *   status_dev[b]      0 = done; 1 = the block is not safely full rank (a pivot or the inverse-iteration
+ *                      estimate of lambda_min fell below the floor): its outputs are undefined and the
+ *                      caller must take the exact eigen path for it. */
+int64_t vb_setup_nmax(void);
+int vb_setup_dense(vb_ctx* ctx, int64_t nblocks, const int64_t* n_host, const double* R_dev,
+                   double* W_dev, const double* z_dev, const double* reg_dev, double* mle_dev,
+                   double* rmle_dev, double* ridge_dev, double* chi_dev, double* lam_dev,
+                   int32_t* status_dev);
 
 /* ---- fit state ----------------------------------------------------------------------
  * vb_fit_create       allocate the device state for K components, P cohorts, M SNPs, A annotations

@@ -459,6 +459,25 @@ def golden_cli_multi(ref, outdir):
     shutil.rmtree(tmp)
 
 
+def golden_cli_sim(ref, outdir):
+    """The reference's own `vilma sim` golden (tests/test.py:2200-2246, --seed 143): its input files
+    and the committed output copy_vilma_sim_run.simpop1.simgwas.tsv.  (The reference's sim path stores
+    LD in HDF5 -- h5py is not installed here -- so the golden is the reference's committed file, not a
+    re-run.)"""
+    td = os.path.join(REF, 'tests', 'test_data')
+    out = {}
+    for f in ['ld_manifest.tsv', 'ld_variants.tsv', 'good_sumstats_beta.tsv', 'good_annotations.tsv']:
+        out['in_' + f] = np.array(read_text(os.path.join(td, f)))
+    out['in_ld_matrix.npy'] = np.load(os.path.join(td, 'ld_matrix.npy'))
+    out['in_sim_weights.npy'] = np.load(os.path.join(td, 'sim_weights.npy'))
+    out['weights_npz_hyper_delta'] = np.load(os.path.join(td, 'sim_weights.npz'))['hyper_delta']
+    with open(os.path.join(td, 'copy_vilma_run.covariance.pkl'), 'rb') as fh:
+        out['covariance'] = np.array(pickle.load(fh)[0])
+    out['argv'] = np.array('--names simpop1 --seed 143')
+    out['gold_simgwas_tsv'] = np.array(read_text(os.path.join(td, 'copy_vilma_sim_run.simpop1.simgwas.tsv')))
+    np.savez_compressed(os.path.join(outdir, 'cli_sim.npz'), **out)
+
+
 # --------------------------------------------------------------------------
 # VI goldens
 # --------------------------------------------------------------------------
@@ -631,6 +650,8 @@ if __name__ == '__main__':
         golden_cli_fit(ref, HERE)
         golden_example(ref, HERE)
         golden_cli_multi(ref, HERE)
+    if not sel or 'sim' in sel:
+        golden_cli_sim(ref, HERE)
     if not sel or 'vischeme' in sel:
         golden_vischeme(ref, HERE)
     if not sel or any(s.startswith('syn') for s in sel):

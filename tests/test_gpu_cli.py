@@ -98,3 +98,24 @@ def test_loader_ld_dot_known_answer(tmp_path):
         ld, missing = load.load_ld_from_schema(os.path.join(d, manifest), variants, [], 1., False)
         v = np.random.random(13)
         assert np.allclose(ld.dot(v), truth.dot(v))
+
+
+def test_cli_sim_matches_reference_golden(tmp_path):
+    """`vilma sim` against the reference's own golden output
+    (tests/test.py:2200-2246, copy_vilma_sim_run.simpop1.simgwas.tsv, --seed 143), with the weights
+    given as a .npy matrix and as a fitted model's .npz; both LD products run on the GPU."""
+    fx = load_case('cli_sim')
+    d = materialize(fx, str(tmp_path))
+    with open(os.path.join(d, 'covs.pkl'), 'wb') as fh:
+        pickle.dump([list(fx['covariance'])], fh)
+    np.savez(os.path.join(d, 'sim_weights_model.npz'), hyper_delta=fx['weights_npz_hyper_delta'])
+    gold = read_tsv(fx['gold_simgwas_tsv'])
+    for weights, out in (('sim_weights.npy', 'run_npy'), ('sim_weights_model.npz', 'run_npz')):
+        run_cli(['sim', '--ld-schema', os.path.join(d, 'ld_manifest.tsv'),
+                 '--sumstats', os.path.join(d, 'good_sumstats_beta.tsv'),
+                 '--annotations', os.path.join(d, 'good_annotations.tsv'),
+                 '--covariance', os.path.join(d, 'covs.pkl'), '--weights', os.path.join(d, weights),
+                 '--output', os.path.join(d, out), '--names', 'simpop1', '--seed', '143'])
+        got = read_tsv(open(os.path.join(d, out + '.simpop1.simgwas.tsv')).read())
+        assert frames_close(gold, got)             # the reference's own tolerance (check_data_frame)
+        assert frames_close(gold, got, rtol=1e-9, atol=1e-12)

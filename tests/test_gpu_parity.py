@@ -225,12 +225,13 @@ def test_line_search_from_huge_L():
 
 @pytest.mark.parametrize('symmetric', [1, 0])
 def test_big_block_slabs_and_factor(symmetric):
-    """Symmetric-packed blocks (ragged sizes, many panels/groups), full-storage blocks wider than
-    one column slab (n > 2048 with packing off, n > 4096 always) and tall factor blocks."""
+    """Symmetric-packed blocks (ragged sizes, many panels/groups; blocks wider than VB_SYM_NMAX = 2816 are
+    cut into 2 and 3 column slabs: 3000, 5000, 5700), full-storage blocks wider than one column slab
+    (packing off) and tall factor blocks."""
     from vilma_b200.engine import DeviceContext, DeviceLD, set_option
     rng = np.random.default_rng(0)
     ctx = DeviceContext.get()
-    sizes = [2500, 37, 1, 8, 515, 2816, 3000]
+    sizes = [2500, 37, 1, 8, 515, 2816, 3000, 5000, 5700, 2817]
     mats = []
     for n in sizes:
         a = rng.standard_normal((n, n))
@@ -259,7 +260,7 @@ def test_big_block_slabs_and_factor(symmetric):
     idx = perm[off:]
     ref[idx] = U @ (s * (U.T @ x[idx]))
     assert np.allclose(y, ref, rtol=1e-12, atol=1e-11 * np.abs(ref).max())
-    dense = sum((4 * n * (n + 1) if (symmetric and n <= 2816) else 8 * n * n) for n in sizes)
+    dense = sum((4 * n * (n + 1) if symmetric else 8 * n * n) for n in sizes)
     assert ld.bytes == dense + 16 * n3 * r3
     # bit-reproducible across launches (dynamic scheduling must not change the summation order)
     assert np.array_equal(y, ld.dot(x))

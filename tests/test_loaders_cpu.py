@@ -127,3 +127,39 @@ def test_cli_fit_flag_surface_matches_reference():
     ref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden',
                                       'cli_fit_flags.json')))
     assert ours == ref
+
+
+def test_sim_draws_match_reference_loop():
+    """vilma_b200.sim vectorises sim.sim_components (one np.random.choice per SNP in the reference,
+    sim.py:73-96) and the 'ip,ik,kqp->qi' einsum (:99-137): same seed -> the same draws, bit for bit."""
+    from oracle import ref_loader
+    if not ref_loader.available()[0]:
+        pytest.skip('oracle/_ref is not installed')
+    import importlib
+    ref_loader.import_reference()
+    ref_sim = importlib.import_module('vilma.sim')
+    from vilma_b200 import sim
+    rng = np.random.default_rng(2)
+    M, A, K, P = 3000, 3, 5, 2
+    ann = np.zeros((M, A))
+    ann[np.arange(M), rng.integers(0, A, M)] = 1
+    w = rng.random((A, K))
+    w /= w.sum(axis=1, keepdims=True)
+    covs = []
+    for _ in range(K):
+        a = rng.standard_normal((P, P))
+        covs.append(a @ a.T + 0.1 * np.eye(P))
+    covs = np.array(covs)
+    np.random.seed(5)
+    want_c = ref_sim.sim_components(ann, w)
+    np.random.seed(5)
+    got_c = sim.sim_components(ann, w)
+    assert np.array_equal(want_c, got_c)
+    np.random.seed(6)
+    want_e = ref_sim.sim_true_effects(ann, w, covs)
+    np.random.seed(6)
+    got_e = sim.sim_true_effects(ann, w, covs)
+    assert np.allclose(want_e, got_e, rtol=1e-14, atol=0)
+    # and the stream is left in the same place
+    assert np.random.random_sample() == (np.random.seed(6), ref_sim.sim_true_effects(ann, w, covs),
+                                         np.random.random_sample())[2]

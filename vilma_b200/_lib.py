@@ -32,6 +32,8 @@ SIGNATURES = {
     'vb_ld_finalize': (C.c_int, [C.c_void_p, c_i64p, C.c_int64]),
     'vb_ld_dot': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'vb_ld_bytes': (C.c_int64, [C.c_void_p]),
+    'vb_setup_nmax': (C.c_int64, []),
+    'vb_setup_dense': (C.c_int, [C.c_void_p, C.c_int64, c_i64p] + [C.c_void_p] * 10),
     'vb_fit_create': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
     'vb_fit_destroy': (C.c_int, [C.c_void_p]),
     'vb_fit_set_fusion': (C.c_int, [C.c_void_p, C.c_int]),

@@ -276,7 +276,11 @@ __global__ void vb_ld_finish_kernel(const double* __restrict__ yb, int64_t len, 
 #define VB_SYM_R 8
 #define VB_SYM_CC 512
 #ifndef VB_SYM_NMAX
-#define VB_SYM_NMAX 2816      // largest block stored packed (accumulators must fit 2 CTAs / SM)
+#define VB_SYM_NMAX 2816      // widest column slab of a packed block (accumulators must fit 2 CTAs / SM)
+#endif
+#define VB_SYM_BLOCK_MAX 65528   // largest block stored packed (16-bit local row indices); larger ones are stored in full
+#ifndef VB_SYM_BELOW_BYTES
+#define VB_SYM_BELOW_BYTES (1024 * 1024)   // group size below a slab's diagonal tile (full-width panels)
 #endif
 #define VB_SYM_STAGE_A (VB_SYM_R * VB_SYM_CC * 8)
 #define VB_SYM_STAGE_X (VB_SYM_CC * 8)
@@ -298,7 +302,14 @@ __global__ void vb_ld_finish_kernel(const double* __restrict__ yb, int64_t len, 
 #define VB_SYM_GROUP_BYTES (512 * 1024)
 #endif
 
-enum { VB_SYM_FIRST = 1, VB_SYM_LASTPANEL = 2, VB_SYM_LASTGROUP = 4, VB_SYM_VALID = 0x8000 };
+// A block wider than VB_SYM_NMAX is cut into COLUMN SLABS of <= VB_SYM_NMAX columns: slab t holds, for
+// every row r >= J0_t, the columns [J0_t, min(J1_t, r + 8)) -- its diagonal tile (a packed symmetric
+// block of its own) followed by full-width panels for the rows below the tile.  Row / column indices of
+// the items are local to the slab, so the column accumulators stay <= VB_SYM_NMAX wide; the elements
+// below the tile are still used twice (row part into y[J1_t..n), column part into y[J0_t..J1_t)): a
+// block of any size streams 4 n (n + 1) bytes instead of 8 n^2.  Groups below the tile (flag BELOW) emit
+// their column sums [0, w) followed by their own rows' sums [w, w + nrows_g).
+enum { VB_SYM_FIRST = 1, VB_SYM_LASTPANEL = 2, VB_SYM_LASTGROUP = 4, VB_SYM_BELOW = 8, VB_SYM_VALID = 0x8000 };
 
 struct __align__(16) VbSymItem {
     uint32_t a_off16;    // chunk offset in the LD store, 16-byte units
@@ -308,11 +319,13 @@ struct __align__(16) VbSymItem {
     uint16_t c0_2;       // chunk's first column within the block / 2
     uint16_t elig2;      // column pairs of this chunk left of the diagonal tile
     uint16_t flags;
-    uint16_t r0;         // panel's first row within the block
+    uint16_t r0;         // panel's first row within the slab
     uint16_t grow0;      // first row of the panel's group
     uint32_t out_off;    // LASTGROUP: offset of the group's partial vector
-    uint32_t out_len;    // LASTGROUP: its length
+    uint16_t out_len;    // LASTGROUP: its length (column sums, with the group's row sums merged in unless BELOW)
+    uint16_t nrows_g;    // LASTGROUP + BELOW: rows of the group, whose sums follow the column sums
 };
+static_assert(sizeof(VbSymItem) == 32, "VbSymItem is copied as two 16-byte words");
 struct VbSymGroup {
     uint32_t first_item, n_items;
 };
@@ -540,15 +553,24 @@ vb_ld_sym_kernel(const double* __restrict__ mat, const VbSymItem* __restrict__ i
             if (item.flags & VB_SYM_LASTGROUP) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const uint32_t grow0 = item.grow0;
+                const bool below = item.flags & VB_SYM_BELOW;
                 for (uint32_t j = threadIdx.x; j < item.out_len; j += VB_LD_CONSUMER_WARPS * 32) {
                     double v = acccol[j];
-                    if (j >= grow0) {
+                    if (!below && j >= grow0) {
 #pragma unroll
                         for (int w = 0; w < VB_LD_CONSUMER_WARPS; ++w)
                             v += rowpart[w * VB_SYM_GROUP_ROWS + (j - grow0)];
                     }
                     ypart[(size_t)item.out_off + j] = v;
                     acccol[j] = 0.0;
+                }
+                if (below) {
+                    for (uint32_t j = threadIdx.x; j < item.nrows_g; j += VB_LD_CONSUMER_WARPS * 32) {
+                        double v = 0.0;
+#pragma unroll
+                        for (int w = 0; w < VB_LD_CONSUMER_WARPS; ++w) v += rowpart[w * VB_SYM_GROUP_ROWS + j];
+                        ypart[(size_t)item.out_off + item.out_len + j] = v;
+                    }
                 }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
@@ -557,22 +579,40 @@ vb_ld_sym_kernel(const double* __restrict__ mat, const VbSymItem* __restrict__ i
     }
 }
 
-// Pack a dense symmetric n x n block (row stride ld) into the panel/chunk layout above.
-// grid.x = number of panels.  Panel p starts at 32 p (p + 1) doubles (closed form, see host).
-__global__ void vb_pack_sym_kernel(const double* __restrict__ R, int64_t ld, int n,
+// Doubles one column slab occupies: `nrows` rows (the slab's first row is its first column), tile width w.
+static inline __host__ __device__ size_t vb_sym_tile_doubles(int64_t w) {
+    const int64_t pf = w / VB_SYM_R;
+    return (size_t)32 * pf * (pf + 1) + ((w % VB_SYM_R) ? (size_t)VB_SYM_R * ((w + 1) & ~int64_t(1)) : 0);
+}
+static inline __host__ __device__ size_t vb_sym_slab_doubles(int64_t nrows, int64_t w) {
+    const int64_t below = nrows > w ? (nrows - w + VB_SYM_R - 1) / VB_SYM_R : 0;
+    return vb_sym_tile_doubles(w) + (size_t)below * VB_SYM_R * w;
+}
+// Pack one column slab of a dense symmetric block into the panel/chunk layout above.  R points at the
+// slab's corner element (row J0, column J0) of the row-major block (row stride ld); the slab has `nrows`
+// rows and tile width w (nrows > w only when w is a multiple of 8).  grid.x = panels of the slab.
+// Tile panel q starts at 32 q (q + 1) doubles; panels below the tile are 8 x w each.
+__global__ void vb_pack_sym_kernel(const double* __restrict__ R, int64_t ld, int nrows, int w,
                                    double* __restrict__ out) {
-    const int p = blockIdx.x;
-    const int r0 = p * VB_SYM_R;
-    int W = min(r0 + VB_SYM_R, n);
-    W = (W + 1) & ~1;
-    double* pout = out + (size_t)32 * p * (p + 1);
+    const int q = blockIdx.x;
+    const int r0 = q * VB_SYM_R;
+    int W;
+    double* pout;
+    if (r0 < w) {
+        W = min(r0 + VB_SYM_R, w);
+        W = (W + 1) & ~1;
+        pout = out + (size_t)32 * q * (q + 1);
+    } else {
+        W = w;
+        pout = out + vb_sym_tile_doubles(w) + (size_t)(q - w / VB_SYM_R) * VB_SYM_R * w;
+    }
     for (int c0 = 0; c0 < W; c0 += VB_SYM_CC) {
         const int wc = min(VB_SYM_CC, W - c0);
         double* cout = pout + (size_t)c0 * VB_SYM_R;
         for (int idx = threadIdx.x; idx < VB_SYM_R * wc; idx += blockDim.x) {
             const int i = idx / wc, c = idx % wc;
             const int r = r0 + i, col = c0 + c;
-            cout[idx] = (r < n && col < n) ? R[(size_t)r * ld + col] : 0.0;
+            cout[idx] = (r < nrows && col < w) ? R[(size_t)r * ld + col] : 0.0;
         }
     }
 }
@@ -590,12 +630,14 @@ struct VbSymGroupOut {
 // its row.  gfirst < 0: the position belongs to a slab-form block.
 struct __align__(16) VbFinRec {
     int32_t pos, snp, gfirst;
-    uint32_t loc_ncover;     // row within the block | (number of covering groups << 16)
+    uint32_t loc_ncover;     // column within its slab (12 bits) | covering groups << 12 (12 bits) | earlier slabs << 24
 };
 __global__ void vb_ld_finish_sym_kernel(const double* __restrict__ yb, int64_t len, int nslab,
                                         const double* __restrict__ ypart,
                                         const VbFinRec* __restrict__ rec,
                                         const VbSymGroupOut* __restrict__ gout,
+                                        const uint32_t* __restrict__ xstart,
+                                        const uint32_t* __restrict__ xoffs,
                                         const double* __restrict__ xb, int64_t nreal,
                                         double* __restrict__ y_snp, double* __restrict__ partial,
                                         const VbFinalArgs fa) {
@@ -608,10 +650,10 @@ __global__ void vb_ld_finish_sym_kernel(const double* __restrict__ yb, int64_t l
         const int32_t q = r.pos;
         double v;
         if (r.gfirst >= 0) {
-            const uint32_t l = r.loc_ncover & 0xffffu;
+            const uint32_t l = r.loc_ncover & 0xfffu;
             v = 0.0;
             uint32_t g = (uint32_t)r.gfirst;          // groups before it do not reach row l
-            const uint32_t gend = g + (r.loc_ncover >> 16);
+            const uint32_t gend = g + ((r.loc_ncover >> 12) & 0xfffu);
             // eight, then four independent loads in flight per step (the first rows of a 2816-row block
             // are covered by ~60 groups: the longest chain sets the kernel's tail); the summation
             // order stays g-ascending
@@ -637,6 +679,12 @@ __global__ void vb_ld_finish_sym_kernel(const double* __restrict__ yb, int64_t l
             for (; g < gend; ++g) {
                 const VbSymGroupOut go = gout[g];
                 if (l < go.len) v += __ldg(&ypart[(size_t)go.off + l]);
+            }
+            // rows of a wide block also collect their row sums from the slabs to the left (slab order)
+            const uint32_t nx = r.loc_ncover >> 24;
+            if (nx) {
+                const uint32_t* xo = xoffs + xstart[j];
+                for (uint32_t e = 0; e < nx; ++e) v += __ldg(&ypart[xo[e]]);
             }
         } else {
             v = yb[q];

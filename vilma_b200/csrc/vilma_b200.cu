@@ -13,6 +13,7 @@
 #include "ld_kernels.cuh"
 #include "snp_kernels.cuh"
 #include "snp_tile_kernel.cuh"
+#include "setup_kernels.cuh"
 
 static_assert(VB_MAX_POPS <= VB_MAXP, "header / kernel cohort limits disagree");
 
@@ -69,6 +70,13 @@ struct LdSlab {          // a row-major matrix rows x ld (ld even), the unit the
     int64_t x_off;       // offset (doubles, even) into xall of the x segment
     int64_t y_off;       // output offset (doubles) of row 0
 };
+struct SymSlab {                   // one column slab of a symmetric-packed block (see ld_kernels.cuh)
+    int64_t J0, w;                 // first column within the block, width of its diagonal tile
+    size_t off;                    // offset (doubles) of its panels in LdPop::mat
+    uint32_t g0, ng;               // its groups [g0, g0 + ng): the tile's first, then those below the tile
+    uint32_t gb0;                  // first group below the tile
+    int64_t Rg;                    // rows per group below the tile
+};
 struct LdBlock {
     int64_t n, r;                  // r < 0: dense
     int64_t xpos, tpos;            // padded block-order / rank-space offsets
@@ -76,8 +84,7 @@ struct LdBlock {
     std::vector<int> slabs2;       // phase 2: dense R or U
     bool filled = false;
     bool sym = false;              // dense block stored symmetric-packed
-    size_t sym_off = 0;            // offset (doubles) of its packed panels in LdPop::mat
-    uint32_t g0 = 0, ng = 0;       // its groups
+    std::vector<SymSlab> sslabs;   // its column slabs (one unless n > VB_SYM_NMAX)
 };
 struct LdPop {
     bool begun = false, finalized = false;
@@ -105,6 +112,7 @@ struct LdPop {
     int64_t n_sgroups = 0;
     double* ypart = nullptr;
     VbFinRec* finrec = nullptr;    // per block-order position: finish-kernel record
+    uint32_t *xstart = nullptr, *xoffs = nullptr;   // wide blocks: row sums a position takes from slabs to its left
     std::vector<VbSymGroupOut> gout_host;
     int64_t bytes = 0;             // algorithmic bytes per mat-vec
 };
@@ -153,7 +161,7 @@ struct vb_ctx {
     std::vector<cudaEvent_t> ev[VB_PROF_CATS];
     size_t ev_used[VB_PROF_CATS] = {0, 0, 0, 0};
 };
-#define VB_PROF_PAIRS 4096
+#define VB_PROF_PAIRS 32768
 static inline void prof_begin(vb_ctx* c, int cat) {
     if (c->profiling && c->ev_used[cat] + 2 <= c->ev[cat].size())
         cudaEventRecord(c->ev[cat][c->ev_used[cat]], c->stream);
@@ -274,7 +282,7 @@ extern "C" const char* vb_source_hash(void) { return g_source_hash + 15; }
 //       K (P+1) KB fits 32 KB per CTA.
 //   "snp_tile" (default -1 = automatic): the K-split tile kernel (snp_tile_kernel.cuh) with W warps per
 //       32-SNP tile; 0 = never, W > 0 = always with that many warps.
-extern "C" int64_t vb_ld_sym_nmax(void) { return VB_SYM_NMAX; }
+extern "C" int64_t vb_ld_sym_nmax(void) { return VB_SYM_BLOCK_MAX; }
 extern "C" int vb_set_option(const char* name, int64_t value) {
     if (name && std::strcmp(name, "ld_symmetric") == 0) {
         g_disable_sym = (value == 0);
@@ -333,7 +341,7 @@ static void free_ld(LdPop& L) {
     cudaFree(L.items1); cudaFree(L.items2); cudaFree(L.sched);
     cudaFree(L.pos); cudaFree(L.snp); cudaFree(L.xbpos); cudaFree(L.fin_counter);
     cudaFree(L.sitems); cudaFree(L.sgroups); cudaFree(L.gout); cudaFree(L.bref); cudaFree(L.ypart);
-    cudaFree(L.finrec);
+    cudaFree(L.finrec); cudaFree(L.xstart); cudaFree(L.xoffs);
     L = LdPop();
 }
 static void free_fit(Fit& f) {
@@ -539,73 +547,103 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
     for (size_t bi = 0; bi < L.blocks.size(); ++bi) {
         LdBlock& b = L.blocks[bi];
         bref[bi].g0 = bref[bi].ng = 0;
-        if (b.r < 0 && b.n <= VB_SYM_NMAX && !g_disable_sym) {
-            // symmetric-packed: panels of 8 rows, chunks of <= 512 columns, groups of ~0.5 MB
+        if (b.r < 0 && b.n <= VB_SYM_BLOCK_MAX && !g_disable_sym) {
+            // symmetric-packed: column slabs of <= VB_SYM_NMAX columns; within a slab panels of 8 rows,
+            // chunks of <= 512 columns, groups of ~0.5 MB (1 MB below the slab's diagonal tile)
             b.sym = true;
-            b.sym_off = cursor;
-            b.g0 = (uint32_t)sgroups.size();
-            const int64_t n = b.n, npan = (n + VB_SYM_R - 1) / VB_SYM_R;
-            size_t group_bytes = 0;
-            int64_t grow0 = 0;
-            // at most ~12 byte-limited groups per block: the finish kernel walks a block's groups
-            const size_t block_bytes = (size_t)4 * n * (n + 1);
-            const size_t group_target = std::max<size_t>(group_bytes_base, block_bytes / VB_SYM_MAX_GROUPS);
-            VbSymGroup cur;
-            cur.first_item = (uint32_t)sitems.size();
-            cur.n_items = 0;
-            for (int64_t p = 0; p < npan; ++p) {
-                const int64_t r0 = p * VB_SYM_R;
-                const int64_t W = even_up(std::min<int64_t>(r0 + VB_SYM_R, n));
-                const size_t poff = cursor + (size_t)32 * p * (p + 1);
-                for (int64_t c0 = 0; c0 < W; c0 += VB_SYM_CC) {
-                    const int64_t wc = std::min<int64_t>(VB_SYM_CC, W - c0);
-                    VbSymItem it;
-                    const size_t a_off = poff + (size_t)c0 * VB_SYM_R;
-                    if ((a_off >> 1) > 0xffffffffull)
-                        return vb_fail("LD store of one cohort exceeds 64 GiB on this rank");
-                    it.a_off16 = (uint32_t)(a_off >> 1);
-                    it.x_off2 = (uint32_t)((b.xpos + c0) >> 1);
-                    it.xr_off2 = (uint32_t)((b.xpos + r0) >> 1);
-                    it.wc2 = (uint16_t)(wc >> 1);
-                    it.c0_2 = (uint16_t)(c0 >> 1);
-                    const int64_t elig = std::max<int64_t>(0, std::min<int64_t>(wc, r0 - c0));
-                    it.elig2 = (uint16_t)(elig >> 1);
-                    it.flags = VB_SYM_VALID;
-                    if (c0 == 0) it.flags |= VB_SYM_FIRST;
-                    if (c0 + VB_SYM_CC >= W) it.flags |= VB_SYM_LASTPANEL;
-                    it.r0 = (uint16_t)r0;
-                    it.grow0 = (uint16_t)grow0;
-                    it.out_off = 0;
-                    it.out_len = 0;
-                    sitems.push_back(it);
-                    cur.n_items++;
-                    group_bytes += (size_t)wc * VB_SYM_R * 8;
+            const int64_t n = b.n;
+            const int64_t wmax = VB_SYM_NMAX & ~int64_t(7);
+            const int64_t T = (n + wmax - 1) / wmax;
+            const int64_t wt = T == 1 ? n : ((((n + T - 1) / T) + 7) & ~int64_t(7));
+            bref[bi].g0 = (uint32_t)sgroups.size();
+            for (int64_t J0 = 0; J0 < n; J0 += wt) {
+                SymSlab sl;
+                sl.J0 = J0;
+                sl.w = std::min<int64_t>(wt, n - J0);
+                sl.off = cursor;
+                sl.g0 = (uint32_t)sgroups.size();
+                const int64_t nr = n - J0, w = sl.w;                   // rows of the slab, tile width
+                const int64_t npan = (nr + VB_SYM_R - 1) / VB_SYM_R;
+                const int64_t qt = (w + VB_SYM_R - 1) / VB_SYM_R;      // panels of the tile
+                if (nr > w && (w % VB_SYM_R)) return vb_fail("internal: ragged tile above full-width panels");
+                sl.Rg = std::max<int64_t>(VB_SYM_R, std::min<int64_t>(
+                    VB_SYM_GROUP_ROWS, (int64_t)(VB_SYM_BELOW_BYTES / (8 * VB_SYM_R * std::max<int64_t>(w, 1))) * VB_SYM_R));
+                const size_t tile_doubles = vb_sym_tile_doubles(w);
+                size_t group_bytes = 0;
+                int64_t grow0 = 0;
+                const size_t group_target = std::max<size_t>(group_bytes_base, (size_t)4 * w * (w + 1) / VB_SYM_MAX_GROUPS);
+                VbSymGroup cur;
+                cur.first_item = (uint32_t)sitems.size();
+                cur.n_items = 0;
+                sl.gb0 = 0;
+                bool gb0_set = false;
+                for (int64_t q = 0; q < npan; ++q) {
+                    const int64_t r0 = q * VB_SYM_R;
+                    const bool below = q >= qt;
+                    const int64_t W = below ? w : even_up(std::min<int64_t>(r0 + VB_SYM_R, w));
+                    const size_t poff = below ? sl.off + tile_doubles + (size_t)(q - qt) * VB_SYM_R * w
+                                              : sl.off + (size_t)32 * q * (q + 1);
+                    if (below && !gb0_set) { sl.gb0 = (uint32_t)sgroups.size(); gb0_set = true; }
+                    for (int64_t c0 = 0; c0 < W; c0 += VB_SYM_CC) {
+                        const int64_t wc = std::min<int64_t>(VB_SYM_CC, W - c0);
+                        VbSymItem it;
+                        const size_t a_off = poff + (size_t)c0 * VB_SYM_R;
+                        if ((a_off >> 1) > 0xffffffffull)
+                            return vb_fail("LD store of one cohort exceeds 64 GiB on this rank");
+                        it.a_off16 = (uint32_t)(a_off >> 1);
+                        it.x_off2 = (uint32_t)((b.xpos + J0 + c0) >> 1);
+                        it.xr_off2 = (uint32_t)((b.xpos + J0 + r0) >> 1);
+                        it.wc2 = (uint16_t)(wc >> 1);
+                        it.c0_2 = (uint16_t)(c0 >> 1);
+                        const int64_t elig = below ? wc : std::max<int64_t>(0, std::min<int64_t>(wc, r0 - c0));
+                        it.elig2 = (uint16_t)(elig >> 1);
+                        it.flags = VB_SYM_VALID;
+                        if (c0 == 0) it.flags |= VB_SYM_FIRST;
+                        if (c0 + VB_SYM_CC >= W) it.flags |= VB_SYM_LASTPANEL;
+                        it.r0 = (uint16_t)r0;
+                        it.grow0 = (uint16_t)grow0;
+                        it.out_off = 0;
+                        it.out_len = 0;
+                        it.nrows_g = 0;
+                        sitems.push_back(it);
+                        cur.n_items++;
+                        group_bytes += (size_t)wc * VB_SYM_R * 8;
+                    }
+                    const int64_t rows_in_group = r0 + VB_SYM_R - grow0;
+                    const bool end_group = q == npan - 1 || q == qt - 1 ||
+                        (below ? rows_in_group >= sl.Rg
+                               : (group_bytes >= group_target || rows_in_group + VB_SYM_R > VB_SYM_GROUP_ROWS));
+                    if (end_group) {
+                        VbSymItem& last = sitems.back();
+                        last.flags |= VB_SYM_LASTGROUP;
+                        last.out_off = (uint32_t)ypart_len;
+                        VbSymGroupOut go;
+                        go.off = last.out_off;
+                        if (below) {
+                            last.flags |= VB_SYM_BELOW;
+                            last.out_len = (uint16_t)w;
+                            last.nrows_g = (uint16_t)(std::min<int64_t>(r0 + VB_SYM_R, nr) - grow0);
+                        } else {
+                            last.out_len = (uint16_t)std::min<int64_t>(r0 + VB_SYM_R, w);
+                        }
+                        go.len = last.out_len;
+                        if (ypart_len + go.len + last.nrows_g > 0xffffffffull) return vb_fail("LD partial buffer too large");
+                        ypart_len += go.len + last.nrows_g;
+                        gout.push_back(go);
+                        sgroups.push_back(cur);
+                        sgroup_bytes.push_back(group_bytes);
+                        cur.first_item = (uint32_t)sitems.size();
+                        cur.n_items = 0;
+                        group_bytes = 0;
+                        grow0 = r0 + VB_SYM_R;
+                    }
                 }
-                if (group_bytes >= group_target || p == npan - 1 ||
-                    r0 + 2 * VB_SYM_R - grow0 > VB_SYM_GROUP_ROWS) {
-                    VbSymItem& last = sitems.back();
-                    last.flags |= VB_SYM_LASTGROUP;
-                    last.out_off = (uint32_t)ypart_len;
-                    last.out_len = (uint32_t)std::min<int64_t>(r0 + VB_SYM_R, n);
-                    VbSymGroupOut go;
-                    go.off = last.out_off;
-                    go.len = last.out_len;
-                    if (ypart_len + go.len > 0xffffffffull) return vb_fail("LD partial buffer too large");
-                    ypart_len += go.len;
-                    gout.push_back(go);
-                    sgroups.push_back(cur);
-                    sgroup_bytes.push_back(group_bytes);
-                    cur.first_item = (uint32_t)sitems.size();
-                    cur.n_items = 0;
-                    group_bytes = 0;
-                    grow0 = r0 + VB_SYM_R;
-                }
+                sl.ng = (uint32_t)sgroups.size() - sl.g0;
+                if (!gb0_set) sl.gb0 = sl.g0 + sl.ng;
+                cursor += vb_sym_slab_doubles(nr, w);
+                b.sslabs.push_back(sl);
             }
-            b.ng = (uint32_t)sgroups.size() - b.g0;
-            bref[bi].g0 = b.g0;
-            bref[bi].ng = b.ng;
-            const int64_t pf = n / VB_SYM_R;
-            cursor += (size_t)32 * pf * (pf + 1) + ((n % VB_SYM_R) ? (size_t)VB_SYM_R * even_up(n) : 0);
+            bref[bi].ng = (uint32_t)sgroups.size() - bref[bi].g0;
             L.bytes += 4 * n * (n + 1);
         } else if (b.r < 0) {
             add_slabs(L, b.slabs2, b.n, b.n, b.xpos, b.xpos, L.xb_len, cursor, dummy2);
@@ -679,9 +717,13 @@ extern "C" int vb_ld_set_dense(vb_ld* h, int64_t b, const double* R, int64_t ld,
             dR = tmp;
             dld = B.n;
         }
-        const int npan = (int)((B.n + VB_SYM_R - 1) / VB_SYM_R);
-        vb_pack_sym_kernel<<<npan, 256, 0, ctx->stream>>>(dR, dld, (int)B.n, L.mat + B.sym_off);
-        CK_LAUNCH(ctx);
+        for (const SymSlab& sl : B.sslabs) {
+            const int64_t nr = B.n - sl.J0;
+            const int npan = (int)((nr + VB_SYM_R - 1) / VB_SYM_R);
+            vb_pack_sym_kernel<<<npan, 256, 0, ctx->stream>>>(dR + (size_t)sl.J0 * dld + sl.J0, dld, (int)nr,
+                                                              (int)sl.w, L.mat + sl.off);
+            CK_LAUNCH(ctx);
+        }
         if (!on_device) {
             CK(cudaStreamSynchronize(ctx->stream));
             cudaFree(tmp);
@@ -775,6 +817,10 @@ extern "C" int vb_ld_finalize(vb_ld* h, const int64_t* perm_host, int64_t nperm)
     std::vector<int32_t> pos(std::max<int64_t>(nperm, 1)), snp(std::max<int64_t>(nperm, 1));
     std::vector<char> seen(L.M, 0);
     std::vector<VbFinRec> rec(std::max<int64_t>(nperm, 1));
+    std::vector<uint32_t> xstart, xoffs;            // wide blocks only
+    bool any_wide = false;
+    for (auto& b : L.blocks) any_wide = any_wide || b.sslabs.size() > 1;
+    if (any_wide) xstart.assign(std::max<int64_t>(nperm, 1), 0);
     int64_t j = 0;
     for (size_t bi = 0; bi < L.blocks.size(); ++bi) {
         LdBlock& b = L.blocks[bi];
@@ -782,11 +828,29 @@ extern "C" int vb_ld_finalize(vb_ld* h, const int64_t* perm_host, int64_t nperm)
             rec[j].gfirst = -1;
             rec[j].loc_ncover = 0;
             if (b.sym) {
-                // first group of the block whose partial vector covers row t (lengths increase)
-                uint32_t g = b.g0;
-                while (g + 1 < b.g0 + b.ng && L.gout_host[g].len <= (uint32_t)t) ++g;
+                // the slab whose columns contain t, and the first of its groups whose partial vector
+                // covers column l = t - J0 (lengths increase through the tile, then stay at w)
+                size_t si = 0;
+                while (si + 1 < b.sslabs.size() && t >= b.sslabs[si].J0 + b.sslabs[si].w) ++si;
+                const SymSlab& sl = b.sslabs[si];
+                const uint32_t l = (uint32_t)(t - sl.J0);
+                uint32_t g = sl.g0;
+                while (g + 1 < sl.g0 + sl.ng && L.gout_host[g].len <= l) ++g;
+                const uint32_t ncover = sl.g0 + sl.ng - g;
+                if (l > 0xfff || ncover > 0xfff || si > 0xff) return vb_fail("internal: finish record overflow");
                 rec[j].gfirst = (int32_t)g;
-                rec[j].loc_ncover = (uint32_t)t | ((b.g0 + b.ng - g) << 16);
+                rec[j].loc_ncover = l | (ncover << 12) | ((uint32_t)si << 24);
+                if (si > 0) {
+                    // its row sums from the slabs to the left: one entry per slab, in slab order
+                    if (xoffs.size() + si > 0xffffffffull) return vb_fail("LD finish table too large");
+                    xstart[j] = (uint32_t)xoffs.size();
+                    for (size_t s2 = 0; s2 < si; ++s2) {
+                        const SymSlab& le = b.sslabs[s2];
+                        const int64_t below = t - (le.J0 + le.w);           // row index below that slab's tile
+                        const uint32_t gb = le.gb0 + (uint32_t)(below / le.Rg);
+                        xoffs.push_back(L.gout_host[gb].off + L.gout_host[gb].len + (uint32_t)(below % le.Rg));
+                    }
+                }
             }
             const int64_t i = perm_host[j];
             if (i < 0 || i >= L.M) return vb_fail("vb_ld_finalize: perm[%lld]=%lld out of range", (long long)j, (long long)i);
@@ -810,6 +874,13 @@ extern "C" int vb_ld_finalize(vb_ld* h, const int64_t* perm_host, int64_t nperm)
     if (L.n_sgroups > 0) {
         CK(cudaMalloc(&L.finrec, rec.size() * sizeof(VbFinRec)));
         CK(cudaMemcpy(L.finrec, rec.data(), rec.size() * sizeof(VbFinRec), cudaMemcpyHostToDevice));
+        if (any_wide) {
+            if (xoffs.empty()) xoffs.push_back(0);
+            CK(cudaMalloc(&L.xstart, xstart.size() * sizeof(uint32_t)));
+            CK(cudaMemcpy(L.xstart, xstart.data(), xstart.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&L.xoffs, xoffs.size() * sizeof(uint32_t)));
+            CK(cudaMemcpy(L.xoffs, xoffs.data(), xoffs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
     }
     CK(cudaMalloc(&L.pos, pos.size() * sizeof(int32_t)));
     CK(cudaMalloc(&L.snp, snp.size() * sizeof(int32_t)));
@@ -864,7 +935,8 @@ static int ld_apply(vb_ctx* ctx, LdPop& L, const double* x_snp, double* y_snp, d
         CK_LAUNCH(ctx);
         prof_begin(ctx, 2);
         vb_ld_finish_sym_kernel<<<grid_fin, 256, 0, st>>>(L.yb, L.xb_len, L.nslab2, L.ypart, L.finrec,
-                                                          L.gout, L.xall, L.nreal, y_snp, partial, fa);
+                                                          L.gout, L.xstart, L.xoffs, L.xall, L.nreal, y_snp,
+                                                          partial, fa);
         prof_end(ctx, 2);
         CK_LAUNCH(ctx);
     } else {
@@ -884,6 +956,55 @@ extern "C" int vb_ld_dot(vb_ld* h, const double* x_dev, double* y_dev) {
     LdPop& L = h->L;
     CK(cudaMemsetAsync(y_dev, 0, (size_t)L.M * sizeof(double), ctx->stream));
     return ld_apply(ctx, L, x_dev, y_dev, nullptr, 296);
+}
+
+// ------------------------------------------------------------------------------------
+// set-up on the device (dense, numerically full-rank blocks)
+// ------------------------------------------------------------------------------------
+extern "C" int64_t vb_setup_nmax(void) { return 4096; }
+extern "C" int vb_setup_dense(vb_ctx* ctx, int64_t nblocks, const int64_t* n_host, const double* R_dev,
+                              double* W_dev, const double* z_dev, const double* reg_dev, double* mle_dev,
+                              double* rmle_dev, double* ridge_dev, double* chi_dev, double* lam_dev,
+                              int32_t* status_dev) {
+    if (!ctx || !n_host || nblocks < 1) return vb_fail("vb_setup_dense: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<VbSetupBlock> blk(nblocks);
+    std::vector<int64_t> order(nblocks);
+    int64_t moff = 0, voff = 0, nmax = 0;
+    for (int64_t b = 0; b < nblocks; ++b) {
+        if (n_host[b] < 1 || n_host[b] > vb_setup_nmax())
+            return vb_fail("vb_setup_dense: block %lld has n=%lld (1..%lld supported)", (long long)b,
+                           (long long)n_host[b], (long long)vb_setup_nmax());
+        blk[b].mat_off = moff; blk[b].vec_off = voff; blk[b].n = (int32_t)n_host[b]; blk[b].pad = (int32_t)b;
+        moff += n_host[b] * n_host[b];
+        voff += n_host[b];
+        nmax = std::max(nmax, n_host[b]);
+        order[b] = b;
+    }
+    // largest blocks first: the tail of the dynamic schedule is made of the cheapest ones
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t c) { return n_host[a] > n_host[c]; });
+    std::vector<VbSetupBlock> sched(nblocks);
+    for (int64_t b = 0; b < nblocks; ++b) sched[b] = blk[order[b]];
+    VbSetupBlock* d_blk = nullptr;
+    uint32_t* d_cnt = nullptr;
+    CK(cudaMalloc(&d_blk, nblocks * sizeof(VbSetupBlock)));
+    CK(cudaMalloc(&d_cnt, sizeof(uint32_t)));
+    CK(cudaMemcpyAsync(d_blk, sched.data(), nblocks * sizeof(VbSetupBlock), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t), ctx->stream));
+    const size_t smem = (2 * (size_t)nmax + 32 * 33 + 2 * 64 * 33) * sizeof(double);
+    CK(cudaFuncSetAttribute(vb_setup_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(200 * 1024) / (smem + 2048)));
+    const int grid = (int)std::min<int64_t>(nblocks, (int64_t)ctx->num_sms * per_sm);
+    vb_setup_dense_kernel<<<grid, VB_SETUP_THREADS, smem, ctx->stream>>>(
+        d_blk, (int)nblocks, d_cnt, R_dev, W_dev, z_dev, reg_dev, mle_dev, rmle_dev, ridge_dev, chi_dev,
+        lam_dev, status_dev, (int)nmax);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_blk);
+    cudaFree(d_cnt);
+    if (e != cudaSuccess) return vb_fail("vb_setup_dense: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------

@@ -1,18 +1,20 @@
-"""Command line front end: `vilma fit ...` (drop-in for vilma.frontend, fit sub-command only).
+"""Command line front end: `vilma fit ...` and `vilma sim ...` (drop-in for vilma.frontend).
 
-The reference's other sub-commands (make_ld_schema, check_ld_schema, sim) are pre-/post-
-processing outside the fitting hot path and are not part of this package.
+The reference's other sub-commands (make_ld_schema, check_ld_schema) are pre-processing /
+diagnostics outside the fitting hot path and are not part of this package.
 """
 import logging
 import sys
 from argparse import ArgumentParser
 
 from . import REFERENCE_VERSION, VERSION
+from .sim import args as sim_args
+from .sim import main as sim
 from .vi_options import args as fit_args
 from .vi_options import main as fit
 
-COMMANDS = {'fit': {'cmd': fit, 'parser': fit_args}}
-OUT_OF_SCOPE = ('make_ld_schema', 'check_ld_schema', 'sim')
+COMMANDS = {'fit': {'cmd': fit, 'parser': fit_args}, 'sim': {'cmd': sim, 'parser': sim_args}}
+OUT_OF_SCOPE = ('make_ld_schema', 'check_ld_schema')
 
 
 def main(argv=None):
@@ -31,7 +33,7 @@ def main(argv=None):
                                 help='Log all information (as opposed to just warnings)')
     argv = sys.argv[1:] if argv is None else list(argv)
     if argv and argv[0] in OUT_OF_SCOPE:
-        parser.error('%s is not part of vilma_b200 (only the `fit` path is); use the '
+        parser.error('%s is not part of vilma_b200 (only the `fit` path and `sim` are); use the '
                      'reference vilma for it' % argv[0])
     args = parser.parse_args(argv)
     try:

@@ -166,6 +166,10 @@ def _consume_mmap_rng():
     np.random.choice(_MMAP_CHARS, size=100)
 
 
+def _make_block(accepted, ldthresh):
+    return LowRankMatrix(accepted, ldthresh, lazy=ldthresh >= 1.0)
+
+
 def load_ld_from_schema(schema_path, variants, denylist, ldthresh, mmap=False):
     """Block-diagonal LD of a schema, matched and oriented to `variants` (load.py:237-354).
 
@@ -211,7 +215,9 @@ def load_ld_from_schema(schema_path, variants, denylist, ldthresh, mmap=False):
             perm.append(idx[~mismatch])
             if mmap:
                 _consume_mmap_rng()
-            pipe.submit(LowRankMatrix, accepted, ldthresh)
+            # --ldthresh 1 (no truncation): the eigendecomposition is postponed -- the GPU set-up
+            # (BlockDiagonalMatrix.device_setup) only needs it for blocks that are not safely full rank
+            pipe.submit(_make_block, accepted, ldthresh)
 
         svds = pipe.results()
     finally:

@@ -32,9 +32,31 @@ def _svd_threshold(matrix, ld_thresh):
 
 
 class LowRankMatrix():
-    """Low rank plus diagonal representation of a symmetric block."""
+    """Low rank plus diagonal representation of a symmetric block.
 
-    def __init__(self, X=None, t=1.0, u=None, s=None, v=None, D=None, hdf_file=None):
+    `lazy=True` (only with a matrix X and t >= 1, i.e. no truncation) postpones the
+    eigendecomposition until something reads `u`, `s`, `v` or `inv_s`: the GPU set-up
+    (BlockDiagonalMatrix.device_setup) certifies per block that no eigenvalue would be dropped and
+    then never needs the factors -- the block's operator is X itself."""
+
+    _LAZY = ('u', 's', 'v', 'inv_s')
+
+    def __init__(self, X=None, t=1.0, u=None, s=None, v=None, D=None, hdf_file=None, lazy=False):
+        self._X = None
+        self.full_rank_certified = False       # set by the GPU set-up: every eigenvalue is kept
+        if X is not None and lazy and t >= 1.0:
+            if any(a is not None for a in (u, s, v, D)):
+                raise ValueError('Cannot provide both a matrix and an SVD decomposition')
+            X = np.asarray(X, dtype=np.float64)
+            if not np.allclose(X, X.T):
+                raise ValueError('Provided matrix is not symmetric')
+            if hdf_file is not None:
+                logging.info('hdf_file is ignored: vilma_b200 keeps LD factors in HBM, not on disk')
+            self._X = X
+            self._t = t
+            self.D = np.zeros(X.shape[0])
+            self.shape = X.shape
+            return
         if X is not None:
             if any(a is not None for a in (u, s, v, D)):
                 raise ValueError('Cannot provide both a matrix and an SVD decomposition')
@@ -50,6 +72,29 @@ class LowRankMatrix():
         if hdf_file is not None:
             logging.info('hdf_file is ignored: vilma_b200 keeps LD factors in HBM, not on disk')
         self.D = np.array(D, dtype=np.float64)
+        self._set_factors(u, s, v)
+
+    def __getattr__(self, name):
+        # only reached when the attribute is missing: the postponed factors of a lazy block
+        if name in LowRankMatrix._LAZY and self.__dict__.get('_X') is not None:
+            u, s, v = _svd_threshold(self._X, self._t)
+            self._set_factors(u, s, v)
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    @property
+    def factorized(self):
+        return 'u' in self.__dict__
+
+    def symmetric_matrix(self):
+        """The block as LAPACK's eigh sees it in the reference (lower triangle mirrored), or None when
+        the block was not given as a matrix."""
+        if self._X is None:
+            return None
+        low = np.tril(self._X)
+        return low + np.tril(self._X, -1).T
+
+    def _set_factors(self, u, s, v):
         big = s > (1e-12 * np.max(s))
         if big.sum() > 0:
             self.u = np.array(u[:, big], dtype=np.float64)
@@ -90,6 +135,8 @@ class LowRankMatrix():
         return vector / self.D - out
 
     def diag(self):
+        if self._X is not None and not self.factorized:
+            return np.diag(self._X).astype(np.float64) + self.D      # every eigenpair kept: the matrix itself
         return np.einsum('ik,ki->i', self.u * self.s, self.v) + self.D
 
     def matrix_power(self, power):
@@ -99,6 +146,8 @@ class LowRankMatrix():
         return LowRankMatrix(u=self.u, s=self.s**power, v=self.v, D=self.D)
 
     def get_rank(self):
+        if self.full_rank_certified and not self.factorized:
+            return self.shape[0]
         if np.allclose(self.D, 0):
             if self.s.shape[0] > 1:
                 return self.s.shape[0]
@@ -152,6 +201,9 @@ class BlockDiagonalMatrix():
     def _device_block(m, choose_storage):
         if not np.all(m.D == 0):
             raise NotImplementedError('device LD blocks must have a zero diagonal part D')
+        if m.full_rank_certified and not m.factorized:
+            # the GPU set-up showed that the reference keeps every eigenpair: U diag(s) U^T is X
+            return {'n': m.shape[0], 'kind': 'dense', 'R': m.symmetric_matrix()}
         n, r = m.u.shape
         if m.s.shape[0] == 1 and m.s[0] == 0:
             # rank-0 dummy block (matrix_structures.py:141-145): the zero matrix
@@ -176,6 +228,110 @@ class BlockDiagonalMatrix():
             self._device[key] = DeviceLD(ctx, self.shape[0], self.device_blocks(),
                                          self.perm[:nreal])
         return self._device[key]
+
+    def device_setup(self, z_scores, regularizer, ctx=None):
+        """Set-up products of VIScheme.__init__ (variational_inference.py:236-252) for this operator:
+
+            mle   = pinv(R) z            (self.inverse.dot)
+            rmle  = R mle                (self.dot)
+            ridge = (R + diag(reg))^-1 rmle   (self.ridge_inverse_dot)
+            chi   = z . mle,   rank = rank(R)
+
+        Dense blocks that were loaded lazily go through the GPU (`vb_setup_dense`: two Cholesky
+        factorisations per block, which also certify that the reference would keep every eigenpair);
+        blocks the kernel declines, truncated or factor-form blocks take the exact host path (eigh,
+        pseudo-inverse, Woodbury -- the reference's own LAPACK calls) on the set-up thread pool.
+        Returns dict(mle, rmle, ridge, chi, rank, gpu_blocks, host_blocks) in this operator's SNP order."""
+        from ._pool import map_blocks
+        n_tot = self.shape[0]
+        z = np.asarray(z_scores, dtype=np.float64)[self.perm]
+        reg = np.zeros(n_tot)
+        reg[:] = regularizer
+        reg = reg[self.perm]
+        out = {k: np.zeros(n_tot) for k in ('mle', 'rmle', 'ridge')}
+        chi, rank = 0.0, 0
+        bounds = list(zip(self.starts[:-1], self.starts[1:]))
+        gpu_ids = [b for b, m in enumerate(self.matrices)
+                   if m._X is not None and not m.factorized and np.all(m.D == 0)]
+        done = set()
+        if gpu_ids:
+            done = self._device_setup_blocks(gpu_ids, bounds, z, reg, out, ctx)
+            for b in done:
+                lo, hi = bounds[b]
+                chi += float(z[lo:hi].dot(out['mle'][lo:hi]))
+                rank += hi - lo
+        rest = [b for b in range(len(self.matrices)) if b not in done]
+
+        def host_one(b):
+            m = self.matrices[b]
+            lo, hi = bounds[b]
+            mle = m.inverse_dot(z[lo:hi])
+            rmle = m._host_dot(mle)
+            shifted = LowRankMatrix(u=m.u, s=m.s, v=m.v, D=m.D + reg[lo:hi])
+            return mle, rmle, shifted.inverse_dot(rmle), m.get_rank()
+        for b, (mle, rmle, ridge, r) in zip(rest, map_blocks(host_one, rest)):
+            lo, hi = bounds[b]
+            out['mle'][lo:hi], out['rmle'][lo:hi], out['ridge'][lo:hi] = mle, rmle, ridge
+            chi += float(z[lo:hi].dot(mle))
+            rank += r
+        res = {k: v[self.inv_perm] for k, v in out.items()}
+        res.update(chi=chi, rank=rank, gpu_blocks=len(done), host_blocks=len(rest))
+        return res
+
+    def _device_setup_blocks(self, ids, bounds, z, reg, out, ctx, chunk_bytes=1 << 30):
+        """Run vb_setup_dense over the lazily loaded dense blocks `ids`, in chunks of ~1 GB of matrix
+        data; fills `out` for the blocks the kernel certified and returns their ids."""
+        import ctypes as C
+        import torch
+        from . import _lib
+        from .engine import DeviceContext
+        if ctx is None:
+            ctx = DeviceContext.get()
+        lib = ctx.lib
+        nmax = int(lib.vb_setup_nmax())
+        ids = [b for b in ids if self.matrices[b].shape[0] <= nmax]
+        dev = torch.device('cuda', ctx.device)
+        done = set()
+        i = 0
+        while i < len(ids):
+            chunk, nbytes = [], 0
+            while i < len(ids) and (not chunk or nbytes + 8 * self.matrices[ids[i]].shape[0]**2 <= chunk_bytes):
+                chunk.append(ids[i])
+                nbytes += 8 * self.matrices[ids[i]].shape[0]**2
+                i += 1
+            ns = np.array([self.matrices[b].shape[0] for b in chunk], dtype=np.int64)
+            host = torch.empty(int((ns**2).sum()), dtype=torch.float64, pin_memory=True)
+            hv = host.numpy()
+            off = 0
+            for b, n in zip(chunk, ns):
+                hv[off:off + n * n] = self.matrices[b].symmetric_matrix().reshape(-1)
+                off += n * n
+            R = host.to(dev, non_blocking=True)
+            W = torch.empty_like(R)
+            zc = torch.as_tensor(np.concatenate([z[bounds[b][0]:bounds[b][1]] for b in chunk]), device=dev)
+            rc = torch.as_tensor(np.concatenate([reg[bounds[b][0]:bounds[b][1]] for b in chunk]), device=dev)
+            mle, rmle, ridge = (torch.zeros_like(zc) for _ in range(3))
+            chi = torch.zeros(len(chunk), dtype=torch.float64, device=dev)
+            lam = torch.zeros(2 * len(chunk), dtype=torch.float64, device=dev)
+            status = torch.ones(len(chunk), dtype=torch.int32, device=dev)
+            ptr = lambda t: C.c_void_p(t.data_ptr())
+            _lib.check(lib.vb_setup_dense(ctx.handle, len(chunk), ns.ctypes.data_as(_lib.c_i64p), ptr(R),
+                                          ptr(W), ptr(zc), ptr(rc), ptr(mle), ptr(rmle), ptr(ridge),
+                                          ptr(chi), ptr(lam), ptr(status)))
+            st = status.cpu().numpy()
+            mle, rmle, ridge = mle.cpu().numpy(), rmle.cpu().numpy(), ridge.cpu().numpy()
+            off = 0
+            for k, (b, n) in enumerate(zip(chunk, ns)):
+                if st[k] == 0:
+                    lo, hi = bounds[b]
+                    out['mle'][lo:hi] = mle[off:off + n]
+                    out['rmle'][lo:hi] = rmle[off:off + n]
+                    out['ridge'][lo:hi] = ridge[off:off + n]
+                    self.matrices[b].full_rank_certified = True
+                    done.add(b)
+                off += n
+            del R, W
+        return done
 
     def restrict(self, snps):
         """The operator of the LD blocks that live entirely inside the sorted global SNP set `snps`

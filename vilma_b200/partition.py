@@ -10,7 +10,7 @@ import numpy as np
 
 def block_cost(n, r):
     """Bytes one mat-vec reads for a block (packed dense vs two factor passes)."""
-    dense = 4 * n * (n + 1) if n <= 2816 else 8 * n * n
+    dense = 4 * n * (n + 1) if n <= 65528 else 8 * n * n      # symmetric-packed (csrc/ld_kernels.cuh)
     return float(min(dense, 16 * n * r))
 
 
@@ -108,7 +108,9 @@ def host_block_lists(ld_mats):
         blocks = []
         for b, m in enumerate(ld.matrices):
             snps = np.asarray(ld.perm[ld.starts[b]:ld.starts[b + 1]], dtype=np.int64)
-            blocks.append((snps, block_cost(m.u.shape[0], m.u.shape[1])))
+            n = m.shape[0]
+            r = m.u.shape[1] if getattr(m, 'factorized', True) else n      # (lazy dense blocks: full rank assumed)
+            blocks.append((snps, block_cost(n, r)))
         out.append(blocks)
     return out
 

@@ -176,18 +176,30 @@ class VIScheme():
             self.chi_stat = np.zeros(self.num_pops)
             self.ld_ranks = np.zeros(self.num_pops)
             self.inverse_betas = np.zeros_like(self.marginal_effects)
+            self.setup_report = []
             for p in range(self.num_pops):
                 ld = self._local_ld[p]
                 se = self.std_errs[p, snps]
                 z_scores = self.marginal_effects[p, snps] / se
-                mle = ld.inverse.dot(z_scores)
-                self.chi_stat[p] = z_scores.dot(mle)
-                this_adj_marg = ld.dot(np.copy(mle), ctx=self._context())
-                this_adj_marg = this_adj_marg / se
-                self.adj_marginal_effects[p, snps] = this_adj_marg
-                self.ld_ranks[p] = ld.get_rank()
                 prior = (2 * gwas_N[p] * init_hg[p] / (self.std_errs[p, :]**-2).sum())
-                inv_z_scores = ld.ridge_inverse_dot(this_adj_marg * se, se**2 / prior)
+                if any(m._X is not None and not m.factorized for m in ld.matrices) \
+                        and self._engine_factory is None:
+                    # lazily loaded dense blocks: pseudo-inverse product, R mle and the ridge start on
+                    # the GPU (two Cholesky factorisations per block), exact host path for the rest
+                    res = ld.device_setup(z_scores, se**2 / prior, ctx=self._context())
+                    self.chi_stat[p] = res['chi']
+                    this_adj_marg = res['rmle'] / se
+                    self.ld_ranks[p] = res['rank']
+                    inv_z_scores = res['ridge']
+                    self.setup_report.append((res['gpu_blocks'], res['host_blocks']))
+                else:
+                    mle = ld.inverse.dot(z_scores)
+                    self.chi_stat[p] = z_scores.dot(mle)
+                    this_adj_marg = ld.dot(np.copy(mle), ctx=self._context())
+                    this_adj_marg = this_adj_marg / se
+                    self.ld_ranks[p] = ld.get_rank()
+                    inv_z_scores = ld.ridge_inverse_dot(this_adj_marg * se, se**2 / prior)
+                self.adj_marginal_effects[p, snps] = this_adj_marg
                 self.inverse_betas[p, snps] = inv_z_scores * se
             if sharded:
                 self.adj_marginal_effects = self._comm.sum(self.adj_marginal_effects)
