@@ -270,9 +270,6 @@ __global__ void vb_ld_finish_kernel(const double* __restrict__ yb, int64_t len, 
 // of consecutive panels (~0.5 MB, the unit of dynamic scheduling); a group writes one partial
 // vector which vb_ld_finish_kernel sums in fixed order.  Algorithmic bytes: 4 n (n + 1).
 // =====================================================================================
-#ifndef VB_SYM_PREFETCH
-#define VB_SYM_PREFETCH 0   // see VB_LD_PREFETCH
-#endif
 #define VB_SYM_R 8
 #define VB_SYM_CC 512
 #ifndef VB_SYM_NMAX
@@ -297,7 +294,7 @@ __global__ void vb_ld_finish_kernel(const double* __restrict__ yb, int64_t len, 
 #define VB_SYM_GROUP_ROWS 256                 // max rows of a group (per-warp row partials in smem)
 #endif
 #define VB_SYM_SMEM (VB_SYM_STAGES * VB_SYM_STAGE + VB_SYM_ACC * 8 + 8 * VB_SYM_GROUP_ROWS * 8 + \
-                     2 * VB_SYM_STAGES * 8 + VB_SYM_STAGES * 32)
+                     2 * VB_SYM_STAGES * 8 + VB_SYM_STAGES * 48)
 #ifndef VB_SYM_GROUP_BYTES
 #define VB_SYM_GROUP_BYTES (512 * 1024)
 #endif
@@ -324,17 +321,149 @@ struct __align__(16) VbSymItem {
     uint32_t out_off;    // LASTGROUP: offset of the group's partial vector
     uint16_t out_len;    // LASTGROUP: its length (column sums, with the group's row sums merged in unless BELOW)
     uint16_t nrows_g;    // LASTGROUP + BELOW: rows of the group, whose sums follow the column sums
+    uint32_t blk;        // block of this operator the item belongs to (fused finish)
+    uint32_t pad_[3];
 };
-static_assert(sizeof(VbSymItem) == 32, "VbSymItem is copied as two 16-byte words");
+static_assert(sizeof(VbSymItem) == 48, "VbSymItem is three 16-byte words");
 struct VbSymGroup {
     uint32_t first_item, n_items;
 };
+
+// ---- finish fused into the mat-vec (operators made of symmetric-packed blocks only) ---------------
+// The CTA that flushes the LAST group of a block (per-block counter) turns the block's group partials
+// into y right away: per row the fixed-order sum over the covering groups (and, for wide blocks, the row
+// sums of the slabs to its left), the [inv_perm] scatter and the block's share of sum z (R z).  The CTA
+// that finishes the last block adds the blocks' shares in block order, and -- for the last cohort of an
+// evaluation -- runs the final reduction and the rank exchange.  No separate finish launch, no tail.
+struct VbSymBlockRef {
+    uint32_t g0, ng;     // groups of this block: [g0, g0+ng)
+};
+struct VbSymGroupOut {
+    uint32_t off, len;
+};
+// One 16-byte record per block-order position (one coalesced LDG.128 instead of four table loads and a
+// dependent block lookup): where its z sits, which SNP it is, and which groups' partial vectors cover
+// its row.  gfirst < 0: the position belongs to a slab-form block.
+struct __align__(16) VbFinRec {
+    int32_t pos, snp, gfirst;
+    uint32_t loc_ncover;     // column within its slab (12 bits) | covering groups << 12 (12 bits) | earlier slabs << 24
+};
+struct VbSymBlockFin {
+    uint32_t pos0;       // first block-order position (index into the finish records) of the block
+    uint32_t n;          // its rows
+    uint32_t ng;         // its groups (all slabs)
+    uint32_t pad;
+};
+struct VbFuseFin {
+    int enabled;
+    uint32_t nblocks;
+    const VbFinRec* rec;
+    const VbSymGroupOut* gout;
+    const uint32_t* xstart;
+    const uint32_t* xoffs;
+    const VbSymBlockFin* bfin;
+    uint32_t* block_cnt;      // [nblocks] groups flushed per block; reset by the finishing CTA
+    uint32_t* done_cnt;       // [2]: blocks finished, CTAs that reduced statistic rows
+    double* part_blk;         // [nblocks] sum z (R z) of each block
+    double* y_snp;            // [M] output in SNP order
+    double* part_fin;         // this cohort's row of VbFinalArgs::part_fin: [0] receives the cohort's total
+    VbFinalArgs fa;
+};
+// y of one row from the group partials: fixed order (covering groups ascending, then the slabs to the left).
+__device__ __forceinline__ double vb_sym_row_sum(const VbFinRec& r, uint32_t j, const double* __restrict__ ypart,
+                                                 const VbSymGroupOut* __restrict__ gout,
+                                                 const uint32_t* __restrict__ xstart,
+                                                 const uint32_t* __restrict__ xoffs) {
+    const uint32_t l = r.loc_ncover & 0xfffu;
+    double v = 0.0;
+    uint32_t g = (uint32_t)r.gfirst;          // groups before it do not reach column l
+    const uint32_t gend = g + ((r.loc_ncover >> 12) & 0xfffu);
+    // eight, then four independent loads in flight per step (the first rows of a 2816-wide slab are
+    // covered by ~60 groups: the longest chain sets the tail); the summation order stays g-ascending
+    for (; g + 8 <= gend; g += 8) {
+        VbSymGroupOut o[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = gout[g + t];
+        double tv[8];
+        tv[0] = l < o[0].len ? __ldcg(&ypart[(size_t)o[0].off + l]) : 0.0;
+#pragma unroll
+        for (int t = 1; t < 8; ++t) tv[t] = __ldcg(&ypart[(size_t)o[t].off + l]);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v += tv[t];
+    }
+    for (; g + 4 <= gend; g += 4) {
+        const VbSymGroupOut o0 = gout[g], o1 = gout[g + 1], o2 = gout[g + 2], o3 = gout[g + 3];
+        const double t0 = l < o0.len ? __ldcg(&ypart[(size_t)o0.off + l]) : 0.0;
+        const double t1 = __ldcg(&ypart[(size_t)o1.off + l]);
+        const double t2 = __ldcg(&ypart[(size_t)o2.off + l]);
+        const double t3 = __ldcg(&ypart[(size_t)o3.off + l]);
+        v += t0; v += t1; v += t2; v += t3;
+    }
+    for (; g < gend; ++g) {
+        const VbSymGroupOut go = gout[g];
+        if (l < go.len) v += __ldcg(&ypart[(size_t)go.off + l]);
+    }
+    const uint32_t nx = r.loc_ncover >> 24;
+    if (nx) {
+        const uint32_t* xo = xoffs + xstart[j];
+        for (uint32_t e = 0; e < nx; ++e) v += __ldcg(&ypart[xo[e]]);
+    }
+    return v;
+}
+
+// Consumer warps (threads 0..255) of the CTA that flushed the last group of block `blk`.
+__device__ __forceinline__ void vb_sym_block_finish(const VbFuseFin& ff, uint32_t blk,
+                                                    const double* __restrict__ ypart,
+                                                    const double* __restrict__ xb, double* scratch, int* s_flag) {
+    __threadfence();                               // the other CTAs' partial vectors (published before their count)
+    const VbSymBlockFin bf = ff.bfin[blk];
+    double acc = 0.0;
+    for (uint32_t t = threadIdx.x; t < bf.n; t += 256) {
+        const uint32_t j = bf.pos0 + t;
+        const VbFinRec r = ff.rec[j];
+        const double v = vb_sym_row_sum(r, j, ypart, ff.gout, ff.xstart, ff.xoffs);
+        ff.y_snp[r.snp] = v;
+        acc = fma(__ldcg(&xb[r.pos]), v, acc);
+    }
+    acc = vb_block_sum<true>(acc, scratch);
+    if (threadIdx.x == 0) {
+        ff.part_blk[blk] = acc;
+        __threadfence();
+        const uint32_t d = atomicAdd(&ff.done_cnt[0], 1u);
+        *s_flag = (d + 1 == ff.nblocks) ? 2 : 1;
+        if (*s_flag == 2) ff.done_cnt[0] = 0;
+    }
+    vb_sync<true>();
+    if (*s_flag != 2) return;
+    // ---- last block of this cohort's operator: the cohort's sum z (R z), blocks in order
+    __threadfence();
+    double tot = 0.0;
+    for (uint32_t b = threadIdx.x; b < ff.nblocks; b += 256) tot += __ldcg(&ff.part_blk[b]);
+    tot = vb_block_sum<true>(tot, scratch);
+    if (threadIdx.x == 0) ff.part_fin[0] = tot;
+    if (!ff.fa.do_final) return;
+    // ---- last cohort of the evaluation: statistics and the rank exchange
+    const int P = ff.fa.P;
+    const int nrows = VB_NSNPSTAT(P) + ff.fa.akf + (ff.fa.part_diff ? 10 : 0);
+    if (threadIdx.x == 0) {
+        // the statistic rows reduced by the first CTAs of this launch (long done; bounded wait)
+        const unsigned long long t0 = vb_globaltimer();
+        while (atomicAdd(&ff.done_cnt[1], 0u) < (uint32_t)nrows && vb_globaltimer() - t0 < 2000000000ull) {}
+        ff.done_cnt[1] = 0;
+        __threadfence();
+        for (int p = 0; p < P; ++p)
+            ff.fa.stats[2 * P + p] = p == P - 1 ? tot : __ldcg(&ff.fa.part_fin[(size_t)p * ff.fa.n_part_fin]);
+        __threadfence();
+    }
+    vb_sync<true>();
+    if (ff.fa.xr.enabled) vb_xrank_exchange<true>(ff.fa.xr, ff.fa.stats);
+}
 
 __global__ void __launch_bounds__(VB_LD_THREADS, VB_SYM_CTAS_PER_SM)
 vb_ld_sym_kernel(const double* __restrict__ mat, const VbSymItem* __restrict__ items,
                  const VbSymGroup* __restrict__ groups, uint32_t n_groups,
                  uint32_t* __restrict__ sched, const double* __restrict__ x,
-                 double* __restrict__ ypart) {
+                 double* __restrict__ ypart, const VbFuseFin ff) {
     extern __shared__ __align__(128) unsigned char smem[];
     double* acccol = reinterpret_cast<double*>(smem + VB_SYM_STAGES * VB_SYM_STAGE);
     double* rowpart = acccol + VB_SYM_ACC;            // [8 warps][VB_SYM_GROUP_ROWS] row partials
@@ -351,89 +480,24 @@ vb_ld_sym_kernel(const double* __restrict__ mat, const VbSymItem* __restrict__ i
         vb_fence_mbar_init();
     }
     for (int j = threadIdx.x; j < VB_SYM_ACC + 8 * VB_SYM_GROUP_ROWS; j += blockDim.x) acccol[j] = 0.0;
+    __shared__ double fin_scratch[32];
+    __shared__ int fin_flag;
     __syncthreads();
+    if (ff.enabled && ff.fa.do_final) {
+        // the per-SNP kernel's partial rows are complete: the first CTAs reduce them straight into stats[]
+        const int nrows = VB_NSNPSTAT(ff.fa.P) + ff.fa.akf + (ff.fa.part_diff ? 10 : 0);
+        int mine = 0;
+        for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+            vb_reduce_row(ff.fa, row, fin_scratch);
+            ++mine;
+        }
+        if (mine && threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&ff.done_cnt[1], (uint32_t)mine);
+        }
+        __syncthreads();
+    }
 
-#if VB_SYM_PREFETCH
-    if (warp == VB_LD_CONSUMER_WARPS) {
-        // producer warp: descriptors are fetched 32 at a time (coalesced), one batch ahead of use;
-        // lane 0 issues the three TMA copies of each item.
-        const uint64_t pol_stream = vb_policy_evict_first();
-        const uint64_t pol_keep = vb_policy_evict_last();
-        uint32_t stage = 0, phase = 0;
-        uint32_t g = 0, g_next = 0;
-        if (lane == 0) {
-            g = atomicAdd(&sched[0], 1u);
-            g_next = atomicAdd(&sched[0], 1u);
-        }
-        g = __shfl_sync(0xffffffffu, g, 0);
-        g_next = __shfl_sync(0xffffffffu, g_next, 0);
-        VbSymGroup grp;
-        grp.first_item = 0; grp.n_items = 0;
-        if (g < n_groups) grp = groups[g];
-        uint32_t boff = 0;
-        const uint4* items4 = reinterpret_cast<const uint4*>(items);
-        uint4 cur_lo = make_uint4(0, 0, 0, 0), cur_hi = make_uint4(0, 0, 0, 0);
-        if (g < n_groups && lane < grp.n_items) {
-            cur_lo = items4[2 * (size_t)(grp.first_item + lane)];
-            cur_hi = items4[2 * (size_t)(grp.first_item + lane) + 1];
-        }
-        while (g < n_groups) {
-            // which batch comes next: the rest of this group, or the first batch of the next one
-            uint32_t ng = g, nboff = boff + 32;
-            VbSymGroup ngrp = grp;
-            uint32_t after = 0;
-            if (nboff >= grp.n_items) {
-                ng = g_next;
-                nboff = 0;
-                if (lane == 0) after = atomicAdd(&sched[0], 1u);
-                after = __shfl_sync(0xffffffffu, after, 0);
-                g_next = after;
-                ngrp.first_item = 0; ngrp.n_items = 0;
-                if (ng < n_groups) ngrp = groups[ng];
-            }
-            uint4 nxt_lo = make_uint4(0, 0, 0, 0), nxt_hi = make_uint4(0, 0, 0, 0);
-            if (ng < n_groups && nboff + lane < ngrp.n_items) {
-                nxt_lo = items4[2 * (size_t)(ngrp.first_item + nboff + lane)];
-                nxt_hi = items4[2 * (size_t)(ngrp.first_item + nboff + lane) + 1];
-            }
-            const uint32_t cnt = min(32u, grp.n_items - boff);
-            for (uint32_t j = 0; j < cnt; ++j) {
-                uint4 lo, hi;
-                lo.x = __shfl_sync(0xffffffffu, cur_lo.x, j); lo.y = __shfl_sync(0xffffffffu, cur_lo.y, j);
-                lo.z = __shfl_sync(0xffffffffu, cur_lo.z, j); lo.w = __shfl_sync(0xffffffffu, cur_lo.w, j);
-                hi.x = __shfl_sync(0xffffffffu, cur_hi.x, j); hi.y = __shfl_sync(0xffffffffu, cur_hi.y, j);
-                hi.z = __shfl_sync(0xffffffffu, cur_hi.z, j); hi.w = __shfl_sync(0xffffffffu, cur_hi.w, j);
-                if (lane == 0) {
-                    vb_mbar_wait(&empty[stage], phase ^ 1);
-                    unsigned char* sa = smem + stage * VB_SYM_STAGE;
-                    const uint32_t wc2 = lo.w & 0xffffu;
-                    const uint32_t bytes_x = wc2 * 16u;
-                    const uint32_t bytes_a = bytes_x * VB_SYM_R;
-                    reinterpret_cast<uint4*>(&slot[stage])[0] = lo;
-                    reinterpret_cast<uint4*>(&slot[stage])[1] = hi;
-                    vb_mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_x + VB_SYM_STAGE_XR);
-                    vb_bulk_g2s(sa, reinterpret_cast<const unsigned char*>(mat) + (size_t)lo.x * 16,
-                                bytes_a, &full[stage], pol_stream);
-                    vb_bulk_g2s(sa + VB_SYM_STAGE_A, x + (size_t)lo.y * 2, bytes_x, &full[stage], pol_keep);
-                    vb_bulk_g2s(sa + VB_SYM_STAGE_A + VB_SYM_STAGE_X, x + (size_t)lo.z * 2,
-                                VB_SYM_STAGE_XR, &full[stage], pol_keep);
-                }
-                if (++stage == VB_SYM_STAGES) { stage = 0; phase ^= 1; }
-            }
-            g = ng; grp = ngrp; boff = nboff;
-            cur_lo = nxt_lo; cur_hi = nxt_hi;
-        }
-        if (lane == 0) {
-            vb_mbar_wait(&empty[stage], phase ^ 1);
-            slot[stage].flags = 0;
-            vb_mbar_arrive(&full[stage]);
-            const uint32_t done = atomicAdd(&sched[1], 1u);
-            if (done == gridDim.x - 1) {
-                sched[0] = 0;
-                sched[1] = 0;
-            }
-        }
-#else
     if (warp == VB_LD_CONSUMER_WARPS) {
         if (lane == 0) {
             const uint64_t pol_stream = vb_policy_evict_first();
@@ -470,7 +534,6 @@ vb_ld_sym_kernel(const double* __restrict__ mat, const VbSymItem* __restrict__ i
                 sched[1] = 0;
             }
         }
-#endif
     } else {
         uint32_t stage = 0, phase = 0;
         double rowacc[VB_SYM_R], xr[VB_SYM_R];
@@ -572,6 +635,18 @@ vb_ld_sym_kernel(const double* __restrict__ mat, const VbSymItem* __restrict__ i
                         ypart[(size_t)item.out_off + item.out_len + j] = v;
                     }
                 }
+                if (ff.enabled) {
+                    // publish this group's partial vector, then count it against its block
+                    __threadfence();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (threadIdx.x == 0) {
+                        const uint32_t c = atomicAdd(&ff.block_cnt[item.blk], 1u);
+                        fin_flag = (c + 1 == ff.bfin[item.blk].ng);
+                        if (fin_flag) ff.block_cnt[item.blk] = 0;
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (fin_flag) vb_sym_block_finish(ff, item.blk, ypart, x, fin_scratch, &fin_flag);
+                }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             if (++stage == VB_SYM_STAGES) { stage = 0; phase ^= 1; }
@@ -619,19 +694,6 @@ __global__ void vb_pack_sym_kernel(const double* __restrict__ R, int64_t ld, int
 
 // Finish for operators with symmetric blocks: positions of symmetric blocks sum their block's
 // group partial vectors (fixed order); other positions take the slab outputs as before.
-struct VbSymBlockRef {
-    uint32_t g0, ng;     // groups of this block: [g0, g0+ng)
-};
-struct VbSymGroupOut {
-    uint32_t off, len;
-};
-// One 16-byte record per block-order position (one coalesced LDG.128 instead of four table loads and a
-// dependent block lookup): where its z sits, which SNP it is, and which groups' partial vectors cover
-// its row.  gfirst < 0: the position belongs to a slab-form block.
-struct __align__(16) VbFinRec {
-    int32_t pos, snp, gfirst;
-    uint32_t loc_ncover;     // column within its slab (12 bits) | covering groups << 12 (12 bits) | earlier slabs << 24
-};
 __global__ void vb_ld_finish_sym_kernel(const double* __restrict__ yb, int64_t len, int nslab,
                                         const double* __restrict__ ypart,
                                         const VbFinRec* __restrict__ rec,
@@ -650,42 +712,7 @@ __global__ void vb_ld_finish_sym_kernel(const double* __restrict__ yb, int64_t l
         const int32_t q = r.pos;
         double v;
         if (r.gfirst >= 0) {
-            const uint32_t l = r.loc_ncover & 0xfffu;
-            v = 0.0;
-            uint32_t g = (uint32_t)r.gfirst;          // groups before it do not reach row l
-            const uint32_t gend = g + ((r.loc_ncover >> 12) & 0xfffu);
-            // eight, then four independent loads in flight per step (the first rows of a 2816-row block
-            // are covered by ~60 groups: the longest chain sets the kernel's tail); the summation
-            // order stays g-ascending
-            for (; g + 8 <= gend; g += 8) {
-                VbSymGroupOut o[8];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) o[t] = gout[g + t];
-                double tv[8];
-                tv[0] = l < o[0].len ? __ldg(&ypart[(size_t)o[0].off + l]) : 0.0;
-#pragma unroll
-                for (int t = 1; t < 8; ++t) tv[t] = __ldg(&ypart[(size_t)o[t].off + l]);
-#pragma unroll
-                for (int t = 0; t < 8; ++t) v += tv[t];
-            }
-            for (; g + 4 <= gend; g += 4) {
-                const VbSymGroupOut o0 = gout[g], o1 = gout[g + 1], o2 = gout[g + 2], o3 = gout[g + 3];
-                const double t0 = l < o0.len ? __ldg(&ypart[(size_t)o0.off + l]) : 0.0;
-                const double t1 = __ldg(&ypart[(size_t)o1.off + l]);
-                const double t2 = __ldg(&ypart[(size_t)o2.off + l]);
-                const double t3 = __ldg(&ypart[(size_t)o3.off + l]);
-                v += t0; v += t1; v += t2; v += t3;
-            }
-            for (; g < gend; ++g) {
-                const VbSymGroupOut go = gout[g];
-                if (l < go.len) v += __ldg(&ypart[(size_t)go.off + l]);
-            }
-            // rows of a wide block also collect their row sums from the slabs to the left (slab order)
-            const uint32_t nx = r.loc_ncover >> 24;
-            if (nx) {
-                const uint32_t* xo = xoffs + xstart[j];
-                for (uint32_t e = 0; e < nx; ++e) v += __ldg(&ypart[xo[e]]);
-            }
+            v = vb_sym_row_sum(r, (uint32_t)j, ypart, gout, xstart, xoffs);
         } else {
             v = yb[q];
             for (int s = 1; s < nslab; ++s) v += yb[(size_t)s * len + q];

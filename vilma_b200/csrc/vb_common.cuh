@@ -137,6 +137,21 @@ __device__ __forceinline__ double vb_log_pos(double x) {
 }
 
 // ---------------------------------------------------------------- reductions
+// Block-wide helpers come in two flavours: the whole CTA (__syncthreads) or, inside the warp-specialised
+// LD kernel, its 8 consumer warps only (named barrier 1 over threads 0..255; the producer warp never joins).
+template <bool CONSUMERS>
+__device__ __forceinline__ void vb_sync() {
+    if constexpr (CONSUMERS) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else __syncthreads();
+}
+template <bool CONSUMERS>
+__device__ __forceinline__ int vb_nwarps() {
+    return CONSUMERS ? 8 : (int)((blockDim.x + 31) >> 5);
+}
+template <bool CONSUMERS>
+__device__ __forceinline__ int vb_nthreads() {
+    return CONSUMERS ? 256 : (int)blockDim.x;
+}
 __device__ __forceinline__ double vb_warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -148,13 +163,14 @@ __device__ __forceinline__ double vb_warp_max(double v) {
     return v;
 }
 // Deterministic block sum (fixed tree).  `scratch` holds >= 32 doubles.  Result valid in thread 0.
+template <bool CONSUMERS = false>
 __device__ __forceinline__ double vb_block_sum(double v, double* scratch) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nwarp = (blockDim.x + 31) >> 5;
+    const int nwarp = vb_nwarps<CONSUMERS>();
     v = vb_warp_sum(v);
-    __syncthreads();
+    vb_sync<CONSUMERS>();
     if (lane == 0) scratch[warp] = v;
-    __syncthreads();
+    vb_sync<CONSUMERS>();
     double r = 0.0;
     if (warp == 0) {
         r = lane < nwarp ? scratch[lane] : 0.0;
@@ -217,18 +233,19 @@ __device__ __forceinline__ unsigned long long vb_globaltimer() {
     return t;
 }
 // All threads of the last block call this after the local statistics are in stats[0 .. n_sum+n_max).
+template <bool CONSUMERS = false>
 __device__ __forceinline__ void vb_xrank_exchange(const VbXrank& xr, double* stats) {
     const int n = xr.n_sum + xr.n_max;
     const int slot = xr.epoch & 1;
-    __syncthreads();
+    vb_sync<CONSUMERS>();
     if (xr.nranks > 1) {
         // 1. my vector -> every rank's mailbox (own included, so the summation order is uniform)
-        for (int idx = threadIdx.x; idx < n * xr.nranks; idx += blockDim.x) {
+        for (int idx = threadIdx.x; idx < n * xr.nranks; idx += vb_nthreads<CONSUMERS>()) {
             const int r = idx / n, t = idx % n;
             xr.peer_box[r][((size_t)slot * VB_XR_MAXRANKS + xr.rank) * VB_XR_MAXVALS + t] = __ldcg(&stats[t]);
         }
         __threadfence_system();
-        __syncthreads();
+        vb_sync<CONSUMERS>();
         if (threadIdx.x < xr.nranks) {
             volatile uint32_t* fl = xr.peer_flag[threadIdx.x] + slot * VB_XR_MAXRANKS + xr.rank;
             *fl = xr.epoch;
@@ -245,7 +262,7 @@ __device__ __forceinline__ void vb_xrank_exchange(const VbXrank& xr, double* sta
             }
         }
         __threadfence_system();
-        __syncthreads();
+        vb_sync<CONSUMERS>();
         // 3. combine in rank order
         if (threadIdx.x < n) {
             const volatile double* box = xr.peer_box[xr.rank] + (size_t)slot * VB_XR_MAXRANKS * VB_XR_MAXVALS;
@@ -261,7 +278,7 @@ __device__ __forceinline__ void vb_xrank_exchange(const VbXrank& xr, double* sta
         xr.host_out[slot * VB_XR_MAXVALS + threadIdx.x] = __ldcg(&stats[threadIdx.x]);
     }
     __threadfence_system();
-    __syncthreads();
+    vb_sync<CONSUMERS>();
     if (threadIdx.x == 0) {
         volatile uint32_t* hf = xr.host_flag + slot;
         *hf = (xr.nranks > 1 && *xr.dev_err) ? 0xffffffffu : xr.epoch;

@@ -59,6 +59,7 @@ static bool g_disable_sym = false;
 static int g_tile_mode = -1;         // vb_set_option("snp_tile", ...): see tile_plan()
 static bool g_ann_slots = true;      // vb_set_option("snp_ann_slots", 0): fused annotation sums by warp shuffles only
 static bool g_snp3_park = true;      // vb_set_option("snp3_park", 0): three-pass kernel parks logits in the output buffers
+static bool g_fused_finish = true;   // vb_set_option("ld_fused_finish", 0): separate finish kernel after the symmetric mat-vec
 static bool g_three_pass = true;     // vb_set_option("snp_three_pass", 0): always the online single-pass kernel   // vb_set_option("ld_symmetric", 0): store dense blocks in full
 
 // ------------------------------------------------------------------------------------
@@ -113,6 +114,12 @@ struct LdPop {
     double* ypart = nullptr;
     VbFinRec* finrec = nullptr;    // per block-order position: finish-kernel record
     uint32_t *xstart = nullptr, *xoffs = nullptr;   // wide blocks: row sums a position takes from slabs to its left
+    // finish fused into the symmetric mat-vec (all blocks symmetric-packed)
+    bool all_sym = false;
+    VbSymBlockFin* bfin = nullptr;
+    uint32_t *block_cnt = nullptr, *done_cnt = nullptr;
+    double* part_blk = nullptr;
+    std::vector<uint32_t> block_ng;
     std::vector<VbSymGroupOut> gout_host;
     int64_t bytes = 0;             // algorithmic bytes per mat-vec
 };
@@ -288,6 +295,10 @@ extern "C" int vb_set_option(const char* name, int64_t value) {
         g_disable_sym = (value == 0);
         return 0;
     }
+    if (name && std::strcmp(name, "ld_fused_finish") == 0) {
+        g_fused_finish = (value != 0);
+        return 0;
+    }
     if (name && std::strcmp(name, "snp_three_pass") == 0) {
         g_three_pass = (value != 0);
         return 0;
@@ -342,6 +353,7 @@ static void free_ld(LdPop& L) {
     cudaFree(L.pos); cudaFree(L.snp); cudaFree(L.xbpos); cudaFree(L.fin_counter);
     cudaFree(L.sitems); cudaFree(L.sgroups); cudaFree(L.gout); cudaFree(L.bref); cudaFree(L.ypart);
     cudaFree(L.finrec); cudaFree(L.xstart); cudaFree(L.xoffs);
+    cudaFree(L.bfin); cudaFree(L.block_cnt); cudaFree(L.done_cnt); cudaFree(L.part_blk);
     L = LdPop();
 }
 static void free_fit(Fit& f) {
@@ -605,6 +617,8 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
                         it.out_off = 0;
                         it.out_len = 0;
                         it.nrows_g = 0;
+                        it.blk = (uint32_t)bi;
+                        it.pad_[0] = it.pad_[1] = it.pad_[2] = 0;
                         sitems.push_back(it);
                         cur.n_items++;
                         group_bytes += (size_t)wc * VB_SYM_R * 8;
@@ -656,6 +670,10 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
             L.bytes += 16 * b.n * b.r;
         }
     }
+    L.all_sym = !L.blocks.empty();
+    for (auto& b : L.blocks) L.all_sym = L.all_sym && b.sym;
+    L.block_ng.resize(L.blocks.size());
+    for (size_t bi = 0; bi < L.blocks.size(); ++bi) L.block_ng[bi] = bref[bi].ng;
     L.mat_len = std::max<size_t>(cursor, 2);
     CK(cudaMalloc(&L.mat, L.mat_len * sizeof(double)));
     CK(cudaMemsetAsync(L.mat, 0, L.mat_len * sizeof(double), ctx->stream));
@@ -874,6 +892,24 @@ extern "C" int vb_ld_finalize(vb_ld* h, const int64_t* perm_host, int64_t nperm)
     if (L.n_sgroups > 0) {
         CK(cudaMalloc(&L.finrec, rec.size() * sizeof(VbFinRec)));
         CK(cudaMemcpy(L.finrec, rec.data(), rec.size() * sizeof(VbFinRec), cudaMemcpyHostToDevice));
+        if (L.all_sym) {
+            std::vector<VbSymBlockFin> bf(L.blocks.size());
+            uint32_t p0 = 0;
+            for (size_t bi = 0; bi < L.blocks.size(); ++bi) {
+                bf[bi].pos0 = p0;
+                bf[bi].n = (uint32_t)L.blocks[bi].n;
+                bf[bi].ng = L.block_ng[bi];
+                bf[bi].pad = 0;
+                p0 += (uint32_t)L.blocks[bi].n;
+            }
+            CK(cudaMalloc(&L.bfin, bf.size() * sizeof(VbSymBlockFin)));
+            CK(cudaMemcpy(L.bfin, bf.data(), bf.size() * sizeof(VbSymBlockFin), cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&L.block_cnt, bf.size() * sizeof(uint32_t)));
+            CK(cudaMemset(L.block_cnt, 0, bf.size() * sizeof(uint32_t)));
+            CK(cudaMalloc(&L.done_cnt, 2 * sizeof(uint32_t)));
+            CK(cudaMemset(L.done_cnt, 0, 2 * sizeof(uint32_t)));
+            CK(cudaMalloc(&L.part_blk, bf.size() * sizeof(double)));
+        }
         if (any_wide) {
             if (xoffs.empty()) xoffs.push_back(0);
             CK(cudaMalloc(&L.xstart, xstart.size() * sizeof(uint32_t)));
@@ -927,12 +963,27 @@ static int ld_apply(vb_ctx* ctx, LdPop& L, const double* x_snp, double* y_snp, d
         prof_end(ctx, 0);
         CK_LAUNCH(ctx);
     }
+    VbFuseFin ff;
+    std::memset(&ff, 0, sizeof(ff));
+    // the finish fused into the mat-vec needs its partial-sum slot: callers without one (vb_ld_dot) and
+    // operators that mix block forms keep the separate finish kernel
+    const bool fused = g_fused_finish && L.all_sym && L.n_sgroups > 0 && partial != nullptr;
+    if (fused) {
+        ff.enabled = 1;
+        ff.nblocks = (uint32_t)L.blocks.size();
+        ff.rec = L.finrec; ff.gout = L.gout; ff.xstart = L.xstart; ff.xoffs = L.xoffs;
+        ff.bfin = L.bfin; ff.block_cnt = L.block_cnt; ff.done_cnt = L.done_cnt; ff.part_blk = L.part_blk;
+        ff.y_snp = y_snp;
+        ff.part_fin = partial;
+        ff.fa = fa;
+    }
     if (L.n_sgroups > 0) {
         prof_begin(ctx, 0);
         vb_ld_sym_kernel<<<ctx->num_sms * VB_SYM_CTAS_PER_SM, VB_LD_THREADS, VB_SYM_SMEM, st>>>(
-            L.mat, L.sitems, L.sgroups, (uint32_t)L.n_sgroups, L.sched + 4, L.xall, L.ypart);
+            L.mat, L.sitems, L.sgroups, (uint32_t)L.n_sgroups, L.sched + 4, L.xall, L.ypart, ff);
         prof_end(ctx, 0);
         CK_LAUNCH(ctx);
+        if (fused) return 0;
         prof_begin(ctx, 2);
         vb_ld_finish_sym_kernel<<<grid_fin, 256, 0, st>>>(L.yb, L.xb_len, L.nslab2, L.ypart, L.finrec,
                                                           L.gout, L.xstart, L.xoffs, L.xall, L.nreal, y_snp,
