@@ -127,6 +127,13 @@ int vb_fit_destroy(vb_ctx* ctx);
 /* fuse_ann != 0: evaluations also return the per-annotation sums of delta (see below); used on
  * multi-GPU runs where a separate pass + reduction per hyper step costs more than it saves */
 int vb_fit_set_fusion(vb_ctx* ctx, int fuse_ann);
+/* on != 0 (fits WITHOUT --learn-scaling): the per-SNP tile kernel caches, per (component, SNP), what
+ * _set_vi_sigma (variational_inference.py:712-733) precomputes in the reference and no update changes:
+ * c_ki = log|S_ki| and d_ki = sum_p (sld_pi/tau_p) S_ki,pp -- 16 K M bytes instead of the reference's three
+ * [K,P,P,M] arrays -- filled by the first evaluation after tau / the grid / the SNP data changed.  With the
+ * cache the C statistics come back merged: stats[P] = tau_0 * sum_p C_p / tau_p, stats[P+1 .. 2P) = 0 (the
+ * log-likelihood formula below is unchanged; the tau update needs the per-cohort values, hence the restriction). */
+int vb_fit_set_cache(vb_ctx* ctx, int on);
 int vb_fit_set_snp_data(vb_ctx* ctx, const double* adj_host, const double* se_host,
                         const double* sld_host, const double* scalings_host,
                         const int32_t* ann_host);

@@ -32,7 +32,7 @@ struct VbSetupBlock {
     int64_t mat_off;     // offset (doubles) of the n x n row-major block in R / W
     int64_t vec_off;     // offset of its entries in the block-order vectors
     int32_t n;
-    int32_t pad;
+    int32_t index;       // position of the block in the caller's arrays (chi, status, lam_est): the schedule is by size
 };
 
 // In-place lower Cholesky of the n x n row-major matrix A (lower triangle referenced and overwritten).
@@ -258,7 +258,7 @@ vb_setup_dense_kernel(const VbSetupBlock* __restrict__ blocks, int nblocks, uint
                 c = fma(z[blk.vec_off + i], s_x[i], c);
             }
             c = vb_block_sum(c, scratch);
-            if (tid == 0) chi[b] = c;
+            if (tid == 0) chi[blk.index] = c;
             __syncthreads();
             // R mle (the reference multiplies back: adj_marginal_effects = (R mle) / se)
             for (int i = tid; i < n; i += VB_SETUP_THREADS) {
@@ -313,9 +313,9 @@ vb_setup_dense_kernel(const VbSetupBlock* __restrict__ blocks, int nblocks, uint
             for (int i = tid; i < n; i += VB_SETUP_THREADS) ridge[blk.vec_off + i] = s_x[i];
         }
         if (tid == 0) {
-            status[b] = st;
-            lam_est[2 * b] = lmin;
-            lam_est[2 * b + 1] = norm_inf;
+            status[blk.index] = st;
+            lam_est[2 * blk.index] = lmin;
+            lam_est[2 * blk.index + 1] = norm_inf;
         }
         __syncthreads();
     }

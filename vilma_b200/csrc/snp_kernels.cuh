@@ -59,6 +59,10 @@ struct VbSnpArgs {
     int fuse_ann;                // 1: per-warp shuffle sums; 2 (vb_snp3_kernel only): per-thread shared-memory slots
     int nsp;                     // row stride of `partial`
     double* partial;             // [gridDim.x][VB_NSNPSTAT(P)]
+    // tile kernel: cached per-(component, SNP) constants c_ki, d_ki ([K][M] each; see snp_tile_kernel.cuh)
+    double* kcache_c;
+    double* kcache_d;
+    double tau0;                 // error_scaling of cohort 0 (the merged C statistic is reported as C_0 = tau_0 X)
 };
 
 // ---- symmetric P x P helpers, lower-triangular packed: idx(i,j) = i(i+1)/2 + j, j <= i

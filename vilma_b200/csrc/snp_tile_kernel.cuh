@@ -25,7 +25,7 @@
 #include "snp_kernels.cuh"
 
 #ifndef VB_TILE_UNROLL_A
-#define VB_TILE_UNROLL_A 2        // independent components in flight per thread (the chain log -> exp is ~100 dependent fp64 ops)
+#define VB_TILE_UNROLL_A 1        // measured (tools/snp_bench.py, round 2): unrolling x2 is within +-2 %, x1 spills nothing
 #endif
 #ifndef VB_TILE_UNROLL_B
 #define VB_TILE_UNROLL_B 4
@@ -37,8 +37,19 @@
 #define VB_TILE_SMEM_PREC 1         // Prec_k (packed lower triangle) and log|Sigma_k| staged in shared memory once per CTA
 #endif
 #ifndef VB_TILE_REGPF
-#define VB_TILE_REGPF 1             // the next component's mu is loaded into registers one iteration ahead
-#endif
+#define VB_TILE_REGPF(P) ((P) <= 2)   // the next component's mu is loaded into registers one iteration ahead
+#endif                                // (measured: +7 % for P = 2, K = 582; -3 % for P = 3 and 5, where registers are scarce)
+// Per-(component, SNP) cache of what depends on neither mu nor delta: Lambda_ki = Prec_k + diag(sld_i / tau)
+// is the same in every evaluation until tau changes, so its log-determinant c_ki = -log|Lambda_ki| and
+// d_ki = sum_p (sld_pi / tau_p) (Lambda_ki^-1)_pp are kept in HBM ([K][M] doubles each).  The kernel is bound
+// by fp64 issue, not by bytes (a REFRESH moves half the bytes of a TRIAL in 90 % of its time): reading 16 more
+// bytes per (k, i) buys ~60 of ~270 fp64 instructions per component in a TRIAL (no log, no inverse of L, no
+// diagonal of S) and the whole factorisation in a REFRESH.  VB_CACHE_FILL computes as before and writes the
+// two arrays; VB_CACHE_USE reads them.  With the cache the second moments are accumulated already weighted,
+// sum_p (sld_p/tau_p)(mu'_p^2 + S_pp), so the per-cohort C_p statistics collapse into one number (returned
+// as C_0 = tau_0 x sum_p C_p / tau_p, zeros elsewhere): exact for the objective, not usable for the tau step,
+// hence only without --learn-scaling.
+enum { VB_CACHE_NONE = 0, VB_CACHE_FILL = 1, VB_CACHE_USE = 2 };
 #define VB_TILE_SNPS 32
 #define VB_TILE_MAXW 16
 // packed lower triangle of Prec_k padded to an even count (16-byte rows: LDS.128 broadcasts) + log|Sigma_k| slot
@@ -54,6 +65,9 @@ struct VbLdl {
     double det;
     __device__ __forceinline__ static constexpr int sl(int i, int j) { return i * (i - 1) / 2 + j; }   // j < i
 
+    // WITH_N: N receives L^-1 (needed for the diagonal of Lambda^-1); otherwise N keeps L itself and solve<false>
+    // substitutes forward and back (same flops, no inverse: the cached-constants path)
+    template <bool WITH_N = true>
     __device__ __forceinline__ void factor(const double (&lam)[P * (P + 1) / 2]) {
         double L[NL > 0 ? NL : 1], U[NL > 0 ? NL : 1];      // U_ij = L_ij D_j
         det = 1.0;
@@ -73,6 +87,11 @@ struct VbLdl {
                 }
             }
         }
+        if constexpr (!WITH_N) {
+#pragma unroll
+            for (int t = 0; t < NL; ++t) N[t] = L[t];
+            return;
+        }
         // N = L^-1: N_ij = -(L_ij + sum_{j<k<i} L_ik N_kj)
 #pragma unroll
         for (int j = 0; j < P; ++j)
@@ -84,22 +103,40 @@ struct VbLdl {
                 N[sl(i, j)] = -v;
             }
     }
-    // x = Lambda^-1 b = N^T D^-1 N b
+    // x = Lambda^-1 b = N^T D^-1 N b   (WITH_N)   or   L^-T D^-1 L^-1 b by substitution
+    template <bool WITH_N = true>
     __device__ __forceinline__ void solve(const double (&b)[P], double (&x)[P]) const {
         double y[P];
+        if constexpr (WITH_N) {
 #pragma unroll
-        for (int i = 0; i < P; ++i) {
-            double v = b[i];
+            for (int i = 0; i < P; ++i) {
+                double v = b[i];
 #pragma unroll
-            for (int j = 0; j < i; ++j) v = fma(N[sl(i, j)], b[j], v);
-            y[i] = v * inv[i];
-        }
+                for (int j = 0; j < i; ++j) v = fma(N[sl(i, j)], b[j], v);
+                y[i] = v * inv[i];
+            }
 #pragma unroll
-        for (int j = 0; j < P; ++j) {
-            double v = y[j];
+            for (int j = 0; j < P; ++j) {
+                double v = y[j];
 #pragma unroll
-            for (int i = j + 1; i < P; ++i) v = fma(N[sl(i, j)], y[i], v);
-            x[j] = v;
+                for (int i = j + 1; i < P; ++i) v = fma(N[sl(i, j)], y[i], v);
+                x[j] = v;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < P; ++i) {                      // L y = b
+                double v = b[i];
+#pragma unroll
+                for (int j = 0; j < i; ++j) v = fma(-N[sl(i, j)], y[j], v);
+                y[i] = v;
+            }
+#pragma unroll
+            for (int j = P - 1; j >= 0; --j) {                 // L^T x = D^-1 y
+                double v = y[j] * inv[j];
+#pragma unroll
+                for (int i = j + 1; i < P; ++i) v = fma(-N[sl(i, j)], x[i], v);
+                x[j] = v;
+            }
         }
     }
     // diagonal of Lambda^-1: S_pp = inv_p + sum_{k>p} N_kp^2 inv_k
@@ -130,18 +167,9 @@ template <int P> struct VbTileCfg {
     static constexpr int MINB = (P == 1) ? 2 : 1;
 };
 
-// --- experimental (VB_TILE_PAIR=1, off by default; not yet measured on a GPU) -----------------------
-// `#pragma unroll 2` on the component loop leaves the two copies SEQUENTIAL in the SASS (the remainder
-// test between them ends the basic block), so a thread still walks one ~100-deep fp64 dependency chain
-// at a time with 4 warps per scheduler.  The paired loop computes two components in one straight-line
-// block (the second one clamped and masked when K runs out) and folds both into the online moments
-// without a branch, so the scheduler can interleave the two chains.
-#ifndef VB_TILE_PAIR
-#define VB_TILE_PAIR 0
-#endif
 template <int P>
 struct VbTileComp {
-    double lk, lkh, quad, sigsum, mu[P], sd[P];     // lkh = lk - log h_k
+    double lk, lkh, quad, sigsum, m2w, mu[P], sd[P];     // lkh = lk - log h_k; m2w = sum_p dt_p (mu'_p^2 + S_pp)
 };
 // Lambda = Prec_k + diag(dt) as a packed lower triangle, from the shared-memory copy (packed, 16-byte
 // rows: the compiler fuses the uniform loads into LDS.128 broadcasts) or from the global [P][P] array.
@@ -167,58 +195,71 @@ __device__ __forceinline__ void vb_tile_load_lambda(const double* __restrict__ p
 #pragma unroll
     for (int p = 0; p < P; ++p) lam[VB_TRI(p, p)] += dt[p];
 }
-// One mixture component of one SNP: Lambda, eta, mu' = S eta, logit and the KL pieces.  `mu` holds the
-// accepted mu on entry (already in registers: loaded one iteration ahead) and mu' on return (TRIAL).
-template <int P, int MODE>
+// One mixture component of one SNP: Lambda, eta, mu' = S eta, logit and the KL pieces.  `mu_in` = the
+// accepted mu (registers); c.mu = mu' on return (TRIAL) or mu (REFRESH).  CACHE == VB_CACHE_USE: `cl_in`
+// (-log|Lambda|) and `dss_in` (sum_p dt_p S_pp) come from the cache and S is only formed where mu' needs
+// it; otherwise they are computed (and returned through cl_out / dss_out for VB_CACHE_FILL).
+template <int P, int MODE, int CACHE>
 __device__ __forceinline__ VbTileComp<P> vb_tile_component(
     const double* __restrict__ pk, const double (&mu_in)[P], const double (&dt)[P],
-    const double (&g)[P], double step, double one_minus_step, double gk, double loghk, double logdetk) {
+    const double (&g)[P], double step, double one_minus_step, double gk, double loghk, double logdetk,
+    double cl_in, double dss_in, double& cl_out, double& dss_out) {
     constexpr int NT = P * (P + 1) / 2;
+    constexpr bool USE = CACHE == VB_CACHE_USE;
     VbTileComp<P> c;
-    double lam[NT], eta[P], det;
+    double lam[NT], eta[P], det = 1.0;
     vb_tile_load_lambda<P>(pk, dt, lam);
 #pragma unroll
-    for (int p = 0; p < P; ++p) c.mu[p] = mu_in[p];
+    for (int p = 0; p < P; ++p) { c.mu[p] = mu_in[p]; c.sd[p] = 0.0; }
     vb_sym_matvec<P>(lam, c.mu, eta);
     if constexpr (MODE == VB_MODE_TRIAL) {
 #pragma unroll
         for (int p = 0; p < P; ++p) eta[p] = step * g[p] + one_minus_step * eta[p];
     }
-    if constexpr (P <= 2) {
-        double S[NT];
-        vb_small_inverse<P>(lam, S, det);
-        if constexpr (MODE == VB_MODE_TRIAL) vb_sym_matvec<P>(S, eta, c.mu);
+    if constexpr (!USE || MODE == VB_MODE_TRIAL) {
+        if constexpr (P <= 2) {
+            double S[NT];
+            vb_small_inverse<P>(lam, S, det);
+            if constexpr (MODE == VB_MODE_TRIAL) vb_sym_matvec<P>(S, eta, c.mu);
 #pragma unroll
-        for (int p = 0; p < P; ++p) c.sd[p] = S[VB_TRI(p, p)];
-    } else {
-        VbLdl<P> f;
-        f.factor(lam);
-        det = f.det;
-        if constexpr (MODE == VB_MODE_TRIAL) f.solve(eta, c.mu);
-        f.diag(c.sd);
+            for (int p = 0; p < P; ++p) c.sd[p] = S[VB_TRI(p, p)];
+        } else {
+            VbLdl<P> f;
+            f.template factor<!USE>(lam);
+            det = f.det;
+            if constexpr (MODE == VB_MODE_TRIAL) f.template solve<!USE>(eta, c.mu);
+            if constexpr (!USE) f.diag(c.sd);
+        }
     }
-    const double cl = -vb_log_pos(det);
-    double dot = 0.0, dmm = 0.0, dss = 0.0;
+    double cl, dss = 0.0, dot = 0.0, dmm = 0.0;
+    if constexpr (USE) cl = cl_in;
+    else cl = -vb_log_pos(det);
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         dot = fma(c.mu[p], eta[p], dot);
         dmm = fma(dt[p] * c.mu[p], c.mu[p], dmm);
-        dss = fma(dt[p], c.sd[p], dss);
+        if constexpr (!USE) dss = fma(dt[p], c.sd[p], dss);
     }
+    if constexpr (USE) dss = dss_in;
+    cl_out = cl;
+    dss_out = dss;
     c.lk = 0.5 * (cl + dot) + gk;
     c.lkh = c.lk - loghk;
     c.quad = dot - dmm;
     c.sigsum = logdetk - cl + ((double)P - dss);
+    c.m2w = dmm + dss;
     return c;
 }
 
-template <int P, int MODE>
+template <int P, int MODE, int CACHE>
 __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp_tile_kernel(const VbSnpArgs a) {
     static_assert(MODE != VB_MODE_EVAL, "EVAL has no softmax: use vb_snp_kernel");
     constexpr int NT = P * (P + 1) / 2;
     constexpr int NS = VB_NSNPSTAT(P);
     constexpr int NV = VB_TILE_NV(P);
     constexpr int UNROLL_A = VB_TILE_UNROLL_A, UNROLL_B = VB_TILE_UNROLL_B;
+    constexpr bool USE = CACHE == VB_CACHE_USE;
+    constexpr bool REGPF = VB_TILE_REGPF(P);
     extern __shared__ double s_tile[];
     const int K = a.K;
     const int64_t M = a.M;
@@ -289,122 +330,62 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
         const double* logh = a.logh + (size_t)an * K;
         const double* gfull = a.gfull + (size_t)an * K;
 
-        // ---- pass A: this thread's slice, online softmax moments
+        // ---- pass A: this thread's slice, online softmax moments.  sm2[p] = sum_k w_k (mu'_p^2 + S_pp);
+        //      with the cache only their dt-weighted sum over p is kept, in sm2[0]
         double mx = -1.0e300, s0 = 0.0, sKd = 0.0, sKq = 0.0, sKs = 0.0, spm[P], sm2[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) { spm[p] = 0.0; sm2[p] = 0.0; }
         const double* pmu_in = a.mu_in + (size_t)warp * PM + i;
         double* pmu_out = (MODE == VB_MODE_TRIAL) ? a.mu_out + (size_t)warp * PM + i : nullptr;
         const size_t kstride = (size_t)W * PM;
+        // cached constants [K][M]: c_ki and d_ki
+        const double* pkc = (CACHE != VB_CACHE_NONE) ? a.kcache_c + (size_t)warp * M + i : nullptr;
+        const double* pkd = (CACHE != VB_CACHE_NONE) ? a.kcache_d + (size_t)warp * M + i : nullptr;
+        const size_t cstride = (size_t)W * M;
         double* sl = s_logit;
-#if VB_TILE_PAIR
-        double mu1[P], mu2[P];
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            mu1[p] = (warp < K) ? __ldg(pmu_in + (size_t)p * M) : 0.0;
-            mu2[p] = (warp + W < K) ? __ldg(pmu_in + kstride + (size_t)p * M) : mu1[p];
-        }
-        for (int k = warp; k < K; k += 2 * W, pmu_in += 2 * kstride, sl += 2 * W * 32) {
-            const bool has2 = k + W < K;
-            const int k2 = has2 ? k + W : k;                       // clamped: recomputes k, masked below
-            double nx1[P], nx2[P];
-#pragma unroll
-            for (int p = 0; p < P; ++p) { nx1[p] = mu1[p]; nx2[p] = mu2[p]; }
-#if VB_TILE_REGPF
-            if (k + 2 * W < K) {
-#pragma unroll
-                for (int p = 0; p < P; ++p) nx1[p] = __ldg(pmu_in + 2 * kstride + (size_t)p * M);
-            }
-            if (k + 3 * W < K) {
-#pragma unroll
-                for (int p = 0; p < P; ++p) nx2[p] = __ldg(pmu_in + 3 * kstride + (size_t)p * M);
-            }
-#endif
-            if (VB_TILE_PREFETCH > 0 && k + 2 * VB_TILE_PREFETCH * W < K) {
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    vb_prefetch_l2(pmu_in + 2 * VB_TILE_PREFETCH * kstride + (size_t)p * M);
-                    vb_prefetch_l2(pmu_in + (2 * VB_TILE_PREFETCH + 1) * kstride + (size_t)p * M);
-                }
-            }
-#if VB_TILE_SMEM_PREC
-            const double ld1 = k_prec[(size_t)k * KSTR + NTP - 1], ld2 = k_prec[(size_t)k2 * KSTR + NTP - 1];
-#else
-            const double ld1 = g_logdet[k], ld2 = g_logdet[k2];
-#endif
-            const VbTileComp<P> c1 = vb_tile_component<P, MODE>(
-                k_prec + (size_t)k * KSTR, mu1, dt, g, step, one_minus_step, gfull[k], logh[k], ld1);
-            const VbTileComp<P> c2 = vb_tile_component<P, MODE>(
-                k_prec + (size_t)k2 * KSTR, mu2, dt, g, step, one_minus_step, gfull[k2], logh[k2], ld2);
-            if constexpr (MODE == VB_MODE_TRIAL) {
-                if (valid) {
-#pragma unroll
-                    for (int p = 0; p < P; ++p) pmu_out[(size_t)p * M] = c1.mu[p];
-                    if (has2) {
-#pragma unroll
-                        for (int p = 0; p < P; ++p) pmu_out[kstride + (size_t)p * M] = c2.mu[p];
-                    }
-                }
-                pmu_out += 2 * kstride;
-            }
-            sl[0] = c1.lk;
-            if (has2) sl[W * 32] = c2.lk;
-            // branch-free online update with both: new maximum, one rescale of the running sums, two weights
-            const double lk2 = has2 ? c2.lk : -1.0e300;
-            const double nmx = fmax(mx, fmax(c1.lk, lk2));
-            const double r = vb_exp_nonpos(mx - nmx);
-            const double w1 = vb_exp_nonpos(c1.lk - nmx);
-            const double w2 = has2 ? vb_exp_nonpos(lk2 - nmx) : 0.0;
-            mx = nmx;
-            s0 = fma(s0, r, w1 + w2);
-            sKd = fma(sKd, r, fma(w1, c1.lkh, w2 * c2.lkh));
-            sKq = fma(sKq, r, fma(w1, c1.quad, w2 * c2.quad));
-            sKs = fma(sKs, r, fma(w1, c1.sigsum, w2 * c2.sigsum));
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                spm[p] = fma(spm[p], r, fma(w1, c1.mu[p], w2 * c2.mu[p]));
-                sm2[p] = fma(sm2[p], r, fma(w1, fma(c1.mu[p], c1.mu[p], c1.sd[p]),
-                                            w2 * fma(c2.mu[p], c2.mu[p], c2.sd[p])));
-            }
-#if VB_TILE_REGPF
-#pragma unroll
-            for (int p = 0; p < P; ++p) { mu1[p] = nx1[p]; mu2[p] = nx2[p]; }
-#else
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                if (k + 2 * W < K) mu1[p] = __ldg(pmu_in + 2 * kstride + (size_t)p * M);
-                mu2[p] = (k + 3 * W < K) ? __ldg(pmu_in + 3 * kstride + (size_t)p * M) : mu1[p];
-            }
-#endif
-        }
-#else
         double mu_cur[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) mu_cur[p] = (warp < K) ? __ldg(pmu_in + (size_t)p * M) : 0.0;
 #pragma unroll UNROLL_A
         for (int k = warp; k < K; k += W, pmu_in += kstride, sl += W * 32) {
             double mu_nx[P];
-#if VB_TILE_REGPF
-            // the next component's mu: issued now, consumed one iteration later (its latency hides
-            // behind this component's ~200-300 dependent fp64 instructions)
+            if constexpr (REGPF) {
+                // the next component's mu: issued now, consumed one iteration later
 #pragma unroll
-            for (int p = 0; p < P; ++p) mu_nx[p] = mu_cur[p];
-            if (k + W < K) {
+                for (int p = 0; p < P; ++p) mu_nx[p] = mu_cur[p];
+                if (k + W < K) {
 #pragma unroll
-                for (int p = 0; p < P; ++p) mu_nx[p] = __ldg(pmu_in + kstride + (size_t)p * M);
+                    for (int p = 0; p < P; ++p) mu_nx[p] = __ldg(pmu_in + kstride + (size_t)p * M);
+                }
             }
-#endif
             if (VB_TILE_PREFETCH > 0 && k + VB_TILE_PREFETCH * W < K) {
 #pragma unroll
                 for (int p = 0; p < P; ++p) vb_prefetch_l2(pmu_in + VB_TILE_PREFETCH * kstride + (size_t)p * M);
+                if constexpr (USE) {
+                    vb_prefetch_l2(pkc + VB_TILE_PREFETCH * cstride);
+                    vb_prefetch_l2(pkd + VB_TILE_PREFETCH * cstride);
+                }
+            }
+            double cl_in = 0.0, dss_in = 0.0, cl_out, dss_out;
+            if constexpr (USE) {
+                cl_in = __ldg(pkc);
+                dss_in = __ldg(pkd);
             }
 #if VB_TILE_SMEM_PREC
             const double ldk = k_prec[(size_t)k * KSTR + NTP - 1];
 #else
             const double ldk = g_logdet[k];
 #endif
-            const VbTileComp<P> c = vb_tile_component<P, MODE>(
-                k_prec + (size_t)k * KSTR, mu_cur, dt, g, step, one_minus_step, gfull[k], logh[k], ldk);
+            const VbTileComp<P> c = vb_tile_component<P, MODE, CACHE>(
+                k_prec + (size_t)k * KSTR, mu_cur, dt, g, step, one_minus_step, gfull[k], logh[k], ldk,
+                cl_in, dss_in, cl_out, dss_out);
+            if constexpr (CACHE == VB_CACHE_FILL) {
+                if (valid) {
+                    const_cast<double*>(pkc)[0] = cl_out;
+                    const_cast<double*>(pkd)[0] = dss_out;
+                }
+            }
+            if constexpr (CACHE != VB_CACHE_NONE) { pkc += cstride; pkd += cstride; }
             if constexpr (MODE == VB_MODE_TRIAL) {
                 if (valid) {
 #pragma unroll
@@ -420,7 +401,10 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
             if (d > 0.0) {
                 s0 *= e; sKd *= e; sKq *= e; sKs *= e;
 #pragma unroll
-                for (int p = 0; p < P; ++p) { spm[p] *= e; sm2[p] *= e; }
+                for (int p = 0; p < P; ++p) {
+                    spm[p] *= e;
+                    if (!USE || p == 0) sm2[p] *= e;
+                }
                 mx = c.lk;
                 w = 1.0;
             }
@@ -431,19 +415,19 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 spm[p] = fma(w, c.mu[p], spm[p]);
-                sm2[p] = fma(w, fma(c.mu[p], c.mu[p], c.sd[p]), sm2[p]);
+                if constexpr (!USE) sm2[p] = fma(w, fma(c.mu[p], c.mu[p], c.sd[p]), sm2[p]);
             }
-#if VB_TILE_REGPF
+            if constexpr (USE) sm2[0] = fma(w, c.m2w, sm2[0]);
+            if constexpr (REGPF) {
 #pragma unroll
-            for (int p = 0; p < P; ++p) mu_cur[p] = mu_nx[p];
-#else
-            if (k + W < K) {
+                for (int p = 0; p < P; ++p) mu_cur[p] = mu_nx[p];
+            } else {
+                if (k + W < K) {
 #pragma unroll
-                for (int p = 0; p < P; ++p) mu_cur[p] = __ldg(pmu_in + kstride + (size_t)p * M);
+                    for (int p = 0; p < P; ++p) mu_cur[p] = __ldg(pmu_in + kstride + (size_t)p * M);
+                }
             }
-#endif
         }
-#endif
         // ---- merge the W slices of each SNP (warp order)
         if (W > 1) {
             double* mine = s_merge + ((size_t)warp * NV) * 32 + lane;
@@ -464,7 +448,7 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
                     spm[p] = fma(r, o[(5 + p) * 32], spm[p]);
-                    sm2[p] = fma(r, o[(5 + P + p) * 32], sm2[p]);
+                    if (!USE || p == 0) sm2[p] = fma(r, o[(5 + P + p) * 32], sm2[p]);
                 }
             }
             mx = gmx;
@@ -493,19 +477,26 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
             tKd += sKd * inv_den - log_norm;
             tKq += 0.5 * sKq * inv_den;
             tKs += 0.5 * sKs * inv_den;
+            double wpm2 = 0.0;                  // sum_p dt_p pm_p^2 (cache path)
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const double pm = spm[p] * inv_den;
-                const double pv = sm2[p] * inv_den - pm * pm;
                 a.pm_out[(size_t)p * M + i] = pm;
                 if (a.xbpos[p]) {
                     const int32_t q = a.xbpos[p][i];
                     if (q >= 0) a.xb[p][q] = pm / a.se[(size_t)p * M + i];
                 }
-                if (a.pv_out) a.pv_out[(size_t)p * M + i] = pv;
                 tA[p] = fma(pm, a.adj[(size_t)p * M + i], tA[p]);
-                tC[p] = fma(a.sld[(size_t)p * M + i], pv, tC[p]);
+                if constexpr (USE) {
+                    wpm2 = fma(dt[p] * pm, pm, wpm2);
+                } else {
+                    const double pv = sm2[p] * inv_den - pm * pm;
+                    if (a.pv_out) a.pv_out[(size_t)p * M + i] = pv;
+                    tC[p] = fma(a.sld[(size_t)p * M + i], pv, tC[p]);
+                }
             }
+            // sum_p (sld_p / tau_p) pv_p in one piece; reported as C_0 = tau_0 x that (the host divides by tau_0)
+            if constexpr (USE) tC[0] += (sm2[0] * inv_den - wpm2) * a.tau0;
         }
     }
 

@@ -59,7 +59,7 @@ static bool g_disable_sym = false;
 static int g_tile_mode = -1;         // vb_set_option("snp_tile", ...): see tile_plan()
 static bool g_ann_slots = true;      // vb_set_option("snp_ann_slots", 0): fused annotation sums by warp shuffles only
 static bool g_snp3_park = true;      // vb_set_option("snp3_park", 0): three-pass kernel parks logits in the output buffers
-static bool g_fused_finish = true;   // vb_set_option("ld_fused_finish", 0): separate finish kernel after the symmetric mat-vec
+static int g_fused_finish = -1;      // vb_set_option("ld_fused_finish", v): -1 automatic, 0 separate finish kernel, 1 always fused
 static bool g_three_pass = true;     // vb_set_option("snp_three_pass", 0): always the online single-pass kernel   // vb_set_option("ld_symmetric", 0): store dense blocks in full
 
 // ------------------------------------------------------------------------------------
@@ -140,6 +140,9 @@ struct Fit {
     double* scratch3 = nullptr;    // [3][P][M]
     double *pm_prev = nullptr, *pm_ckpt = nullptr, *pm_next = nullptr;
     int akf = 0, nsp = 0;          // fused annotation sums per evaluation; partial row stride
+    // tile kernel: cached per-(component, SNP) constants (snp_tile_kernel.cuh); merged C statistic when on
+    bool kcache_on = false, kcache_valid = false;
+    double *kcache_c = nullptr, *kcache_d = nullptr;
     int64_t mutations = 0;         // bumped by every public vb_fit_* call (guards speculative work)
     double* part_snp = nullptr;
     int grid_snp = 0;
@@ -296,7 +299,7 @@ extern "C" int vb_set_option(const char* name, int64_t value) {
         return 0;
     }
     if (name && std::strcmp(name, "ld_fused_finish") == 0) {
-        g_fused_finish = (value != 0);
+        g_fused_finish = (int)value;
         return 0;
     }
     if (name && std::strcmp(name, "snp_three_pass") == 0) {
@@ -365,6 +368,7 @@ static void free_fit(Fit& f) {
     }
     cudaFree(f.scratch3); cudaFree(f.pm_prev); cudaFree(f.pm_ckpt); cudaFree(f.pm_next);
     cudaFree(f.part_snp); cudaFree(f.part_fin); cudaFree(f.part_ann); cudaFree(f.part_diff);
+    cudaFree(f.kcache_c); cudaFree(f.kcache_d);
     f = Fit();
 }
 
@@ -967,7 +971,12 @@ static int ld_apply(vb_ctx* ctx, LdPop& L, const double* x_snp, double* y_snp, d
     std::memset(&ff, 0, sizeof(ff));
     // the finish fused into the mat-vec needs its partial-sum slot: callers without one (vb_ld_dot) and
     // operators that mix block forms keep the separate finish kernel
-    const bool fused = g_fused_finish && L.all_sym && L.n_sgroups > 0 && partial != nullptr;
+    // (a block's finish stalls the CTA that flushed its last group for a few microseconds: worth it when a
+    // CTA finishes about one block per launch -- multi-GPU shards -- not when it finishes six: measured on
+    // C2, 1700 blocks over 296 CTAs: 0.806 ms fused vs 0.706 + 0.045 ms separate)
+    const int64_t ctas = (int64_t)ctx->num_sms * VB_SYM_CTAS_PER_SM;
+    const bool want_fused = g_fused_finish > 0 || (g_fused_finish < 0 && (int64_t)L.blocks.size() <= 2 * ctas);
+    const bool fused = want_fused && L.all_sym && L.n_sgroups > 0 && partial != nullptr;
     if (fused) {
         ff.enabled = 1;
         ff.nblocks = (uint32_t)L.blocks.size();
@@ -1026,7 +1035,7 @@ extern "C" int vb_setup_dense(vb_ctx* ctx, int64_t nblocks, const int64_t* n_hos
         if (n_host[b] < 1 || n_host[b] > vb_setup_nmax())
             return vb_fail("vb_setup_dense: block %lld has n=%lld (1..%lld supported)", (long long)b,
                            (long long)n_host[b], (long long)vb_setup_nmax());
-        blk[b].mat_off = moff; blk[b].vec_off = voff; blk[b].n = (int32_t)n_host[b]; blk[b].pad = (int32_t)b;
+        blk[b].mat_off = moff; blk[b].vec_off = voff; blk[b].n = (int32_t)n_host[b]; blk[b].index = (int32_t)b;
         moff += n_host[b] * n_host[b];
         voff += n_host[b];
         nmax = std::max(nmax, n_host[b]);
@@ -1133,6 +1142,19 @@ extern "C" int vb_fit_set_fusion(vb_ctx* ctx, int fuse_ann) {
     f.akf = on ? f.A * f.K : 0;
     return 0;
 }
+// on != 0: the K-split tile kernel keeps c_ki = -log|Lambda_ki| and d_ki = sum_p (sld/tau)_p S_ki,pp in HBM
+// between evaluations (2 K M doubles) and returns the C statistics merged (see include/vilma_b200.h)
+extern "C" int vb_fit_set_cache(vb_ctx* ctx, int on) {
+    if (!ctx || !ctx->fit.created) return vb_fail("fit state not created");
+    Fit& f = ctx->fit;
+    f.kcache_on = on != 0;
+    f.kcache_valid = false;
+    if (!f.kcache_on) {
+        cudaFree(f.kcache_c); cudaFree(f.kcache_d);
+        f.kcache_c = f.kcache_d = nullptr;
+    }
+    return 0;
+}
 extern "C" int vb_fit_destroy(vb_ctx* ctx) {
     if (!ctx) return 0;
     cudaSetDevice(ctx->device);
@@ -1158,6 +1180,7 @@ extern "C" int vb_fit_set_snp_data(vb_ctx* ctx, const double* adj, const double*
     CK(cudaMemcpyAsync(f.scal, scal, PM * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.ann, ann, (size_t)f.M * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    f.kcache_valid = false;
     return 0;
 }
 extern "C" int vb_fit_set_mixture(vb_ctx* ctx, const double* prec, const double* logdet) {
@@ -1165,6 +1188,7 @@ extern "C" int vb_fit_set_mixture(vb_ctx* ctx, const double* prec, const double*
     CK(cudaMemcpyAsync(f.prec, prec, (size_t)f.K * f.P * f.P * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.logdet, logdet, (size_t)f.K * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    f.kcache_valid = false;
     return 0;
 }
 extern "C" int vb_fit_set_hyper(vb_ctx* ctx, const double* hyper) {
@@ -1198,6 +1222,8 @@ static int fit_set_hyper_tables(vb_ctx* ctx, const double* hyper, const double* 
 }
 extern "C" int vb_fit_set_tau(vb_ctx* ctx, const double* tau) {
     NEED_FIT(ctx);
+    for (int p = 0; p < f.P; ++p)
+        if (f.inv_tau[p] != 1.0 / tau[p]) f.kcache_valid = false;     // Lambda_ki changed
     for (int p = 0; p < f.P; ++p) f.inv_tau[p] = 1.0 / tau[p];
     CK(cudaMemcpyAsync(f.inv_tau_dev, f.inv_tau, VB_MAXP * 8, cudaMemcpyHostToDevice, ctx->stream));
     // pageable source: cudaMemcpyAsync returns once the data is staged, so no stream sync is needed
@@ -1294,14 +1320,20 @@ extern "C" int vb_debug_tile_plan(int P, int K, int64_t M, int akf, int num_sms,
     *W = tp.W; *grid = tp.grid; *smem_bytes = (int64_t)tp.smem;
     return 0;
 }
-template <int P, int MODE>
-static void launch_tile_one(const VbSnpArgs& a, const TilePlan& tp, cudaStream_t st) {
+template <int P, int MODE, int CACHE>
+static void launch_tile_cache(const VbSnpArgs& a, const TilePlan& tp, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(vb_snp_tile_kernel<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(vb_snp_tile_kernel<P, MODE, CACHE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set = true;
     }
-    vb_snp_tile_kernel<P, MODE><<<tp.grid, 32 * tp.W, tp.smem, st>>>(a);
+    vb_snp_tile_kernel<P, MODE, CACHE><<<tp.grid, 32 * tp.W, tp.smem, st>>>(a);
+}
+template <int P, int MODE>
+static void launch_tile_one(const VbSnpArgs& a, const TilePlan& tp, cudaStream_t st, int cache) {
+    if (cache == VB_CACHE_USE) launch_tile_cache<P, MODE, VB_CACHE_USE>(a, tp, st);
+    else if (cache == VB_CACHE_FILL) launch_tile_cache<P, MODE, VB_CACHE_FILL>(a, tp, st);
+    else launch_tile_cache<P, MODE, VB_CACHE_NONE>(a, tp, st);
 }
 template <int MODE>
 static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
@@ -1310,15 +1342,37 @@ static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
     if constexpr (MODE != VB_MODE_EVAL) {
         const TilePlan tp = tile_plan(ctx, ctx->fit, a.fuse_ann ? a.A * a.K : 0);
         if (tp.W > 0) {
-            ctx->fit.snp_grid_used = tp.grid;
+            Fit& f = ctx->fit;
+            f.snp_grid_used = tp.grid;
+            // cached constants: the first evaluation after tau / the grid / the SNP data changed fills them
+            int cache = VB_CACHE_NONE;
+            VbSnpArgs ac = a;
+            if (f.kcache_on && !a.pv_out) {
+                if (!f.kcache_c) {
+                    const size_t KM = (size_t)f.K * f.M;
+                    if (cudaMalloc(&f.kcache_c, KM * 8) != cudaSuccess || cudaMalloc(&f.kcache_d, KM * 8) != cudaSuccess) {
+                        cudaGetLastError();
+                        cudaFree(f.kcache_c);
+                        f.kcache_c = f.kcache_d = nullptr;
+                        f.kcache_on = false;               // not enough memory: keep recomputing
+                    }
+                }
+                if (f.kcache_on) {
+                    cache = f.kcache_valid ? VB_CACHE_USE : VB_CACHE_FILL;
+                    ac.kcache_c = f.kcache_c;
+                    ac.kcache_d = f.kcache_d;
+                    ac.tau0 = 1.0 / f.inv_tau[0];
+                    f.kcache_valid = true;
+                }
+            }
             prof_begin(ctx, 1);
             switch (P) {
-                case 1: launch_tile_one<1, MODE>(a, tp, st); break;
-                case 2: launch_tile_one<2, MODE>(a, tp, st); break;
-                case 3: launch_tile_one<3, MODE>(a, tp, st); break;
-                case 4: launch_tile_one<4, MODE>(a, tp, st); break;
-                case 5: launch_tile_one<5, MODE>(a, tp, st); break;
-                case 6: launch_tile_one<6, MODE>(a, tp, st); break;
+                case 1: launch_tile_one<1, MODE>(ac, tp, st, cache); break;
+                case 2: launch_tile_one<2, MODE>(ac, tp, st, cache); break;
+                case 3: launch_tile_one<3, MODE>(ac, tp, st, cache); break;
+                case 4: launch_tile_one<4, MODE>(ac, tp, st, cache); break;
+                case 5: launch_tile_one<5, MODE>(ac, tp, st, cache); break;
+                case 6: launch_tile_one<6, MODE>(ac, tp, st, cache); break;
                 default: return vb_fail("unsupported cohort count %d", P);
             }
             prof_end(ctx, 1);

@@ -220,6 +220,14 @@ class CudaEngine:
         self._diff = torch.zeros(self.N_DIFF, dtype=torch.float64, device=dev)
         self.ld_bytes = sum(ld_.bytes for ld_ in self.lds)
         self.native_ready = False
+        self.merged_c = False
+
+    def set_cache(self, on):
+        """Keep log|S_ki| and sum_p (sld/tau)_p S_ki,pp in HBM between evaluations (tile kernel).  The C
+        statistics then come back merged into stats[P] (see include/vilma_b200.h): only for fits that do
+        not learn the error scaling."""
+        _lib.check(self.lib.vb_fit_set_cache(self.ctx.handle, 1 if on else 0))
+        self.merged_c = bool(on)
 
     # ---- small inputs
     def set_hyper(self, hyper):

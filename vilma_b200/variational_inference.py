@@ -518,6 +518,11 @@ class VIScheme():
     def _update_error_scaling_dev(self):
         """tau_p = [chi_p - 2 pm.adj + z^T R z + sum sld pv] / rank_p   (reference :472-486)."""
         P = self.num_pops
+        if getattr(self._eng, 'merged_c', False):
+            # (direct call on a model that does not learn tau: the cached-constants path merges the
+            # per-cohort C statistics; evaluate the resident state with the kernel that keeps them apart)
+            self._res_stats = self._comm.sum(self._eng.eval())
+            self.n_evals += 1
         s = self._res_stats
         self.error_scaling = (self.chi_stat - 2 * s[0:P] + s[2 * P:3 * P] + s[P:2 * P]) \
             / self.ld_ranks
@@ -602,6 +607,9 @@ class MultiPopVI(VIScheme):
                     lds.append(ld.to_device(ctx))
             self._eng = CudaEngine(ctx, lds, **pieces)
             self._eng.init_comm(self._comm)
+            # state-independent per-(component, SNP) constants stay in HBM between evaluations unless the
+            # error scaling is learned (its update needs the per-cohort C statistics the cache merges)
+            self._eng.set_cache(not self.scale_se)
         self._eng.set_tau(self.error_scaling)
 
     # ------------------------------------------------------------------ hidden state
