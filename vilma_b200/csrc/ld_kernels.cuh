@@ -654,6 +654,163 @@ vb_ld_sym_kernel(const double* __restrict__ mat, const VbSymItem* __restrict__ i
     }
 }
 
+// =====================================================================================
+// Factor blocks read ONCE: R_b = U diag(s) U^T with s >= 0 is stored as U' = U diag(sqrt(s)) cut into
+// chunks of c columns, a chunk being c x n_pad column-major and contiguous (one TMA bulk copy).  A chunk
+// staged in shared memory is used twice before it is released:
+//     pass 1   t_j  = sum_i U'[i][j] x[i]        one warp per column, fixed shuffle tree
+//     pass 2   y_i += sum_j U'[i][j] t_j         every thread owns its row pairs, accumulators in registers
+// so a mat-vec streams 8 n r bytes instead of the 16 n r of the two-pass form (V' = diag(s) U^T, then U):
+// with --ldthresh truncation (r < n/2) that is also less than the 4 n (n+1) of the packed dense block.
+// Groups of consecutive chunks of a block (~0.5 MB, the unit of dynamic claiming) emit one partial y
+// vector each, summed in group order by the finish kernel like the symmetric kernel's.  n <= VB_SYM_NMAX.
+// =====================================================================================
+#define VB_FAC_STAGE (44 * 1024)                    // bytes per stage: x (n_pad) + c columns (c n_pad)
+#define VB_FAC_STAGES 2
+#define VB_FAC_MAXC 32
+#define VB_FAC_RP ((VB_SYM_NMAX / 2 + 255) / 256)   // row pairs per thread (6)
+#define VB_FAC_SMEM (VB_FAC_STAGES * VB_FAC_STAGE + VB_FAC_MAXC * 8 + 2 * VB_FAC_STAGES * 8 + VB_FAC_STAGES * 16)
+enum { VB_FAC_FIRST = 1, VB_FAC_LASTGROUP = 4, VB_FAC_VALID = 0x8000 };
+struct __align__(16) VbFacItem {
+    uint32_t a_off16;    // chunk offset in the LD store, 16-byte units
+    uint32_t x_off2;     // x offset of the block, units of 2 doubles
+    uint16_t n2;         // n_pad / 2
+    uint16_t c;          // columns in this chunk
+    uint16_t flags;
+    uint16_t pad;
+    uint32_t out_off;    // LASTGROUP: offset of the group's partial vector (length 2 n2)
+};
+static inline __host__ __device__ int vb_fac_chunk_cols(int64_t n_pad) {
+    const int64_t c = (int64_t)VB_FAC_STAGE / (8 * n_pad) - 1;
+    return (int)(c < 1 ? 1 : (c > VB_FAC_MAXC ? VB_FAC_MAXC : c));
+}
+
+__global__ void __launch_bounds__(VB_LD_THREADS, 2)
+vb_ld_fac_kernel(const double* __restrict__ mat, const VbFacItem* __restrict__ items,
+                 const VbSymGroup* __restrict__ groups, uint32_t n_groups, uint32_t* __restrict__ sched,
+                 const double* __restrict__ x, double* __restrict__ ypart) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    double* s_t = reinterpret_cast<double*>(smem + VB_FAC_STAGES * VB_FAC_STAGE);       // [VB_FAC_MAXC]
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_t + VB_FAC_MAXC);
+    uint64_t* empty = full + VB_FAC_STAGES;
+    VbFacItem* slot = reinterpret_cast<VbFacItem*>(empty + VB_FAC_STAGES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < VB_FAC_STAGES; ++s) {
+            vb_mbar_init(&full[s], 1);
+            vb_mbar_init(&empty[s], VB_LD_CONSUMER_WARPS);
+        }
+        vb_fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp == VB_LD_CONSUMER_WARPS) {
+        if (lane == 0) {
+            const uint64_t pol_stream = vb_policy_evict_first();
+            const uint64_t pol_keep = vb_policy_evict_last();
+            uint32_t stage = 0, phase = 0;
+            uint32_t g = atomicAdd(&sched[0], 1u);
+            while (g < n_groups) {
+                const uint32_t g_next = atomicAdd(&sched[0], 1u);
+                const VbSymGroup grp = groups[g];
+                for (uint32_t it = grp.first_item; it < grp.first_item + grp.n_items; ++it) {
+                    const VbFacItem item = items[it];
+                    vb_mbar_wait(&empty[stage], phase ^ 1);
+                    unsigned char* sa = smem + stage * VB_FAC_STAGE;
+                    const uint32_t bytes_x = (uint32_t)item.n2 * 16u;
+                    const uint32_t bytes_a = bytes_x * item.c;
+                    slot[stage] = item;
+                    vb_mbar_arrive_expect_tx(&full[stage], bytes_a + bytes_x);
+                    vb_bulk_g2s(sa, x + (size_t)item.x_off2 * 2, bytes_x, &full[stage], pol_keep);
+                    vb_bulk_g2s(sa + bytes_x, reinterpret_cast<const unsigned char*>(mat) + (size_t)item.a_off16 * 16,
+                                bytes_a, &full[stage], pol_stream);
+                    if (++stage == VB_FAC_STAGES) { stage = 0; phase ^= 1; }
+                }
+                g = g_next;
+            }
+            vb_mbar_wait(&empty[stage], phase ^ 1);
+            slot[stage].flags = 0;
+            vb_mbar_arrive(&full[stage]);
+            const uint32_t done = atomicAdd(&sched[1], 1u);
+            if (done == gridDim.x - 1) {
+                sched[0] = 0;
+                sched[1] = 0;
+            }
+        }
+    } else {
+        uint32_t stage = 0, phase = 0;
+        double2 yacc[VB_FAC_RP];
+#pragma unroll
+        for (int m = 0; m < VB_FAC_RP; ++m) yacc[m] = make_double2(0.0, 0.0);
+        while (true) {
+            vb_mbar_wait(&full[stage], phase);
+            const VbFacItem item = slot[stage];
+            if (!(item.flags & VB_FAC_VALID)) break;
+            const int n2 = item.n2, c = item.c;
+            const double2* sx = reinterpret_cast<const double2*>(smem + stage * VB_FAC_STAGE);
+            const double2* sa = sx + n2;                                  // column j starts at sa + j * n2
+            // pass 1: t_j = U'[:, j] . x   (warp w takes columns w, w + 8, ...)
+            for (int j = warp; j < c; j += VB_LD_CONSUMER_WARPS) {
+                const double2* col = sa + (size_t)j * n2;
+                double a0 = 0.0, a1 = 0.0;
+                int i = lane;
+                for (; i + 32 < n2; i += 64) {
+                    const double2 u0 = col[i], x0 = sx[i], u1 = col[i + 32], x1 = sx[i + 32];
+                    a0 = fma(u0.x, x0.x, a0); a0 = fma(u0.y, x0.y, a0);
+                    a1 = fma(u1.x, x1.x, a1); a1 = fma(u1.y, x1.y, a1);
+                }
+                if (i < n2) {
+                    const double2 u0 = col[i], x0 = sx[i];
+                    a0 = fma(u0.x, x0.x, a0); a0 = fma(u0.y, x0.y, a0);
+                }
+                const double t = vb_warp_sum(a0 + a1);
+                if (lane == 0) s_t[j] = t;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // pass 2: y_i += sum_j U'[i][j] t_j   (thread owns row pairs tid, tid + 256, ...)
+#pragma unroll
+            for (int m = 0; m < VB_FAC_RP; ++m) {
+                const int i = threadIdx.x + 256 * m;
+                if (i < n2) {
+                    double2 acc = yacc[m];
+                    for (int j = 0; j < c; ++j) {
+                        const double2 u = sa[(size_t)j * n2 + i];
+                        const double t = s_t[j];
+                        acc.x = fma(u.x, t, acc.x);
+                        acc.y = fma(u.y, t, acc.y);
+                    }
+                    yacc[m] = acc;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) vb_mbar_arrive(&empty[stage]);
+            if (item.flags & VB_FAC_LASTGROUP) {
+                double2* out = reinterpret_cast<double2*>(ypart + item.out_off);
+#pragma unroll
+                for (int m = 0; m < VB_FAC_RP; ++m) {
+                    const int i = threadIdx.x + 256 * m;
+                    if (i < n2) out[i] = yacc[m];
+                    yacc[m] = make_double2(0.0, 0.0);
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");          // s_t is rewritten by the next stage's pass 1
+            if (++stage == VB_FAC_STAGES) { stage = 0; phase ^= 1; }
+        }
+    }
+}
+
+// U (n x r row-major) and s -> the chunked column-major U' = U diag(sqrt(s)) of the kernel above.
+// grid.x = chunks; chunk q = columns [q c, q c + cq), each n_pad doubles (zero padded).
+__global__ void vb_pack_fac_kernel(const double* __restrict__ U, const double* __restrict__ sv, int n, int r,
+                                   int n_pad, int c, double* __restrict__ out) {
+    const int q = blockIdx.x;
+    const int j0 = q * c, cq = min(c, r - j0);
+    double* cout = out + (size_t)q * c * n_pad;
+    for (int idx = threadIdx.x; idx < cq * n_pad; idx += blockDim.x) {
+        const int j = idx / n_pad, i = idx - j * n_pad;
+        cout[idx] = i < n ? U[(size_t)i * r + j0 + j] * sqrt(sv[j0 + j]) : 0.0;
+    }
+}
+
 // Doubles one column slab occupies: `nrows` rows (the slab's first row is its first column), tile width w.
 static inline __host__ __device__ size_t vb_sym_tile_doubles(int64_t w) {
     const int64_t pf = w / VB_SYM_R;

@@ -63,6 +63,7 @@ struct VbSnpArgs {
     double* kcache_c;
     double* kcache_d;
     double tau0;                 // error_scaling of cohort 0 (the merged C statistic is reported as C_0 = tau_0 X)
+    int ring_depth;              // tile kernel: slots of the per-warp TMA ring (0 = plain loads)
 };
 
 // ---- symmetric P x P helpers, lower-triangular packed: idx(i,j) = i(i+1)/2 + j, j <= i

@@ -251,7 +251,13 @@ __device__ __forceinline__ VbTileComp<P> vb_tile_component(
     return c;
 }
 
-template <int P, int MODE, int CACHE>
+// RING: the state each component needs -- P rows of mu (and the two cached constants) for the tile's 32 SNPs,
+// 256 bytes each -- is brought into shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier) that every
+// warp issues for ITS OWN components D iterations ahead (a per-warp ring: no producer warp, no cross-warp
+// barrier, it runs on across tile boundaries).  With plain loads the kernel sat on the long scoreboard (ncu,
+// P = 5: 8 warps per SM cannot keep enough 8-byte loads in flight: 2 TB/s); the ring keeps W x D x P x 256 B
+// per CTA in flight regardless of occupancy.  Needs an even M (16-byte aligned rows).
+template <int P, int MODE, int CACHE, bool RING>
 __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp_tile_kernel(const VbSnpArgs a) {
     static_assert(MODE != VB_MODE_EVAL, "EVAL has no softmax: use vb_snp_kernel");
     constexpr int NT = P * (P + 1) / 2;
@@ -291,6 +297,25 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
     }
 #endif
     for (int j = threadIdx.x; j < AKf; j += blockDim.x) s_ann[j] = 0.0;
+    // per-warp TMA ring: D slots of (P [+2]) x 32 doubles, one mbarrier each
+    constexpr int SLOT_ROWS = P + (USE ? 2 : 0);
+    constexpr int SLOTD = SLOT_ROWS * 32;
+    const int D = RING ? a.ring_depth : 0;
+    double* my_ring = nullptr;
+    uint64_t* my_bar = nullptr;
+    if constexpr (RING) {
+#if VB_TILE_SMEM_PREC
+        double* ring0 = s_prec + (size_t)K * NTP;
+#else
+        double* ring0 = s_ann + ((AKf + 1) & ~1);
+#endif
+        my_ring = ring0 + (size_t)warp * D * SLOTD;
+        my_bar = reinterpret_cast<uint64_t*>(ring0 + (size_t)W * D * SLOTD) + warp * D;
+        if (lane == 0) {
+            for (int j = 0; j < D; ++j) vb_mbar_init(&my_bar[j], 1);
+            vb_fence_mbar_init();
+        }
+    }
     __syncthreads();
 
     double tA[P], tC[P], tKd = 0.0, tKq = 0.0, tKs = 0.0;       // warp 0 only
@@ -306,6 +331,35 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
     const double* const g_logdet = a.logdet;
 #endif
     const int64_t ntiles = (M + VB_TILE_SNPS - 1) / VB_TILE_SNPS;
+    // ring fetch iterator: the (tile, component) this warp fetches next, in the order it computes them
+    int64_t f_tile = blockIdx.x;
+    int f_k = warp;
+    uint32_t f_n = 0, c_n = 0;                    // fetches issued / components consumed by this warp
+    uint64_t pol_stream = 0;
+    if constexpr (RING) pol_stream = vb_policy_evict_first();
+    auto ring_issue = [&]() {
+        if (f_tile >= ntiles || f_k >= K) return;         // (f_k >= K only when this warp owns no component)
+        if (lane == 0) {
+            const uint32_t slot = f_n % (uint32_t)D;
+            const int64_t c0 = f_tile * VB_TILE_SNPS;
+            const uint32_t bytes = (uint32_t)(c0 + VB_TILE_SNPS <= M ? VB_TILE_SNPS : M - c0) * 8u;
+            double* dst = my_ring + (size_t)slot * SLOTD;
+            vb_mbar_arrive_expect_tx(&my_bar[slot], bytes * SLOT_ROWS);
+            const double* src = a.mu_in + (size_t)f_k * PM + c0;
+#pragma unroll
+            for (int p = 0; p < P; ++p) vb_bulk_g2s(dst + p * 32, src + (size_t)p * M, bytes, &my_bar[slot], pol_stream);
+            if constexpr (USE) {
+                vb_bulk_g2s(dst + P * 32, a.kcache_c + (size_t)f_k * M + c0, bytes, &my_bar[slot], pol_stream);
+                vb_bulk_g2s(dst + (P + 1) * 32, a.kcache_d + (size_t)f_k * M + c0, bytes, &my_bar[slot], pol_stream);
+            }
+        }
+        ++f_n;
+        f_k += W;
+        if (f_k >= K) { f_k = warp; f_tile += gridDim.x; }
+    };
+    if constexpr (RING) {
+        for (int j = 0; j < D; ++j) ring_issue();
+    }
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t i0 = tile * VB_TILE_SNPS + lane;
@@ -344,12 +398,28 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
         const size_t cstride = (size_t)W * M;
         double* sl = s_logit;
         double mu_cur[P];
+        if constexpr (!RING) {
 #pragma unroll
-        for (int p = 0; p < P; ++p) mu_cur[p] = (warp < K) ? __ldg(pmu_in + (size_t)p * M) : 0.0;
+            for (int p = 0; p < P; ++p) mu_cur[p] = (warp < K) ? __ldg(pmu_in + (size_t)p * M) : 0.0;
+        }
 #pragma unroll UNROLL_A
         for (int k = warp; k < K; k += W, pmu_in += kstride, sl += W * 32) {
             double mu_nx[P];
-            if constexpr (REGPF) {
+            double cl_in = 0.0, dss_in = 0.0, cl_out, dss_out;
+            if constexpr (RING) {
+                // this component's rows have landed?  (slot and phase follow the count of consumed components)
+                const uint32_t slot = c_n % (uint32_t)D;
+                vb_mbar_wait(&my_bar[slot], (c_n / (uint32_t)D) & 1u);
+                const double* src = my_ring + (size_t)slot * SLOTD + lane;
+#pragma unroll
+                for (int p = 0; p < P; ++p) mu_cur[p] = src[p * 32];
+                if constexpr (USE) { cl_in = src[P * 32]; dss_in = src[(P + 1) * 32]; }
+                ++c_n;
+                // every lane holds its values: the slot goes back to the copy engine for the component D ahead
+                __syncwarp();
+                ring_issue();
+            }
+            if constexpr (REGPF && !RING) {
                 // the next component's mu: issued now, consumed one iteration later
 #pragma unroll
                 for (int p = 0; p < P; ++p) mu_nx[p] = mu_cur[p];
@@ -358,7 +428,7 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
                     for (int p = 0; p < P; ++p) mu_nx[p] = __ldg(pmu_in + kstride + (size_t)p * M);
                 }
             }
-            if (VB_TILE_PREFETCH > 0 && k + VB_TILE_PREFETCH * W < K) {
+            if (!RING && VB_TILE_PREFETCH > 0 && k + VB_TILE_PREFETCH * W < K) {
 #pragma unroll
                 for (int p = 0; p < P; ++p) vb_prefetch_l2(pmu_in + VB_TILE_PREFETCH * kstride + (size_t)p * M);
                 if constexpr (USE) {
@@ -366,8 +436,7 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
                     vb_prefetch_l2(pkd + VB_TILE_PREFETCH * cstride);
                 }
             }
-            double cl_in = 0.0, dss_in = 0.0, cl_out, dss_out;
-            if constexpr (USE) {
+            if constexpr (USE && !RING) {
                 cl_in = __ldg(pkc);
                 dss_in = __ldg(pkd);
             }
@@ -418,7 +487,9 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
                 if constexpr (!USE) sm2[p] = fma(w, fma(c.mu[p], c.mu[p], c.sd[p]), sm2[p]);
             }
             if constexpr (USE) sm2[0] = fma(w, c.m2w, sm2[0]);
-            if constexpr (REGPF) {
+            if constexpr (RING) {
+                (void)mu_nx;
+            } else if constexpr (REGPF) {
 #pragma unroll
                 for (int p = 0; p < P; ++p) mu_cur[p] = mu_nx[p];
             } else {
@@ -519,11 +590,13 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
 }
 
 // Shared memory one CTA of the tile kernel needs (bytes).
-static inline size_t vb_tile_smem(int K, int P, int W, int akf) {
+// ring_rows = rows of a ring slot (P, or P + 2 with the cached constants), depth = slots per warp (0: no ring)
+static inline size_t vb_tile_smem(int K, int P, int W, int akf, int ring_rows = 0, int depth = 0) {
     const size_t kslots = (size_t)(K + W - 1) / W;
     size_t n = kslots * W * 32 + (size_t)W * VB_TILE_NV(P) * 32 + (size_t)((akf + 1) & ~1);
 #if VB_TILE_SMEM_PREC
     n += (size_t)K * VB_TILE_NTP(P);
 #endif
+    n += (size_t)W * depth * ring_rows * 32 + (size_t)((W * depth + 1) & ~1);      // slots + one mbarrier each
     return n * sizeof(double);
 }

@@ -60,6 +60,7 @@ static int g_tile_mode = -1;         // vb_set_option("snp_tile", ...): see tile
 static bool g_ann_slots = true;      // vb_set_option("snp_ann_slots", 0): fused annotation sums by warp shuffles only
 static bool g_snp3_park = true;      // vb_set_option("snp3_park", 0): three-pass kernel parks logits in the output buffers
 static int g_fused_finish = -1;      // vb_set_option("ld_fused_finish", v): -1 automatic, 0 separate finish kernel, 1 always fused
+static bool g_tile_ring = true;      // vb_set_option("snp_tile_ring", 0): the tile kernel loads its state with plain loads
 static bool g_three_pass = true;     // vb_set_option("snp_three_pass", 0): always the online single-pass kernel   // vb_set_option("ld_symmetric", 0): store dense blocks in full
 
 // ------------------------------------------------------------------------------------
@@ -300,6 +301,10 @@ extern "C" int vb_set_option(const char* name, int64_t value) {
     }
     if (name && std::strcmp(name, "ld_fused_finish") == 0) {
         g_fused_finish = (int)value;
+        return 0;
+    }
+    if (name && std::strcmp(name, "snp_tile_ring") == 0) {
+        g_tile_ring = (value != 0);
         return 0;
     }
     if (name && std::strcmp(name, "snp_three_pass") == 0) {
@@ -1129,8 +1134,8 @@ extern "C" int vb_fit_create(vb_ctx* ctx, int K, int P, int64_t M, int A, vb_ld*
 // fuse_ann != 0: every evaluation also accumulates the per-annotation sums of that state's delta
 // (needs A*K <= 48 and A <= 4, silently off otherwise).  Worth it when a separate pass + reduction
 // per hyper step costs more than ~5 % extra per-SNP kernel time, i.e. on multi-GPU runs.
-struct TilePlan { int W, grid; size_t smem; };
-static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf);
+struct TilePlan { int W, grid; size_t smem; int depth; };
+static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf, int ring_rows = 0);
 // fuse_ann == 2: only where the sums are nearly free -- the three-pass kernel's per-thread
 // shared-memory slots (P <= 2, A*K <= 16), e.g. the single-cohort default grid on one GPU.
 extern "C" int vb_fit_set_fusion(vb_ctx* ctx, int fuse_ann) {
@@ -1276,8 +1281,8 @@ extern "C" int vb_fit_get_params_dev(vb_ctx* ctx, double* mu_dev, double* delta_
 // Launch geometry of the tile kernel: W warps per 32-SNP tile and CTAs per SM, chosen to maximise
 // resident threads under the shared-memory (logits + merge scratch) and register limits; ties go to
 // the smaller W (shorter merge).  Returns W = 0 when the thread-per-SNP kernels should run.
-static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf) {
-    TilePlan best{0, 0, 0};
+static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf, int ring_rows) {
+    TilePlan best{0, 0, 0, 0};
     if (g_tile_mode == 0) return best;
     // automatic: large grids and P >= 3 (where thread-per-SNP parks K logits per SNP in HBM and pays
     // three logs and square roots per component); the tuned three-pass kernel keeps small P <= 2 grids
@@ -1286,20 +1291,29 @@ static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf) {
                                 : (f.P <= 3 ? VbTileCfg<3>::THREADS_PER_SM : VbTileCfg<5>::THREADS_PER_SM);
     const int maxw = std::min(VB_TILE_MAXW, (f.P == 1 ? VbTileCfg<1>::MAXT : (f.P <= 3 ? VbTileCfg<3>::MAXT : VbTileCfg<5>::MAXT)) / 32);
     const size_t cap = 227 * 1024;
+    // with the TMA ring every warp wants >= 4 slots (a slot = one component's rows for the tile): plans
+    // are ranked by resident threads first, then by ring depth
+    const bool ring = ring_rows > 0 && g_tile_ring && (f.M % 2 == 0);
+    const int want_depth = ring ? 6 : 0, min_depth = ring ? 2 : 0;
     int best_threads = 0;
     static const int kWidths[] = {1, 2, 3, 4, 6, 8, 12, 16};     // warps per tile (k is split round-robin: any W works)
     for (int W : kWidths) {
         if (W > maxw) break;
         if (g_tile_mode > 0 && W != g_tile_mode) continue;
-        const size_t sm = vb_tile_smem(f.K, f.P, W, akf);
-        if (sm > cap) continue;
-        int ctas = std::min<int>(std::min<int>(target / (32 * W), (int)(cap / (sm + 1024))), 16);
+        if (vb_tile_smem(f.K, f.P, W, akf, ring_rows, min_depth) > cap) continue;
+        int ctas = std::min<int>(target / (32 * W), 16);
+        // CTAs per SM the shared memory allows at the minimum depth, then the deepest ring that keeps them
+        while (ctas >= 1 && (vb_tile_smem(f.K, f.P, W, akf, ring_rows, min_depth) + 1024) * ctas > cap + 1024) --ctas;
         if (ctas < 1) continue;
+        int depth = min_depth;
+        while (depth < want_depth && (vb_tile_smem(f.K, f.P, W, akf, ring_rows, depth + 1) + 1024) * ctas <= cap + 1024) ++depth;
+        const size_t sm = vb_tile_smem(f.K, f.P, W, akf, ring_rows, depth);
         const int threads = ctas * 32 * W;
         if (threads > best_threads) {
             best_threads = threads;
             best.W = W;
             best.smem = sm;
+            best.depth = depth;
             const int64_t tiles = (f.M + VB_TILE_SNPS - 1) / VB_TILE_SNPS;
             best.grid = (int)std::min<int64_t>(std::min<int64_t>((int64_t)ctx->num_sms * ctas, tiles), f.grid_snp);
         }
@@ -1316,18 +1330,23 @@ extern "C" int vb_debug_tile_plan(int P, int K, int64_t M, int akf, int num_sms,
     Fit f;
     f.P = P; f.K = K; f.M = M;
     f.grid_snp = (int)std::min<int64_t>((M + 127) / 128, (int64_t)num_sms * 16);
-    const TilePlan tp = tile_plan(&ctx, f, akf);
+    const TilePlan tp = tile_plan(&ctx, f, akf, P);
     *W = tp.W; *grid = tp.grid; *smem_bytes = (int64_t)tp.smem;
     return 0;
 }
-template <int P, int MODE, int CACHE>
-static void launch_tile_cache(const VbSnpArgs& a, const TilePlan& tp, cudaStream_t st) {
+template <int P, int MODE, int CACHE, bool RING>
+static void launch_tile_ring(const VbSnpArgs& a, const TilePlan& tp, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(vb_snp_tile_kernel<P, MODE, CACHE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(vb_snp_tile_kernel<P, MODE, CACHE, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set = true;
     }
-    vb_snp_tile_kernel<P, MODE, CACHE><<<tp.grid, 32 * tp.W, tp.smem, st>>>(a);
+    vb_snp_tile_kernel<P, MODE, CACHE, RING><<<tp.grid, 32 * tp.W, tp.smem, st>>>(a);
+}
+template <int P, int MODE, int CACHE>
+static void launch_tile_cache(const VbSnpArgs& a, const TilePlan& tp, cudaStream_t st) {
+    if (tp.depth > 0) launch_tile_ring<P, MODE, CACHE, true>(a, tp, st);
+    else launch_tile_ring<P, MODE, CACHE, false>(a, tp, st);
 }
 template <int P, int MODE>
 static void launch_tile_one(const VbSnpArgs& a, const TilePlan& tp, cudaStream_t st, int cache) {
@@ -1340,7 +1359,9 @@ static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
     cudaStream_t st = ctx->stream;
     ctx->fit.snp_grid_used = grid;
     if constexpr (MODE != VB_MODE_EVAL) {
-        const TilePlan tp = tile_plan(ctx, ctx->fit, a.fuse_ann ? a.A * a.K : 0);
+        Fit& f0 = ctx->fit;
+        const bool cache_use = f0.kcache_on && !a.pv_out && f0.kcache_c && f0.kcache_valid;
+        const TilePlan tp = tile_plan(ctx, ctx->fit, a.fuse_ann ? a.A * a.K : 0, P + (cache_use ? 2 : 0));
         if (tp.W > 0) {
             Fit& f = ctx->fit;
             f.snp_grid_used = tp.grid;
@@ -1365,6 +1386,7 @@ static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
                     f.kcache_valid = true;
                 }
             }
+            ac.ring_depth = tp.depth;
             prof_begin(ctx, 1);
             switch (P) {
                 case 1: launch_tile_one<1, MODE>(ac, tp, st, cache); break;
