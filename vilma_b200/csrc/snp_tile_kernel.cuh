@@ -39,16 +39,18 @@
 #ifndef VB_TILE_REGPF
 #define VB_TILE_REGPF(P) ((P) <= 2)   // the next component's mu is loaded into registers one iteration ahead
 #endif                                // (measured: +7 % for P = 2, K = 582; -3 % for P = 3 and 5, where registers are scarce)
-// Per-(component, SNP) cache of what depends on neither mu nor delta: Lambda_ki = Prec_k + diag(sld_i / tau)
-// is the same in every evaluation until tau changes, so its log-determinant c_ki = -log|Lambda_ki| and
-// d_ki = sum_p (sld_pi / tau_p) (Lambda_ki^-1)_pp are kept in HBM ([K][M] doubles each).  The kernel is bound
-// by fp64 issue, not by bytes (a REFRESH moves half the bytes of a TRIAL in 90 % of its time): reading 16 more
-// bytes per (k, i) buys ~60 of ~270 fp64 instructions per component in a TRIAL (no log, no inverse of L, no
-// diagonal of S) and the whole factorisation in a REFRESH.  VB_CACHE_FILL computes as before and writes the
-// two arrays; VB_CACHE_USE reads them.  With the cache the second moments are accumulated already weighted,
-// sum_p (sld_p/tau_p)(mu'_p^2 + S_pp), so the per-cohort C_p statistics collapse into one number (returned
-// as C_0 = tau_0 x sum_p C_p / tau_p, zeros elsewhere): exact for the objective, not usable for the tau step,
-// hence only without --learn-scaling.
+// Per-(component, SNP) cache for the delta refresh.  A REFRESH (hyper / tau step: delta recomputed from the
+// resident mu, variational_inference.py:632-641) changes nothing in a component but the additive term of its
+// logit: with b_ki = (c_ki + mu_ki . Lambda_ki mu_ki) / 2 the logit is b_ki + g^delta_k, and the pieces the
+// objective needs -- q_ki = (mu^T Prec_k mu + sigma_summary_ki) / 2 and m_ki = sum_p (sld_pi / tau_p)(mu_kpi^2 +
+// S_ki,pp) -- depend on mu and Lambda only.  Every kernel that computes them for a state (a TRIAL for its
+// output, a REFRESH that finds no cache) writes the three numbers next to that state's mu ([3][K][M] doubles per
+// mu buffer, VB_CACHE_FILL); a REFRESH of a state that has them (VB_CACHE_USE) reads mu and the three numbers
+// and does the softmax and the weighted sums only: no Lambda, no factorisation, no logarithm -- a third of the
+// instructions.  The kernel is bound by dependent-issue latency at 8-16 warps per SM, not by bytes (ncu: DRAM
+// 21 % of peak), so 24 more bytes per (k, i) in a TRIAL are cheap.  With the cache the statistics come back
+// merged -- KL_delta carries the whole KL, C_0 = tau_0 sum_p C_p / tau_p -- exact for the objective, not usable
+// for the tau step: only without --learn-scaling.
 enum { VB_CACHE_NONE = 0, VB_CACHE_FILL = 1, VB_CACHE_USE = 2 };
 #define VB_TILE_SNPS 32
 #define VB_TILE_MAXW 16
@@ -65,9 +67,6 @@ struct VbLdl {
     double det;
     __device__ __forceinline__ static constexpr int sl(int i, int j) { return i * (i - 1) / 2 + j; }   // j < i
 
-    // WITH_N: N receives L^-1 (needed for the diagonal of Lambda^-1); otherwise N keeps L itself and solve<false>
-    // substitutes forward and back (same flops, no inverse: the cached-constants path)
-    template <bool WITH_N = true>
     __device__ __forceinline__ void factor(const double (&lam)[P * (P + 1) / 2]) {
         double L[NL > 0 ? NL : 1], U[NL > 0 ? NL : 1];      // U_ij = L_ij D_j
         det = 1.0;
@@ -87,11 +86,6 @@ struct VbLdl {
                 }
             }
         }
-        if constexpr (!WITH_N) {
-#pragma unroll
-            for (int t = 0; t < NL; ++t) N[t] = L[t];
-            return;
-        }
         // N = L^-1: N_ij = -(L_ij + sum_{j<k<i} L_ik N_kj)
 #pragma unroll
         for (int j = 0; j < P; ++j)
@@ -103,40 +97,22 @@ struct VbLdl {
                 N[sl(i, j)] = -v;
             }
     }
-    // x = Lambda^-1 b = N^T D^-1 N b   (WITH_N)   or   L^-T D^-1 L^-1 b by substitution
-    template <bool WITH_N = true>
+    // x = Lambda^-1 b = N^T D^-1 N b
     __device__ __forceinline__ void solve(const double (&b)[P], double (&x)[P]) const {
         double y[P];
-        if constexpr (WITH_N) {
 #pragma unroll
-            for (int i = 0; i < P; ++i) {
-                double v = b[i];
+        for (int i = 0; i < P; ++i) {
+            double v = b[i];
 #pragma unroll
-                for (int j = 0; j < i; ++j) v = fma(N[sl(i, j)], b[j], v);
-                y[i] = v * inv[i];
-            }
+            for (int j = 0; j < i; ++j) v = fma(N[sl(i, j)], b[j], v);
+            y[i] = v * inv[i];
+        }
 #pragma unroll
-            for (int j = 0; j < P; ++j) {
-                double v = y[j];
+        for (int j = 0; j < P; ++j) {
+            double v = y[j];
 #pragma unroll
-                for (int i = j + 1; i < P; ++i) v = fma(N[sl(i, j)], y[i], v);
-                x[j] = v;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < P; ++i) {                      // L y = b
-                double v = b[i];
-#pragma unroll
-                for (int j = 0; j < i; ++j) v = fma(-N[sl(i, j)], y[j], v);
-                y[i] = v;
-            }
-#pragma unroll
-            for (int j = P - 1; j >= 0; --j) {                 // L^T x = D^-1 y
-                double v = y[j] * inv[j];
-#pragma unroll
-                for (int i = j + 1; i < P; ++i) v = fma(-N[sl(i, j)], x[i], v);
-                x[j] = v;
-            }
+            for (int i = j + 1; i < P; ++i) v = fma(N[sl(i, j)], y[i], v);
+            x[j] = v;
         }
     }
     // diagonal of Lambda^-1: S_pp = inv_p + sum_{k>p} N_kp^2 inv_k
@@ -169,7 +145,7 @@ template <int P> struct VbTileCfg {
 
 template <int P>
 struct VbTileComp {
-    double lk, lkh, quad, sigsum, m2w, mu[P], sd[P];     // lkh = lk - log h_k; m2w = sum_p dt_p (mu'_p^2 + S_pp)
+    double base, lk, lkh, quad, sigsum, m2w, mu[P], sd[P];   // lkh = lk - log h_k; m2w = sum_p dt_p (mu'_p^2 + S_pp)
 };
 // Lambda = Prec_k + diag(dt) as a packed lower triangle, from the shared-memory copy (packed, 16-byte
 // rows: the compiler fuses the uniform loads into LDS.128 broadcasts) or from the global [P][P] array.
@@ -196,54 +172,46 @@ __device__ __forceinline__ void vb_tile_load_lambda(const double* __restrict__ p
     for (int p = 0; p < P; ++p) lam[VB_TRI(p, p)] += dt[p];
 }
 // One mixture component of one SNP: Lambda, eta, mu' = S eta, logit and the KL pieces.  `mu_in` = the
-// accepted mu (registers); c.mu = mu' on return (TRIAL) or mu (REFRESH).  CACHE == VB_CACHE_USE: `cl_in`
-// (-log|Lambda|) and `dss_in` (sum_p dt_p S_pp) come from the cache and S is only formed where mu' needs
-// it; otherwise they are computed (and returned through cl_out / dss_out for VB_CACHE_FILL).
-template <int P, int MODE, int CACHE>
+// accepted mu (registers); c.mu = mu' on return (TRIAL) or mu (REFRESH).  c.base = (c + mu'.eta) / 2 is the
+// logit without its g^delta term.
+template <int P, int MODE>
 __device__ __forceinline__ VbTileComp<P> vb_tile_component(
     const double* __restrict__ pk, const double (&mu_in)[P], const double (&dt)[P],
-    const double (&g)[P], double step, double one_minus_step, double gk, double loghk, double logdetk,
-    double cl_in, double dss_in, double& cl_out, double& dss_out) {
+    const double (&g)[P], double step, double one_minus_step, double gk, double loghk, double logdetk) {
     constexpr int NT = P * (P + 1) / 2;
-    constexpr bool USE = CACHE == VB_CACHE_USE;
     VbTileComp<P> c;
-    double lam[NT], eta[P], det = 1.0;
+    double lam[NT], eta[P], det;
     vb_tile_load_lambda<P>(pk, dt, lam);
 #pragma unroll
-    for (int p = 0; p < P; ++p) { c.mu[p] = mu_in[p]; c.sd[p] = 0.0; }
+    for (int p = 0; p < P; ++p) c.mu[p] = mu_in[p];
     vb_sym_matvec<P>(lam, c.mu, eta);
     if constexpr (MODE == VB_MODE_TRIAL) {
 #pragma unroll
         for (int p = 0; p < P; ++p) eta[p] = step * g[p] + one_minus_step * eta[p];
     }
-    if constexpr (!USE || MODE == VB_MODE_TRIAL) {
-        if constexpr (P <= 2) {
-            double S[NT];
-            vb_small_inverse<P>(lam, S, det);
-            if constexpr (MODE == VB_MODE_TRIAL) vb_sym_matvec<P>(S, eta, c.mu);
+    if constexpr (P <= 2) {
+        double S[NT];
+        vb_small_inverse<P>(lam, S, det);
+        if constexpr (MODE == VB_MODE_TRIAL) vb_sym_matvec<P>(S, eta, c.mu);
 #pragma unroll
-            for (int p = 0; p < P; ++p) c.sd[p] = S[VB_TRI(p, p)];
-        } else {
-            VbLdl<P> f;
-            f.template factor<!USE>(lam);
-            det = f.det;
-            if constexpr (MODE == VB_MODE_TRIAL) f.template solve<!USE>(eta, c.mu);
-            if constexpr (!USE) f.diag(c.sd);
-        }
+        for (int p = 0; p < P; ++p) c.sd[p] = S[VB_TRI(p, p)];
+    } else {
+        VbLdl<P> f;
+        f.factor(lam);
+        det = f.det;
+        if constexpr (MODE == VB_MODE_TRIAL) f.solve(eta, c.mu);
+        f.diag(c.sd);
     }
-    double cl, dss = 0.0, dot = 0.0, dmm = 0.0;
-    if constexpr (USE) cl = cl_in;
-    else cl = -vb_log_pos(det);
+    const double cl = -vb_log_pos(det);
+    double dss = 0.0, dot = 0.0, dmm = 0.0;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         dot = fma(c.mu[p], eta[p], dot);
         dmm = fma(dt[p] * c.mu[p], c.mu[p], dmm);
-        if constexpr (!USE) dss = fma(dt[p], c.sd[p], dss);
+        dss = fma(dt[p], c.sd[p], dss);
     }
-    if constexpr (USE) dss = dss_in;
-    cl_out = cl;
-    dss_out = dss;
-    c.lk = 0.5 * (cl + dot) + gk;
+    c.base = 0.5 * (cl + dot);
+    c.lk = c.base + gk;
     c.lkh = c.lk - loghk;
     c.quad = dot - dmm;
     c.sigsum = logdetk - cl + ((double)P - dss);
@@ -252,11 +220,11 @@ __device__ __forceinline__ VbTileComp<P> vb_tile_component(
 }
 
 // RING: the state each component needs -- P rows of mu (and the two cached constants) for the tile's 32 SNPs,
-// 256 bytes each -- is brought into shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier) that every
-// warp issues for ITS OWN components D iterations ahead (a per-warp ring: no producer warp, no cross-warp
-// barrier, it runs on across tile boundaries).  With plain loads the kernel sat on the long scoreboard (ncu,
-// P = 5: 8 warps per SM cannot keep enough 8-byte loads in flight: 2 TB/s); the ring keeps W x D x P x 256 B
-// per CTA in flight regardless of occupancy.  Needs an even M (16-byte aligned rows).
+// 256 bytes each -- is copied into shared memory asynchronously (cp.async, 8 bytes per lane: LDGSTS) by every
+// warp for ITS OWN components D iterations ahead: a per-warp ring in which each lane later reads back exactly
+// what it copied, so it needs no barrier at all (cp.async.wait_group), holds no registers while the data is
+// in flight and runs on across tile boundaries.  (A first version used 1-D TMA bulk copies + mbarriers: 48M
+// copies of 256 B per launch were slower than plain loads -- P = 5 trial 12.1 vs 9.7 ms.)
 template <int P, int MODE, int CACHE, bool RING>
 __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp_tile_kernel(const VbSnpArgs a) {
     static_assert(MODE != VB_MODE_EVAL, "EVAL has no softmax: use vb_snp_kernel");
@@ -265,6 +233,8 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
     constexpr int NV = VB_TILE_NV(P);
     constexpr int UNROLL_A = VB_TILE_UNROLL_A, UNROLL_B = VB_TILE_UNROLL_B;
     constexpr bool USE = CACHE == VB_CACHE_USE;
+    constexpr bool MERGED = CACHE != VB_CACHE_NONE;
+    static_assert(!USE || MODE == VB_MODE_REFRESH, "only a refresh can reuse a state's cached pieces");
     constexpr bool REGPF = VB_TILE_REGPF(P);
     extern __shared__ double s_tile[];
     const int K = a.K;
@@ -282,7 +252,7 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
     constexpr int NTP = VB_TILE_NTP(P);
 #if VB_TILE_SMEM_PREC
     double* s_prec = s_ann + ((AKf + 1) & ~1);
-    for (int j = threadIdx.x; j < K * NTP; j += blockDim.x) {
+    for (int j = threadIdx.x; j < (USE ? 0 : K * NTP); j += blockDim.x) {     // (a cached refresh needs no Prec_k)
         const int k = j / NTP, t = j - k * NTP;
         double v = 0.0;
         if (t < NT) {
@@ -298,23 +268,17 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
 #endif
     for (int j = threadIdx.x; j < AKf; j += blockDim.x) s_ann[j] = 0.0;
     // per-warp TMA ring: D slots of (P [+2]) x 32 doubles, one mbarrier each
-    constexpr int SLOT_ROWS = P + (USE ? 2 : 0);
+    constexpr int SLOT_ROWS = P + (USE ? 3 : 0);
     constexpr int SLOTD = SLOT_ROWS * 32;
     const int D = RING ? a.ring_depth : 0;
     double* my_ring = nullptr;
-    uint64_t* my_bar = nullptr;
     if constexpr (RING) {
 #if VB_TILE_SMEM_PREC
         double* ring0 = s_prec + (size_t)K * NTP;
 #else
         double* ring0 = s_ann + ((AKf + 1) & ~1);
 #endif
-        my_ring = ring0 + (size_t)warp * D * SLOTD;
-        my_bar = reinterpret_cast<uint64_t*>(ring0 + (size_t)W * D * SLOTD) + warp * D;
-        if (lane == 0) {
-            for (int j = 0; j < D; ++j) vb_mbar_init(&my_bar[j], 1);
-            vb_fence_mbar_init();
-        }
+        my_ring = ring0 + (size_t)warp * D * SLOTD + lane;
     }
     __syncthreads();
 
@@ -335,27 +299,25 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
     int64_t f_tile = blockIdx.x;
     int f_k = warp;
     uint32_t f_n = 0, c_n = 0;                    // fetches issued / components consumed by this warp
-    uint64_t pol_stream = 0;
-    if constexpr (RING) pol_stream = vb_policy_evict_first();
     auto ring_issue = [&]() {
-        if (f_tile >= ntiles || f_k >= K) return;         // (f_k >= K only when this warp owns no component)
-        if (lane == 0) {
-            const uint32_t slot = f_n % (uint32_t)D;
-            const int64_t c0 = f_tile * VB_TILE_SNPS;
-            const uint32_t bytes = (uint32_t)(c0 + VB_TILE_SNPS <= M ? VB_TILE_SNPS : M - c0) * 8u;
-            double* dst = my_ring + (size_t)slot * SLOTD;
-            vb_mbar_arrive_expect_tx(&my_bar[slot], bytes * SLOT_ROWS);
-            const double* src = a.mu_in + (size_t)f_k * PM + c0;
+        // one commit group per call, empty once this warp has nothing left to fetch (keeps the counts aligned)
+        if (f_tile < ntiles && f_k < K) {
+            const int64_t ii = f_tile * VB_TILE_SNPS + lane;
+            const int64_t ic = ii < M ? ii : M - 1;
+            double* dst = my_ring + (size_t)(f_n % (uint32_t)D) * SLOTD;
+            const double* src = a.mu_in + (size_t)f_k * PM + ic;
 #pragma unroll
-            for (int p = 0; p < P; ++p) vb_bulk_g2s(dst + p * 32, src + (size_t)p * M, bytes, &my_bar[slot], pol_stream);
+            for (int p = 0; p < P; ++p) vb_cp_async8(dst + p * 32, src + (size_t)p * M);
             if constexpr (USE) {
-                vb_bulk_g2s(dst + P * 32, a.kcache_c + (size_t)f_k * M + c0, bytes, &my_bar[slot], pol_stream);
-                vb_bulk_g2s(dst + (P + 1) * 32, a.kcache_d + (size_t)f_k * M + c0, bytes, &my_bar[slot], pol_stream);
+#pragma unroll
+                for (int t = 0; t < 3; ++t)
+                    vb_cp_async8(dst + (P + t) * 32, a.kc_in + ((size_t)t * K + f_k) * M + ic);
             }
+            f_k += W;
+            if (f_k >= K) { f_k = warp; f_tile += gridDim.x; }
         }
+        vb_cp_async_commit();
         ++f_n;
-        f_k += W;
-        if (f_k >= K) { f_k = warp; f_tile += gridDim.x; }
     };
     if constexpr (RING) {
         for (int j = 0; j < D; ++j) ring_issue();
@@ -392,9 +354,10 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
         const double* pmu_in = a.mu_in + (size_t)warp * PM + i;
         double* pmu_out = (MODE == VB_MODE_TRIAL) ? a.mu_out + (size_t)warp * PM + i : nullptr;
         const size_t kstride = (size_t)W * PM;
-        // cached constants [K][M]: c_ki and d_ki
-        const double* pkc = (CACHE != VB_CACHE_NONE) ? a.kcache_c + (size_t)warp * M + i : nullptr;
-        const double* pkd = (CACHE != VB_CACHE_NONE) ? a.kcache_d + (size_t)warp * M + i : nullptr;
+        // the state's cached pieces [3][K][M]: read (USE) or written (FILL) for this thread's components
+        const size_t KMs = (size_t)K * M;
+        const double* pkc = USE ? a.kc_in + (size_t)warp * M + i : nullptr;
+        double* pko = (CACHE == VB_CACHE_FILL) ? a.kc_out + (size_t)warp * M + i : nullptr;
         const size_t cstride = (size_t)W * M;
         double* sl = s_logit;
         double mu_cur[P];
@@ -405,18 +368,16 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
 #pragma unroll UNROLL_A
         for (int k = warp; k < K; k += W, pmu_in += kstride, sl += W * 32) {
             double mu_nx[P];
-            double cl_in = 0.0, dss_in = 0.0, cl_out, dss_out;
+            double cb = 0.0, cq = 0.0, cm = 0.0;                 // cached pieces of this component (USE)
             if constexpr (RING) {
-                // this component's rows have landed?  (slot and phase follow the count of consumed components)
-                const uint32_t slot = c_n % (uint32_t)D;
-                vb_mbar_wait(&my_bar[slot], (c_n / (uint32_t)D) & 1u);
-                const double* src = my_ring + (size_t)slot * SLOTD + lane;
+                // D groups are in flight; the oldest one is this component's (each lane reads back its own copies)
+                vb_cp_async_wait(D - 1);
+                const double* src = my_ring + (size_t)(c_n % (uint32_t)D) * SLOTD;
 #pragma unroll
                 for (int p = 0; p < P; ++p) mu_cur[p] = src[p * 32];
-                if constexpr (USE) { cl_in = src[P * 32]; dss_in = src[(P + 1) * 32]; }
+                if constexpr (USE) { cb = src[P * 32]; cq = src[(P + 1) * 32]; cm = src[(P + 2) * 32]; }
                 ++c_n;
-                // every lane holds its values: the slot goes back to the copy engine for the component D ahead
-                __syncwarp();
+                // the slot is free again (its values are in registers): fetch the component D ahead into it
                 ring_issue();
             }
             if constexpr (REGPF && !RING) {
@@ -432,29 +393,39 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
 #pragma unroll
                 for (int p = 0; p < P; ++p) vb_prefetch_l2(pmu_in + VB_TILE_PREFETCH * kstride + (size_t)p * M);
                 if constexpr (USE) {
-                    vb_prefetch_l2(pkc + VB_TILE_PREFETCH * cstride);
-                    vb_prefetch_l2(pkd + VB_TILE_PREFETCH * cstride);
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) vb_prefetch_l2(pkc + t * KMs + VB_TILE_PREFETCH * cstride);
                 }
             }
             if constexpr (USE && !RING) {
-                cl_in = __ldg(pkc);
-                dss_in = __ldg(pkd);
+                cb = __ldg(pkc); cq = __ldg(pkc + KMs); cm = __ldg(pkc + 2 * KMs);
             }
+            if constexpr (USE) pkc += cstride;
+            // per-component results: logit, KL piece(s), weighted second moment, mu
+            VbTileComp<P> c;
+            if constexpr (USE) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) { c.mu[p] = mu_cur[p]; c.sd[p] = 0.0; }
+                c.base = cb;
+                c.lk = cb + gfull[k];
+                c.lkh = (c.lk - logh[k]) + cq;                 // the whole KL piece of the component
+                c.quad = 0.0; c.sigsum = 0.0;
+                c.m2w = cm;
+            } else {
 #if VB_TILE_SMEM_PREC
-            const double ldk = k_prec[(size_t)k * KSTR + NTP - 1];
+                const double ldk = k_prec[(size_t)k * KSTR + NTP - 1];
 #else
-            const double ldk = g_logdet[k];
+                const double ldk = g_logdet[k];
 #endif
-            const VbTileComp<P> c = vb_tile_component<P, MODE, CACHE>(
-                k_prec + (size_t)k * KSTR, mu_cur, dt, g, step, one_minus_step, gfull[k], logh[k], ldk,
-                cl_in, dss_in, cl_out, dss_out);
-            if constexpr (CACHE == VB_CACHE_FILL) {
-                if (valid) {
-                    const_cast<double*>(pkc)[0] = cl_out;
-                    const_cast<double*>(pkd)[0] = dss_out;
+                c = vb_tile_component<P, MODE>(k_prec + (size_t)k * KSTR, mu_cur, dt, g, step, one_minus_step,
+                                               gfull[k], logh[k], ldk);
+                if constexpr (MERGED) {
+                    const double q = 0.5 * (c.quad + c.sigsum);
+                    if (valid) { pko[0] = c.base; pko[KMs] = q; pko[2 * KMs] = c.m2w; }
+                    pko += cstride;
+                    c.lkh += q;
                 }
             }
-            if constexpr (CACHE != VB_CACHE_NONE) { pkc += cstride; pkd += cstride; }
             if constexpr (MODE == VB_MODE_TRIAL) {
                 if (valid) {
 #pragma unroll
@@ -468,25 +439,28 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
             const double e = vb_exp_nonpos(-fabs(d));
             double w = e;
             if (d > 0.0) {
-                s0 *= e; sKd *= e; sKq *= e; sKs *= e;
+                s0 *= e; sKd *= e;
+                if constexpr (!MERGED) { sKq *= e; sKs *= e; }
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
                     spm[p] *= e;
-                    if (!USE || p == 0) sm2[p] *= e;
+                    if (!MERGED || p == 0) sm2[p] *= e;
                 }
                 mx = c.lk;
                 w = 1.0;
             }
             s0 += w;
             sKd = fma(w, c.lkh, sKd);
-            sKq = fma(w, c.quad, sKq);
-            sKs = fma(w, c.sigsum, sKs);
+            if constexpr (!MERGED) {
+                sKq = fma(w, c.quad, sKq);
+                sKs = fma(w, c.sigsum, sKs);
+            }
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 spm[p] = fma(w, c.mu[p], spm[p]);
-                if constexpr (!USE) sm2[p] = fma(w, fma(c.mu[p], c.mu[p], c.sd[p]), sm2[p]);
+                if constexpr (!MERGED) sm2[p] = fma(w, fma(c.mu[p], c.mu[p], c.sd[p]), sm2[p]);
             }
-            if constexpr (USE) sm2[0] = fma(w, c.m2w, sm2[0]);
+            if constexpr (MERGED) sm2[0] = fma(w, c.m2w, sm2[0]);
             if constexpr (RING) {
                 (void)mu_nx;
             } else if constexpr (REGPF) {
@@ -519,7 +493,7 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
                     spm[p] = fma(r, o[(5 + p) * 32], spm[p]);
-                    if (!USE || p == 0) sm2[p] = fma(r, o[(5 + P + p) * 32], sm2[p]);
+                    if (!MERGED || p == 0) sm2[p] = fma(r, o[(5 + P + p) * 32], sm2[p]);
                 }
             }
             mx = gmx;
@@ -548,7 +522,7 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
             tKd += sKd * inv_den - log_norm;
             tKq += 0.5 * sKq * inv_den;
             tKs += 0.5 * sKs * inv_den;
-            double wpm2 = 0.0;                  // sum_p dt_p pm_p^2 (cache path)
+            double wpm2 = 0.0;                  // sum_p dt_p pm_p^2 (merged statistics)
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const double pm = spm[p] * inv_den;
@@ -558,7 +532,7 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
                     if (q >= 0) a.xb[p][q] = pm / a.se[(size_t)p * M + i];
                 }
                 tA[p] = fma(pm, a.adj[(size_t)p * M + i], tA[p]);
-                if constexpr (USE) {
+                if constexpr (MERGED) {
                     wpm2 = fma(dt[p] * pm, pm, wpm2);
                 } else {
                     const double pv = sm2[p] * inv_den - pm * pm;
@@ -567,7 +541,7 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
                 }
             }
             // sum_p (sld_p / tau_p) pv_p in one piece; reported as C_0 = tau_0 x that (the host divides by tau_0)
-            if constexpr (USE) tC[0] += (sm2[0] * inv_den - wpm2) * a.tau0;
+            if constexpr (MERGED) tC[0] += (sm2[0] * inv_den - wpm2) * a.tau0;
         }
     }
 
@@ -597,6 +571,6 @@ static inline size_t vb_tile_smem(int K, int P, int W, int akf, int ring_rows = 
 #if VB_TILE_SMEM_PREC
     n += (size_t)K * VB_TILE_NTP(P);
 #endif
-    n += (size_t)W * depth * ring_rows * 32 + (size_t)((W * depth + 1) & ~1);      // slots + one mbarrier each
+    n += (size_t)W * depth * ring_rows * 32;                                        // per-warp ring slots
     return n * sizeof(double);
 }

@@ -142,8 +142,9 @@ struct Fit {
     double *pm_prev = nullptr, *pm_ckpt = nullptr, *pm_next = nullptr;
     int akf = 0, nsp = 0;          // fused annotation sums per evaluation; partial row stride
     // tile kernel: cached per-(component, SNP) constants (snp_tile_kernel.cuh); merged C statistic when on
-    bool kcache_on = false, kcache_valid = false;
-    double *kcache_c = nullptr, *kcache_d = nullptr;
+    bool kcache_on = false;
+    bool kc_valid[2] = {false, false};             // kc[s] holds the pieces of the state in mu[s]
+    double* kc[2] = {nullptr, nullptr};            // [3][K][M] each
     int64_t mutations = 0;         // bumped by every public vb_fit_* call (guards speculative work)
     double* part_snp = nullptr;
     int grid_snp = 0;
@@ -373,7 +374,7 @@ static void free_fit(Fit& f) {
     }
     cudaFree(f.scratch3); cudaFree(f.pm_prev); cudaFree(f.pm_ckpt); cudaFree(f.pm_next);
     cudaFree(f.part_snp); cudaFree(f.part_fin); cudaFree(f.part_ann); cudaFree(f.part_diff);
-    cudaFree(f.kcache_c); cudaFree(f.kcache_d);
+    cudaFree(f.kc[0]); cudaFree(f.kc[1]);
     f = Fit();
 }
 
@@ -1147,16 +1148,16 @@ extern "C" int vb_fit_set_fusion(vb_ctx* ctx, int fuse_ann) {
     f.akf = on ? f.A * f.K : 0;
     return 0;
 }
-// on != 0: the K-split tile kernel keeps c_ki = -log|Lambda_ki| and d_ki = sum_p (sld/tau)_p S_ki,pp in HBM
-// between evaluations (2 K M doubles) and returns the C statistics merged (see include/vilma_b200.h)
+// on != 0: the K-split tile kernel keeps three numbers per (component, SNP) next to every mu buffer, which a
+// delta refresh reuses instead of refactoring Lambda_ki; statistics then come back merged (include/vilma_b200.h)
 extern "C" int vb_fit_set_cache(vb_ctx* ctx, int on) {
     if (!ctx || !ctx->fit.created) return vb_fail("fit state not created");
     Fit& f = ctx->fit;
     f.kcache_on = on != 0;
-    f.kcache_valid = false;
+    f.kc_valid[0] = f.kc_valid[1] = false;
     if (!f.kcache_on) {
-        cudaFree(f.kcache_c); cudaFree(f.kcache_d);
-        f.kcache_c = f.kcache_d = nullptr;
+        cudaFree(f.kc[0]); cudaFree(f.kc[1]);
+        f.kc[0] = f.kc[1] = nullptr;
     }
     return 0;
 }
@@ -1185,7 +1186,7 @@ extern "C" int vb_fit_set_snp_data(vb_ctx* ctx, const double* adj, const double*
     CK(cudaMemcpyAsync(f.scal, scal, PM * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.ann, ann, (size_t)f.M * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    f.kcache_valid = false;
+    f.kc_valid[0] = f.kc_valid[1] = false;
     return 0;
 }
 extern "C" int vb_fit_set_mixture(vb_ctx* ctx, const double* prec, const double* logdet) {
@@ -1193,7 +1194,7 @@ extern "C" int vb_fit_set_mixture(vb_ctx* ctx, const double* prec, const double*
     CK(cudaMemcpyAsync(f.prec, prec, (size_t)f.K * f.P * f.P * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.logdet, logdet, (size_t)f.K * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    f.kcache_valid = false;
+    f.kc_valid[0] = f.kc_valid[1] = false;
     return 0;
 }
 extern "C" int vb_fit_set_hyper(vb_ctx* ctx, const double* hyper) {
@@ -1228,7 +1229,7 @@ static int fit_set_hyper_tables(vb_ctx* ctx, const double* hyper, const double* 
 extern "C" int vb_fit_set_tau(vb_ctx* ctx, const double* tau) {
     NEED_FIT(ctx);
     for (int p = 0; p < f.P; ++p)
-        if (f.inv_tau[p] != 1.0 / tau[p]) f.kcache_valid = false;     // Lambda_ki changed
+        if (f.inv_tau[p] != 1.0 / tau[p]) f.kc_valid[0] = f.kc_valid[1] = false;     // Lambda_ki changed
     for (int p = 0; p < f.P; ++p) f.inv_tau[p] = 1.0 / tau[p];
     CK(cudaMemcpyAsync(f.inv_tau_dev, f.inv_tau, VB_MAXP * 8, cudaMemcpyHostToDevice, ctx->stream));
     // pageable source: cudaMemcpyAsync returns once the data is staged, so no stream sync is needed
@@ -1246,6 +1247,7 @@ static int fit_set_params(vb_ctx* ctx, const double* mu, const double* delta_mk,
     CK_LAUNCH(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
     f.trial_kind = -1;
+    f.kc_valid[0] = f.kc_valid[1] = false;         // a new mu: its cached pieces are gone
     return 0;
 }
 extern "C" int vb_fit_set_params(vb_ctx* ctx, const double* mu, const double* delta_mk) {
@@ -1293,7 +1295,7 @@ static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf, int ring_row
     const size_t cap = 227 * 1024;
     // with the TMA ring every warp wants >= 4 slots (a slot = one component's rows for the tile): plans
     // are ranked by resident threads first, then by ring depth
-    const bool ring = ring_rows > 0 && g_tile_ring && (f.M % 2 == 0);
+    const bool ring = ring_rows > 0 && g_tile_ring;
     const int want_depth = ring ? 6 : 0, min_depth = ring ? 2 : 0;
     int best_threads = 0;
     static const int kWidths[] = {1, 2, 3, 4, 6, 8, 12, 16};     // warps per tile (k is split round-robin: any W works)
@@ -1350,8 +1352,10 @@ static void launch_tile_cache(const VbSnpArgs& a, const TilePlan& tp, cudaStream
 }
 template <int P, int MODE>
 static void launch_tile_one(const VbSnpArgs& a, const TilePlan& tp, cudaStream_t st, int cache) {
-    if (cache == VB_CACHE_USE) launch_tile_cache<P, MODE, VB_CACHE_USE>(a, tp, st);
-    else if (cache == VB_CACHE_FILL) launch_tile_cache<P, MODE, VB_CACHE_FILL>(a, tp, st);
+    if constexpr (MODE == VB_MODE_REFRESH) {
+        if (cache == VB_CACHE_USE) { launch_tile_cache<P, MODE, VB_CACHE_USE>(a, tp, st); return; }
+    }
+    if (cache == VB_CACHE_FILL) launch_tile_cache<P, MODE, VB_CACHE_FILL>(a, tp, st);
     else launch_tile_cache<P, MODE, VB_CACHE_NONE>(a, tp, st);
 }
 template <int MODE>
@@ -1359,33 +1363,39 @@ static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
     cudaStream_t st = ctx->stream;
     ctx->fit.snp_grid_used = grid;
     if constexpr (MODE != VB_MODE_EVAL) {
-        Fit& f0 = ctx->fit;
-        const bool cache_use = f0.kcache_on && !a.pv_out && f0.kcache_c && f0.kcache_valid;
-        const TilePlan tp = tile_plan(ctx, ctx->fit, a.fuse_ann ? a.A * a.K : 0, P + (cache_use ? 2 : 0));
-        if (tp.W > 0) {
-            Fit& f = ctx->fit;
-            f.snp_grid_used = tp.grid;
-            // cached constants: the first evaluation after tau / the grid / the SNP data changed fills them
-            int cache = VB_CACHE_NONE;
-            VbSnpArgs ac = a;
-            if (f.kcache_on && !a.pv_out) {
-                if (!f.kcache_c) {
-                    const size_t KM = (size_t)f.K * f.M;
-                    if (cudaMalloc(&f.kcache_c, KM * 8) != cudaSuccess || cudaMalloc(&f.kcache_d, KM * 8) != cudaSuccess) {
-                        cudaGetLastError();
-                        cudaFree(f.kcache_c);
-                        f.kcache_c = f.kcache_d = nullptr;
-                        f.kcache_on = false;               // not enough memory: keep recomputing
-                    }
-                }
-                if (f.kcache_on) {
-                    cache = f.kcache_valid ? VB_CACHE_USE : VB_CACHE_FILL;
-                    ac.kcache_c = f.kcache_c;
-                    ac.kcache_d = f.kcache_d;
-                    ac.tau0 = 1.0 / f.inv_tau[0];
-                    f.kcache_valid = true;
-                }
+        Fit& f = ctx->fit;
+        // cached per-(component, SNP) pieces: a TRIAL writes those of its output state, a REFRESH reuses the
+        // accepted state's when it has them and writes them otherwise (see snp_tile_kernel.cuh)
+        int cache = VB_CACHE_NONE;
+        VbSnpArgs ac = a;
+        const int akf_ = a.fuse_ann ? a.A * a.K : 0;
+        const bool tiled = tile_plan(ctx, f, akf_, P).W > 0;
+        if (tiled && f.kcache_on && !a.pv_out) {
+            const size_t len = (size_t)3 * f.K * f.M * 8;
+            if (!f.kc[0] && (cudaMalloc(&f.kc[0], len) != cudaSuccess || cudaMalloc(&f.kc[1], len) != cudaSuccess)) {
+                cudaGetLastError();
+                cudaFree(f.kc[0]);
+                f.kc[0] = f.kc[1] = nullptr;
+                f.kcache_on = false;               // not enough memory: keep recomputing
             }
+            if (f.kcache_on) {
+                if (MODE == VB_MODE_TRIAL) {
+                    cache = VB_CACHE_FILL;
+                    ac.kc_out = f.kc[1 - f.cur_mu];
+                } else if (f.kc_valid[f.cur_mu]) {
+                    cache = VB_CACHE_USE;
+                    ac.kc_in = f.kc[f.cur_mu];
+                } else {
+                    cache = VB_CACHE_FILL;
+                    ac.kc_out = f.kc[f.cur_mu];
+                }
+                ac.tau0 = 1.0 / f.inv_tau[0];
+            }
+        }
+        const TilePlan tp = tile_plan(ctx, f, akf_, P + (cache == VB_CACHE_USE ? 3 : 0));
+        if (tiled && tp.W > 0) {
+            f.snp_grid_used = tp.grid;
+            if (cache == VB_CACHE_FILL) f.kc_valid[MODE == VB_MODE_TRIAL ? 1 - f.cur_mu : f.cur_mu] = true;
             ac.ring_depth = tp.depth;
             prof_begin(ctx, 1);
             switch (P) {
@@ -1700,6 +1710,7 @@ extern "C" int vb_fit_init_mu(vb_ctx* ctx) {
     }
     CK_LAUNCH(ctx);
     f.trial_kind = -1;
+    f.kc_valid[0] = f.kc_valid[1] = false;
     return 0;
 }
 

@@ -223,9 +223,10 @@ class CudaEngine:
         self.merged_c = False
 
     def set_cache(self, on):
-        """Keep log|S_ki| and sum_p (sld/tau)_p S_ki,pp in HBM between evaluations (tile kernel).  The C
-        statistics then come back merged into stats[P] (see include/vilma_b200.h): only for fits that do
-        not learn the error scaling."""
+        """Keep each state's per-(component, SNP) logit base / KL share / weighted second moment in HBM
+        (K-split tile kernel) so that delta refreshes need no covariance algebra.  Trial and refresh
+        statistics then come back merged (see include/vilma_b200.h): only for fits that do not learn
+        the error scaling; eval() always returns them unmerged."""
         _lib.check(self.lib.vb_fit_set_cache(self.ctx.handle, 1 if on else 0))
         self.merged_c = bool(on)
 
