@@ -127,16 +127,6 @@ int vb_fit_destroy(vb_ctx* ctx);
 /* fuse_ann != 0: evaluations also return the per-annotation sums of delta (see below); used on
  * multi-GPU runs where a separate pass + reduction per hyper step costs more than it saves */
 int vb_fit_set_fusion(vb_ctx* ctx, int fuse_ann);
-/* on != 0 (fits WITHOUT --learn-scaling): the K-split per-SNP kernel keeps, next to each of the two mu
- * buffers, three numbers per (component, SNP) -- the logit without its g^delta term, the component's share of
- * the beta KL, and its dt-weighted second moment ([3][K][M] doubles per buffer) -- so that a delta refresh
- * (vb_fit_refresh_delta; _nat_to_not_vi_delta, variational_inference.py:632-641) re-weights the components
- * without rebuilding S_ki = (Prec_k + diag(sld_i/tau))^-1 (the reference keeps three [K,P,P,M] arrays for the
- * same purpose, :712-733).  With the cache the statistics of trials and refreshes come back merged:
- * stats[3P] = KL_delta + KL_quad + KL_sigma (stats[3P+1] = stats[3P+2] = 0) and stats[P] = tau_0 * sum_p C_p /
- * tau_p (stats[P+1 .. 2P) = 0): the objective formulas below are unchanged, the tau update (:472-486) needs the
- * per-cohort values -- hence the restriction; vb_fit_eval always returns them unmerged. */
-int vb_fit_set_cache(vb_ctx* ctx, int on);
 int vb_fit_set_snp_data(vb_ctx* ctx, const double* adj_host, const double* se_host,
                         const double* sld_host, const double* scalings_host,
                         const int32_t* ann_host);

@@ -28,7 +28,7 @@ def spd_grid(K, P, rng):
     return covs
 
 
-def run_case(ctx, P, K, M, reps, A=1, fuse=0, cache=0):
+def run_case(ctx, P, K, M, reps, A=1, fuse=0):
     import torch
     from vilma_b200.engine import CudaEngine, DeviceLD
     rng = np.random.default_rng(7)
@@ -57,8 +57,6 @@ def run_case(ctx, P, K, M, reps, A=1, fuse=0, cache=0):
     if fuse:
         from vilma_b200 import _lib
         _lib.check(ctx.lib.vb_fit_set_fusion(ctx.handle, fuse))
-    if cache:
-        eng.set_cache(True)
     gen = torch.Generator(device=dev)
     gen.manual_seed(3)
     mu = 1e-3 * torch.randn((K, P, M), generator=gen, device=dev, dtype=torch.float64)
@@ -100,7 +98,6 @@ def main():
     ap.add_argument('--reps', type=int, default=5)
     ap.add_argument('--ann', type=int, default=1)
     ap.add_argument('--fuse', type=int, default=0, help='vb_fit_set_fusion value (annotation sums ride along)')
-    ap.add_argument('--cache', type=int, default=0, help='1: cached per-(component, SNP) constants (tile kernel)')
     ap.add_argument('--opt', action='append', default=[], help='vb_set_option name=value')
     ap.add_argument('--peak', type=float, default=6553.0)
     a = ap.parse_args()
@@ -115,8 +112,8 @@ def main():
         # keep 2 x (mu + delta) under ~60 GB
         while 16 * K * (P + 1) * M > 60e9:
             M //= 2
-        out, ft, fr, stats = run_case(ctx, P, K, M, a.reps, a.ann, a.fuse, a.cache)
-        print('fuse=%d cache=%d ' % (a.fuse, a.cache) + 'opts=%s P=%d K=%d M=%d A=%d  trial %.3f ms (floor %.3f, %.2f of HBM peak)  refresh %.3f ms '
+        out, ft, fr, stats = run_case(ctx, P, K, M, a.reps, a.ann, a.fuse)
+        print('fuse=%d ' % a.fuse + 'opts=%s P=%d K=%d M=%d A=%d  trial %.3f ms (floor %.3f, %.2f of HBM peak)  refresh %.3f ms '
               '(floor %.3f, %.2f)  eval %.3f ms  checksum %.12e' % (
                   ','.join(a.opt) or '-', P, K, M, a.ann, out['trial'], ft / a.peak / 1e6,
                   ft / a.peak / 1e6 / out['trial'], out['refresh'], fr / a.peak / 1e6,

@@ -37,7 +37,6 @@ SIGNATURES = {
     'vb_fit_create': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_void_p)]),
     'vb_fit_destroy': (C.c_int, [C.c_void_p]),
     'vb_fit_set_fusion': (C.c_int, [C.c_void_p, C.c_int]),
-    'vb_fit_set_cache': (C.c_int, [C.c_void_p, C.c_int]),
     'vb_fit_set_snp_data': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'vb_fit_set_mixture': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'vb_fit_set_hyper': (C.c_int, [C.c_void_p, C.c_void_p]),

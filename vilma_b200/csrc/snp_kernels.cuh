@@ -59,11 +59,6 @@ struct VbSnpArgs {
     int fuse_ann;                // 1: per-warp shuffle sums; 2 (vb_snp3_kernel only): per-thread shared-memory slots
     int nsp;                     // row stride of `partial`
     double* partial;             // [gridDim.x][VB_NSNPSTAT(P)]
-    // tile kernel: a state's cached per-(component, SNP) pieces b, q, m ([3][K][M]; see snp_tile_kernel.cuh)
-    const double* kc_in;         // of the accepted state (VB_CACHE_USE)
-    double* kc_out;              // of the state being written / refreshed (VB_CACHE_FILL)
-    double tau0;                 // error_scaling of cohort 0 (the merged C statistic is reported as C_0 = tau_0 X)
-    int ring_depth;              // tile kernel: slots of the per-warp TMA ring (0 = plain loads)
 };
 
 // ---- symmetric P x P helpers, lower-triangular packed: idx(i,j) = i(i+1)/2 + j, j <= i

@@ -25,13 +25,13 @@
 #include "snp_kernels.cuh"
 
 #ifndef VB_TILE_UNROLL_A
-#define VB_TILE_UNROLL_A 1        // measured (tools/snp_bench.py, round 2): unrolling x2 is within +-2 %, x1 spills nothing
+#define VB_TILE_UNROLL_A 1        // measured (tools/snp_bench.py, round 2): unrolling x2 is within +-2 % and spills; x1 does not
 #endif
 #ifndef VB_TILE_UNROLL_B
 #define VB_TILE_UNROLL_B 4
 #endif
 #ifndef VB_TILE_PREFETCH
-#define VB_TILE_PREFETCH 4          // components ahead whose mu is prefetched into L2
+#define VB_TILE_PREFETCH 2          // components ahead whose mu is prefetched into L2 (0: -15 %, 4: -1 %, 8: -3 %)
 #endif
 #ifndef VB_TILE_SMEM_PREC
 #define VB_TILE_SMEM_PREC 1         // Prec_k (packed lower triangle) and log|Sigma_k| staged in shared memory once per CTA
@@ -39,19 +39,6 @@
 #ifndef VB_TILE_REGPF
 #define VB_TILE_REGPF(P) ((P) <= 2)   // the next component's mu is loaded into registers one iteration ahead
 #endif                                // (measured: +7 % for P = 2, K = 582; -3 % for P = 3 and 5, where registers are scarce)
-// Per-(component, SNP) cache for the delta refresh.  A REFRESH (hyper / tau step: delta recomputed from the
-// resident mu, variational_inference.py:632-641) changes nothing in a component but the additive term of its
-// logit: with b_ki = (c_ki + mu_ki . Lambda_ki mu_ki) / 2 the logit is b_ki + g^delta_k, and the pieces the
-// objective needs -- q_ki = (mu^T Prec_k mu + sigma_summary_ki) / 2 and m_ki = sum_p (sld_pi / tau_p)(mu_kpi^2 +
-// S_ki,pp) -- depend on mu and Lambda only.  Every kernel that computes them for a state (a TRIAL for its
-// output, a REFRESH that finds no cache) writes the three numbers next to that state's mu ([3][K][M] doubles per
-// mu buffer, VB_CACHE_FILL); a REFRESH of a state that has them (VB_CACHE_USE) reads mu and the three numbers
-// and does the softmax and the weighted sums only: no Lambda, no factorisation, no logarithm -- a third of the
-// instructions.  The kernel is bound by dependent-issue latency at 8-16 warps per SM, not by bytes (ncu: DRAM
-// 21 % of peak), so 24 more bytes per (k, i) in a TRIAL are cheap.  With the cache the statistics come back
-// merged -- KL_delta carries the whole KL, C_0 = tau_0 sum_p C_p / tau_p -- exact for the objective, not usable
-// for the tau step: only without --learn-scaling.
-enum { VB_CACHE_NONE = 0, VB_CACHE_FILL = 1, VB_CACHE_USE = 2 };
 #define VB_TILE_SNPS 32
 #define VB_TILE_MAXW 16
 // packed lower triangle of Prec_k padded to an even count (16-byte rows: LDS.128 broadcasts) + log|Sigma_k| slot
@@ -145,7 +132,7 @@ template <int P> struct VbTileCfg {
 
 template <int P>
 struct VbTileComp {
-    double base, lk, lkh, quad, sigsum, m2w, mu[P], sd[P];   // lkh = lk - log h_k; m2w = sum_p dt_p (mu'_p^2 + S_pp)
+    double lk, lkh, quad, sigsum, mu[P], sd[P];     // lkh = lk - log h_k
 };
 // Lambda = Prec_k + diag(dt) as a packed lower triangle, from the shared-memory copy (packed, 16-byte
 // rows: the compiler fuses the uniform loads into LDS.128 broadcasts) or from the global [P][P] array.
@@ -171,9 +158,8 @@ __device__ __forceinline__ void vb_tile_load_lambda(const double* __restrict__ p
 #pragma unroll
     for (int p = 0; p < P; ++p) lam[VB_TRI(p, p)] += dt[p];
 }
-// One mixture component of one SNP: Lambda, eta, mu' = S eta, logit and the KL pieces.  `mu_in` = the
-// accepted mu (registers); c.mu = mu' on return (TRIAL) or mu (REFRESH).  c.base = (c + mu'.eta) / 2 is the
-// logit without its g^delta term.
+// One mixture component of one SNP: Lambda, eta, mu' = S eta, logit and the KL pieces.  `mu` holds the
+// accepted mu on entry (already in registers: loaded one iteration ahead) and mu' on return (TRIAL).
 template <int P, int MODE>
 __device__ __forceinline__ VbTileComp<P> vb_tile_component(
     const double* __restrict__ pk, const double (&mu_in)[P], const double (&dt)[P],
@@ -203,38 +189,27 @@ __device__ __forceinline__ VbTileComp<P> vb_tile_component(
         f.diag(c.sd);
     }
     const double cl = -vb_log_pos(det);
-    double dss = 0.0, dot = 0.0, dmm = 0.0;
+    double dot = 0.0, dmm = 0.0, dss = 0.0;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         dot = fma(c.mu[p], eta[p], dot);
         dmm = fma(dt[p] * c.mu[p], c.mu[p], dmm);
         dss = fma(dt[p], c.sd[p], dss);
     }
-    c.base = 0.5 * (cl + dot);
-    c.lk = c.base + gk;
+    c.lk = 0.5 * (cl + dot) + gk;
     c.lkh = c.lk - loghk;
     c.quad = dot - dmm;
     c.sigsum = logdetk - cl + ((double)P - dss);
-    c.m2w = dmm + dss;
     return c;
 }
 
-// RING: the state each component needs -- P rows of mu (and the two cached constants) for the tile's 32 SNPs,
-// 256 bytes each -- is copied into shared memory asynchronously (cp.async, 8 bytes per lane: LDGSTS) by every
-// warp for ITS OWN components D iterations ahead: a per-warp ring in which each lane later reads back exactly
-// what it copied, so it needs no barrier at all (cp.async.wait_group), holds no registers while the data is
-// in flight and runs on across tile boundaries.  (A first version used 1-D TMA bulk copies + mbarriers: 48M
-// copies of 256 B per launch were slower than plain loads -- P = 5 trial 12.1 vs 9.7 ms.)
-template <int P, int MODE, int CACHE, bool RING>
+template <int P, int MODE>
 __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp_tile_kernel(const VbSnpArgs a) {
     static_assert(MODE != VB_MODE_EVAL, "EVAL has no softmax: use vb_snp_kernel");
     constexpr int NT = P * (P + 1) / 2;
     constexpr int NS = VB_NSNPSTAT(P);
     constexpr int NV = VB_TILE_NV(P);
     constexpr int UNROLL_A = VB_TILE_UNROLL_A, UNROLL_B = VB_TILE_UNROLL_B;
-    constexpr bool USE = CACHE == VB_CACHE_USE;
-    constexpr bool MERGED = CACHE != VB_CACHE_NONE;
-    static_assert(!USE || MODE == VB_MODE_REFRESH, "only a refresh can reuse a state's cached pieces");
     constexpr bool REGPF = VB_TILE_REGPF(P);
     extern __shared__ double s_tile[];
     const int K = a.K;
@@ -252,7 +227,7 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
     constexpr int NTP = VB_TILE_NTP(P);
 #if VB_TILE_SMEM_PREC
     double* s_prec = s_ann + ((AKf + 1) & ~1);
-    for (int j = threadIdx.x; j < (USE ? 0 : K * NTP); j += blockDim.x) {     // (a cached refresh needs no Prec_k)
+    for (int j = threadIdx.x; j < K * NTP; j += blockDim.x) {
         const int k = j / NTP, t = j - k * NTP;
         double v = 0.0;
         if (t < NT) {
@@ -267,19 +242,6 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
     }
 #endif
     for (int j = threadIdx.x; j < AKf; j += blockDim.x) s_ann[j] = 0.0;
-    // per-warp TMA ring: D slots of (P [+2]) x 32 doubles, one mbarrier each
-    constexpr int SLOT_ROWS = P + (USE ? 3 : 0);
-    constexpr int SLOTD = SLOT_ROWS * 32;
-    const int D = RING ? a.ring_depth : 0;
-    double* my_ring = nullptr;
-    if constexpr (RING) {
-#if VB_TILE_SMEM_PREC
-        double* ring0 = s_prec + (size_t)K * NTP;
-#else
-        double* ring0 = s_ann + ((AKf + 1) & ~1);
-#endif
-        my_ring = ring0 + (size_t)warp * D * SLOTD + lane;
-    }
     __syncthreads();
 
     double tA[P], tC[P], tKd = 0.0, tKq = 0.0, tKs = 0.0;       // warp 0 only
@@ -295,33 +257,6 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
     const double* const g_logdet = a.logdet;
 #endif
     const int64_t ntiles = (M + VB_TILE_SNPS - 1) / VB_TILE_SNPS;
-    // ring fetch iterator: the (tile, component) this warp fetches next, in the order it computes them
-    int64_t f_tile = blockIdx.x;
-    int f_k = warp;
-    uint32_t f_n = 0, c_n = 0;                    // fetches issued / components consumed by this warp
-    auto ring_issue = [&]() {
-        // one commit group per call, empty once this warp has nothing left to fetch (keeps the counts aligned)
-        if (f_tile < ntiles && f_k < K) {
-            const int64_t ii = f_tile * VB_TILE_SNPS + lane;
-            const int64_t ic = ii < M ? ii : M - 1;
-            double* dst = my_ring + (size_t)(f_n % (uint32_t)D) * SLOTD;
-            const double* src = a.mu_in + (size_t)f_k * PM + ic;
-#pragma unroll
-            for (int p = 0; p < P; ++p) vb_cp_async8(dst + p * 32, src + (size_t)p * M);
-            if constexpr (USE) {
-#pragma unroll
-                for (int t = 0; t < 3; ++t)
-                    vb_cp_async8(dst + (P + t) * 32, a.kc_in + ((size_t)t * K + f_k) * M + ic);
-            }
-            f_k += W;
-            if (f_k >= K) { f_k = warp; f_tile += gridDim.x; }
-        }
-        vb_cp_async_commit();
-        ++f_n;
-    };
-    if constexpr (RING) {
-        for (int j = 0; j < D; ++j) ring_issue();
-    }
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t i0 = tile * VB_TILE_SNPS + lane;
@@ -346,42 +281,23 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
         const double* logh = a.logh + (size_t)an * K;
         const double* gfull = a.gfull + (size_t)an * K;
 
-        // ---- pass A: this thread's slice, online softmax moments.  sm2[p] = sum_k w_k (mu'_p^2 + S_pp);
-        //      with the cache only their dt-weighted sum over p is kept, in sm2[0]
+        // ---- pass A: this thread's slice, online softmax moments
         double mx = -1.0e300, s0 = 0.0, sKd = 0.0, sKq = 0.0, sKs = 0.0, spm[P], sm2[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) { spm[p] = 0.0; sm2[p] = 0.0; }
         const double* pmu_in = a.mu_in + (size_t)warp * PM + i;
         double* pmu_out = (MODE == VB_MODE_TRIAL) ? a.mu_out + (size_t)warp * PM + i : nullptr;
         const size_t kstride = (size_t)W * PM;
-        // the state's cached pieces [3][K][M]: read (USE) or written (FILL) for this thread's components
-        const size_t KMs = (size_t)K * M;
-        const double* pkc = USE ? a.kc_in + (size_t)warp * M + i : nullptr;
-        double* pko = (CACHE == VB_CACHE_FILL) ? a.kc_out + (size_t)warp * M + i : nullptr;
-        const size_t cstride = (size_t)W * M;
         double* sl = s_logit;
         double mu_cur[P];
-        if constexpr (!RING) {
 #pragma unroll
-            for (int p = 0; p < P; ++p) mu_cur[p] = (warp < K) ? __ldg(pmu_in + (size_t)p * M) : 0.0;
-        }
+        for (int p = 0; p < P; ++p) mu_cur[p] = (warp < K) ? __ldg(pmu_in + (size_t)p * M) : 0.0;
 #pragma unroll UNROLL_A
         for (int k = warp; k < K; k += W, pmu_in += kstride, sl += W * 32) {
             double mu_nx[P];
-            double cb = 0.0, cq = 0.0, cm = 0.0;                 // cached pieces of this component (USE)
-            if constexpr (RING) {
-                // D groups are in flight; the oldest one is this component's (each lane reads back its own copies)
-                vb_cp_async_wait(D - 1);
-                const double* src = my_ring + (size_t)(c_n % (uint32_t)D) * SLOTD;
-#pragma unroll
-                for (int p = 0; p < P; ++p) mu_cur[p] = src[p * 32];
-                if constexpr (USE) { cb = src[P * 32]; cq = src[(P + 1) * 32]; cm = src[(P + 2) * 32]; }
-                ++c_n;
-                // the slot is free again (its values are in registers): fetch the component D ahead into it
-                ring_issue();
-            }
-            if constexpr (REGPF && !RING) {
-                // the next component's mu: issued now, consumed one iteration later
+            if constexpr (REGPF) {
+                // the next component's mu: issued now, consumed one iteration later (its latency hides
+                // behind this component's ~200-300 dependent fp64 instructions)
 #pragma unroll
                 for (int p = 0; p < P; ++p) mu_nx[p] = mu_cur[p];
                 if (k + W < K) {
@@ -389,43 +305,17 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
                     for (int p = 0; p < P; ++p) mu_nx[p] = __ldg(pmu_in + kstride + (size_t)p * M);
                 }
             }
-            if (!RING && VB_TILE_PREFETCH > 0 && k + VB_TILE_PREFETCH * W < K) {
+            if (VB_TILE_PREFETCH > 0 && k + VB_TILE_PREFETCH * W < K) {
 #pragma unroll
                 for (int p = 0; p < P; ++p) vb_prefetch_l2(pmu_in + VB_TILE_PREFETCH * kstride + (size_t)p * M);
-                if constexpr (USE) {
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) vb_prefetch_l2(pkc + t * KMs + VB_TILE_PREFETCH * cstride);
-                }
             }
-            if constexpr (USE && !RING) {
-                cb = __ldg(pkc); cq = __ldg(pkc + KMs); cm = __ldg(pkc + 2 * KMs);
-            }
-            if constexpr (USE) pkc += cstride;
-            // per-component results: logit, KL piece(s), weighted second moment, mu
-            VbTileComp<P> c;
-            if constexpr (USE) {
-#pragma unroll
-                for (int p = 0; p < P; ++p) { c.mu[p] = mu_cur[p]; c.sd[p] = 0.0; }
-                c.base = cb;
-                c.lk = cb + gfull[k];
-                c.lkh = (c.lk - logh[k]) + cq;                 // the whole KL piece of the component
-                c.quad = 0.0; c.sigsum = 0.0;
-                c.m2w = cm;
-            } else {
 #if VB_TILE_SMEM_PREC
-                const double ldk = k_prec[(size_t)k * KSTR + NTP - 1];
+            const double ldk = k_prec[(size_t)k * KSTR + NTP - 1];
 #else
-                const double ldk = g_logdet[k];
+            const double ldk = g_logdet[k];
 #endif
-                c = vb_tile_component<P, MODE>(k_prec + (size_t)k * KSTR, mu_cur, dt, g, step, one_minus_step,
-                                               gfull[k], logh[k], ldk);
-                if constexpr (MERGED) {
-                    const double q = 0.5 * (c.quad + c.sigsum);
-                    if (valid) { pko[0] = c.base; pko[KMs] = q; pko[2 * KMs] = c.m2w; }
-                    pko += cstride;
-                    c.lkh += q;
-                }
-            }
+            const VbTileComp<P> c = vb_tile_component<P, MODE>(
+                k_prec + (size_t)k * KSTR, mu_cur, dt, g, step, one_minus_step, gfull[k], logh[k], ldk);
             if constexpr (MODE == VB_MODE_TRIAL) {
                 if (valid) {
 #pragma unroll
@@ -439,34 +329,26 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
             const double e = vb_exp_nonpos(-fabs(d));
             double w = e;
             if (d > 0.0) {
-                s0 *= e; sKd *= e;
-                if constexpr (!MERGED) { sKq *= e; sKs *= e; }
+                s0 *= e; sKd *= e; sKq *= e; sKs *= e;
 #pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    spm[p] *= e;
-                    if (!MERGED || p == 0) sm2[p] *= e;
-                }
+                for (int p = 0; p < P; ++p) { spm[p] *= e; sm2[p] *= e; }
                 mx = c.lk;
                 w = 1.0;
             }
             s0 += w;
             sKd = fma(w, c.lkh, sKd);
-            if constexpr (!MERGED) {
-                sKq = fma(w, c.quad, sKq);
-                sKs = fma(w, c.sigsum, sKs);
-            }
+            sKq = fma(w, c.quad, sKq);
+            sKs = fma(w, c.sigsum, sKs);
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 spm[p] = fma(w, c.mu[p], spm[p]);
-                if constexpr (!MERGED) sm2[p] = fma(w, fma(c.mu[p], c.mu[p], c.sd[p]), sm2[p]);
+                sm2[p] = fma(w, fma(c.mu[p], c.mu[p], c.sd[p]), sm2[p]);
             }
-            if constexpr (MERGED) sm2[0] = fma(w, c.m2w, sm2[0]);
-            if constexpr (RING) {
-                (void)mu_nx;
-            } else if constexpr (REGPF) {
+            if constexpr (REGPF) {
 #pragma unroll
                 for (int p = 0; p < P; ++p) mu_cur[p] = mu_nx[p];
             } else {
+                (void)mu_nx;
                 if (k + W < K) {
 #pragma unroll
                     for (int p = 0; p < P; ++p) mu_cur[p] = __ldg(pmu_in + kstride + (size_t)p * M);
@@ -493,7 +375,7 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
                     spm[p] = fma(r, o[(5 + p) * 32], spm[p]);
-                    if (!MERGED || p == 0) sm2[p] = fma(r, o[(5 + P + p) * 32], sm2[p]);
+                    sm2[p] = fma(r, o[(5 + P + p) * 32], sm2[p]);
                 }
             }
             mx = gmx;
@@ -522,26 +404,19 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
             tKd += sKd * inv_den - log_norm;
             tKq += 0.5 * sKq * inv_den;
             tKs += 0.5 * sKs * inv_den;
-            double wpm2 = 0.0;                  // sum_p dt_p pm_p^2 (merged statistics)
 #pragma unroll
             for (int p = 0; p < P; ++p) {
                 const double pm = spm[p] * inv_den;
+                const double pv = sm2[p] * inv_den - pm * pm;
                 a.pm_out[(size_t)p * M + i] = pm;
                 if (a.xbpos[p]) {
                     const int32_t q = a.xbpos[p][i];
                     if (q >= 0) a.xb[p][q] = pm / a.se[(size_t)p * M + i];
                 }
+                if (a.pv_out) a.pv_out[(size_t)p * M + i] = pv;
                 tA[p] = fma(pm, a.adj[(size_t)p * M + i], tA[p]);
-                if constexpr (MERGED) {
-                    wpm2 = fma(dt[p] * pm, pm, wpm2);
-                } else {
-                    const double pv = sm2[p] * inv_den - pm * pm;
-                    if (a.pv_out) a.pv_out[(size_t)p * M + i] = pv;
-                    tC[p] = fma(a.sld[(size_t)p * M + i], pv, tC[p]);
-                }
+                tC[p] = fma(a.sld[(size_t)p * M + i], pv, tC[p]);
             }
-            // sum_p (sld_p / tau_p) pv_p in one piece; reported as C_0 = tau_0 x that (the host divides by tau_0)
-            if constexpr (MERGED) tC[0] += (sm2[0] * inv_den - wpm2) * a.tau0;
         }
     }
 
@@ -564,13 +439,11 @@ __global__ void __launch_bounds__(VbTileCfg<P>::MAXT, VbTileCfg<P>::MINB) vb_snp
 }
 
 // Shared memory one CTA of the tile kernel needs (bytes).
-// ring_rows = rows of a ring slot (P, or P + 2 with the cached constants), depth = slots per warp (0: no ring)
-static inline size_t vb_tile_smem(int K, int P, int W, int akf, int ring_rows = 0, int depth = 0) {
+static inline size_t vb_tile_smem(int K, int P, int W, int akf) {
     const size_t kslots = (size_t)(K + W - 1) / W;
     size_t n = kslots * W * 32 + (size_t)W * VB_TILE_NV(P) * 32 + (size_t)((akf + 1) & ~1);
 #if VB_TILE_SMEM_PREC
     n += (size_t)K * VB_TILE_NTP(P);
 #endif
-    n += (size_t)W * depth * ring_rows * 32;                                        // per-warp ring slots
     return n * sizeof(double);
 }

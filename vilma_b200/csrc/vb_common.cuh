@@ -61,26 +61,6 @@ __device__ __forceinline__ void vb_bulk_g2s(void* smem_dst, const void* gsrc, ui
         : "memory");
 }
 
-// Ampere-style asynchronous copy global -> shared, 8 bytes per thread (SASS: LDGSTS): no register is held
-// while the data is in flight; completion is tracked per thread in commit groups.
-__device__ __forceinline__ void vb_cp_async8(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(vb_smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void vb_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-// wait until at most `pending` of this thread's most recent groups are still in flight (pending <= 7)
-__device__ __forceinline__ void vb_cp_async_wait(int pending) {
-    switch (pending) {
-        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
-        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
-    }
-}
-
 // L2 prefetch of a global address (no register, no scoreboard): the per-SNP kernels hold one 8-byte
 // load of the state per thread in flight, which caps them at ~threads x 8 B / HBM latency
 // (~1.2-2.4 TB/s); prefetching a few components ahead turns those loads into L2 hits.

@@ -60,7 +60,6 @@ static int g_tile_mode = -1;         // vb_set_option("snp_tile", ...): see tile
 static bool g_ann_slots = true;      // vb_set_option("snp_ann_slots", 0): fused annotation sums by warp shuffles only
 static bool g_snp3_park = true;      // vb_set_option("snp3_park", 0): three-pass kernel parks logits in the output buffers
 static int g_fused_finish = -1;      // vb_set_option("ld_fused_finish", v): -1 automatic, 0 separate finish kernel, 1 always fused
-static bool g_tile_ring = true;      // vb_set_option("snp_tile_ring", 0): the tile kernel loads its state with plain loads
 static bool g_three_pass = true;     // vb_set_option("snp_three_pass", 0): always the online single-pass kernel   // vb_set_option("ld_symmetric", 0): store dense blocks in full
 
 // ------------------------------------------------------------------------------------
@@ -141,10 +140,6 @@ struct Fit {
     double* scratch3 = nullptr;    // [3][P][M]
     double *pm_prev = nullptr, *pm_ckpt = nullptr, *pm_next = nullptr;
     int akf = 0, nsp = 0;          // fused annotation sums per evaluation; partial row stride
-    // tile kernel: cached per-(component, SNP) constants (snp_tile_kernel.cuh); merged C statistic when on
-    bool kcache_on = false;
-    bool kc_valid[2] = {false, false};             // kc[s] holds the pieces of the state in mu[s]
-    double* kc[2] = {nullptr, nullptr};            // [3][K][M] each
     int64_t mutations = 0;         // bumped by every public vb_fit_* call (guards speculative work)
     double* part_snp = nullptr;
     int grid_snp = 0;
@@ -304,10 +299,6 @@ extern "C" int vb_set_option(const char* name, int64_t value) {
         g_fused_finish = (int)value;
         return 0;
     }
-    if (name && std::strcmp(name, "snp_tile_ring") == 0) {
-        g_tile_ring = (value != 0);
-        return 0;
-    }
     if (name && std::strcmp(name, "snp_three_pass") == 0) {
         g_three_pass = (value != 0);
         return 0;
@@ -374,7 +365,6 @@ static void free_fit(Fit& f) {
     }
     cudaFree(f.scratch3); cudaFree(f.pm_prev); cudaFree(f.pm_ckpt); cudaFree(f.pm_next);
     cudaFree(f.part_snp); cudaFree(f.part_fin); cudaFree(f.part_ann); cudaFree(f.part_diff);
-    cudaFree(f.kc[0]); cudaFree(f.kc[1]);
     f = Fit();
 }
 
@@ -977,11 +967,11 @@ static int ld_apply(vb_ctx* ctx, LdPop& L, const double* x_snp, double* y_snp, d
     std::memset(&ff, 0, sizeof(ff));
     // the finish fused into the mat-vec needs its partial-sum slot: callers without one (vb_ld_dot) and
     // operators that mix block forms keep the separate finish kernel
-    // (a block's finish stalls the CTA that flushed its last group for a few microseconds: worth it when a
-    // CTA finishes about one block per launch -- multi-GPU shards -- not when it finishes six: measured on
-    // C2, 1700 blocks over 296 CTAs: 0.806 ms fused vs 0.706 + 0.045 ms separate)
-    const int64_t ctas = (int64_t)ctx->num_sms * VB_SYM_CTAS_PER_SM;
-    const bool want_fused = g_fused_finish > 0 || (g_fused_finish < 0 && (int64_t)L.blocks.size() <= 2 * ctas);
+    // (a block's finish stalls the CTA that flushed its last group for a few microseconds: measured on C2,
+    // 1700 blocks over 296 CTAs, 0.806 ms fused vs 0.706 + 0.045 ms separate; and on 1/8 and 1/4 shards --
+    // 212 / 425 blocks -- 0.164 vs 0.107 + 0.021 ms and 0.260 vs 0.194 + 0.024 ms: the separate kernel's
+    // massively parallel gather wins at every size, so automatic = off; the fused path stays selectable)
+    const bool want_fused = g_fused_finish > 0;
     const bool fused = want_fused && L.all_sym && L.n_sgroups > 0 && partial != nullptr;
     if (fused) {
         ff.enabled = 1;
@@ -1135,8 +1125,8 @@ extern "C" int vb_fit_create(vb_ctx* ctx, int K, int P, int64_t M, int A, vb_ld*
 // fuse_ann != 0: every evaluation also accumulates the per-annotation sums of that state's delta
 // (needs A*K <= 48 and A <= 4, silently off otherwise).  Worth it when a separate pass + reduction
 // per hyper step costs more than ~5 % extra per-SNP kernel time, i.e. on multi-GPU runs.
-struct TilePlan { int W, grid; size_t smem; int depth; };
-static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf, int ring_rows = 0);
+struct TilePlan { int W, grid; size_t smem; };
+static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf);
 // fuse_ann == 2: only where the sums are nearly free -- the three-pass kernel's per-thread
 // shared-memory slots (P <= 2, A*K <= 16), e.g. the single-cohort default grid on one GPU.
 extern "C" int vb_fit_set_fusion(vb_ctx* ctx, int fuse_ann) {
@@ -1146,19 +1136,6 @@ extern "C" int vb_fit_set_fusion(vb_ctx* ctx, int fuse_ann) {
     if (fuse_ann == 2)
         on = on && f.P <= 2 && f.A * f.K <= VB_FUSE_ANN_SLOTS && g_three_pass && tile_plan(ctx, f, 0).W == 0;
     f.akf = on ? f.A * f.K : 0;
-    return 0;
-}
-// on != 0: the K-split tile kernel keeps three numbers per (component, SNP) next to every mu buffer, which a
-// delta refresh reuses instead of refactoring Lambda_ki; statistics then come back merged (include/vilma_b200.h)
-extern "C" int vb_fit_set_cache(vb_ctx* ctx, int on) {
-    if (!ctx || !ctx->fit.created) return vb_fail("fit state not created");
-    Fit& f = ctx->fit;
-    f.kcache_on = on != 0;
-    f.kc_valid[0] = f.kc_valid[1] = false;
-    if (!f.kcache_on) {
-        cudaFree(f.kc[0]); cudaFree(f.kc[1]);
-        f.kc[0] = f.kc[1] = nullptr;
-    }
     return 0;
 }
 extern "C" int vb_fit_destroy(vb_ctx* ctx) {
@@ -1186,7 +1163,6 @@ extern "C" int vb_fit_set_snp_data(vb_ctx* ctx, const double* adj, const double*
     CK(cudaMemcpyAsync(f.scal, scal, PM * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.ann, ann, (size_t)f.M * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    f.kc_valid[0] = f.kc_valid[1] = false;
     return 0;
 }
 extern "C" int vb_fit_set_mixture(vb_ctx* ctx, const double* prec, const double* logdet) {
@@ -1194,7 +1170,6 @@ extern "C" int vb_fit_set_mixture(vb_ctx* ctx, const double* prec, const double*
     CK(cudaMemcpyAsync(f.prec, prec, (size_t)f.K * f.P * f.P * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(f.logdet, logdet, (size_t)f.K * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    f.kc_valid[0] = f.kc_valid[1] = false;
     return 0;
 }
 extern "C" int vb_fit_set_hyper(vb_ctx* ctx, const double* hyper) {
@@ -1228,8 +1203,6 @@ static int fit_set_hyper_tables(vb_ctx* ctx, const double* hyper, const double* 
 }
 extern "C" int vb_fit_set_tau(vb_ctx* ctx, const double* tau) {
     NEED_FIT(ctx);
-    for (int p = 0; p < f.P; ++p)
-        if (f.inv_tau[p] != 1.0 / tau[p]) f.kc_valid[0] = f.kc_valid[1] = false;     // Lambda_ki changed
     for (int p = 0; p < f.P; ++p) f.inv_tau[p] = 1.0 / tau[p];
     CK(cudaMemcpyAsync(f.inv_tau_dev, f.inv_tau, VB_MAXP * 8, cudaMemcpyHostToDevice, ctx->stream));
     // pageable source: cudaMemcpyAsync returns once the data is staged, so no stream sync is needed
@@ -1247,7 +1220,6 @@ static int fit_set_params(vb_ctx* ctx, const double* mu, const double* delta_mk,
     CK_LAUNCH(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
     f.trial_kind = -1;
-    f.kc_valid[0] = f.kc_valid[1] = false;         // a new mu: its cached pieces are gone
     return 0;
 }
 extern "C" int vb_fit_set_params(vb_ctx* ctx, const double* mu, const double* delta_mk) {
@@ -1283,8 +1255,8 @@ extern "C" int vb_fit_get_params_dev(vb_ctx* ctx, double* mu_dev, double* delta_
 // Launch geometry of the tile kernel: W warps per 32-SNP tile and CTAs per SM, chosen to maximise
 // resident threads under the shared-memory (logits + merge scratch) and register limits; ties go to
 // the smaller W (shorter merge).  Returns W = 0 when the thread-per-SNP kernels should run.
-static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf, int ring_rows) {
-    TilePlan best{0, 0, 0, 0};
+static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf) {
+    TilePlan best{0, 0, 0};
     if (g_tile_mode == 0) return best;
     // automatic: large grids and P >= 3 (where thread-per-SNP parks K logits per SNP in HBM and pays
     // three logs and square roots per component); the tuned three-pass kernel keeps small P <= 2 grids
@@ -1293,29 +1265,20 @@ static TilePlan tile_plan(const vb_ctx* ctx, const Fit& f, int akf, int ring_row
                                 : (f.P <= 3 ? VbTileCfg<3>::THREADS_PER_SM : VbTileCfg<5>::THREADS_PER_SM);
     const int maxw = std::min(VB_TILE_MAXW, (f.P == 1 ? VbTileCfg<1>::MAXT : (f.P <= 3 ? VbTileCfg<3>::MAXT : VbTileCfg<5>::MAXT)) / 32);
     const size_t cap = 227 * 1024;
-    // with the TMA ring every warp wants >= 4 slots (a slot = one component's rows for the tile): plans
-    // are ranked by resident threads first, then by ring depth
-    const bool ring = ring_rows > 0 && g_tile_ring;
-    const int want_depth = ring ? 6 : 0, min_depth = ring ? 2 : 0;
     int best_threads = 0;
     static const int kWidths[] = {1, 2, 3, 4, 6, 8, 12, 16};     // warps per tile (k is split round-robin: any W works)
     for (int W : kWidths) {
         if (W > maxw) break;
         if (g_tile_mode > 0 && W != g_tile_mode) continue;
-        if (vb_tile_smem(f.K, f.P, W, akf, ring_rows, min_depth) > cap) continue;
-        int ctas = std::min<int>(target / (32 * W), 16);
-        // CTAs per SM the shared memory allows at the minimum depth, then the deepest ring that keeps them
-        while (ctas >= 1 && (vb_tile_smem(f.K, f.P, W, akf, ring_rows, min_depth) + 1024) * ctas > cap + 1024) --ctas;
+        const size_t sm = vb_tile_smem(f.K, f.P, W, akf);
+        if (sm > cap) continue;
+        int ctas = std::min<int>(std::min<int>(target / (32 * W), (int)(cap / (sm + 1024))), 16);
         if (ctas < 1) continue;
-        int depth = min_depth;
-        while (depth < want_depth && (vb_tile_smem(f.K, f.P, W, akf, ring_rows, depth + 1) + 1024) * ctas <= cap + 1024) ++depth;
-        const size_t sm = vb_tile_smem(f.K, f.P, W, akf, ring_rows, depth);
         const int threads = ctas * 32 * W;
         if (threads > best_threads) {
             best_threads = threads;
             best.W = W;
             best.smem = sm;
-            best.depth = depth;
             const int64_t tiles = (f.M + VB_TILE_SNPS - 1) / VB_TILE_SNPS;
             best.grid = (int)std::min<int64_t>(std::min<int64_t>((int64_t)ctx->num_sms * ctas, tiles), f.grid_snp);
         }
@@ -1332,79 +1295,35 @@ extern "C" int vb_debug_tile_plan(int P, int K, int64_t M, int akf, int num_sms,
     Fit f;
     f.P = P; f.K = K; f.M = M;
     f.grid_snp = (int)std::min<int64_t>((M + 127) / 128, (int64_t)num_sms * 16);
-    const TilePlan tp = tile_plan(&ctx, f, akf, P);
+    const TilePlan tp = tile_plan(&ctx, f, akf);
     *W = tp.W; *grid = tp.grid; *smem_bytes = (int64_t)tp.smem;
     return 0;
 }
-template <int P, int MODE, int CACHE, bool RING>
-static void launch_tile_ring(const VbSnpArgs& a, const TilePlan& tp, cudaStream_t st) {
+template <int P, int MODE>
+static void launch_tile_one(const VbSnpArgs& a, const TilePlan& tp, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(vb_snp_tile_kernel<P, MODE, CACHE, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(vb_snp_tile_kernel<P, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set = true;
     }
-    vb_snp_tile_kernel<P, MODE, CACHE, RING><<<tp.grid, 32 * tp.W, tp.smem, st>>>(a);
-}
-template <int P, int MODE, int CACHE>
-static void launch_tile_cache(const VbSnpArgs& a, const TilePlan& tp, cudaStream_t st) {
-    if (tp.depth > 0) launch_tile_ring<P, MODE, CACHE, true>(a, tp, st);
-    else launch_tile_ring<P, MODE, CACHE, false>(a, tp, st);
-}
-template <int P, int MODE>
-static void launch_tile_one(const VbSnpArgs& a, const TilePlan& tp, cudaStream_t st, int cache) {
-    if constexpr (MODE == VB_MODE_REFRESH) {
-        if (cache == VB_CACHE_USE) { launch_tile_cache<P, MODE, VB_CACHE_USE>(a, tp, st); return; }
-    }
-    if (cache == VB_CACHE_FILL) launch_tile_cache<P, MODE, VB_CACHE_FILL>(a, tp, st);
-    else launch_tile_cache<P, MODE, VB_CACHE_NONE>(a, tp, st);
+    vb_snp_tile_kernel<P, MODE><<<tp.grid, 32 * tp.W, tp.smem, st>>>(a);
 }
 template <int MODE>
 static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
     cudaStream_t st = ctx->stream;
     ctx->fit.snp_grid_used = grid;
     if constexpr (MODE != VB_MODE_EVAL) {
-        Fit& f = ctx->fit;
-        // cached per-(component, SNP) pieces: a TRIAL writes those of its output state, a REFRESH reuses the
-        // accepted state's when it has them and writes them otherwise (see snp_tile_kernel.cuh)
-        int cache = VB_CACHE_NONE;
-        VbSnpArgs ac = a;
-        const int akf_ = a.fuse_ann ? a.A * a.K : 0;
-        const bool tiled = tile_plan(ctx, f, akf_, P).W > 0;
-        if (tiled && f.kcache_on && !a.pv_out) {
-            const size_t len = (size_t)3 * f.K * f.M * 8;
-            if (!f.kc[0] && (cudaMalloc(&f.kc[0], len) != cudaSuccess || cudaMalloc(&f.kc[1], len) != cudaSuccess)) {
-                cudaGetLastError();
-                cudaFree(f.kc[0]);
-                f.kc[0] = f.kc[1] = nullptr;
-                f.kcache_on = false;               // not enough memory: keep recomputing
-            }
-            if (f.kcache_on) {
-                if (MODE == VB_MODE_TRIAL) {
-                    cache = VB_CACHE_FILL;
-                    ac.kc_out = f.kc[1 - f.cur_mu];
-                } else if (f.kc_valid[f.cur_mu]) {
-                    cache = VB_CACHE_USE;
-                    ac.kc_in = f.kc[f.cur_mu];
-                } else {
-                    cache = VB_CACHE_FILL;
-                    ac.kc_out = f.kc[f.cur_mu];
-                }
-                ac.tau0 = 1.0 / f.inv_tau[0];
-            }
-        }
-        const TilePlan tp = tile_plan(ctx, f, akf_, P + (cache == VB_CACHE_USE ? 3 : 0));
-        if (tiled && tp.W > 0) {
-            f.snp_grid_used = tp.grid;
-            if (cache == VB_CACHE_FILL) f.kc_valid[MODE == VB_MODE_TRIAL ? 1 - f.cur_mu : f.cur_mu] = true;
-            ac.ring_depth = tp.depth;
+        const TilePlan tp = tile_plan(ctx, ctx->fit, a.fuse_ann ? a.A * a.K : 0);
+        if (tp.W > 0) {
+            ctx->fit.snp_grid_used = tp.grid;
             prof_begin(ctx, 1);
             switch (P) {
-                case 1: launch_tile_one<1, MODE>(ac, tp, st, cache); break;
-                case 2: launch_tile_one<2, MODE>(ac, tp, st, cache); break;
-                case 3: launch_tile_one<3, MODE>(ac, tp, st, cache); break;
-                case 4: launch_tile_one<4, MODE>(ac, tp, st, cache); break;
-                case 5: launch_tile_one<5, MODE>(ac, tp, st, cache); break;
-                case 6: launch_tile_one<6, MODE>(ac, tp, st, cache); break;
+                case 1: launch_tile_one<1, MODE>(a, tp, st); break;
+                case 2: launch_tile_one<2, MODE>(a, tp, st); break;
+                case 3: launch_tile_one<3, MODE>(a, tp, st); break;
+                case 4: launch_tile_one<4, MODE>(a, tp, st); break;
+                case 5: launch_tile_one<5, MODE>(a, tp, st); break;
+                case 6: launch_tile_one<6, MODE>(a, tp, st); break;
                 default: return vb_fail("unsupported cohort count %d", P);
             }
             prof_end(ctx, 1);
@@ -1710,7 +1629,6 @@ extern "C" int vb_fit_init_mu(vb_ctx* ctx) {
     }
     CK_LAUNCH(ctx);
     f.trial_kind = -1;
-    f.kc_valid[0] = f.kc_valid[1] = false;
     return 0;
 }
 

@@ -220,15 +220,6 @@ class CudaEngine:
         self._diff = torch.zeros(self.N_DIFF, dtype=torch.float64, device=dev)
         self.ld_bytes = sum(ld_.bytes for ld_ in self.lds)
         self.native_ready = False
-        self.merged_c = False
-
-    def set_cache(self, on):
-        """Keep each state's per-(component, SNP) logit base / KL share / weighted second moment in HBM
-        (K-split tile kernel) so that delta refreshes need no covariance algebra.  Trial and refresh
-        statistics then come back merged (see include/vilma_b200.h): only for fits that do not learn
-        the error scaling; eval() always returns them unmerged."""
-        _lib.check(self.lib.vb_fit_set_cache(self.ctx.handle, 1 if on else 0))
-        self.merged_c = bool(on)
 
     # ---- small inputs
     def set_hyper(self, hyper):

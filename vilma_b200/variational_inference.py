@@ -436,7 +436,6 @@ class VIScheme():
         self._hyper = hyper.copy()
         self._gtable = numerics.vi_delta_grad_table(self._hyper, self.log_det)
         self._res_stats = stats.copy()
-        self._res_split = False            # (trial / refresh statistics: merged when the cache is on)
         self._res_obj = float(io.obj)
         self._res_valid = True
         self._resident = None
@@ -519,21 +518,11 @@ class VIScheme():
     def _update_error_scaling_dev(self):
         """tau_p = [chi_p - 2 pm.adj + z^T R z + sum sld pv] / rank_p   (reference :472-486)."""
         P = self.num_pops
-        self._split_stats()
         s = self._res_stats
         self.error_scaling = (self.chi_stat - 2 * s[0:P] + s[2 * P:3 * P] + s[P:2 * P]) \
             / self.ld_ranks
         self._eng.set_tau(self.error_scaling)
         self._res_valid = False
-
-    def _split_stats(self):
-        """Per-cohort C and separate KL statistics of the resident state.  Trials / refreshes of a model
-        that does not learn tau return them merged (cached-pieces path of the tile kernel): re-evaluate
-        with the kernel that keeps them apart (direct API calls only; optimize() never needs this)."""
-        if getattr(self._eng, 'merged_c', False) and not self._res_split:
-            self._res_stats = self._comm.sum(self._eng.eval())
-            self.n_evals += 1
-            self._res_split = True
 
     def _update_error_scaling(self, params):
         self._make_resident(params)
@@ -582,7 +571,6 @@ class MultiPopVI(VIScheme):
         self._res_valid = False
         self._res_obj = None
         self._res_stats = None
-        self._res_split = True
         self._hyper = None
         self.n_trials = 0
         self.n_evals = 0
@@ -614,9 +602,6 @@ class MultiPopVI(VIScheme):
                     lds.append(ld.to_device(ctx))
             self._eng = CudaEngine(ctx, lds, **pieces)
             self._eng.init_comm(self._comm)
-            # state-independent per-(component, SNP) constants stay in HBM between evaluations unless the
-            # error scaling is learned (its update needs the per-cohort C statistics the cache merges)
-            self._eng.set_cache(not self.scale_se)
         self._eng.set_tau(self.error_scaling)
 
     # ------------------------------------------------------------------ hidden state
@@ -738,7 +723,6 @@ class MultiPopVI(VIScheme):
         """Cache the reduced statistics / objective of the (new) accepted device state.
         `resident` is the host tuple it corresponds to, or None if it only lives in HBM."""
         self._res_stats = stats
-        self._res_split = resident is not None        # (uploaded states are evaluated by the unmerged kernel)
         ll, kl = self._objective(stats)
         self._res_obj = ll - kl
         self._resident = resident
@@ -947,7 +931,6 @@ class MultiPopVI(VIScheme):
     # ------------------------------------------------------------------ KL pieces
     def _delta_KL(self, vi_mu, vi_delta, hyper_delta):
         self._make_resident((vi_mu, vi_delta, hyper_delta))
-        self._split_stats()
         return float(self._res_stats[3 * self.num_pops])
 
     def _beta_KL(self, vi_mu, vi_delta, hyper_delta):
