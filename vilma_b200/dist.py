@@ -44,17 +44,18 @@ def index_runs(idx):
     return [(int(idx[a]), int(idx[b - 1]) + 1, int(a)) for a, b in zip(lo, hi)]
 
 
-def take_runs(arr, idx, axis):
+def take_runs(arr, idx, axis, alloc=None):
     """arr.take(idx, axis) for a sorted `idx`, as a few slice copies (whole LD blocks are contiguous
-    SNP ranges) instead of a gather."""
+    SNP ranges) instead of a gather.  `alloc(shape)` supplies the output (e.g. page-locked memory)."""
     arr = np.asarray(arr)
     runs = index_runs(idx)
-    if len(runs) > max(64, len(idx) // 16):          # scattered indices: a plain gather is as good
-        return np.ascontiguousarray(arr.take(idx, axis=axis))
-    sl = [slice(None)] * arr.ndim
     shape = list(arr.shape)
     shape[axis] = len(idx)
-    out = np.empty(shape, dtype=arr.dtype)
+    out = np.empty(shape, dtype=arr.dtype) if alloc is None else alloc(tuple(shape))
+    if len(runs) > max(64, len(idx) // 16):          # scattered indices: a plain gather is as good
+        np.take(arr, idx, axis=axis, out=out)
+        return out
+    sl = [slice(None)] * arr.ndim
     dst = [slice(None)] * arr.ndim
     for g0, g1, l0 in runs:
         sl[axis] = slice(g0, g1)
@@ -164,11 +165,16 @@ class TorchComm(SingleComm):
         """Assemble several global arrays from per-rank shards along their SNP axes through ONE
         node-shared host mapping (a file in /dev/shm mapped by every rank): each rank copies only its
         own shard -- 1/N of the bytes -- and every rank ends up with the same zero-copy view.  Replaces
-        an all-gather to every GPU followed by N full device->host copies.  Returns None when the ranks
-        do not share a host or /dev/shm lacks the space (callers fall back to gather_snp_axis)."""
+        an all-gather to every GPU followed by N full device->host copies.  Mappings are pooled: one
+        whose arrays have been dropped on EVERY rank is written again (its pages are already faulted in:
+        first-touching 268 MB of fresh tmpfs pages costs more than the copies), otherwise a new one is
+        created.  Returns None when the ranks do not share a host or /dev/shm lacks the space (callers
+        fall back to gather_snp_axis)."""
         import mmap
         import os
         import socket
+        import weakref
+        import torch
         shapes, offs, total = [], [], 0
         for a, ax in zip(locals_, axes):
             shp = list(a.shape)
@@ -177,28 +183,51 @@ class TorchComm(SingleComm):
             offs.append(total)
             total += int(np.prod(shp)) * 8
             total = (total + 4095) & ~4095
-        hosts = self.allgather_bytes(socket.gethostname().encode())
-        ok = len(set(hosts)) == 1
-        name = b''
-        if self.rank == 0 and ok:
-            try:
-                st = os.statvfs('/dev/shm')
-                if st.f_bavail * st.f_frsize > total + (64 << 20):
-                    self._shm_seq = getattr(self, '_shm_seq', 0) + 1
-                    name = ('/dev/shm/vilma_b200_%d_%d' % (os.getpid(), self._shm_seq)).encode()
-                    fd = os.open(name.decode(), os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
-                    os.ftruncate(fd, total)
-                    os.close(fd)
-            except OSError:
-                name = b''
-        name = self.broadcast_bytes(name)
-        if not name:
+        if not hasattr(self, '_shm_pool'):
+            self._shm_pool = []              # [mmap, size, [weakrefs of the arrays handed out]]
+            hosts = self.allgather_bytes(socket.gethostname().encode())
+            self._shm_same_host = len(set(hosts)) == 1
+        if not self._shm_same_host:
             return None
-        fd = os.open(name.decode(), os.O_RDWR)
-        try:
-            mm = mmap.mmap(fd, total)
-        finally:
-            os.close(fd)
+        # a pooled mapping of this size that nobody references any more -- on any rank?
+        free = [i for i, (mm, size, refs) in enumerate(self._shm_pool)
+                if size == total and all(r() is None for r in refs)]
+        flag = torch.zeros(len(self._shm_pool) + 1, dtype=torch.int32)
+        for i in free:
+            flag[i] = 1
+        if self._backend == 'nccl':
+            flag = flag.cuda()
+        self._dist.all_reduce(flag, op=self._dist.ReduceOp.MIN)
+        flag = flag.cpu().numpy()
+        reuse = next((i for i in range(len(self._shm_pool)) if flag[i] == 1), None)
+        if reuse is not None:
+            mm = self._shm_pool[reuse][0]
+        else:
+            name = b''
+            if self.rank == 0:
+                try:
+                    st = os.statvfs('/dev/shm')
+                    if st.f_bavail * st.f_frsize > total + (64 << 20):
+                        self._shm_seq = getattr(self, '_shm_seq', 0) + 1
+                        name = ('/dev/shm/vilma_b200_%d_%d' % (os.getpid(), self._shm_seq)).encode()
+                        fd = os.open(name.decode(), os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+                        os.ftruncate(fd, total)
+                        os.close(fd)
+                except OSError:
+                    name = b''
+            name = self.broadcast_bytes(name)
+            if not name:
+                return None
+            fd = os.open(name.decode(), os.O_RDWR)
+            try:
+                mm = mmap.mmap(fd, total)
+            finally:
+                os.close(fd)
+            self.barrier()                       # everybody has it mapped
+            if self.rank == 0:
+                os.unlink(name.decode())         # the mappings live on
+            self._shm_pool.append([mm, total, []])
+            reuse = len(self._shm_pool) - 1
         runs = index_runs(snps)
         outs = []
         for a, ax, shp, off in zip(locals_, axes, shapes, offs):
@@ -210,9 +239,8 @@ class TorchComm(SingleComm):
                 src[ax] = slice(l0, l0 + (g1 - g0))
                 g[tuple(dst)] = a[tuple(src)]
             outs.append(g)
+        self._shm_pool[reuse][2] = [weakref.ref(o.base if o.base is not None else o) for o in outs]
         self.barrier()                       # every shard is in place
-        if self.rank == 0:
-            os.unlink(name.decode())         # the mapping lives on until the last view is dropped
         return outs
 
     def barrier(self):

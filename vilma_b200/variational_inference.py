@@ -717,7 +717,8 @@ class MultiPopVI(VIScheme):
             # this rank's shard only crosses PCIe: whole LD blocks are contiguous SNP ranges, so the
             # shard is cut out on the host with a few slice copies
             from .dist import take_runs
-            self._eng.set_params(take_runs(vi_mu, snps, 2), take_runs(vi_delta, snps, 0))
+            alloc = getattr(self._eng, '_host_array', None)       # page-locked: the copies run at PCIe speed
+            self._eng.set_params(take_runs(vi_mu, snps, 2, alloc), take_runs(vi_delta, snps, 0, alloc))
 
     def _set_result(self, stats, resident):
         """Cache the reduced statistics / objective of the (new) accepted device state.
