@@ -678,7 +678,7 @@ def measure(vi, ctx, info, comm, device, args, hbm_peak, peak_src, sampler=None,
     init = vi._initialize()
     info['initialize_s'] = time.time() - t0
     log('[rank %d] _initialize %.1fs' % (comm.rank, info['initialize_s']))
-    pin = [torch.from_numpy(np.array(a)).pin_memory() for a in init]
+    pin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in init]
     init = tuple(t.numpy() for t in pin)
     ckpt = {'vi_mu': init[0], 'vi_delta': init[1], 'hyper_delta': init[2],
             'error_scaling': np.ones(P)}
@@ -804,6 +804,16 @@ def measure(vi, ctx, info, comm, device, args, hbm_peak, peak_src, sampler=None,
             wrapper.__wrapped__ = fn
             return wrapper
         vi.begin_loop = timed('upload+first evaluation', vi.begin_loop)
+        vi._upload = timed('(upload alone)', vi._upload)
+        if os.environ.get('VILMA_B200_E2E_MARKS'):
+            vi._eng.eval = timed('(eval)', vi._eng.eval)
+            vi._comm.sum = timed('(comm.sum)', vi._comm.sum)
+            vi._set_result = timed('(set_result)', vi._set_result)
+            vi._fingerprint = timed('(fingerprint)', vi._fingerprint)
+            vi._objective = timed('(objective)', vi._objective)
+            import gc
+            gc.callbacks.append(lambda ph, inf: log('[gc %s gen %s at %.1f ms]' % (ph, inf.get('generation'), (time.perf_counter() - t0) * 1e3)))
+            vi._eng.pm_mark = timed('(pm_mark)', vi._eng.pm_mark)
         vi.run_loop = timed('iterations', vi.run_loop)
         vi._download = timed('download', vi._download)
         t0 = time.perf_counter()
@@ -812,8 +822,8 @@ def measure(vi, ctx, info, comm, device, args, hbm_peak, peak_src, sampler=None,
         e2e_s = time.perf_counter() - t0
         log('[rank %d] e2e %.1f ms: %s' % (comm.rank, e2e_s * 1e3,
                                            ', '.join('%s %.1f ms' % (k, v * 1e3) for k, v in marks.items())))
-        vi.begin_loop, vi.run_loop, vi._download = (getattr(f, '__wrapped__', f) for f in
-                                                    (vi.begin_loop, vi.run_loop, vi._download))
+        vi.begin_loop, vi.run_loop, vi._download, vi._upload = (
+            getattr(f, '__wrapped__', f) for f in (vi.begin_loop, vi.run_loop, vi._download, vi._upload))
         e2e_s = float(comm.max(np.array([e2e_s]))[0])
         e2e_trials = vi.n_trials - tr0
         e2e_steps = vi.num_its_run

@@ -139,6 +139,20 @@ int vb_fit_get_params(vb_ctx* ctx, double* vi_mu_host, double* vi_delta_mk_host)
 /* the same with device buffers (multi-GPU: shards are gathered / scattered on the device) */
 int vb_fit_set_params_dev(vb_ctx* ctx, const double* vi_mu_dev, const double* vi_delta_mk_dev);
 int vb_fit_get_params_dev(vb_ctx* ctx, double* vi_mu_dev, double* vi_delta_mk_dev);
+/* Sharded transfers (multi-GPU): `snps_host[M]` = global index of each SNP this rank owns, of M_total.
+ * The *_shard calls move only this rank's SNPs between the device state and GLOBAL host arrays in the
+ * reference layouts (vi_mu [K,P,M_total], vi_delta [M_total,K]); they replace gathering
+ * `variational_inference.py:340-394`'s parameter tuple on every rank.  set: any host memory (runs of
+ * consecutive SNPs are cut out into page-locked staging by a few host threads).  get: the GPU scatters
+ * into the arrays itself, so they must be memory it can address -- page-locked allocations or memory
+ * registered with vb_host_register, e.g. one node-shared mapping of which every rank fills in its own
+ * part; it fails (no fallback) on plain pageable memory: ask vb_host_accessible. */
+int vb_fit_set_shard(vb_ctx* ctx, const int64_t* snps_host, int64_t M_total);
+int vb_fit_set_params_shard(vb_ctx* ctx, const double* vi_mu_global_host, const double* vi_delta_mk_global_host);
+int vb_fit_get_params_shard(vb_ctx* ctx, double* vi_mu_global_host, double* vi_delta_mk_global_host);
+int vb_host_accessible(const void* host);            /* 1 if device kernels can address it */
+int vb_host_register(void* host, int64_t bytes);     /* cudaHostRegister(portable | mapped) */
+int vb_host_unregister(void* host);
 
 /* ---- evaluations: each fills stats_dev[0 .. 3P+3) for ONE parameter state; stats_dev must hold
  * 3P+3+58 doubles: with vb_fit_set_fusion(ctx, 1) and A*K <= 48, entries [3P+3, 3P+3+A*K) receive

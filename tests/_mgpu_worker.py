@@ -41,6 +41,19 @@ for name in sys.argv[1:]:
         assert np.allclose(params[2], fx['final_hyper_delta'], rtol=1e-6, atol=1e-12)
         assert np.allclose(vi.error_scaling, fx['final_error_scaling'], rtol=1e-8)
         assert np.allclose(vi.real_posterior_mean(*params), fx['final_post_mean'], rtol=1e-6, atol=1e-9)
+        # the fitted parameters came back through the node-shared, page-locked mapping the GPUs scattered
+        # their SNPs into (every rank sees all of them: compared above); uploading them again cuts this
+        # rank's runs out again and must reproduce the state bit for bit
+        final_elbo = vi.elbo(params)
+        assert vi._eng.host_accessible(np.asarray(params[0])) and vi._eng.host_accessible(np.asarray(params[1]))
+        vi._resident = None
+        again = vi.elbo(params)          # (evaluated by the given-state kernel: same value, other rounding)
+        assert np.isclose(again, final_elbo, rtol=1e-10, atol=0)
+        back = vi._download()
+        assert np.array_equal(back[0], params[0]) and np.array_equal(back[1], params[1])
+        # a pageable, non-contiguous copy: same state
+        vi._resident = None
+        assert vi.elbo((np.asfortranarray(params[0]), np.array(params[1]), np.array(params[2]))) == again
         if rank == 0:
             print('ok', name, 'native' if native else 'python', flush=True)
 dist.barrier()

@@ -46,6 +46,12 @@ SIGNATURES = {
     'vb_fit_get_params': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'vb_fit_set_params_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'vb_fit_get_params_dev': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    'vb_fit_set_shard': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    'vb_fit_set_params_shard': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    'vb_fit_get_params_shard': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    'vb_host_accessible': (C.c_int, [C.c_void_p]),
+    'vb_host_register': (C.c_int, [C.c_void_p, C.c_int64]),
+    'vb_host_unregister': (C.c_int, [C.c_void_p]),
     'vb_fit_eval': (C.c_int, [C.c_void_p, C.c_void_p]),
     'vb_fit_beta_trial': (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
     'vb_fit_refresh_delta': (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -70,6 +70,9 @@ def _to_numpy(t):
     return t.detach().cpu().numpy().astype(np.float64, copy=True)
 
 
+_SHM_POOL = []      # node-shared result mappings of this process (TorchComm.shared_arrays)
+
+
 class TorchComm(SingleComm):
     """All-reduce through the default torch.distributed process group."""
 
@@ -129,7 +132,8 @@ class TorchComm(SingleComm):
         full = torch.zeros((M, flat.shape[1]), dtype=rows.dtype, device=dev)
         full.index_copy_(0, where, rows)
         out = full.cpu().numpy()
-        return np.moveaxis(out.reshape((M,) + rest), 0, axis)
+        # (C-contiguous in the caller's axis order: a moved-axis view makes every later pass a transposing copy)
+        return np.ascontiguousarray(np.moveaxis(out.reshape((M,) + rest), 0, axis))
 
     def gather_device(self, local, snps, M, axis):
         """gather_snp_axis for a torch tensor that already lives on the gathering device; the
@@ -161,48 +165,46 @@ class TorchComm(SingleComm):
         host.copy_(full)
         return host.numpy()
 
-    def gather_shared(self, locals_, snps, M, axes):
-        """Assemble several global arrays from per-rank shards along their SNP axes through ONE
-        node-shared host mapping (a file in /dev/shm mapped by every rank): each rank copies only its
-        own shard -- 1/N of the bytes -- and every rank ends up with the same zero-copy view.  Replaces
-        an all-gather to every GPU followed by N full device->host copies.  Mappings are pooled: one
-        whose arrays have been dropped on EVERY rank is written again (its pages are already faulted in:
-        first-touching 268 MB of fresh tmpfs pages costs more than the copies), otherwise a new one is
-        created.  Returns None when the ranks do not share a host or /dev/shm lacks the space (callers
-        fall back to gather_snp_axis)."""
+    def shared_arrays(self, shapes):
+        """float64 arrays of the given shapes inside ONE node-shared host mapping (a file in /dev/shm
+        mapped by every rank): what one rank writes, every rank reads -- each rank fills in its own shard
+        and all of them end up with the same zero-copy view, instead of an all-gather to every GPU
+        followed by N full device->host copies.  Mappings are pooled: one whose arrays have been dropped
+        on EVERY rank is handed out again (its pages are already faulted in and, where the caller had it
+        page-locked, still registered), otherwise a new one is created.  Returns (arrays, entry) -- `entry`
+        is the pool record, a dict the caller may keep notes in ('address', 'nbytes' are set) -- or None
+        when the ranks do not share a host or /dev/shm lacks the space.  Collective."""
         import mmap
         import os
         import socket
         import weakref
         import torch
-        shapes, offs, total = [], [], 0
-        for a, ax in zip(locals_, axes):
-            shp = list(a.shape)
-            shp[ax] = M
-            shapes.append(tuple(shp))
+        shapes = [tuple(int(v) for v in shp) for shp in shapes]
+        offs, total = [], 0
+        for shp in shapes:
             offs.append(total)
             total += int(np.prod(shp)) * 8
             total = (total + 4095) & ~4095
-        if not hasattr(self, '_shm_pool'):
-            self._shm_pool = []              # [mmap, size, [weakrefs of the arrays handed out]]
+        if not hasattr(self, '_shm_same_host'):
             hosts = self.allgather_bytes(socket.gethostname().encode())
             self._shm_same_host = len(set(hosts)) == 1
         if not self._shm_same_host:
             return None
+        # The pool belongs to the process, not to this communicator object, and its mappings are never
+        # unmapped: a caller may have page-locked one with the CUDA driver, and unmapping a registered
+        # range leaves a stale registration behind that a later mapping at the same address would inherit.
+        self._shm_pool = _SHM_POOL
         # a pooled mapping of this size that nobody references any more -- on any rank?
-        free = [i for i, (mm, size, refs) in enumerate(self._shm_pool)
-                if size == total and all(r() is None for r in refs)]
         flag = torch.zeros(len(self._shm_pool) + 1, dtype=torch.int32)
-        for i in free:
-            flag[i] = 1
+        for i, e in enumerate(self._shm_pool):
+            if e['nbytes'] == total and all(r() is None for r in e['refs']):
+                flag[i] = 1
         if self._backend == 'nccl':
             flag = flag.cuda()
         self._dist.all_reduce(flag, op=self._dist.ReduceOp.MIN)
         flag = flag.cpu().numpy()
-        reuse = next((i for i in range(len(self._shm_pool)) if flag[i] == 1), None)
-        if reuse is not None:
-            mm = self._shm_pool[reuse][0]
-        else:
+        entry = next((self._shm_pool[i] for i in range(len(self._shm_pool)) if flag[i] == 1), None)
+        if entry is None:
             name = b''
             if self.rank == 0:
                 try:
@@ -226,20 +228,39 @@ class TorchComm(SingleComm):
             self.barrier()                       # everybody has it mapped
             if self.rank == 0:
                 os.unlink(name.decode())         # the mappings live on
-            self._shm_pool.append([mm, total, []])
-            reuse = len(self._shm_pool) - 1
+            base = np.frombuffer(mm, dtype=np.uint8)
+            entry = {'mm': mm, 'nbytes': total, 'refs': [], 'address': int(base.ctypes.data)}
+            del base
+            self._shm_pool.append(entry)
+        outs = [np.frombuffer(entry['mm'], dtype=np.float64, count=int(np.prod(shp)), offset=off).reshape(shp)
+                for shp, off in zip(shapes, offs)]
+        entry['refs'] = [weakref.ref(o.base if o.base is not None else o) for o in outs]
+        return outs, entry
+
+    @staticmethod
+    def fill_shared(globals_, locals_, snps, axes):
+        """Host copy of this rank's shards into the shared arrays (runs of consecutive SNPs)."""
         runs = index_runs(snps)
-        outs = []
-        for a, ax, shp, off in zip(locals_, axes, shapes, offs):
-            g = np.frombuffer(mm, dtype=np.float64, count=int(np.prod(shp)), offset=off).reshape(shp)
+        for g, a, ax in zip(globals_, locals_, axes):
             src = [slice(None)] * a.ndim
             dst = [slice(None)] * a.ndim
             for g0, g1, l0 in runs:
                 dst[ax] = slice(g0, g1)
                 src[ax] = slice(l0, l0 + (g1 - g0))
                 g[tuple(dst)] = a[tuple(src)]
-            outs.append(g)
-        self._shm_pool[reuse][2] = [weakref.ref(o.base if o.base is not None else o) for o in outs]
+
+    def gather_shared(self, locals_, snps, M, axes):
+        """shared_arrays + fill_shared + barrier: global arrays assembled from per-rank host shards."""
+        shapes = []
+        for a, ax in zip(locals_, axes):
+            shp = list(a.shape)
+            shp[ax] = M
+            shapes.append(shp)
+        got = self.shared_arrays(shapes)
+        if got is None:
+            return None
+        outs, _ = got
+        self.fill_shared(outs, locals_, snps, axes)
         self.barrier()                       # every shard is in place
         return outs
 

@@ -259,6 +259,37 @@ class CudaEngine:
         _lib.check(self.lib.vb_fit_get_params(self.ctx.handle, _lib.np_ptr(mu), _lib.np_ptr(dmk)))
         return mu, dmk
 
+    # ---- sharded transfers against GLOBAL host arrays the device can address (multi-GPU)
+    def set_shard(self, snps, M_total):
+        idx = np.ascontiguousarray(snps, dtype=np.int64)
+        assert idx.shape == (self.M,)
+        _lib.check(self.lib.vb_fit_set_shard(self.ctx.handle, _lib.np_ptr(idx), int(M_total)))
+        self._shard_total = int(M_total)
+
+    def host_accessible(self, arr):
+        """True if kernels can read/write `arr` in place (page-locked or registered, C-contiguous float64)."""
+        return (isinstance(arr, np.ndarray) and arr.dtype == np.float64 and arr.flags.c_contiguous
+                and bool(self.lib.vb_host_accessible(C.c_void_p(arr.ctypes.data))))
+
+    def host_register(self, address, nbytes):
+        """Page-lock and map a host range (e.g. a node-shared mapping); False if the driver declines."""
+        return self.lib.vb_host_register(C.c_void_p(address), int(nbytes)) == 0
+
+    def host_unregister(self, address):
+        return self.lib.vb_host_unregister(C.c_void_p(address)) == 0
+
+    def set_params_shard(self, vi_mu_global, vi_delta_global):
+        mu = np.ascontiguousarray(vi_mu_global, dtype=np.float64)
+        dmk = np.ascontiguousarray(vi_delta_global, dtype=np.float64)
+        assert mu.shape == (self.K, self.P, self._shard_total) and dmk.shape == (self._shard_total, self.K)
+        _lib.check(self.lib.vb_fit_set_params_shard(self.ctx.handle, _lib.np_ptr(mu), _lib.np_ptr(dmk)))
+
+    def get_params_shard(self, vi_mu_global, vi_delta_global):
+        assert vi_mu_global.shape == (self.K, self.P, self._shard_total)
+        assert vi_delta_global.shape == (self._shard_total, self.K)
+        _lib.check(self.lib.vb_fit_get_params_shard(self.ctx.handle, C.c_void_p(vi_mu_global.ctypes.data),
+                                                    C.c_void_p(vi_delta_global.ctypes.data)))
+
     def get_params_device(self):
         """(vi_mu [K,P,M], vi_delta [M,K]) of this rank as torch CUDA tensors."""
         torch = _torch()

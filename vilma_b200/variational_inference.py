@@ -602,6 +602,8 @@ class MultiPopVI(VIScheme):
                     lds.append(ld.to_device(ctx))
             self._eng = CudaEngine(ctx, lds, **pieces)
             self._eng.init_comm(self._comm)
+            if len(snps) != M:
+                self._eng.set_shard(snps, M)
         self._eng.set_tau(self.error_scaling)
 
     # ------------------------------------------------------------------ hidden state
@@ -716,9 +718,12 @@ class MultiPopVI(VIScheme):
         else:
             # this rank's shard only crosses PCIe: whole LD blocks are contiguous SNP ranges, so the
             # shard is cut out on the host with a few slice copies
-            from .dist import take_runs
-            alloc = getattr(self._eng, '_host_array', None)       # page-locked: the copies run at PCIe speed
-            self._eng.set_params(take_runs(vi_mu, snps, 2, alloc), take_runs(vi_delta, snps, 0, alloc))
+            eng = self._eng
+            if hasattr(eng, 'set_params_shard'):
+                eng.set_params_shard(vi_mu, vi_delta)      # (native: run copies into page-locked staging)
+            else:
+                from .dist import take_runs
+                eng.set_params(take_runs(vi_mu, snps, 2), take_runs(vi_delta, snps, 0))
 
     def _set_result(self, stats, resident):
         """Cache the reduced statistics / objective of the (new) accepted device state.
@@ -734,15 +739,31 @@ class MultiPopVI(VIScheme):
         """Resident state -> host tuple (new arrays, reference layouts)."""
         if self._resident is not None:
             return self._resident
-        mu, delta = self._eng.get_params()            # this rank's shard: 1/N of the bytes over PCIe
-        shared = None
-        if self._comm.world > 1 and hasattr(self._comm, 'gather_shared'):
-            shared = self._comm.gather_shared([mu, delta], self._snps, self.num_loci, [2, 0])
-        if shared is not None:
-            mu, delta = shared
+        eng, comm = self._eng, self._comm
+        got = None
+        if comm.world > 1 and hasattr(comm, 'shared_arrays'):
+            K, P, M = self.num_mix, self.num_pops, self.num_loci
+            got = comm.shared_arrays([(K, P, M), (M, K)])
+        if got is not None:
+            # one node-shared host mapping; this rank fills in its own SNPs -- 1/N of the bytes over PCIe.
+            # Where the driver can page-lock the mapping the GPU scatters them there itself.
+            (mu, delta), entry = got
+            if hasattr(eng, 'get_params_shard'):
+                if 'registered' not in entry:
+                    entry['registered'] = eng.host_register(entry['address'], entry['nbytes'])
+                direct = entry['registered']
+            else:
+                direct = False
+            if direct:
+                eng.get_params_shard(mu, delta)
+            else:
+                comm.fill_shared([mu, delta], eng.get_params(), self._snps, [2, 0])
+            comm.barrier()                   # every shard is in place
         else:
-            mu = self._comm.gather_snp_axis(mu, self._snps, self.num_loci, 2)
-            delta = self._comm.gather_snp_axis(delta, self._snps, self.num_loci, 0)
+            mu, delta = eng.get_params()
+            if comm.world > 1:
+                mu = comm.gather_snp_axis(mu, self._snps, self.num_loci, 2)
+                delta = comm.gather_snp_axis(delta, self._snps, self.num_loci, 0)
         self._resident = (mu, delta, np.array(self._hyper))
         for arr in self._resident:
             # the cache is keyed on object identity (_same): an in-place edit by the caller would go
