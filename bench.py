@@ -178,7 +178,7 @@ def build_gpu_problem_multi(comm, device, wl, M_total=M_TOTAL, n_blocks=N_BLOCKS
     """Multi-cohort analogue of build_gpu_problem: every cohort's LD shard is generated in HBM."""
     import torch
     from vilma_b200 import synth
-    from vilma_b200.engine import DeviceContext, DeviceLD, choose_storage, dense_bytes
+    from vilma_b200.engine import DeviceContext, DeviceLD, choose_storage, dense_bytes, factor_bytes
     from vilma_b200.variational_inference import DeviceBlockDiagonalMatrix, MultiPopVI
 
     dev = torch.device('cuda', device)
@@ -256,11 +256,11 @@ def build_gpu_problem_multi(comm, device, wl, M_total=M_TOTAL, n_blocks=N_BLOCKS
                     gwas_N=N, init_hg=np.full(P, INIT_HG), num_its=num_its,
                     comm=comm, device=device, precomputed=pre, local_snps=snps, context=ctx)
     per_block = [dense_bytes(int(n)) if choose_storage(int(n), rank_of(int(n))) == 'dense' or not low_rank
-                 else 16 * int(n) * rank_of(int(n)) for n in n_all]
+                 else factor_bytes(int(n), rank_of(int(n))) for n in n_all]
     info = dict(M=M_total, M_ld=M_ld, blocks=int(n_blocks), K=len(covs), P=P,
                 ld_bytes_total=int(P * sum(per_block)), ld_bytes_rank=int(sum(ld.bytes for ld in lds)),
                 setup_s=time.time() - t0, n_max=int(n_all.max()),
-                ld_store='%d of %d blocks symmetric-packed dense, the rest as factors' % (
+                ld_store='%d of %d blocks symmetric-packed dense, the rest as factors U sqrt(s) read once per mat-vec' % (
                     sum(1 for n in n_all if not low_rank or choose_storage(int(n), rank_of(int(n))) == 'dense'),
                     len(n_all)),
                 rank_total=float(ld_ranks.sum()), name=wl['name'])

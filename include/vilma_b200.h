@@ -40,6 +40,9 @@ const char* vb_last_error(void);
 /* process-wide options (kernel selection; the defaults are the measured best):
  *   "ld_symmetric" (default 1): store dense blocks of n <= vb_ld_sym_nmax() symmetric-packed
  *                  (read when an LD operator is created)
+ *   "ld_factor_once" (default 1): factor blocks of n <= vb_ld_fac_nmax() are stored as U sqrt(s) and read once
+ *                  per mat-vec (8 n r bytes; needs s >= 0); 0 = always V' = diag(s) U^T and U (16 n r bytes)
+ *   "ld_fused_finish" (default 0): 1 = the symmetric kernel also finishes every block whose last group it flushed
  *   "snp_three_pass" (default 1): one- and two-cohort updates with K < 32 use the three-pass softmax kernel
  *   "snp3_park" (default 1): that kernel keeps logits / weights / mu' in shared memory when they fit
  *   "snp_tile" (default -1 = automatic: P >= 3 or K >= 32): the K-split tile kernel; 0 = never,
@@ -50,6 +53,8 @@ int vb_set_option(const char* name, int64_t value);
 int vb_debug_tile_plan(int P, int K, int64_t M, int akf, int num_sms, int* W, int* grid, int64_t* smem_bytes);
 /* largest dense block (rows) that is stored symmetric-packed; larger ones are stored in full */
 int64_t vb_ld_sym_nmax(void);
+/* largest factor block (rows) that is stored in the read-once form (0: option "ld_factor_once" is off) */
+int64_t vb_ld_fac_nmax(void);
 /* device: CUDA ordinal; stream: cudaStream_t (may be NULL). */
 int vb_ctx_create(int device, void* stream, vb_ctx** out);
 int vb_ctx_destroy(vb_ctx* ctx);
@@ -72,12 +77,15 @@ int vb_ctx_profile_read(vb_ctx* ctx, double* total_ms4, int64_t* count4);
  *                  block b is given dense).  M = SNPs on this rank.
  * vb_ld_set_dense  block b as a dense symmetric n x n matrix, row stride `ld` doubles.
  * vb_ld_set_factor block b as U (n x r, row-major, row stride r) and s (r):  R_b = U diag(s) U^T
- *                  (the reference's u, s; its v is u^T and D must be zero on this path).
+ *                  (the reference's u, s; its v is u^T and D must be zero on this path).  Blocks of
+ *                  n <= vb_ld_fac_nmax() need s >= 0 (true of every block the reference builds from a
+ *                  matrix: it drops eigenvalues <= 1e-12 max, matrix_structures.py:18) and fail otherwise.
  * vb_ld_finalize   perm[j] = SNP index (0..M-1, this rank's numbering) of block-order
  *                  position j, for j < sum_b n[b]; SNPs not listed are "missing" (zero rows).
  * vb_ld_dot        y = R x in SNP order (x, y device vectors of length M).
  * vb_ld_bytes      algorithmic bytes one mat-vec reads from the LD store: 4 n (n+1) per
- *                  symmetric-packed dense block, 8 n^2 per full dense block, 16 n r per factor block.
+ *                  symmetric-packed dense block, 8 n^2 per full dense block, 8 n r per read-once
+ *                  factor block (n padded to even), 16 n r per two-pass factor block.
  */
 int vb_ld_create(vb_ctx* ctx, int64_t M, int64_t nblocks, const int64_t* n, const int64_t* rank,
                  vb_ld** out);

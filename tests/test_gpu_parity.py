@@ -261,10 +261,91 @@ def test_big_block_slabs_and_factor(symmetric):
     ref[idx] = U @ (s * (U.T @ x[idx]))
     assert np.allclose(y, ref, rtol=1e-12, atol=1e-11 * np.abs(ref).max())
     dense = sum((4 * n * (n + 1) if symmetric else 8 * n * n) for n in sizes)
-    assert ld.bytes == dense + 16 * n3 * r3
+    assert ld.bytes == dense + 8 * n3 * r3          # the factor block is read once (U sqrt(s))
     # bit-reproducible across launches (dynamic scheduling must not change the summation order)
     assert np.array_equal(y, ld.dot(x))
     ld.close()
+
+
+@pytest.mark.parametrize('once', [1, 0])
+def test_factor_blocks_read_once_and_two_pass(once):
+    """Factor blocks R = U diag(s) U^T in both device forms -- read once as U sqrt(s) (n <= 2816: odd n, a
+    single column, one column per chunk at n = 2816, several groups per block) and the two-pass form
+    V' = diag(s) U^T, U (option off, and always above 2816 rows) -- mixed with packed dense blocks;
+    against the dense product (reference LowRankMatrix.dot, matrix_structures.py:148-152)."""
+    from vilma_b200._lib import VilmaB200Error
+    from vilma_b200.engine import DeviceContext, DeviceLD, fac_nmax, set_option
+    rng = np.random.default_rng(5)
+    ctx = DeviceContext.get()
+    shapes = [(700, 150), (37, 5), (1, 1), (2816, 40), (2815, 333), (513, 256), (3000, 60), (2, 1), (1201, 600)]
+    blocks, refs = [], []
+    for n, r in shapes:
+        U = np.linalg.qr(rng.standard_normal((n, r)))[0]
+        s = rng.uniform(0.0, 2.0, r)
+        s[0] = 0.0                                   # a zero weight is fine in either form
+        blocks.append({'n': n, 'kind': 'factor', 'U': np.ascontiguousarray(U), 's': s})
+        refs.append((U * s) @ U.T)
+    a = rng.standard_normal((300, 300))
+    blocks.insert(3, {'n': 300, 'kind': 'dense', 'R': a + a.T})
+    refs.insert(3, a + a.T)
+    tot = sum(b['n'] for b in blocks)
+    M = tot + 7
+    perm = rng.permutation(M)[:tot]
+    set_option('ld_factor_once', once)
+    try:
+        assert fac_nmax() == (2816 if once else 0)
+        ld = DeviceLD(ctx, M, blocks, perm)
+        bad = None
+        if once:
+            with pytest.raises(VilmaB200Error, match='negative'):
+                bad = DeviceLD(ctx, 8, [{'n': 8, 'kind': 'factor', 'U': np.eye(8)[:, :2].copy(),
+                                         's': np.array([1.0, -0.5])}], np.arange(8))
+    finally:
+        set_option('ld_factor_once', 1)
+    assert bad is None
+    x = rng.standard_normal(M)
+    y = ld.dot(x)
+    ref = np.zeros(M)
+    off = 0
+    expect = 0
+    for b, R in zip(blocks, refs):
+        n = b['n']
+        idx = perm[off:off + n]
+        ref[idx] = R @ x[idx]
+        off += n
+        if b['kind'] == 'dense':
+            expect += 4 * n * (n + 1)
+        else:
+            r = b['U'].shape[1]
+            expect += 8 * (n + (n & 1)) * r if once and n <= 2816 else 16 * n * r
+    assert np.allclose(y, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+    missing = np.setdiff1d(np.arange(M), perm)
+    assert np.all(y[missing] == 0)
+    assert ld.bytes == expect
+    assert np.array_equal(y, ld.dot(x))          # bit-reproducible under dynamic claiming
+    ld.close()
+
+
+def test_low_rank_blocks_never_carry_negative_weights():
+    """The read-once factor form needs s >= 0.  LowRankMatrix keeps only s > 1e-12 max(s), exactly as the
+    reference (matrix_structures.py:18, :119), so a caller-made block with a negative weight loses it before
+    upload, and the device operator is the reference's."""
+    from vilma_b200.matrix_structures import BlockDiagonalMatrix, LowRankMatrix
+    rng = np.random.default_rng(6)
+    n, r = 400, 20
+    U = np.linalg.qr(rng.standard_normal((n, r)))[0]
+    s = rng.uniform(0.5, 2.0, r)
+    s[3] = -0.7
+    blk = LowRankMatrix(u=U, s=s, v=U.T.copy(), D=np.zeros(n))
+    assert blk.s.shape == (r - 1,) and blk.s.min() > 0
+    ld = BlockDiagonalMatrix([blk])
+    x = rng.standard_normal(n)
+    keep = s > 0
+    ref = (U[:, keep] * s[keep]) @ (U[:, keep].T @ x)
+    y = ld.dot(x)
+    assert np.allclose(y, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max()), np.abs(y - ref).max()
+    assert ld.to_device().bytes == 8 * n * (r - 1)
+    ld.release_device()
 
 
 def test_fails_loudly_on_bad_input():

@@ -17,6 +17,7 @@ SIGNATURES = {
     'vb_last_error': (C.c_char_p, []),
     'vb_set_option': (C.c_int, [C.c_char_p, C.c_int64]),
     'vb_ld_sym_nmax': (C.c_int64, []),
+    'vb_ld_fac_nmax': (C.c_int64, []),
     'vb_debug_tile_plan': (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int),
                                      C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     'vb_ctx_create': (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -665,7 +665,9 @@ vb_ld_sym_kernel(const double* __restrict__ mat, const VbSymItem* __restrict__ i
 // Groups of consecutive chunks of a block (~0.5 MB, the unit of dynamic claiming) emit one partial y
 // vector each, summed in group order by the finish kernel like the symmetric kernel's.  n <= VB_SYM_NMAX.
 // =====================================================================================
-#define VB_FAC_STAGE (44 * 1024)                    // bytes per stage: x (n_pad) + c columns (c n_pad)
+#ifndef VB_FAC_STAGE
+#define VB_FAC_STAGE (52 * 1024)                    // bytes per stage: x (n_pad) + c columns (c n_pad); 8 columns at n = 706
+#endif
 #define VB_FAC_STAGES 2
 #define VB_FAC_MAXC 32
 #define VB_FAC_RP ((VB_SYM_NMAX / 2 + 255) / 256)   // row pairs per thread (6)

@@ -61,6 +61,7 @@ static int g_tile_mode = -1;         // vb_set_option("snp_tile", ...): see tile
 static bool g_ann_slots = true;      // vb_set_option("snp_ann_slots", 0): fused annotation sums by warp shuffles only
 static bool g_snp3_park = true;      // vb_set_option("snp3_park", 0): three-pass kernel parks logits in the output buffers
 static int g_fused_finish = -1;      // vb_set_option("ld_fused_finish", v): -1 automatic, 0 separate finish kernel, 1 always fused
+static bool g_factor_once = true;    // vb_set_option("ld_factor_once", 0): factor blocks always in the two-pass form
 static bool g_three_pass = true;     // vb_set_option("snp_three_pass", 0): always the online single-pass kernel   // vb_set_option("ld_symmetric", 0): store dense blocks in full
 
 // ------------------------------------------------------------------------------------
@@ -86,6 +87,11 @@ struct LdBlock {
     std::vector<int> slabs2;       // phase 2: dense R or U
     bool filled = false;
     bool sym = false;              // dense block stored symmetric-packed
+    bool fac1 = false;             // factor block stored read-once (U sqrt(s), chunked column-major)
+    size_t fac_off = 0;            // its offset (doubles) in LdPop::mat
+    int64_t n_pad = 0;
+    int fac_c = 0;                 // columns per chunk
+    uint32_t fg0 = 0, fng = 0;     // its groups in LdPop::fgroups (and, after gout_fbase, in gout)
     std::vector<SymSlab> sslabs;   // its column slabs (one unless n > VB_SYM_NMAX)
 };
 struct LdPop {
@@ -112,6 +118,11 @@ struct LdPop {
     VbSymGroupOut* gout = nullptr;
     VbSymBlockRef* bref = nullptr;
     int64_t n_sgroups = 0;
+    // read-once factor blocks (vb_ld_fac_kernel); their partial vectors follow the symmetric groups' in gout
+    VbFacItem* fitems = nullptr;
+    VbSymGroup* fgroups = nullptr;
+    int64_t n_fgroups = 0;
+    uint32_t gout_fbase = 0;
     double* ypart = nullptr;
     VbFinRec* finrec = nullptr;    // per block-order position: finish-kernel record
     uint32_t *xstart = nullptr, *xoffs = nullptr;   // wide blocks: row sums a position takes from slabs to its left
@@ -295,9 +306,14 @@ extern "C" const char* vb_source_hash(void) { return g_source_hash + 15; }
 //   "snp_tile" (default -1 = automatic): the K-split tile kernel (snp_tile_kernel.cuh) with W warps per
 //       32-SNP tile; 0 = never, W > 0 = always with that many warps.
 extern "C" int64_t vb_ld_sym_nmax(void) { return VB_SYM_BLOCK_MAX; }
+extern "C" int64_t vb_ld_fac_nmax(void) { return g_factor_once ? VB_SYM_NMAX : 0; }
 extern "C" int vb_set_option(const char* name, int64_t value) {
     if (name && std::strcmp(name, "ld_symmetric") == 0) {
         g_disable_sym = (value == 0);
+        return 0;
+    }
+    if (name && std::strcmp(name, "ld_factor_once") == 0) {
+        g_factor_once = (value != 0);
         return 0;
     }
     if (name && std::strcmp(name, "ld_fused_finish") == 0) {
@@ -348,6 +364,8 @@ extern "C" int vb_ctx_create(int device, void* stream, vb_ctx** out) {
     CK(cudaFuncSetAttribute(vb_ld_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             VB_SYM_SMEM));
     CK(cudaFuncSetAttribute(vb_ld_sym_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CK(cudaFuncSetAttribute(vb_ld_fac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VB_FAC_SMEM));
+    CK(cudaFuncSetAttribute(vb_ld_fac_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     *out = c;
     return 0;
 }
@@ -357,6 +375,7 @@ static void free_ld(LdPop& L) {
     cudaFree(L.items1); cudaFree(L.items2); cudaFree(L.sched);
     cudaFree(L.pos); cudaFree(L.snp); cudaFree(L.xbpos); cudaFree(L.fin_counter);
     cudaFree(L.sitems); cudaFree(L.sgroups); cudaFree(L.gout); cudaFree(L.bref); cudaFree(L.ypart);
+    cudaFree(L.fitems); cudaFree(L.fgroups);
     cudaFree(L.finrec); cudaFree(L.xstart); cudaFree(L.xoffs);
     cudaFree(L.bfin); cudaFree(L.block_cnt); cudaFree(L.done_cnt); cudaFree(L.part_blk);
     L = LdPop();
@@ -545,6 +564,8 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
     size_t cursor = 0;
     int ns1 = 1, ns2 = 1;
     for (auto& b : L.blocks) {
+        b.fac1 = b.r >= 0 && g_factor_once && b.n <= VB_SYM_NMAX;
+        if (b.fac1) continue;
         if (b.r < 0) ns2 = std::max(ns2, (int)((b.n + VB_LD_CMAX - 1) / VB_LD_CMAX));
         else {
             ns1 = std::max(ns1, (int)((b.n + VB_LD_CMAX - 1) / VB_LD_CMAX));
@@ -562,6 +583,9 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
     std::vector<size_t> sgroup_bytes;
     std::vector<VbSymGroupOut> gout;
     std::vector<VbSymBlockRef> bref(L.blocks.size());
+    std::vector<VbFacItem> fitems;
+    std::vector<VbSymGroup> fgroups;
+    std::vector<VbSymGroupOut> fgout;
     size_t ypart_len = 0;
     for (size_t bi = 0; bi < L.blocks.size(); ++bi) {
         LdBlock& b = L.blocks[bi];
@@ -669,6 +693,52 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
         } else if (b.r < 0) {
             add_slabs(L, b.slabs2, b.n, b.n, b.xpos, b.xpos, L.xb_len, cursor, dummy2);
             L.bytes += 8 * b.n * b.n;
+        } else if (b.fac1) {
+            // read-once factor: U' = U sqrt(s) in chunks of c columns (c x n_pad column-major, contiguous),
+            // groups of consecutive chunks (~0.5 MB), one partial y vector (n_pad) per group
+            b.n_pad = even_up(b.n);
+            b.fac_c = vb_fac_chunk_cols(b.n_pad);
+            b.fac_off = cursor;
+            b.fg0 = (uint32_t)fgroups.size();
+            VbSymGroup cur;
+            cur.first_item = (uint32_t)fitems.size();
+            cur.n_items = 0;
+            size_t group_bytes = 0;
+            for (int64_t j0 = 0; j0 < b.r; j0 += b.fac_c) {
+                const int64_t cq = std::min<int64_t>(b.fac_c, b.r - j0);
+                const size_t a_off = b.fac_off + (size_t)j0 * b.n_pad;
+                if ((a_off >> 1) > 0xffffffffull) return vb_fail("LD store of one cohort exceeds 64 GiB on this rank");
+                VbFacItem it;
+                it.a_off16 = (uint32_t)(a_off >> 1);
+                it.x_off2 = (uint32_t)(b.xpos >> 1);
+                it.n2 = (uint16_t)(b.n_pad >> 1);
+                it.c = (uint16_t)cq;
+                it.flags = VB_FAC_VALID | (j0 == 0 ? VB_FAC_FIRST : 0);
+                it.pad = 0;
+                it.out_off = 0;
+                fitems.push_back(it);
+                cur.n_items++;
+                group_bytes += (size_t)cq * b.n_pad * 8;
+                if (j0 + cq >= b.r || group_bytes >= group_bytes_base) {
+                    ypart_len = (size_t)even_up((int64_t)ypart_len);          // double2 stores
+                    VbFacItem& last = fitems.back();
+                    last.flags |= VB_FAC_LASTGROUP;
+                    last.out_off = (uint32_t)ypart_len;
+                    VbSymGroupOut go;
+                    go.off = last.out_off;
+                    go.len = (uint32_t)b.n_pad;
+                    if (ypart_len + b.n_pad > 0xffffffffull) return vb_fail("LD partial buffer too large");
+                    ypart_len += b.n_pad;
+                    fgout.push_back(go);
+                    fgroups.push_back(cur);
+                    cur.first_item = (uint32_t)fitems.size();
+                    cur.n_items = 0;
+                    group_bytes = 0;
+                }
+            }
+            b.fng = (uint32_t)fgroups.size() - b.fg0;
+            cursor += (size_t)b.r * b.n_pad;
+            L.bytes += 8 * b.n_pad * b.r;
         } else {
             // phase 1: t = V' x, V' = diag(s) U^T  (r x n), x from xb, out to tb
             add_slabs(L, b.slabs1, b.r, b.n, b.xpos, b.tpos, L.tb_len, cursor, dummy1);
@@ -688,6 +758,15 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
     CK(cudaMalloc(&L.xall, (size_t)(L.xb_len + L.tb_len + 16) * sizeof(double)));
     CK(cudaMemsetAsync(L.xall, 0, (size_t)(L.xb_len + L.tb_len + 16) * sizeof(double), ctx->stream));
     L.n_sgroups = (int64_t)sgroups.size();
+    L.n_fgroups = (int64_t)fgroups.size();
+    L.gout_fbase = (uint32_t)gout.size();
+    gout.insert(gout.end(), fgout.begin(), fgout.end());
+    if (L.n_fgroups > 0) {
+        CK(cudaMalloc(&L.fitems, fitems.size() * sizeof(VbFacItem)));
+        CK(cudaMemcpy(L.fitems, fitems.data(), fitems.size() * sizeof(VbFacItem), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&L.fgroups, fgroups.size() * sizeof(VbSymGroup)));
+        CK(cudaMemcpy(L.fgroups, fgroups.data(), fgroups.size() * sizeof(VbSymGroup), cudaMemcpyHostToDevice));
+    }
     if (L.n_sgroups > 0) {
         CK(cudaMalloc(&L.sitems, sitems.size() * sizeof(VbSymItem)));
         CK(cudaMemcpy(L.sitems, sitems.data(), sitems.size() * sizeof(VbSymItem), cudaMemcpyHostToDevice));
@@ -702,13 +781,15 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
         for (size_t g = 0; g < order.size(); ++g) sched[g] = sgroups[order[g]];
         CK(cudaMalloc(&L.sgroups, sched.size() * sizeof(VbSymGroup)));
         CK(cudaMemcpy(L.sgroups, sched.data(), sched.size() * sizeof(VbSymGroup), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&L.bref, bref.size() * sizeof(VbSymBlockRef)));
+        CK(cudaMemcpy(L.bref, bref.data(), bref.size() * sizeof(VbSymBlockRef), cudaMemcpyHostToDevice));
+    }
+    if (L.n_sgroups + L.n_fgroups > 0) {
         L.gout_host = gout;
         CK(cudaMalloc(&L.gout, gout.size() * sizeof(VbSymGroupOut)));
         CK(cudaMemcpy(L.gout, gout.data(), gout.size() * sizeof(VbSymGroupOut), cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&L.bref, bref.size() * sizeof(VbSymBlockRef)));
-        CK(cudaMemcpy(L.bref, bref.data(), bref.size() * sizeof(VbSymBlockRef), cudaMemcpyHostToDevice));
-        CK(cudaMalloc(&L.ypart, std::max<size_t>(ypart_len, 1) * sizeof(double)));
-        CK(cudaMemsetAsync(L.ypart, 0, std::max<size_t>(ypart_len, 1) * sizeof(double), ctx->stream));
+        CK(cudaMalloc(&L.ypart, (std::max<size_t>(ypart_len, 1) + 2) * sizeof(double)));
+        CK(cudaMemsetAsync(L.ypart, 0, (std::max<size_t>(ypart_len, 1) + 2) * sizeof(double), ctx->stream));
     }
     CK(cudaMalloc(&L.yb, (size_t)L.nslab2 * L.xb_len * sizeof(double)));
     CK(cudaMemsetAsync(L.yb, 0, (size_t)L.nslab2 * L.xb_len * sizeof(double), ctx->stream));
@@ -718,8 +799,8 @@ static int ld_begin(vb_ctx* ctx, LdPop& L, int64_t M, int64_t nblocks, const int
     }
     if (build_items(ctx, L, 1, &L.items1, &L.n_items1)) return 1;
     if (build_items(ctx, L, 2, &L.items2, &L.n_items2)) return 1;
-    CK(cudaMalloc(&L.sched, 6 * sizeof(uint32_t)));
-    CK(cudaMemsetAsync(L.sched, 0, 6 * sizeof(uint32_t), ctx->stream));
+    CK(cudaMalloc(&L.sched, 8 * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(L.sched, 0, 8 * sizeof(uint32_t), ctx->stream));
     return 0;
 }
 
@@ -801,6 +882,22 @@ extern "C" int vb_ld_set_factor(vb_ld* h, int64_t b, const double* U, const doub
         dU = tmpU;
         ds = tmps;
     }
+    if (B.fac1) {
+        std::vector<double> hs((size_t)r);
+        if (on_device) CK(cudaMemcpy(hs.data(), s, (size_t)r * sizeof(double), cudaMemcpyDeviceToHost));
+        else std::memcpy(hs.data(), s, (size_t)r * sizeof(double));
+        for (int64_t k = 0; k < r; ++k)
+            if (!(hs[k] >= 0.0)) {
+                if (!on_device) { cudaStreamSynchronize(ctx->stream); cudaFree(tmpU); cudaFree(tmps); }
+                return vb_fail("vb_ld_set_factor: block %lld has a negative (or NaN) factor weight; the read-once "
+                               "form needs s >= 0 -- declare the block dense or set option ld_factor_once=0",
+                               (long long)b);
+            }
+        const int nchunks = (int)((r + B.fac_c - 1) / B.fac_c);
+        vb_pack_fac_kernel<<<nchunks, 256, 0, ctx->stream>>>(dU, ds, (int)n, (int)r, (int)B.n_pad, B.fac_c,
+                                                             L.mat + B.fac_off);
+        CK_LAUNCH(ctx);
+    }
     int64_t c0 = 0;
     for (int si : B.slabs1) {
         const LdSlab& sl = L.slabs[si];
@@ -876,6 +973,11 @@ extern "C" int vb_ld_finalize(vb_ld* h, const int64_t* perm_host, int64_t nperm)
                         xoffs.push_back(L.gout_host[gb].off + L.gout_host[gb].len + (uint32_t)(below % le.Rg));
                     }
                 }
+            } else if (b.fac1) {
+                // every group of the block emits a full-length partial vector
+                if (t > 0xfff || b.fng > 0xfff) return vb_fail("internal: finish record overflow");
+                rec[j].gfirst = (int32_t)(L.gout_fbase + b.fg0);
+                rec[j].loc_ncover = (uint32_t)t | (b.fng << 12);
             }
             const int64_t i = perm_host[j];
             if (i < 0 || i >= L.M) return vb_fail("vb_ld_finalize: perm[%lld]=%lld out of range", (long long)j, (long long)i);
@@ -896,7 +998,7 @@ extern "C" int vb_ld_finalize(vb_ld* h, const int64_t* perm_host, int64_t nperm)
         CK(cudaMalloc(&L.fin_counter, sizeof(uint32_t)));
         CK(cudaMemset(L.fin_counter, 0, sizeof(uint32_t)));
     }
-    if (L.n_sgroups > 0) {
+    if (L.n_sgroups + L.n_fgroups > 0) {
         CK(cudaMalloc(&L.finrec, rec.size() * sizeof(VbFinRec)));
         CK(cudaMemcpy(L.finrec, rec.data(), rec.size() * sizeof(VbFinRec), cudaMemcpyHostToDevice));
         if (L.all_sym) {
@@ -989,6 +1091,13 @@ static int ld_apply(vb_ctx* ctx, LdPop& L, const double* x_snp, double* y_snp, d
         ff.part_fin = partial;
         ff.fa = fa;
     }
+    if (L.n_fgroups > 0) {
+        prof_begin(ctx, 0);
+        vb_ld_fac_kernel<<<ctx->num_sms * 2, VB_LD_THREADS, VB_FAC_SMEM, st>>>(
+            L.mat, L.fitems, L.fgroups, (uint32_t)L.n_fgroups, L.sched + 6, L.xall, L.ypart);
+        prof_end(ctx, 0);
+        CK_LAUNCH(ctx);
+    }
     if (L.n_sgroups > 0) {
         prof_begin(ctx, 0);
         vb_ld_sym_kernel<<<ctx->num_sms * VB_SYM_CTAS_PER_SM, VB_LD_THREADS, VB_SYM_SMEM, st>>>(
@@ -996,6 +1105,8 @@ static int ld_apply(vb_ctx* ctx, LdPop& L, const double* x_snp, double* y_snp, d
         prof_end(ctx, 0);
         CK_LAUNCH(ctx);
         if (fused) return 0;
+    }
+    if (L.n_sgroups + L.n_fgroups > 0) {
         prof_begin(ctx, 2);
         vb_ld_finish_sym_kernel<<<grid_fin, 256, 0, st>>>(L.yb, L.xb_len, L.nslab2, L.ypart, L.finrec,
                                                           L.gout, L.xstart, L.xoffs, L.xall, L.nreal, y_snp,
@@ -1448,13 +1559,15 @@ static int launch_snp(vb_ctx* ctx, const VbSnpArgs& a, int P, int grid) {
         if (P <= 2 && g_three_pass) {       // exact-max softmax, one exp per (k, SNP)
             VbSnpArgs a3 = a;
             size_t sm3 = sm;
-            if (a.fuse_ann && a.A * a.K <= VB_FUSE_ANN_SLOTS && g_ann_slots) {
+            const bool slots = a.fuse_ann && a.A * a.K <= VB_FUSE_ANN_SLOTS && g_ann_slots;
+            if (slots) {
                 a3.fuse_ann = 2;
                 sm3 = (size_t)a.A * a.K * VB_SNP_THREADS * sizeof(double);
             }
             const size_t park = (size_t)a.K * (P + 1) * VB_SNP_THREADS * sizeof(double);
-            // (not together with the fused annotation slots: 43 KB per CTA -> 5 CTAs / SM, measured 12 % slower)
-            if (g_snp3_park && park <= VB_SNP3_PARK_MAX_BYTES && !a.fuse_ann) {
+            // (not together with the fused annotation slots: 43 KB per CTA -> 5 CTAs / SM, measured 12 % slower;
+            // with the sums by warp shuffles -- option snp_ann_slots=0 -- parking stays on)
+            if (g_snp3_park && park <= VB_SNP3_PARK_MAX_BYTES && !slots) {
                 static bool carve_set = false;
                 if (!carve_set) {       // all shared memory, no L1 needed: the kernel streams
                     cudaFuncSetAttribute(vb_snp3_kernel<1, MODE, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

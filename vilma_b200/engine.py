@@ -91,9 +91,20 @@ def dense_bytes(n):
     return 4 * n * (n + 1) if n <= sym_nmax() else 8 * n * n
 
 
+def fac_nmax():
+    """Largest factor block (rows) stored in the read-once form U sqrt(s) (0: switched off)."""
+    return int(_lib.load().vb_ld_fac_nmax())
+
+
+def factor_bytes(n, r):
+    """Bytes one mat-vec streams for a factor block: 8 n r read once when the block fits the read-once
+    kernel (n padded to even), else the two passes V' = diag(s) U^T and U."""
+    return 8 * (n + (n & 1)) * r if n <= fac_nmax() else 16 * n * r
+
+
 def choose_storage(n, r):
-    """'dense' when streaming the (packed) n x n block costs no more than the two factor passes."""
-    return 'dense' if dense_bytes(n) <= 16 * n * r else 'factor'
+    """'dense' when streaming the (packed) n x n block costs no more than the factor form."""
+    return 'dense' if dense_bytes(n) <= factor_bytes(n, r) else 'factor'
 
 
 def set_option(name, value):

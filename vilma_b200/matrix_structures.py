@@ -192,13 +192,13 @@ class BlockDiagonalMatrix():
         """Describe blocks for upload: dense reconstruction when rank is close to n, else factor.
         The reconstructions (one GEMM per block) run on the set-up thread pool."""
         from ._pool import map_blocks
-        from .engine import choose_storage, sym_nmax
-        sym_nmax()          # load the library on this thread before the workers ask for it
+        from .engine import choose_storage, fac_nmax
+        nmax = fac_nmax()   # (loads the library on this thread before the workers ask for it)
         ids = range(len(self.matrices)) if block_ids is None else block_ids
-        return map_blocks(lambda b: self._device_block(self.matrices[b], choose_storage), ids)
+        return map_blocks(lambda b: self._device_block(self.matrices[b], choose_storage, nmax), ids)
 
     @staticmethod
-    def _device_block(m, choose_storage):
+    def _device_block(m, choose_storage, fac_nmax=0):
         if not np.all(m.D == 0):
             raise NotImplementedError('device LD blocks must have a zero diagonal part D')
         if m.full_rank_certified and not m.factorized:
@@ -213,7 +213,8 @@ class BlockDiagonalMatrix():
         # the reference multiplies by v (= u^T for every block built from X); keep its semantics
         # exactly for a caller-supplied v by folding v into the factor only when it is the
         # transpose, else fall back to the dense product.
-        if m.v.shape == m.u.T.shape and np.array_equal(m.v, m.u.T):
+        # (the read-once factor form stores U sqrt(s): a caller-made block with a negative weight goes dense)
+        if m.v.shape == m.u.T.shape and np.array_equal(m.v, m.u.T) and (n > fac_nmax or m.s.min() >= 0):
             return {'n': n, 'kind': 'factor', 'U': m.u, 's': m.s}
         return {'n': n, 'kind': 'dense', 'R': (m.u * m.s).dot(m.v)}
 
