@@ -805,15 +805,6 @@ def measure(vi, ctx, info, comm, device, args, hbm_peak, peak_src, sampler=None,
             return wrapper
         vi.begin_loop = timed('upload+first evaluation', vi.begin_loop)
         vi._upload = timed('(upload alone)', vi._upload)
-        if os.environ.get('VILMA_B200_E2E_MARKS'):
-            vi._eng.eval = timed('(eval)', vi._eng.eval)
-            vi._comm.sum = timed('(comm.sum)', vi._comm.sum)
-            vi._set_result = timed('(set_result)', vi._set_result)
-            vi._fingerprint = timed('(fingerprint)', vi._fingerprint)
-            vi._objective = timed('(objective)', vi._objective)
-            import gc
-            gc.callbacks.append(lambda ph, inf: log('[gc %s gen %s at %.1f ms]' % (ph, inf.get('generation'), (time.perf_counter() - t0) * 1e3)))
-            vi._eng.pm_mark = timed('(pm_mark)', vi._eng.pm_mark)
         vi.run_loop = timed('iterations', vi.run_loop)
         vi._download = timed('download', vi._download)
         t0 = time.perf_counter()

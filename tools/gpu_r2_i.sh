@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l)
 ( time timeout 1500 python -m pytest tests/test_gpu_multi.py -q -x ) > gpurun_out/r2i_multi_n$N.log 2>&1
 tail -25 gpurun_out/r2i_multi_n$N.log
-( time VILMA_B200_E2E_MARKS=1 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 \
+( time timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 \
     bench.py --gpus $N --steps 20 --warmup 5 --extra-workloads none --no-cpu --converge 0 ) > gpurun_out/r2i_bench_n$N.json 2> gpurun_out/r2i_bench_n$N.err
 grep -o "\[rank [0-9]\] e2e[^\[]*" gpurun_out/r2i_bench_n$N.err; tail -3 gpurun_out/r2i_bench_n$N.err
 python - <<PY
