@@ -783,12 +783,15 @@ def measure(vi, ctx, info, comm, device, args, hbm_peak, peak_src, sampler=None,
     }
 
     # ---------------- end-to-end: the public call with host buffers ----------------
-    if with_e2e:
-        vi.num_its = args.steps
+    if with_e2e or converge:
+        # warm the page-locked host allocator: the first cudaHostAlloc of a result buffer costs ~50 ms for C2
+        # and ~7 s for C5's 14.8 GB -- a one-off of the process, not of the call being timed
         vi._resident = None
-        del_me = vi._download()      # warm the page-locked host allocator (first cudaHostAlloc is ~50 ms)
+        del_me = vi._download()
         del del_me
         vi._resident = None
+    if with_e2e:
+        vi.num_its = args.steps
         comm.barrier()
         torch.cuda.synchronize()
         tr0 = vi.n_trials

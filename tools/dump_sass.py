@@ -17,6 +17,7 @@ LIB = os.environ.get('VILMA_B200_LIB', os.path.join(ROOT, 'vilma_b200', 'libvilm
 KERNELS = {
     'vb_ld_sym_kernel': r'vb_ld_sym_kernel',
     'vb_ld_matvec_kernel': r'vb_ld_matvec_kernel',
+    'vb_ld_fac_kernel': r'vb_ld_fac_kernel',
     'vb_ld_finish_sym_kernel': r'vb_ld_finish_sym_kernel',
     'vb_snp3_kernel_P1_trial_park': r'vb_snp3_kernelILi1ELi0ELb1EE',
     'vb_snp_tile_kernel_P3_trial': r'vb_snp_tile_kernelILi3ELi0EE',
