@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Build a differently compiled libvilma_b200.so into variants/ and print the tile kernels' ptxas lines.
 
-    python tools/build_variant.py pair -DVB_TILE_PAIR=1 -DVB_TILE_UNROLL_A=1
+    python tools/build_variant.py pf4 -DVB_TILE_PREFETCH=4 -DVB_TILE_UNROLL_A=2
 
-`VILMA_B200_LIB=variants/lib_pair.so python tools/snp_bench.py ...` then measures it (variants/ is
+`VILMA_B200_LIB=variants/lib_pf4.so python tools/snp_bench.py ...` then measures it (variants/ is
 git-ignored but travels with gpurun)."""
 import os
 import re
