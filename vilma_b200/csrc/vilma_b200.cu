@@ -1329,7 +1329,7 @@ extern "C" int vb_fit_set_tau(vb_ctx* ctx, const double* tau) {
 static int fit_set_params(vb_ctx* ctx, const double* mu, const double* delta_mk, cudaMemcpyKind kind) {
     NEED_FIT(ctx);
     const size_t KM = (size_t)f.K * f.M;
-    CK(cudaMemcpyAsync(f.mu[f.cur_mu], mu, KM * f.P * 8, kind, ctx->stream));
+    if (mu) CK(cudaMemcpyAsync(f.mu[f.cur_mu], mu, KM * f.P * 8, kind, ctx->stream));     // (null: already queued)
     // vi_delta arrives in the reference layout [M][K]; stage it in the trial slot, transpose on device
     double* stage = f.delta[1 - f.cur_delta];
     CK(cudaMemcpyAsync(stage, delta_mk, KM * 8, kind, ctx->stream));
@@ -1399,6 +1399,9 @@ extern "C" int vb_fit_set_shard(vb_ctx* ctx, const int64_t* snps_host, int64_t M
     if (!f.shard_idx) CK(cudaMalloc(&f.shard_idx, (size_t)f.M * sizeof(int64_t)));
     CK(cudaMemcpy(f.shard_idx, snps_host, (size_t)f.M * sizeof(int64_t), cudaMemcpyHostToDevice));
     f.shard_total = M_total;
+    // page-locked staging for uploads, allocated here so that no transfer pays for cudaHostAlloc (~4 ms)
+    if (!f.shard_stage)
+        CK(cudaHostAlloc(&f.shard_stage, ((size_t)f.K * f.P + f.K) * (size_t)f.M * 8, cudaHostAllocDefault));
     f.shard_runs.clear();
     for (int64_t j = 0; j < f.M;) {
         int64_t e = j + 1;
@@ -1417,7 +1420,6 @@ extern "C" int vb_fit_set_params_shard(vb_ctx* ctx, const double* mu_g, const do
     NEED_FIT(ctx);
     if (!f.shard_idx) return vb_fail("sharded transfer: call vb_fit_set_shard first");
     const size_t KM = (size_t)f.K * f.M, rows = (size_t)f.K * f.P;
-    if (!f.shard_stage) CK(cudaHostAlloc(&f.shard_stage, (rows + f.K) * (size_t)f.M * 8, cudaHostAllocDefault));
     double* st_mu = f.shard_stage;
     double* st_dl = f.shard_stage + rows * f.M;
     const int64_t* runs = f.shard_runs.data();
@@ -1425,18 +1427,24 @@ extern "C" int vb_fit_set_params_shard(vb_ctx* ctx, const double* mu_g, const do
     const int64_t M = f.M, Mt = f.shard_total;
     const int K = f.K;
     const int T = (int)std::max<size_t>(1, std::min<size_t>(4, KM * (f.P + 1) / (1u << 20)));
-    auto work = [&](int t) {
+    auto run_threads = [&](auto&& work) {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    };
+    // mu first; its DMA runs while the threads cut out delta
+    run_threads([&](int t) {
         for (size_t r = t; r < rows; r += T)
             for (size_t q = 0; q < nruns; ++q)
                 std::memcpy(st_mu + r * M + runs[3 * q + 1], mu_g + r * Mt + runs[3 * q], (size_t)runs[3 * q + 2] * 8);
+    });
+    CK(cudaMemcpyAsync(f.mu[f.cur_mu], st_mu, KM * f.P * 8, cudaMemcpyHostToDevice, ctx->stream));
+    run_threads([&](int t) {
         for (size_t q = t; q < nruns; q += T)
             std::memcpy(st_dl + (size_t)runs[3 * q + 1] * K, dl_g + (size_t)runs[3 * q] * K, (size_t)runs[3 * q + 2] * K * 8);
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < T; ++t) th.emplace_back(work, t);
-    work(0);
-    for (auto& x : th) x.join();
-    return fit_set_params(ctx, st_mu, st_dl, cudaMemcpyHostToDevice);
+    });
+    return fit_set_params(ctx, nullptr, st_dl, cudaMemcpyHostToDevice);
 }
 // device address of a host pointer the GPU can access directly, or nullptr
 static double* device_view(const void* host) {
