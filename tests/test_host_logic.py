@@ -112,6 +112,67 @@ def test_two_ranks_gloo(name, tmp_path):
         assert 'rank %d ok' % r in o
 
 
+_POOL_WORKER = r"""
+import gc, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch.distributed as dist
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:{port}', rank=int(sys.argv[1]), world_size=2)
+from vilma_b200.dist import TorchComm, _SHM_POOL
+comm = TorchComm()
+rank = comm.rank
+shapes = [(3, 2, 1000), (1000, 3)]
+(a, b), e1 = comm.shared_arrays(shapes)
+mine = slice(0, 500) if rank == 0 else slice(500, 1000)
+a[..., mine] = rank + 1.0
+b[mine] = 10.0 * (rank + 1)
+comm.barrier()
+assert np.all(a[..., :500] == 1.0) and np.all(a[..., 500:] == 2.0)          # the other rank's half is visible
+assert np.all(b[:500] == 10.0) and np.all(b[500:] == 20.0)
+addr1 = e1['address']
+# still referenced (here on rank 0 only): a second request must get a NEW mapping on both ranks
+keep = a[0] if rank == 0 else None
+del a, b
+(c, d), e2 = comm.shared_arrays(shapes)
+assert e2 is not e1 and len(_SHM_POOL) == 2
+del c, d, keep
+gc.collect()
+# everything dropped everywhere: the first free mapping of that size is handed out again
+(f, g), e3 = comm.shared_arrays(shapes)
+assert e3 is e1 and e3['address'] == addr1 and len(_SHM_POOL) == 2
+released = []
+e2['release'] = lambda: released.append(1)
+del f, g
+# another size: the unreferenced mappings are released (hook called) and unmapped, one new mapping remains
+(h,), e4 = comm.shared_arrays([(7, 11)])
+assert len(_SHM_POOL) == 1 and _SHM_POOL[0] is e4 and released == [1]
+h[:] = rank
+comm.barrier()
+# a second communicator object shares the process-wide pool
+(k,), e5 = TorchComm().shared_arrays([(7, 11)])
+assert e5 is not e4 and len(_SHM_POOL) == 2          # h is still referenced
+print('rank %d ok' % rank)
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_shared_result_mappings_are_pooled_consistently(tmp_path):
+    """TorchComm.shared_arrays over gloo, world_size=2: one node-shared mapping every rank writes its part
+    of; a mapping is reused only when EVERY rank has dropped its arrays; a request for another size releases
+    the unreferenced ones (through the hook a caller installed when it page-locked them) and the pools of
+    the two ranks keep the same entries throughout (they vote with one all-reduce per request)."""
+    port = 31500 + (os.getpid() % 2000)
+    script = tmp_path / 'pool_worker.py'
+    script.write_text(_POOL_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, 'rank %d failed:\n%s' % (r, o)
+        assert 'rank %d ok' % r in o
+
+
 def test_c_abi_exports_every_declared_symbol():
     """libvilma_b200.so builds for sm_100a without a GPU and exports include/vilma_b200.h."""
     from vilma_b200 import _build, _lib

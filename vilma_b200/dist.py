@@ -171,7 +171,8 @@ class TorchComm(SingleComm):
         and all of them end up with the same zero-copy view, instead of an all-gather to every GPU
         followed by N full device->host copies.  Mappings are pooled: one whose arrays have been dropped
         on EVERY rank is handed out again (its pages are already faulted in and, where the caller had it
-        page-locked, still registered), otherwise a new one is created.  Returns (arrays, entry) -- `entry`
+        page-locked, still registered); when none of the right size is free, the unreferenced ones are
+        released and a new one is created.  Returns (arrays, entry) -- `entry`
         is the pool record, a dict the caller may keep notes in ('address', 'nbytes' are set) -- or None
         when the ranks do not share a host or /dev/shm lacks the space.  Collective."""
         import mmap
@@ -190,20 +191,33 @@ class TorchComm(SingleComm):
             self._shm_same_host = len(set(hosts)) == 1
         if not self._shm_same_host:
             return None
-        # The pool belongs to the process, not to this communicator object, and its mappings are never
-        # unmapped: a caller may have page-locked one with the CUDA driver, and unmapping a registered
-        # range leaves a stale registration behind that a later mapping at the same address would inherit.
-        self._shm_pool = _SHM_POOL
-        # a pooled mapping of this size that nobody references any more -- on any rank?
-        flag = torch.zeros(len(self._shm_pool) + 1, dtype=torch.int32)
-        for i, e in enumerate(self._shm_pool):
-            if e['nbytes'] == total and all(r() is None for r in e['refs']):
+        # The pool belongs to the process, not to this communicator object.  A caller may have page-locked a
+        # mapping with the CUDA driver (entry['release'] undoes that): a mapping is only unmapped through
+        # its release hook -- unmapping a registered range would leave a stale registration behind that a
+        # later mapping at the same address inherits.
+        pool = self._shm_pool = _SHM_POOL
+        # mappings that nobody references any more -- on any rank
+        flag = torch.zeros(len(pool) + 1, dtype=torch.int32)
+        for i, e in enumerate(pool):
+            if all(r() is None for r in e['refs']):
                 flag[i] = 1
         if self._backend == 'nccl':
             flag = flag.cuda()
         self._dist.all_reduce(flag, op=self._dist.ReduceOp.MIN)
         flag = flag.cpu().numpy()
-        entry = next((self._shm_pool[i] for i in range(len(self._shm_pool)) if flag[i] == 1), None)
+        free = [e for i, e in enumerate(pool) if flag[i] == 1]
+        entry = next((e for e in free if e['nbytes'] == total), None)
+        if entry is None:
+            # nothing of this size to hand out again: give the unreferenced mappings back first
+            # (every rank sees the same flags, so the pools stay identical)
+            for e in free:
+                try:
+                    if e.get('release') is not None:
+                        e['release']()
+                    e['mm'].close()
+                except (BufferError, ValueError, OSError):
+                    pass                          # (cannot unmap: it is dropped from the pool all the same --
+                pool.remove(e)                    #  every rank's pool must keep the same entries)
         if entry is None:
             name = b''
             if self.rank == 0:

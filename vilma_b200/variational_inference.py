@@ -767,6 +767,10 @@ class MultiPopVI(VIScheme):
             if hasattr(eng, 'get_params_shard'):
                 if 'registered' not in entry:
                     entry['registered'] = eng.host_register(entry['address'], entry['nbytes'])
+                    if entry['registered']:
+                        from . import _lib
+                        addr = entry['address']
+                        entry['release'] = lambda: _lib.load().vb_host_unregister(_lib.C.c_void_p(addr))
                 direct = entry['registered']
             else:
                 direct = False
