@@ -97,15 +97,17 @@ print('rank', sys.argv[1], 'ok')
 '''
 
 
-@pytest.mark.parametrize('name', ['syn_p1_dense', 'syn_p2_lowrank'])
-def test_two_ranks_gloo(name, tmp_path):
+@pytest.mark.parametrize('name,no_shm', [('syn_p1_dense', '0'), ('syn_p2_lowrank', '0'), ('syn_p1_dense', '1')])
+def test_two_ranks_gloo(name, no_shm, tmp_path):
     """world_size=2 over gloo: sharded SNPs + all-reduced statistics give the single-process
-    trajectory (same decisions on every rank)."""
+    trajectory (same decisions on every rank).  The fitted parameters come back through the node-shared
+    mapping, or -- VILMA_B200_NO_SHM=1, as on a host whose /dev/shm is too small -- through all-gathers."""
     port = 29500 + (os.getpid() % 2000)
     script = tmp_path / 'worker.py'
     script.write_text(_WORKER.format(root=ROOT, port=port, name=name))
+    env = dict(os.environ, VILMA_B200_NO_SHM=no_shm)
     procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
-                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+                              stderr=subprocess.STDOUT, text=True, env=env) for r in range(2)]
     outs = [p.communicate(timeout=600)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, 'rank %d failed:\n%s' % (r, o)

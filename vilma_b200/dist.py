@@ -187,8 +187,9 @@ class TorchComm(SingleComm):
             total += int(np.prod(shp)) * 8
             total = (total + 4095) & ~4095
         if not hasattr(self, '_shm_same_host'):
-            hosts = self.allgather_bytes(socket.gethostname().encode())
-            self._shm_same_host = len(set(hosts)) == 1
+            # (VILMA_B200_NO_SHM=1 on any rank switches the shared mapping off for all of them)
+            hosts = self.allgather_bytes((socket.gethostname() + '|' + os.environ.get('VILMA_B200_NO_SHM', '0')).encode())
+            self._shm_same_host = len(set(hosts)) == 1 and hosts[0].endswith(b'|0')
         if not self._shm_same_host:
             return None
         # The pool belongs to the process, not to this communicator object.  A caller may have page-locked a
