@@ -175,6 +175,22 @@ def test_shared_result_mappings_are_pooled_consistently(tmp_path):
         assert 'rank %d ok' % r in o
 
 
+def test_storage_choice_by_bytes_streamed():
+    """engine.choose_storage picks, per LD block, the device form that streams the fewest bytes per mat-vec:
+    packed dense 4 n (n+1), read-once factor 8 n_pad r (n <= vb_ld_fac_nmax), two-pass factor 16 n r."""
+    from vilma_b200.engine import choose_storage, dense_bytes, fac_nmax, factor_bytes, sym_nmax
+    assert fac_nmax() == 2816 and sym_nmax() == 65528
+    assert dense_bytes(706) == 4 * 706 * 707 and dense_bytes(70000) == 8 * 70000 ** 2
+    assert factor_bytes(706, 211) == 8 * 706 * 211 and factor_bytes(705, 10) == 8 * 706 * 10
+    assert factor_bytes(3000, 100) == 16 * 3000 * 100
+    # --ldthresh 0.99-like panels (r = 0.3 n): factors, read once (round 1 stored them dense: 16 n r > 4 n (n+1))
+    assert choose_storage(706, 211) == 'factor'
+    # the break-even of the read-once form is r = (n + 1) / 2, of the two-pass form r = (n + 1) / 4
+    assert choose_storage(1000, 500) == 'factor' and choose_storage(1000, 501) == 'dense'
+    assert choose_storage(3000, 750) == 'factor' and choose_storage(3000, 751) == 'dense'
+    assert choose_storage(706, 706) == 'dense'
+
+
 def test_c_abi_exports_every_declared_symbol():
     """libvilma_b200.so builds for sm_100a without a GPU and exports include/vilma_b200.h."""
     from vilma_b200 import _build, _lib
