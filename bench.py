@@ -141,7 +141,9 @@ def build_gpu_problem(comm, device, M_total=M_TOTAL, n_blocks=N_BLOCKS, num_its=
 WORKLOADS = {
     'c3': dict(P=3, N=(3e5, 1e5, 5e4), n_ref=0.3, ldthresh=0.99, grid=('simple', 2),
                name='BASELINE configs[2]: synthetic 3-cohort joint fit, per-cohort low-rank LD '
-                    '(reference panel of 0.3 n haplotypes, --ldthresh 0.99), -K 2 grid'),
+                    '(reference panel of 0.3 n haplotypes, --ldthresh 0.99), -K 2 grid restricted to its '
+                    'positive-definite members (the reference constructor rejects the others, '
+                    'variational_inference.py:610-613): 87 components; blocks stored as read-once factors'),
     'c5': dict(P=5, N=(3e5, 1e5, 5e4, 5e4, 2e4), n_ref=2.0, ldthresh=1.0, grid=('custom', 256),
                name='BASELINE configs[4]: synthetic 5-cohort fit, dense per-cohort LD, custom grid of '
                     '256 SPD covariance matrices'),
