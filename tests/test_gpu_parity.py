@@ -267,6 +267,33 @@ def test_big_block_slabs_and_factor(symmetric):
     ld.close()
 
 
+def test_widest_block_of_the_6m_snp_workload():
+    """One symmetric-packed block of 13 827 rows -- the largest block of BASELINE configs[3] (bench.py
+    --workload c4) -- is cut into five column slabs; against the dense product, next to a small block so that
+    the finish kernel mixes single-slab and multi-slab records."""
+    from vilma_b200.engine import DeviceContext, DeviceLD
+    rng = np.random.default_rng(11)
+    ctx = DeviceContext.get()
+    n = 13827
+    a = rng.standard_normal((n, n))
+    big = a + a.T
+    del a
+    small = rng.standard_normal((40, 40))
+    small = small + small.T
+    M = n + 40 + 3
+    perm = rng.permutation(M)[:n + 40]
+    ld = DeviceLD(ctx, M, [{'n': 40, 'kind': 'dense', 'R': small}, {'n': n, 'kind': 'dense', 'R': big}], perm)
+    assert ld.bytes == 4 * n * (n + 1) + 4 * 40 * 41
+    x = rng.standard_normal(M)
+    y = ld.dot(x)
+    ref = np.zeros(M)
+    ref[perm[:40]] = small @ x[perm[:40]]
+    ref[perm[40:]] = big @ x[perm[40:]]
+    assert np.allclose(y, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max()), np.abs(y - ref).max()
+    assert np.array_equal(y, ld.dot(x))
+    ld.close()
+
+
 @pytest.mark.parametrize('once', [1, 0])
 def test_factor_blocks_read_once_and_two_pass(once):
     """Factor blocks R = U diag(s) U^T in both device forms -- read once as U sqrt(s) (n <= 2816: odd n, a
