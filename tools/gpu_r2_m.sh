@@ -3,7 +3,7 @@
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l)
-for rep in a b; do
+for rep in ${REPS:-a b}; do
 ( time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2961$N \
     bench.py --gpus $N --steps 20 --warmup 5 --extra-workloads none --no-cpu ) > gpurun_out/r2m_bench_n${N}_$rep.json 2> gpurun_out/r2m_bench_n${N}_$rep.err
 grep -o "\[rank 0\] e2e[^\[]*" gpurun_out/r2m_bench_n${N}_$rep.err; grep -o "\[rank 0\] native loop[^\[]*" gpurun_out/r2m_bench_n${N}_$rep.err
