@@ -42,6 +42,7 @@ const char* vb_last_error(void);
  *                  (read when an LD operator is created)
  *   "ld_factor_once" (default 1): factor blocks of n <= vb_ld_fac_nmax() are stored as U sqrt(s) and read once
  *                  per mat-vec (8 n r bytes; needs s >= 0); 0 = always V' = diag(s) U^T and U (16 n r bytes)
+ *   "shard_zero_copy" (default 1): vb_fit_set_params_shard reads page-locked sources in place (0: always staged)
  *   "ld_fused_finish" (default 0): 1 = the symmetric kernel also finishes every block whose last group it flushed
  *   "snp_three_pass" (default 1): one- and two-cohort updates with K < 32 use the three-pass softmax kernel
  *   "snp3_park" (default 1): that kernel keeps logits / weights / mu' in shared memory when they fit
@@ -150,8 +151,9 @@ int vb_fit_get_params_dev(vb_ctx* ctx, double* vi_mu_dev, double* vi_delta_mk_de
 /* Sharded transfers (multi-GPU): `snps_host[M]` = global index of each SNP this rank owns, of M_total.
  * The *_shard calls move only this rank's SNPs between the device state and GLOBAL host arrays in the
  * reference layouts (vi_mu [K,P,M_total], vi_delta [M_total,K]); they replace gathering
- * `variational_inference.py:340-394`'s parameter tuple on every rank.  set: any host memory (runs of
- * consecutive SNPs are cut out into page-locked staging by a few host threads).  get: the GPU scatters
+ * `variational_inference.py:340-394`'s parameter tuple on every rank.  set: any host memory -- arrays the
+ * GPU can address are gathered by it directly (zero-copy reads; option "shard_zero_copy", default 1), others
+ * have their runs of consecutive SNPs cut out into page-locked staging by a few host threads.  get: the GPU scatters
  * into the arrays itself, so they must be memory it can address -- page-locked allocations or memory
  * registered with vb_host_register, e.g. one node-shared mapping of which every rank fills in its own
  * part; it fails (no fallback) on plain pageable memory: ask vb_host_accessible. */

@@ -61,6 +61,7 @@ static int g_tile_mode = -1;         // vb_set_option("snp_tile", ...): see tile
 static bool g_ann_slots = true;      // vb_set_option("snp_ann_slots", 0): fused annotation sums by warp shuffles only
 static bool g_snp3_park = true;      // vb_set_option("snp3_park", 0): three-pass kernel parks logits in the output buffers
 static int g_fused_finish = -1;      // vb_set_option("ld_fused_finish", v): -1 automatic, 0 separate finish kernel, 1 always fused
+static bool g_shard_zero_copy = true;   // vb_set_option("shard_zero_copy", 0): sharded uploads always through host staging
 static bool g_factor_once = true;    // vb_set_option("ld_factor_once", 0): factor blocks always in the two-pass form
 static bool g_three_pass = true;     // vb_set_option("snp_three_pass", 0): always the online single-pass kernel   // vb_set_option("ld_symmetric", 0): store dense blocks in full
 
@@ -310,6 +311,10 @@ extern "C" int64_t vb_ld_fac_nmax(void) { return g_factor_once ? VB_SYM_NMAX : 0
 extern "C" int vb_set_option(const char* name, int64_t value) {
     if (name && std::strcmp(name, "ld_symmetric") == 0) {
         g_disable_sym = (value == 0);
+        return 0;
+    }
+    if (name && std::strcmp(name, "shard_zero_copy") == 0) {
+        g_shard_zero_copy = (value != 0);
         return 0;
     }
     if (name && std::strcmp(name, "ld_factor_once") == 0) {
@@ -1392,6 +1397,23 @@ __global__ void vb_shard_delta_kernel(double* __restrict__ glob, const double* _
         glob[idx[j] * K + k] = loc[(size_t)k * M_loc + j];
     }
 }
+static double* device_view(const void* host);
+// the reverse direction (upload from host memory the device can address): zero-copy reads over PCIe
+__global__ void vb_shard_rows_gather_kernel(const double* __restrict__ glob, double* __restrict__ loc,
+                                            const int64_t* __restrict__ idx, int64_t M_loc, int64_t M_tot) {
+    const size_t r = blockIdx.y;
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < M_loc; j += (int64_t)gridDim.x * blockDim.x)
+        loc[r * M_loc + j] = glob[r * M_tot + idx[j]];
+}
+__global__ void vb_shard_delta_gather_kernel(const double* __restrict__ glob, double* __restrict__ loc,
+                                             const int64_t* __restrict__ idx, int64_t M_loc, int K) {
+    const int64_t n = M_loc * K;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = t / K;
+        const int k = (int)(t - j * K);
+        loc[(size_t)k * M_loc + j] = glob[idx[j] * K + k];
+    }
+}
 extern "C" int vb_fit_set_shard(vb_ctx* ctx, const int64_t* snps_host, int64_t M_total) {
     NEED_FIT(ctx);
     for (int64_t j = 0; j < f.M; ++j)
@@ -1413,12 +1435,29 @@ extern "C" int vb_fit_set_shard(vb_ctx* ctx, const int64_t* snps_host, int64_t M
     }
     return 0;
 }
-// Upload of this rank's SNPs from GLOBAL host arrays of any kind (pageable included): a few host threads
-// cut the runs out into page-locked staging (memcpy per run and row), then two full-speed DMA copies.
-// (A zero-copy gather by the GPU was measured at 3.3 GB/s: PCIe reads, unlike writes, are not posted.)
+// Upload of this rank's SNPs from GLOBAL host arrays.  Page-locked / registered sources (option
+// "shard_zero_copy", default on): the GPU gathers its SNPs itself with zero-copy reads -- no host pass.  Any other
+// memory (pageable included): a few host threads cut the runs out into page-locked staging (memcpy per
+// run and row), then two full-speed DMA copies, the first overlapping the second cut.
 extern "C" int vb_fit_set_params_shard(vb_ctx* ctx, const double* mu_g, const double* dl_g) {
     NEED_FIT(ctx);
     if (!f.shard_idx) return vb_fail("sharded transfer: call vb_fit_set_shard first");
+    if (g_shard_zero_copy) {
+        const double* gmu = device_view(mu_g);
+        const double* gdl = device_view(dl_g);
+        if (gmu && gdl) {
+            const int gx = (int)std::min<int64_t>((f.M + 255) / 256, 2048);
+            vb_shard_rows_gather_kernel<<<dim3(gx, f.K * f.P), 256, 0, ctx->stream>>>(gmu, f.mu[f.cur_mu], f.shard_idx,
+                                                                                     f.M, f.shard_total);
+            CK_LAUNCH(ctx);
+            const int gd = (int)std::min<int64_t>((f.M * f.K + 255) / 256, 148 * 64);
+            vb_shard_delta_gather_kernel<<<gd, 256, 0, ctx->stream>>>(gdl, f.delta[f.cur_delta], f.shard_idx, f.M, f.K);
+            CK_LAUNCH(ctx);
+            CK(cudaStreamSynchronize(ctx->stream));
+            f.trial_kind = -1;
+            return 0;
+        }
+    }
     const size_t KM = (size_t)f.K * f.M, rows = (size_t)f.K * f.P;
     double* st_mu = f.shard_stage;
     double* st_dl = f.shard_stage + rows * f.M;
